@@ -1,0 +1,83 @@
+"""ctypes binding of ``liblompc_b200.so`` (C ABI: ``include/lompc_b200.h``).
+
+The library is built in-tree by ``__graft_entry__.build()`` (or ``make -C
+incentive-design-mpc_b200/csrc``).  Loading fails loudly if it is missing:
+this package has no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "liblompc_b200.so")
+
+OK = 0
+ERR_CONSTS, ERR_ARG, ERR_CUDA, ERR_GAMMA, ERR_NEGATIVE, ERR_NOT_CONVERGED, ERR_NO_DEVICE = (
+    -1, -2, -3, -4, -5, -6, -7)
+EV_SMALL, EV_LARGE = 0, 1
+ST_OK, ST_MAXITER, ST_BAD_GAMMA, ST_NEGATIVE = 0, 1, 2, 3
+
+_dp = C.POINTER(C.c_double)
+_ip = C.POINTER(C.c_int32)
+
+# name -> (restype, argtypes); every symbol include/lompc_b200.h declares.
+SIGNATURES = {
+    "lompc_version": (C.c_char_p, []),
+    "lompc_strerror": (C.c_char_p, [C.c_int]),
+    "lompc_last_cuda_error": (C.c_char_p, []),
+    "lompc_device_count": (C.c_int, []),
+    "lompc_create": (C.c_int, [C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int,
+                               C.c_int, C.POINTER(C.c_void_p)]),
+    "lompc_destroy": (C.c_int, [C.c_void_p]),
+    "lompc_sc_modulus": (C.c_double, [C.c_void_p]),
+    "lompc_set_options": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "lompc_solve_batch_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                        C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                        C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lompc_solve_batch_host": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
+                                         C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                         C.c_void_p, C.c_void_p]),
+    "lompc_launch_count": (C.c_int64, []),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Loads the shared library once and types every entry point."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -c 'import __graft_entry__ as g; "
+            "g.build()'` or `make -C incentive-design-mpc_b200/csrc` (no CPU fallback exists)")
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def strerror(code: int) -> str:
+    lib = load()
+    msg = lib.lompc_strerror(code).decode()
+    if code == ERR_CUDA:
+        msg += ": " + lib.lompc_last_cuda_error().decode()
+    return msg
+
+
+def raise_for(code: int) -> None:
+    """Maps C error codes onto the reference's exception types."""
+    if code == OK:
+        return
+    msg = strerror(code)
+    if code in (ERR_CONSTS, ERR_GAMMA):
+        raise AssertionError(msg)  # Python asserts in lompc.py:36-38,87
+    if code == ERR_NEGATIVE:
+        raise ValueError(msg)  # cvxpy nonneg Parameter, lompc.py:78-82
+    if code == ERR_ARG:
+        raise ValueError(msg)
+    raise RuntimeError(msg)

@@ -1,0 +1,280 @@
+// K1: batched lower-level MPC QP solve, one QP per thread (sm_100a, fp64).
+//
+// Replaces LoMPC.solve_lompc (reference lompc.py:137-156) for a whole batch.
+// The QP (lompc.py:92-135) is, per EV,
+//
+//   min  sum_k [ 1/2 d_k w_k^2 + g_k w_k + psi(w_k) ] + c/2 sum_k (s_k - gamma)^2
+//   s.t. s_k = s_{k-1} + w_k  (s = A w, A = tril(ones), lompc.py:69),  0 <= w_k <= w_max
+//
+// with d_k = 2(lmbd_r theta^2 + q lmbd3_k) [+ 2 theta^2/0.81 small EV],
+// g_k = theta (lmbd1_k - lmbd2_k), psi = the large-EV pwl (convex, 4 pieces).
+// That is a scalar-state optimal-control problem, so every linear solve is an
+// O(N) scalar Riccati recursion instead of a dense factorisation.
+//
+// Algorithm (exact, finite): an active-set Newton method built from two sweeps
+// per iteration.
+//   backward sweep  k = N-1..0 : costate p_k = c sum_{j>=k}(s_j - gamma), gradient
+//       q_k = d_k w_k + g_k + p_k, per-coordinate KKT test (which also picks
+//       the working segment / binding set), Riccati recursion of the
+//       equality-constrained problem on that working set -> gains (K, kappa).
+//   forward sweep   k = 0..N-1 : stage-optimal rollout -- each w_k is the exact
+//       minimiser of  stage cost + quadratic cost-to-go  over [0, w_max]
+//       (a fused clip for the box, a min/max ladder for the pwl kinks), and the
+//       objective of the rollout is accumulated on the fly.
+// The rollout is accepted iff it lowers the objective; otherwise the same
+// Riccati gains give the projected-Newton direction on the working set and a
+// backtracking search along its projection arc (always a descent step), so
+// the iteration cannot cycle.  It stops when the KKT residual of the backward
+// sweep is below tol * scale, i.e. at the exact optimum of the active face.
+#pragma once
+#include "lompc_common.cuh"
+
+namespace lompc {
+
+// Shared-memory layout: per-thread columns, element k of thread t at [k*T + t]
+// (conflict-free: a warp touches 32 consecutive doubles).
+template <int NSEG>
+struct SmemLayout {
+  static constexpr int kArrays = (NSEG > 1) ? 7 : 6;  // D,G,KK,KAP,W0,W1 (+INV)
+  __host__ __device__ static size_t bytes(int N, int T) {
+    return (size_t)kArrays * N * T * sizeof(double) + (size_t)N * T;
+  }
+};
+
+template <int NSEG>
+__device__ __forceinline__ double pwl_value(const Consts& cs, double x) {
+  double psi = 0.0;
+#pragma unroll
+  for (int j = 1; j < NSEG; ++j) psi += (cs.slope[j] - cs.slope[j - 1]) * fmax(x - cs.brk[j], 0.0);
+  return psi;
+}
+
+template <int NSEG>
+__global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const SolveArgs a) {
+  extern __shared__ double smem[];
+  const int T = blockDim.x;
+  const int t = threadIdx.x;
+  const int N = cs.N;
+  const int64_t b = (int64_t)blockIdx.x * T + t;
+  const bool live = b < a.B;
+
+  double* D = smem + t;
+  double* G = D + (size_t)N * T;
+  double* KK = G + (size_t)N * T;
+  double* KAP = KK + (size_t)N * T;
+  double* WA = KAP + (size_t)N * T;
+  double* WB = WA + (size_t)N * T;
+  double* INV = WB + (size_t)N * T;  // only touched when NSEG > 1
+  unsigned char* CFG =
+      reinterpret_cast<unsigned char*>(smem + (size_t)SmemLayout<NSEG>::kArrays * N * T) + t;
+  if (!live) return;  // no block-level sync below
+
+  // ---- problem data (lompc.py:101-135 restated) -------------------------------
+  const double* lm = a.lmbd + b * a.lmbd_stride;
+  const double lr = a.lmbd_r[b * a.lmbd_r_stride];
+  const double gam = a.gamma[b];
+  int st = LOMPC_ST_OK;
+  if (gam < 0.0 || lr < 0.0) st = LOMPC_ST_NEGATIVE;  // nonneg parameters, lompc.py:78-82
+  double l2sum = 0.0, gmax = 0.0;
+  for (int k = 0; k < N; ++k) {
+    const double l1 = lm[k], l2 = lm[N + k], l3 = lm[2 * N + k];
+    if (l1 < 0.0 || l2 < 0.0 || l3 < 0.0) st = LOMPC_ST_NEGATIVE;
+    const double g = cs.theta * (l1 - l2);
+    D[k * T] = 2.0 * (lr * cs.theta2 + cs.q_scale * l3) + cs.d_base;
+    G[k * T] = g;
+    WA[k * T] = 0.0;
+    gmax = fmax(gmax, fabs(g));
+    l2sum += l2;
+  }
+  if (gam > cs.y_max) st = LOMPC_ST_BAD_GAMMA;  // lompc.py:87 (asserted before the parameters are set)
+  const double c = cs.c;
+  const double wmax = cs.w_max;
+  const double gscale = fmax(1.0, gmax + c * N * cs.y_max);
+  const double tq = a.tol * gscale;
+  const double cg = c * gam;
+
+  double* W = WA;   // current feasible iterate
+  double* WN = WB;  // candidate
+  double sN = 0.0;  // s_{N-1} of the current iterate
+  double f = 0.5 * c * N * gam * gam;  // objective at w = 0 (without kappa0)
+  double viol = 0.0;
+  int it = 0;
+  bool converged = false;
+  if (st != LOMPC_ST_OK) {
+    converged = true;  // invalid input: report, output zeros
+    viol = 0.0;
+  }
+
+  for (; !converged && it < a.max_iter; ++it) {
+    // ---------------- backward sweep ----------------
+    double P = 0.0, r = 0.0, p = 0.0, s = sN;
+    viol = 0.0;
+    for (int k = N - 1; k >= 0; --k) {
+      const double wk = W[k * T], dk = D[k * T], gk = G[k * T];
+      p = fma(c, s, p) - cg;
+      const double q = fma(dk, wk, gk) + p;
+      // KKT test of coordinate k -> binding flag and working segment
+      bool binding = false;
+      int seg = 0;
+      double v;
+      if (NSEG == 1) {
+        if (wk <= 0.0) {
+          binding = (q >= -tq);
+          v = binding ? 0.0 : -q;
+        } else if (wk >= wmax) {
+          binding = (q <= tq);
+          v = binding ? 0.0 : q;
+        } else {
+          v = fabs(q);
+        }
+      } else {
+        int at = -1;
+#pragma unroll
+        for (int i = 0; i <= NSEG; ++i)
+          if (wk == cs.brk[i]) at = i;
+        if (at >= 0) {
+          const double mq = -q;
+          if (at < NSEG && mq > cs.slope[at] + tq) {
+            seg = at;
+            v = mq - cs.slope[seg];
+          } else if (at > 0 && mq < cs.slope[at - 1] - tq) {
+            seg = at - 1;
+            v = cs.slope[seg] - mq;
+          } else {
+            binding = true;
+            seg = at < NSEG ? at : NSEG - 1;
+            v = 0.0;
+          }
+        } else {
+#pragma unroll
+          for (int j = 1; j < NSEG; ++j) seg += (wk > cs.brk[j]) ? 1 : 0;
+          v = fabs(q + cs.slope[seg]);
+        }
+      }
+      viol = fmax(viol, v);
+      // Riccati step
+      const double Q = c + P;
+      const double rp = r - cg;
+      const double inv = 1.0 / (dk + Q);
+      const double h = gk + ((NSEG > 1) ? cs.slope[seg] : 0.0);
+      if (binding) {
+        P = Q;
+        r = fma(Q, wk, rp);
+      } else {
+        P = Q * dk * inv;
+        r = (dk * rp - Q * h) * inv;
+      }
+      KK[k * T] = Q * inv;
+      KAP[k * T] = (rp + gk) * inv;
+      if (NSEG > 1) INV[k * T] = inv;
+      CFG[k * T] = (unsigned char)((binding ? 1 : 0) | (seg << 1));
+      s -= wk;
+    }
+    if (viol <= tq) {
+      converged = true;
+      break;
+    }
+    // ---------------- forward sweep: stage-optimal rollout ----------------
+    double fn = 0.0;
+    s = 0.0;
+    for (int k = 0; k < N; ++k) {
+      const double x0 = -fma(KK[k * T], s, KAP[k * T]);
+      double x;
+      if (NSEG == 1) {
+        x = x0;
+      } else {
+        const double inv = INV[k * T];
+        x = x0 - cs.slope[NSEG - 1] * inv;
+#pragma unroll
+        for (int j = NSEG - 2; j >= 0; --j)
+          x = fmin(x0 - cs.slope[j] * inv, fmax(cs.brk[j + 1], x));
+      }
+      x = fmin(fmax(x, 0.0), wmax);
+      WN[k * T] = x;
+      s += x;
+      const double e = s - gam;
+      fn += x * fma(0.5 * D[k * T], x, G[k * T]) + 0.5 * c * e * e;
+      if (NSEG > 1) fn += pwl_value<NSEG>(cs, x);
+    }
+    if (fn < f) {
+      double* tmp = W;
+      W = WN;
+      WN = tmp;
+      f = fn;
+      sN = s;
+      continue;
+    }
+    // ---------------- safeguard: projected Newton on the working set ----------------
+    s = 0.0;
+    for (int k = 0; k < N; ++k) {  // equality-constrained solution on the working set
+      const int cfg = CFG[k * T];
+      double x;
+      if (cfg & 1) {
+        x = W[k * T];
+      } else {
+        x = -fma(KK[k * T], s, KAP[k * T]);
+        if (NSEG > 1) x -= cs.slope[cfg >> 1] * INV[k * T];
+      }
+      WN[k * T] = x;
+      s += x;
+    }
+    double alpha = 1.0;
+    bool ok = false;
+    for (int ls = 0; ls < 60 && !ok; ++ls, alpha *= 0.5) {
+      fn = 0.0;
+      s = 0.0;
+      for (int k = 0; k < N; ++k) {
+        const int cfg = CFG[k * T];
+        const double wk = W[k * T];
+        double x = wk;
+        if (!(cfg & 1)) {
+          const int seg = cfg >> 1;
+          x = fma(alpha, WN[k * T] - wk, wk);
+          x = fmin(fmax(x, cs.brk[seg]), cs.brk[seg + 1]);
+        }
+        s += x;
+        const double e = s - gam;
+        fn += x * fma(0.5 * D[k * T], x, G[k * T]) + 0.5 * c * e * e;
+        if (NSEG > 1) fn += pwl_value<NSEG>(cs, x);
+      }
+      ok = fn < f;
+      if (ok) break;
+    }
+    if (!ok) break;  // no representable descent step left: report MAXITER below
+    s = 0.0;
+    for (int k = 0; k < N; ++k) {
+      const int cfg = CFG[k * T];
+      const double wk = W[k * T];
+      if (!(cfg & 1)) {
+        const int seg = cfg >> 1;
+        double x = fma(alpha, WN[k * T] - wk, wk);
+        x = fmin(fmax(x, cs.brk[seg]), cs.brk[seg + 1]);
+        W[k * T] = x;
+        s += x;
+      } else {
+        s += wk;
+      }
+    }
+    f = fn;
+    sN = s;
+  }
+  if (!converged && st == LOMPC_ST_OK) st = LOMPC_ST_MAXITER;
+
+  // ---- outputs: w, cost in the reference's form (lompc.py:155) ----------------
+  double cost = cs.theta * wmax * l2sum;  // theta * lmbd2 @ w_max, lompc.py:130
+  double s = 0.0;
+  double* wo = a.w_out + b * (int64_t)N;
+  for (int k = 0; k < N; ++k) {
+    const double x = W[k * T];
+    wo[k] = x;
+    s += x;
+    cost += x * fma(0.5 * D[k * T], x, G[k * T]) + 0.5 * c * s * (s - 2.0 * gam);
+    if (NSEG > 1) cost += pwl_value<NSEG>(cs, x);
+  }
+  a.cost_out[b] = cost;
+  if (a.status) a.status[b] = st;
+  if (a.iters) a.iters[b] = it;
+  if (a.kkt_res) a.kkt_res[b] = viol / gscale;
+}
+
+}  // namespace lompc

@@ -1,0 +1,177 @@
+"""GPU parity tests of K1 (batched LoMPC solve) through the C ABI, against the
+CPU oracle and the committed golden vectors.  Tolerances (north-star):
+w <= 1e-5 relative to w_max, cost <= 1e-6 relative - the kernel is an exact
+active-set method, so the tests actually hold it to 1e-9 / 1e-10."""
+import os
+
+import numpy as np
+import pytest
+
+from oracle import lompc_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "lompc_golden.npz")
+W_RTOL = 1e-9   # relative to w_max   (north-star bar: 1e-5)
+C_RTOL = 1e-10  # relative to max(1,|cost|) (north-star bar: 1e-6)
+
+
+def _consts(ev):
+    from chargingstation.lompc import LoMPCConstants
+    o = orc.small_ev_consts() if ev == "small" else orc.large_ev_consts()
+    return o, LoMPCConstants(o.delta, o.theta, o.y_max, o.w_max, o.ev_type)
+
+
+@pytest.mark.parametrize("ev", ["small", "large"])
+@pytest.mark.parametrize("N", [12, 24])
+def test_golden_vectors(ev, N):
+    from chargingstation.lompc import LoMPC
+    o, c = _consts(ev)
+    z = np.load(GOLDEN)
+    solver = LoMPC(N, c)
+    for mode in range(4):
+        key = f"{ev}_N{N}_m{mode}"
+        w, cost, info = solver.solve_lompc_batch(z[key + "_lmbd"], z[key + "_lmbd_r"], z[key + "_gamma"],
+                                                 return_info=True)
+        assert np.all(info["status"] == 0)
+        assert np.max(np.abs(w - z[key + "_w"])) <= W_RTOL * o.w_max, key
+        assert np.max(np.abs(cost - z[key + "_cost"]) / np.maximum(1, np.abs(z[key + "_cost"]))) <= C_RTOL, key
+        assert info["kkt_res"].max() <= 1e-10
+
+
+@pytest.mark.parametrize("ev", ["small", "large"])
+@pytest.mark.parametrize("N", [5, 12, 24, 48, 96])
+def test_random_against_oracle(ev, N):
+    """Seeded random inputs as test_lompc.py:34-36 plus the closed-loop regimes."""
+    from chargingstation.lompc import LoMPC
+    o, c = _consts(ev)
+    rng = np.random.default_rng(100 + N)
+    B = 96
+    solver = LoMPC(N, c)
+    th = o.theta
+    lm = np.zeros((B, 3 * N))
+    lr = np.zeros(B)
+    gam = o.y_max * rng.random(B)
+    lm[:32] = th * rng.random((32, 3 * N))
+    lr[:32] = 3 * N * o.delta * rng.random(32)
+    lm[32:64] = 0.05 * th * rng.random((32, 3 * N)) * (rng.random((32, 3 * N)) < 0.5)
+    lm[64:, :2 * N] = 0.05 * th * rng.random((32, 2 * N))
+    w, cost, info = solver.solve_lompc_batch(lm, lr, gam, return_info=True)
+    assert np.all(info["status"] == 0)
+    for b in range(0, B, 4):
+        wo, co, _ = orc.solve_active_set(N, o, lm[b], lr[b], gam[b])
+        assert np.max(np.abs(w[b] - wo)) <= W_RTOL * o.w_max, (b, info["iters"][b])
+        assert abs(cost[b] - co) <= C_RTOL * max(1, abs(co))
+        viol, dist = orc.kkt_certificate(N, o, w[b], lm[b], lr[b], gam[b])
+        assert dist <= 1e-8
+
+
+@pytest.mark.parametrize("ev", ["small", "large"])
+def test_scalar_api_and_errors(ev):
+    """solve_lompc keeps the reference's signature and error behaviour (lompc.py:84-90,137-156)."""
+    from chargingstation.lompc import LoMPC
+    o, c = _consts(ev)
+    N = 12
+    solver = LoMPC(N, c)
+    rng = np.random.default_rng(5)
+    lm = o.theta * rng.random(3 * N)
+    w, cost = solver.solve_lompc(lm, 0.3, 0.4)
+    assert isinstance(w, np.ndarray) and w.shape == (N,) and isinstance(cost, float)
+    wo, co, _ = orc.solve_active_set(N, o, lm, 0.3, 0.4)
+    assert np.max(np.abs(w - wo)) <= W_RTOL * o.w_max
+    assert abs(cost - orc.lompc_cost(N, o, w, lm, 0.3, 0.4)) <= 1e-12 * max(1, abs(cost))
+    with pytest.raises(AssertionError):
+        solver.solve_lompc(lm, 0.0, o.y_max + 1e-3)  # lompc.py:87
+    with pytest.raises(ValueError):
+        solver.solve_lompc(-lm, 0.0, 0.1)  # nonneg cv.Parameter, lompc.py:78
+    # batch entry point reports the same conditions through status / return code
+    gam = np.array([0.1, o.y_max + 0.01])
+    with pytest.raises(AssertionError):
+        solver.solve_lompc_batch(lm, 0.0, gam)
+    # phi / Dphi / get_price0 mirror lompc.py:164-187
+    assert np.allclose(solver.phi(w), orc.phi(N, o, w))
+    assert np.allclose(solver.Dphi(w), orc.Dphi(N, o, w))
+    assert abs(solver.get_price0(w, lm, 0.3) - orc.get_price0(N, o, w, lm, 0.3)) < 1e-12
+    assert solver.get_sc_modulus() == 2 * o.delta * o.theta ** 2
+    assert np.array_equal(solver.get_input_mat(), np.tril(np.ones((N, N))))
+
+
+def test_edge_cases():
+    """gamma = 0 (nothing to charge), gamma = y_max, zero prices, huge prices, B = 0."""
+    from chargingstation.lompc import LoMPC
+    for ev in ("small", "large"):
+        o, c = _consts(ev)
+        N = 24
+        solver = LoMPC(N, c)
+        z = np.zeros(3 * N)
+        w, cost = solver.solve_lompc(z, 0.0, 0.0)
+        assert np.all(w == 0.0) and cost == 0.0
+        w, cost = solver.solve_lompc(z, 0.0, o.y_max)
+        wo, co, _ = orc.solve_active_set(N, o, z, 0.0, o.y_max)
+        assert np.max(np.abs(w - wo)) <= W_RTOL * o.w_max and abs(cost - co) <= C_RTOL * abs(co)
+        big = np.concatenate([1e4 * np.ones(N), np.zeros(2 * N)])
+        w, cost = solver.solve_lompc(big, 0.0, 0.5)
+        assert np.all(w == 0.0)
+        neg = np.concatenate([np.zeros(N), 1e4 * np.ones(N), np.zeros(N)])
+        w, cost = solver.solve_lompc(neg, 0.0, 0.5)
+        assert np.all(w == o.w_max)
+        w0, c0 = solver.solve_lompc_batch(np.zeros((0, 3 * N)), np.zeros(0), np.zeros(0))
+        assert w0.shape == (0, N) and c0.shape == (0,)
+
+
+def test_broadcast_prices_match_per_row():
+    """lmbd_stride = 0 (one price vector for the whole group, price_solver.py:203-204)."""
+    from chargingstation.lompc import LoMPC
+    o, c = _consts("large")
+    N = 24
+    solver = LoMPC(N, c)
+    rng = np.random.default_rng(9)
+    lm = 0.05 * o.theta * rng.random(3 * N)
+    gam = o.y_max - (0.3 + 0.2 * rng.random(333))
+    w1, c1 = solver.solve_lompc_batch(lm, 0.0, gam)
+    w2, c2 = solver.solve_lompc_batch(np.tile(lm, (333, 1)), np.zeros(333), gam)
+    assert np.array_equal(w1, w2) and np.array_equal(c1, c2)
+
+
+def test_full_size_properties():
+    """BASELINE config sizes (65,536 QPs, N = 24): size-independent properties -
+    feasibility, KKT residual reported by the kernel, cost identity, determinism."""
+    from chargingstation.lompc import LoMPC
+    for ev in ("small", "large"):
+        o, c = _consts(ev)
+        N, B = 24, 65536
+        rng = np.random.default_rng(3)
+        lm = o.theta * rng.random((B, 3 * N))
+        lr = 3 * N * o.delta * rng.random(B)
+        gam = o.y_max * rng.random(B)
+        solver = LoMPC(N, c)
+        w, cost, info = solver.solve_lompc_batch(lm, lr, gam, return_info=True)
+        assert np.all(info["status"] == 0)
+        assert w.min() >= 0.0 and w.max() <= o.w_max
+        assert info["kkt_res"].max() <= 1e-10
+        idx = rng.integers(0, B, 64)
+        for b in idx:
+            assert abs(cost[b] - orc.lompc_cost(N, o, w[b], lm[b], lr[b], gam[b])) <= 1e-11 * max(1, abs(cost[b]))
+            viol, dist = orc.kkt_certificate(N, o, w[b], lm[b], lr[b], gam[b])
+            assert dist <= 1e-8
+        w2, cost2 = solver.solve_lompc_batch(lm, lr, gam)
+        assert np.array_equal(w, w2) and np.array_equal(cost, cost2)
+
+
+def test_torch_device_entry_point():
+    import torch
+    from chargingstation.lompc import LoMPC
+    o, c = _consts("small")
+    N, B = 24, 1024
+    rng = np.random.default_rng(2)
+    lm = o.theta * rng.random((B, 3 * N))
+    lr = 3 * N * o.delta * rng.random(B)
+    gam = o.y_max * rng.random(B)
+    solver = LoMPC(N, c)
+    w_h, c_h = solver.solve_lompc_batch(lm, lr, gam)
+    dev = torch.device("cuda:0")
+    w_d, c_d, info = solver.solve_lompc_batch(torch.from_numpy(lm).to(dev), torch.from_numpy(lr).to(dev),
+                                              torch.from_numpy(gam).to(dev), return_info=True)
+    torch.cuda.synchronize()
+    assert np.array_equal(w_d.cpu().numpy(), w_h) and np.array_equal(c_d.cpu().numpy(), c_h)
+    assert int(info["status"].max()) == 0

@@ -1,0 +1,120 @@
+"""CPU tests of the oracle itself (oracle/lompc_oracle.py): three independent
+solvers and the KKT certificate must agree, and the committed golden vectors
+must reproduce.  The reference holds no golden vectors for this path
+(SURVEY.md section 4), so the certificate is what pins parity."""
+import os
+
+import numpy as np
+import pytest
+from scipy.optimize import lsq_linear
+
+from oracle import lompc_oracle as orc
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden", "lompc_golden.npz")
+
+
+def _draw(rng, N, consts, mode):
+    th = consts.theta
+    if mode == 0:
+        return th * rng.random(3 * N), 3 * N * consts.delta * rng.random(), consts.y_max * rng.random()
+    if mode == 1:
+        return 0.05 * th * rng.random(3 * N), 0.0, consts.y_max - (0.3 + 0.2 * rng.random())
+    lm = np.zeros(3 * N)
+    lm[:2 * N] = 0.05 * th * rng.random(2 * N)
+    return lm, 0.0, consts.y_max * rng.random()
+
+
+@pytest.mark.parametrize("ev", ["small", "large"])
+@pytest.mark.parametrize("N", [12, 24])
+def test_cost_identity_and_certificate(ev, N):
+    """1/2 w'Hw + g'w + kappa0 + pwl == the cvxpy expression (lompc.py:101-135)."""
+    consts = orc.small_ev_consts() if ev == "small" else orc.large_ev_consts()
+    rng = np.random.default_rng(7)
+    for trial in range(12):
+        lm, lr, gam = _draw(rng, N, consts, trial % 3)
+        w, cost, _ = orc.solve_active_set(N, consts, lm, lr, gam)
+        d, c, g, k0, ps = orc.lompc_problem_data(N, consts, lm, lr, gam)
+        H = orc.dense_hessian(N, d, c)
+        x = w / consts.w_max
+        pwl = ps * np.sum(np.maximum.reduce([0 * x, x - .125, 1.5 * x - .375, 2 * x - .75]))
+        assert abs(0.5 * w @ H @ w + g @ w + k0 + pwl - cost) <= 1e-12 * max(1, abs(cost))
+        viol, dist = orc.kkt_certificate(N, consts, w, lm, lr, gam)
+        assert viol <= 1e-10 * max(1.0, np.max(np.abs(g)))
+        assert dist <= 1e-9
+        # a perturbed point must be rejected
+        w_bad = np.clip(w + 1e-4 * consts.w_max * rng.standard_normal(N), 0, consts.w_max)
+        viol_bad, _ = orc.kkt_certificate(N, consts, w_bad, lm, lr, gam)
+        assert viol_bad > 1e-6
+
+
+@pytest.mark.parametrize("ev", ["small", "large"])
+def test_ipm_restatement_agrees_with_exact(ev):
+    """The Clarabel-style IPM at its default 1e-8 tolerances lands within the
+    north-star tolerance of the exact optimum (w <= 1e-4*w_max here, cost 1e-6)."""
+    consts = orc.small_ev_consts() if ev == "small" else orc.large_ev_consts()
+    rng = np.random.default_rng(11)
+    N = 24
+    for trial in range(9):
+        lm, lr, gam = _draw(rng, N, consts, trial % 3)
+        w, cost, _ = orc.solve_active_set(N, consts, lm, lr, gam)
+        w2, cost2, _ = orc.solve_ipm(N, consts, lm, lr, gam)
+        assert np.max(np.abs(w - w2)) <= 1e-4 * consts.w_max
+        assert abs(cost - cost2) <= 1e-6 * max(1.0, abs(cost))
+        w3, cost3, _ = orc.solve_ipm(N, consts, lm, lr, gam, tol=1e-12)
+        assert np.max(np.abs(w - w3)) <= 1e-7 * consts.w_max
+
+
+def test_small_ev_matches_bvls():
+    consts = orc.small_ev_consts()
+    rng = np.random.default_rng(13)
+    N = 24
+    for trial in range(9):
+        lm, lr, gam = _draw(rng, N, consts, trial % 3)
+        w, _, _ = orc.solve_active_set(N, consts, lm, lr, gam)
+        d, c, g, _, _ = orc.lompc_problem_data(N, consts, lm, lr, gam)
+        L = np.linalg.cholesky(orc.dense_hessian(N, d, c))
+        res = lsq_linear(L.T, -np.linalg.solve(L, g), bounds=(0, consts.w_max), method="bvls", tol=1e-14)
+        assert np.max(np.abs(res.x - w)) <= 1e-9 * consts.w_max
+
+
+def test_golden_vectors_reproduce():
+    z = np.load(GOLDEN)
+    for ev, consts in (("small", orc.small_ev_consts()), ("large", orc.large_ev_consts())):
+        for N in (12, 24):
+            for mode in range(4):
+                key = f"{ev}_N{N}_m{mode}"
+                lm, lr, gam = z[key + "_lmbd"], z[key + "_lmbd_r"], z[key + "_gamma"]
+                for b in range(0, lm.shape[0], 6):
+                    w, cost, _ = orc.solve_active_set(N, consts, lm[b], lr[b], gam[b])
+                    assert np.max(np.abs(w - z[key + "_w"][b])) <= 1e-12
+                    assert abs(cost - z[key + "_cost"][b]) <= 1e-10 * max(1, abs(cost))
+                assert z[key + "_kkt"].max() <= 1e-10 * 1e4
+
+
+def test_unpriced_solution_shape():
+    """test_lompc.py:43-58 plots the unpriced solution: charge early, never exceed gamma."""
+    consts = orc.small_ev_consts()
+    N = 12
+    w, _, _ = orc.solve_active_set(N, consts, np.zeros(3 * N), 0.0, consts.y_max)
+    assert np.all(w >= -1e-15) and np.all(w <= consts.w_max + 1e-15)
+    assert np.all(np.diff(w) <= 1e-12)
+    assert np.cumsum(w)[-1] <= consts.y_max + 1e-12
+
+
+def test_feature_map():
+    consts = orc.large_ev_consts()
+    N = 6
+    rng = np.random.default_rng(3)
+    w = consts.w_max * rng.random(N)
+    lm = rng.random(3 * N)
+    ph = orc.phi(N, consts, w)
+    J = orc.Dphi(N, consts, w)
+    eps = 1e-7
+    for k in range(N):
+        e = np.zeros(N)
+        e[k] = eps
+        assert np.allclose((orc.phi(N, consts, w + e) - orc.phi(N, consts, w - e)) / (2 * eps), J[:, k], atol=1e-6)
+    # price = lmbd @ phi(w) equals the three price terms of lompc.py:126-135 at lmbd_r = 0
+    q = 3 * consts.theta / (4 * consts.w_max)
+    price = consts.theta * (lm[:N] @ w + lm[N:2 * N] @ (consts.w_max - w)) + q * lm[2 * N:] @ (w * w)
+    assert abs(lm @ ph - price) <= 1e-12 * abs(price)
