@@ -1,0 +1,404 @@
+#!/usr/bin/env python
+"""Benchmark of the LoMPC hot path (BASELINE.json: "LL-MPC QP solves/sec").
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's CUDA path
+    python bench.py --impl reference --gpus N --steps K ...  # reference CPU path (restated)
+
+Workload at N=1 = BASELINE.json configs[1]: 1,024 independent horizon-24
+lower-level MPC QPs (512 small-EV + 512 large-EV), inputs drawn as the
+reference's own timing script does (test/test_lompc.py:34-36), seed 2.  Under
+torchrun every rank runs its own 1,024 QPs (weak scaling, no data-path
+collective: the QPs are independent).  One "step" = one pass of the hot path
+over that batch = two kernel launches (one per EV type).
+
+`value`  : QP solves/s, inputs resident in HBM, CUDA events around each step,
+           L2 flushed between steps, max over ranks.
+`e2e`    : the same metric through the public API (LoMPC.solve_lompc_batch ->
+           C ABI host entry point) with pinned HOST buffers; H2D and D2H copies
+           are inside the timed region.
+`roofline`: this path is FP64-pipe bound, so achieved/peak are
+           FP64 TFLOP/s; peak is the DFMA peak MEASURED in this run; the HBM
+           numbers are reported next to it.
+`cpu_baseline`: oracle/lompc_oracle.c (a C restatement of the cvxpy->CLARABEL
+           interior-point solve; cvxpy itself is not installable here) on all
+           host threads, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "incentive-design-mpc_b200")
+for p in (ROOT, PKG):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+N_HORIZON = 24
+METRIC = "lompc_qp_solves_per_sec"
+UNIT = "QP/s"
+
+# (delta, theta, y_max, w_max, type): example/real_time_price_control.py:26-39
+EV_CONSTS = {"small": (0.05, 10.0, 0.9, 0.25), "large": (0.025, 50.0, 0.9, 0.15)}
+
+
+def draw_workload(batch: int, N: int, seed: int):
+    """configs[1]: half small, half large EVs; test/test_lompc.py:34-36 distributions."""
+    rng = np.random.default_rng(seed)
+    out = {}
+    for ev in ("small", "large"):
+        delta, theta, y_max, w_max = EV_CONSTS[ev]
+        B = batch // 2
+        out[ev] = (theta * rng.random((B, 3 * N)), 3 * N * delta * rng.random(B), y_max * rng.random(B))
+    return out
+
+
+def flops_per_qp(ev: str, N: int, iters_mean: float) -> float:
+    """Algorithmic FP64 flops of one solve (FMA = 2):
+    setup+final cost 16N (25N large), backward sweep 19N (20N), forward sweep 14N (31N);
+    a solve that stops after `it` iterations ran it+1 backward and it forward sweeps."""
+    if ev == "small":
+        return N * (16 + 19 * (iters_mean + 1) + 14 * iters_mean)
+    return N * (25 + 20 * (iters_mean + 1) + 31 * iters_mean)
+
+
+def bytes_per_qp(N: int) -> int:
+    return 8 * (4 * N + 3)  # 8(3N+2) in + 8(N+1) out
+
+
+class ClockSampler:
+    """Samples SM clocks / throttle reasons with NVML while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self.nv = None
+
+    def _loop(self):
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksEventReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksEventReasonSwPowerCap", 0x4): "sw_power_cap",
+        }
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.01)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._loop, daemon=True)
+            self._thr.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(self.samples)}
+
+
+# --------------------------------------------------------------------------- CPU arm
+def cpu_pass(work, N, nthreads=0):
+    """One pass of the restated reference CPU path over the workload; returns threads used."""
+    from oracle import c_oracle, lompc_oracle as orc
+    used = 1
+    for ev, (lm, lr, gam) in work.items():
+        o = orc.small_ev_consts() if ev == "small" else orc.large_ev_consts()
+        _, _, _, used = c_oracle.solve_lompc_batch(N, o, lm, lr, gam, nthreads=nthreads)
+    return used
+
+
+def run_reference(args, rank: int, world: int) -> None:
+    if rank != 0:
+        return
+    work = draw_workload(args.batch, N_HORIZON, 2)
+    for _ in range(max(args.warmup, 1)):
+        used = cpu_pass(work, N_HORIZON)
+    # bound the whole run to a few minutes
+    t0 = time.perf_counter()
+    cpu_pass(work, N_HORIZON)
+    one = time.perf_counter() - t0
+    steps = max(1, min(args.steps, int(120.0 / max(one, 1e-9))))
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        cpu_pass(work, N_HORIZON)
+    dt = (time.perf_counter() - t0) / steps
+    value = args.batch / dt
+    sample = (f"{args.batch} QPs/step ({args.batch // 2} small + {args.batch // 2} large, N={N_HORIZON}), "
+              f"{steps} steps, oracle/lompc_oracle.c IPM tol 1e-8")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": steps, "warmup": args.warmup, "ms_per_step": dt * 1e3, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": used, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+        "note": "cvxpy/CLARABEL are not installable in this image; this arm times the C restatement "
+                "of the reference's interior-point solve on all host threads",
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"BASELINE.json configs[1]: {args.batch} independent horizon-{N_HORIZON} LoMPC QPs per GPU "
+                        f"({args.batch // 2} small-EV + {args.batch // 2} large-EV), inputs as test_lompc.py:34-36, seed 2",
+            "batch_per_gpu": args.batch, "horizon": N_HORIZON,
+            "l2": "flushed between timed steps (256 MiB device memset, outside the events)"}
+
+
+# --------------------------------------------------------------------------- GPU arm
+def run_ours(args, rank: int, local_rank: int, world: int) -> None:
+    import torch
+    import torch.distributed as dist
+    from chargingstation import _native
+    from chargingstation.lompc import LoMPC, LoMPCConstants
+
+    lib = _native.load()
+    if lib.lompc_device_count() <= local_rank:
+        raise RuntimeError("bench.py needs a CUDA device: this path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+
+    N = N_HORIZON
+    work = draw_workload(args.batch, N, 2 + rank)
+    solvers, dev_in, dev_out, host_in, host_out = {}, {}, {}, {}, {}
+    for ev, (lm, lr, gam) in work.items():
+        delta, theta, y_max, w_max = EV_CONSTS[ev]
+        solvers[ev] = LoMPC(N, LoMPCConstants(delta, theta, y_max, w_max, ev), device=local_rank)
+        B = gam.shape[0]
+        dev_in[ev] = tuple(torch.from_numpy(x).to(dev) for x in (lm, lr, gam))
+        dev_out[ev] = (torch.empty((B, N), dtype=torch.float64, device=dev),
+                       torch.empty((B,), dtype=torch.float64, device=dev))
+        pin = lambda a: torch.from_numpy(a).pin_memory().numpy()  # noqa: E731
+        host_in[ev] = tuple(pin(x) for x in (lm, lr, gam))
+        host_out[ev] = (torch.empty((B, N), dtype=torch.float64).pin_memory().numpy(),
+                        torch.empty((B,), dtype=torch.float64).pin_memory().numpy())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    def step_device():
+        for ev in ("small", "large"):
+            solvers[ev].solve_lompc_batch(*dev_in[ev], out=dev_out[ev])
+
+    def step_host():
+        for ev in ("small", "large"):
+            solvers[ev].solve_lompc_batch(*host_in[ev], out=host_out[ev])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # iteration statistics (for the flop model) + a correctness spot check before timing
+    iters_mean = {}
+    for ev in ("small", "large"):
+        _, _, info = solvers[ev].solve_lompc_batch(*dev_in[ev], return_info=True)
+        torch.cuda.synchronize()
+        assert int(info["status"].max()) == 0, "solver reported a non-converged QP"
+        assert float(info["kkt_res"].max()) <= 1e-10
+        iters_mean[ev] = float(info["iters"].double().mean())
+
+    # FP64 peak of this device, measured now
+    tf = _native.C.c_double()
+    ms = _native.C.c_double()
+    _native.raise_for(lib.lompc_measure_fp64_peak(local_rank, 4096, _native.C.byref(tf), _native.C.byref(ms)))
+    fp64_peak = tf.value
+
+    for _ in range(max(args.warmup, 3)):
+        flush.zero_()
+        step_device()
+    sampler = ClockSampler(local_rank)
+    barrier()
+    sampler.start()
+    launches0 = lib.lompc_launch_count()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    for e0, e1 in evs:
+        flush.zero_()  # L2 flush, outside the timed events
+        e0.record()
+        step_device()
+        e1.record()
+    barrier()
+    launches = lib.lompc_launch_count() - launches0
+    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+
+    # end-to-end through the public API with pinned host buffers (wall clock, copies inside)
+    for _ in range(max(args.warmup, 3)):
+        step_host()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        step_host()
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    barrier()
+
+    # saturating batch (explains `value`: 1,024 QPs cannot fill 148 SMs)
+    sat = None
+    if not args.no_saturated:
+        sat = saturated_run(solvers, dev, rank, fp64_peak)
+    clocks = sampler.stop()
+
+    t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_s = float(t[0]), float(t[1])
+
+    if rank == 0:
+        total_qps = args.batch * world
+        ms_per_step = dev_ms / args.steps
+        value = total_qps / (ms_per_step * 1e-3)
+        flops_step = sum(flops_per_qp(ev, N, iters_mean[ev]) * (args.batch // 2) for ev in ("small", "large"))
+        achieved_tf = flops_step / (ms_per_step * 1e-3) / 1e12
+        bytes_step = bytes_per_qp(N) * args.batch
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        hbm_peak = peaks.get("hbm_gbs", 6650.0)
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("bytes_per_launch")
+        except Exception:
+            pass
+        h2d = bytes_per_qp(N) * 0 + 8 * (3 * N + 2) * args.batch
+        d2h = (8 * (N + 1) + 4) * args.batch
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms_per_step, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args),
+            "roofline": {
+                "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
+                "frac": achieved_tf / fp64_peak, "traffic": traffic,
+                "peak_source": "DFMA chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
+                "mean_iters": iters_mean, "flops_per_step": flops_step,
+                "hbm": {"achieved": bytes_step / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
+                        "frac": bytes_step / (ms_per_step * 1e-3) / 1e9 / hbm_peak,
+                        "peak_source": "MEASURED_PEAKS.json" if "hbm_gbs" in peaks else "fallback"},
+                "note": "1,024 QPs = 32 warps cannot fill 148 SMs: this configuration is latency-bound; "
+                        "see `saturated` for the throughput regime of the same kernel",
+            },
+            "e2e": {"value": total_qps * args.steps / e2e_s, "unit": UNIT, "h2d_bytes_per_step": h2d,
+                    "d2h_bytes_per_step": d2h, "ms_per_step": e2e_s / args.steps * 1e3,
+                    "api": "LoMPC.solve_lompc_batch(numpy pinned) -> lompc_solve_batch_host"},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "saturated": sat,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_leg(args)
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def saturated_run(solvers, dev, rank, fp64_peak):
+    """Same kernel, same distributions, at a batch that fills the GPU (2 x 2^19 QPs)."""
+    import torch
+    N = N_HORIZON
+    Bs = 1 << 19
+    rng = np.random.default_rng(1000 + rank)
+    res = {"batch": 2 * Bs, "per_type": {}}
+    tot_ms, tot_flops = 0.0, 0.0
+    for ev in ("small", "large"):
+        delta, theta, y_max, w_max = EV_CONSTS[ev]
+        lm = torch.from_numpy(theta * rng.random((Bs, 3 * N))).to(dev)
+        lr = torch.from_numpy(3 * N * delta * rng.random(Bs)).to(dev)
+        gam = torch.from_numpy(y_max * rng.random(Bs)).to(dev)
+        out = (torch.empty((Bs, N), dtype=torch.float64, device=dev), torch.empty((Bs,), dtype=torch.float64, device=dev))
+        _, _, info = solvers[ev].solve_lompc_batch(lm, lr, gam, return_info=True)
+        it_mean = float(info["iters"].double().mean())
+        for _ in range(3):
+            solvers[ev].solve_lompc_batch(lm, lr, gam, out=out)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        reps = 5
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            solvers[ev].solve_lompc_batch(lm, lr, gam, out=out)  # 2^19 x 792 B = 415 MB > L2
+        e1.record()
+        torch.cuda.synchronize()
+        ms = e0.elapsed_time(e1) / reps
+        fl = flops_per_qp(ev, N, it_mean) * Bs
+        res["per_type"][ev] = {"qp_per_s": Bs / (ms * 1e-3), "ms": ms, "mean_iters": it_mean,
+                               "fp64_tflops": fl / (ms * 1e-3) / 1e12,
+                               "fp64_frac": fl / (ms * 1e-3) / 1e12 / fp64_peak,
+                               "hbm_gbs": bytes_per_qp(N) * Bs / (ms * 1e-3) / 1e9}
+        tot_ms += ms
+        tot_flops += fl
+        del lm, lr, gam, out
+    res["value"] = 2 * Bs / (tot_ms * 1e-3)
+    res["unit"] = UNIT
+    res["fp64_tflops"] = tot_flops / (tot_ms * 1e-3) / 1e12
+    res["fp64_frac"] = res["fp64_tflops"] / fp64_peak
+    res["note"] = "inputs larger than L2 (415 MB per type); CUDA events around 5 back-to-back launches"
+    return res
+
+
+def cpu_baseline_leg(args):
+    work = draw_workload(args.batch, N_HORIZON, 2)
+    used = cpu_pass(work, N_HORIZON)  # warm-up
+    t0 = time.perf_counter()
+    cpu_pass(work, N_HORIZON)
+    one = time.perf_counter() - t0
+    reps = max(1, min(200, int(3.0 / max(one, 1e-9))))
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        cpu_pass(work, N_HORIZON)
+    dt = (time.perf_counter() - t0) / reps
+    return {"value": args.batch / dt, "unit": UNIT, "cores": used, "kind": "port",
+            "sample": f"{reps} passes over the same {args.batch}-QP workload (oracle/lompc_oracle.c, "
+                      f"Clarabel-style IPM, tol 1e-8, OpenMP on {used} threads, {reps * dt:.1f} s wall)"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="QPs per GPU per step (configs[1]: 1024)")
+    ap.add_argument("--no-saturated", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_ours(args, rank, local_rank, world)
+
+
+if __name__ == "__main__":
+    main()

@@ -38,6 +38,7 @@ SIGNATURES = {
                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
     "lompc_launch_count": (C.c_int64, []),
+    "lompc_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, _dp, _dp]),
 }
 
 _lib = None

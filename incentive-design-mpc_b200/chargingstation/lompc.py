@@ -106,7 +106,7 @@ class LoMPC:
                                          np.array([gamma], dtype=np.float64))
         return w[0], float(cost[0])
 
-    def solve_lompc_batch(self, lmbd, lmbd_r, gamma, return_info: bool = False):
+    def solve_lompc_batch(self, lmbd, lmbd_r, gamma, return_info: bool = False, out=None):
         """Batched ``solve_lompc``.
 
         lmbd:   [B, 3N] or [3N] (one price vector broadcast to the batch, the
@@ -116,9 +116,10 @@ class LoMPC:
         torch CUDA fp64 tensors -> torch CUDA tensors (device entry point,
         asynchronous on the current torch stream, no status check).
         Returns (w[B, N], cost[B]) and, with ``return_info``, a dict with
-        ``status``, ``iters`` and ``kkt_res`` per QP."""
+        ``status``, ``iters`` and ``kkt_res`` per QP.  ``out=(w, cost)`` reuses
+        preallocated (e.g. pinned) output buffers."""
         if _is_torch_cuda(gamma):
-            return self._solve_batch_torch(lmbd, lmbd_r, gamma, return_info)
+            return self._solve_batch_torch(lmbd, lmbd_r, gamma, return_info, out)
         N = self.N
         gamma = np.ascontiguousarray(np.atleast_1d(gamma), dtype=np.float64)
         B = gamma.shape[0]
@@ -135,21 +136,29 @@ class LoMPC:
         else:
             assert lmbd_r.shape == (B,)
             lr_stride = 1 if B > 1 else 0
-        w = np.empty((B, N), dtype=np.float64)
-        cost = np.empty((B,), dtype=np.float64)
-        status = np.empty((B,), dtype=np.int32)
-        iters = np.empty((B,), dtype=np.int32)
-        kkt = np.empty((B,), dtype=np.float64)
+        if out is not None:
+            w, cost = out
+            assert w.shape == (B, N) and cost.shape == (B,) and w.dtype == np.float64
+            assert w.flags.c_contiguous and cost.flags.c_contiguous
+        else:
+            w = np.empty((B, N), dtype=np.float64)
+            cost = np.empty((B,), dtype=np.float64)
+        if return_info:
+            status = np.empty((B,), dtype=np.int32)
+            iters = np.empty((B,), dtype=np.int32)
+            kkt = np.empty((B,), dtype=np.float64)
+            ptrs = (status.ctypes.data, iters.ctypes.data, kkt.ctypes.data)
+        else:
+            ptrs = (None, None, None)  # the C side still fetches and checks the status
         rc = self._lib.lompc_solve_batch_host(
             self._h, B, lmbd.ctypes.data, lm_stride, lmbd_r.ctypes.data, lr_stride,
-            gamma.ctypes.data, w.ctypes.data, cost.ctypes.data, status.ctypes.data,
-            iters.ctypes.data, kkt.ctypes.data)
+            gamma.ctypes.data, w.ctypes.data, cost.ctypes.data, *ptrs)
         _native.raise_for(rc)
         if return_info:
             return w, cost, {"status": status, "iters": iters, "kkt_res": kkt}
         return w, cost
 
-    def _solve_batch_torch(self, lmbd, lmbd_r, gamma, return_info):
+    def _solve_batch_torch(self, lmbd, lmbd_r, gamma, return_info, out=None):
         import torch
 
         N = self.N
@@ -163,16 +172,23 @@ class LoMPC:
             lmbd_r = torch.full((1,), float(lmbd_r), dtype=torch.float64, device=dev)
         assert lmbd_r.dtype == torch.float64 and lmbd_r.device == dev
         lr_stride = 0 if lmbd_r.numel() == 1 else 1
-        w = torch.empty((B, N), dtype=torch.float64, device=dev)
-        cost = torch.empty((B,), dtype=torch.float64, device=dev)
-        status = torch.empty((B,), dtype=torch.int32, device=dev)
-        iters = torch.empty((B,), dtype=torch.int32, device=dev)
-        kkt = torch.empty((B,), dtype=torch.float64, device=dev)
+        if out is not None:
+            w, cost = out
+            assert w.shape == (B, N) and w.is_contiguous() and cost.shape == (B,)
+        else:
+            w = torch.empty((B, N), dtype=torch.float64, device=dev)
+            cost = torch.empty((B,), dtype=torch.float64, device=dev)
+        if return_info:
+            status = torch.empty((B,), dtype=torch.int32, device=dev)
+            iters = torch.empty((B,), dtype=torch.int32, device=dev)
+            kkt = torch.empty((B,), dtype=torch.float64, device=dev)
+            ptrs = (status.data_ptr(), iters.data_ptr(), kkt.data_ptr())
+        else:
+            ptrs = (None, None, None)
         stream = torch.cuda.current_stream(dev).cuda_stream
         rc = self._lib.lompc_solve_batch_dev(
             self._h, B, lmbd.data_ptr(), lm_stride, lmbd_r.data_ptr(), lr_stride,
-            gamma.data_ptr(), w.data_ptr(), cost.data_ptr(), status.data_ptr(),
-            iters.data_ptr(), kkt.data_ptr(), stream)
+            gamma.data_ptr(), w.data_ptr(), cost.data_ptr(), *ptrs, stream)
         _native.raise_for(rc)
         if return_info:
             return w, cost, {"status": status, "iters": iters, "kkt_res": kkt}

@@ -84,6 +84,11 @@ int lompc_solve_batch_host(lompc_t* h, int64_t B, const double* lmbd, int64_t lm
                            double* w_out, double* cost_out, int32_t* status, int32_t* iters,
                            double* kkt_res);
 
+/* Measures the device's FP64 FMA peak (TFLOP/s, FMA = 2 flops) with a
+ * register-resident DFMA chain kernel: the roofline denominator of this
+ * FP64-bound path (MEASURED_PEAKS.json has no FP64 figure).                 */
+int lompc_measure_fp64_peak(int device, int iters, double* tflops_out, double* ms_out);
+
 /* Number of kernels this library has launched since load (bench.py's
  * gpu_launches claim is read from here).                                    */
 int64_t lompc_launch_count(void);

@@ -118,3 +118,30 @@ def test_feature_map():
     q = 3 * consts.theta / (4 * consts.w_max)
     price = consts.theta * (lm[:N] @ w + lm[N:2 * N] @ (consts.w_max - w)) + q * lm[2 * N:] @ (w * w)
     assert abs(lm @ ph - price) <= 1e-12 * abs(price)
+
+
+@pytest.mark.parametrize("ev", ["small", "large"])
+def test_c_oracle_matches_numpy_oracle(ev):
+    """oracle/lompc_oracle.c (the timed CPU baseline) restates the same IPM: it must land
+    within the IPM's own accuracy of the exact optimum and reproduce the cost expression."""
+    from oracle import c_oracle
+    consts = orc.small_ev_consts() if ev == "small" else orc.large_ev_consts()
+    rng = np.random.default_rng(17)
+    for N in (12, 24):
+        B = 48
+        lm = consts.theta * rng.random((B, 3 * N))
+        lm[B // 2:] *= 0.05
+        lr = 3 * N * consts.delta * rng.random(B)
+        lr[B // 2:] = 0.0
+        gam = consts.y_max * rng.random(B)
+        w, cost, iters, used = c_oracle.solve_lompc_batch(N, consts, lm, lr, gam, nthreads=2)
+        assert used == 2 and iters.min() > 0
+        for b in range(0, B, 4):
+            wo, co, _ = orc.solve_active_set(N, consts, lm[b], lr[b], gam[b])
+            assert np.max(np.abs(w[b] - wo)) <= 2e-4 * consts.w_max
+            assert abs(cost[b] - co) <= 1e-6 * max(1, abs(co))
+            assert abs(cost[b] - orc.lompc_cost(N, consts, w[b], lm[b], lr[b], gam[b])) <= 1e-12 * max(1, abs(co))
+        wt, ct, _, _ = c_oracle.solve_lompc_batch(N, consts, lm, lr, gam, tol=1e-11, nthreads=2)
+        for b in range(0, B, 4):
+            wo, co, _ = orc.solve_active_set(N, consts, lm[b], lr[b], gam[b])
+            assert np.max(np.abs(wt[b] - wo)) <= 1e-6 * consts.w_max
