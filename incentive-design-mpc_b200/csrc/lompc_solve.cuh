@@ -75,12 +75,14 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
   const double gam = a.gamma[b];
   int st = LOMPC_ST_OK;
   if (gam < 0.0 || lr < 0.0) st = LOMPC_ST_NEGATIVE;  // nonneg parameters, lompc.py:78-82
-  double l2sum = 0.0, gmax = 0.0;
+  double l2sum = 0.0, gmax = 0.0, dmax = 0.0;
   for (int k = 0; k < N; ++k) {
     const double l1 = lm[k], l2 = lm[N + k], l3 = lm[2 * N + k];
     if (l1 < 0.0 || l2 < 0.0 || l3 < 0.0) st = LOMPC_ST_NEGATIVE;
     const double g = cs.theta * (l1 - l2);
-    D[k * T] = 2.0 * (lr * cs.theta2 + cs.q_scale * l3) + cs.d_base;
+    const double d = 2.0 * (lr * cs.theta2 + cs.q_scale * l3) + cs.d_base;
+    D[k * T] = d;
+    dmax = fmax(dmax, d);
     G[k * T] = g;
     WA[k * T] = 0.0;
     gmax = fmax(gmax, fabs(g));
@@ -92,6 +94,13 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
   const double gscale = fmax(1.0, gmax + c * N * cs.y_max);
   const double tq = a.tol * gscale;
   const double cg = c * gam;
+  // A coordinate within `band` of a breakpoint is treated as sitting on it (the
+  // epsilon-binding set of projected Newton: without it a coordinate 1 ulp off a
+  // bound, pushed towards it, would stay "free" and stall the search).
+  const double band = 1e-9 * wmax;
+  // Objective values closer than ftol cannot be ordered in fp64.
+  const double ftol = 1e-15 * (c * N * cs.y_max * cs.y_max +
+                               N * wmax * (gmax + 0.5 * dmax * wmax + cs.slope[NSEG - 1]));
 
   double* W = WA;   // current feasible iterate
   double* WN = WB;  // candidate
@@ -118,10 +127,10 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
       int seg = 0;
       double v;
       if (NSEG == 1) {
-        if (wk <= 0.0) {
+        if (wk <= band) {
           binding = (q >= -tq);
           v = binding ? 0.0 : -q;
-        } else if (wk >= wmax) {
+        } else if (wk >= wmax - band) {
           binding = (q <= tq);
           v = binding ? 0.0 : q;
         } else {
@@ -131,7 +140,7 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
         int at = -1;
 #pragma unroll
         for (int i = 0; i <= NSEG; ++i)
-          if (wk == cs.brk[i]) at = i;
+          if (fabs(wk - cs.brk[i]) <= band) at = i;
         if (at >= 0) {
           const double mq = -q;
           if (at < NSEG && mq > cs.slope[at] + tq) {
@@ -196,11 +205,11 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
       fn += x * fma(0.5 * D[k * T], x, G[k * T]) + 0.5 * c * e * e;
       if (NSEG > 1) fn += pwl_value<NSEG>(cs, x);
     }
-    if (fn < f) {
+    if (fn <= f + ftol) {
       double* tmp = W;
       W = WN;
       WN = tmp;
-      f = fn;
+      f = fmin(f, fn);
       sN = s;
       continue;
     }

@@ -175,3 +175,21 @@ def test_torch_device_entry_point():
     torch.cuda.synchronize()
     assert np.array_equal(w_d.cpu().numpy(), w_h) and np.array_equal(c_d.cpu().numpy(), c_h)
     assert int(info["status"].max()) == 0
+
+
+def test_hard_cases():
+    """Near-degenerate inputs on which an earlier build stalled (tests/golden/gen_hard_cases.py)."""
+    from chargingstation.lompc import LoMPC
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "lompc_hard_cases.npz"))
+    keys = sorted(set("_".join(k.split("_")[:3]) for k in z.files))
+    assert len(keys) >= 8
+    for key in keys:
+        ev, Ns, _ = key.split("_")
+        N = int(Ns[1:])
+        o, c = _consts(ev)
+        solver = LoMPC(N, c)
+        w, cost, info = solver.solve_lompc_batch(z[key + "_lmbd"], z[key + "_lmbd_r"], z[key + "_gamma"],
+                                                 return_info=True)
+        assert np.all(info["status"] == 0), (key, info["status"], info["kkt_res"])
+        assert np.max(np.abs(w - z[key + "_w"])) <= W_RTOL * o.w_max, key
+        assert np.max(np.abs(cost - z[key + "_cost"]) / np.maximum(1, np.abs(z[key + "_cost"]))) <= C_RTOL, key
