@@ -38,6 +38,16 @@ SIGNATURES = {
                                          C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                          C.c_void_p, C.c_void_p]),
     "lompc_launch_count": (C.c_int64, []),
+    "price_group_stats_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 7),
+    "price_w_err_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 11),
+    "price_step_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int] + [C.c_void_p] * 7),
+    "price_regularize_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int] + [C.c_void_p] * 5),
+    "price_lp_rows_dev": (C.c_int, [C.c_int, C.c_int, C.c_int] + [C.c_void_p] * 5),
+    "price_solve_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_void_p]),
+    "price_w0_price0_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 7),
     "lompc_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, _dp, _dp]),
 }
 

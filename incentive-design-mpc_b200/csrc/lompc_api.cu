@@ -7,6 +7,7 @@
 
 #include "lompc_common.cuh"
 #include "lompc_solve.cuh"
+#include "lompc_price.cuh"
 
 namespace {
 
@@ -39,6 +40,10 @@ struct lompc_handle {
   // grow-only device workspace for the _host entry points
   void* ws;
   size_t ws_bytes;
+  // grow-only device workspace of the price loop + pinned poll word
+  void* pws;
+  size_t pws_bytes;
+  int32_t* poll;  // pinned host
 };
 
 namespace {
@@ -128,6 +133,7 @@ int lompc_create(int N, double delta, double theta, double y_max, double w_max, 
   memset(&cs, 0, sizeof(cs));
   cs.N = N;
   cs.large = ev_type == LOMPC_EV_LARGE;
+  cs.delta = delta;
   cs.theta = theta;
   cs.w_max = w_max;
   cs.y_max = y_max;
@@ -157,16 +163,19 @@ int lompc_create(int N, double delta, double theta, double y_max, double w_max, 
   h->delta = delta;
   h->ws = nullptr;
   h->ws_bytes = 0;
+  h->pws = nullptr;
+  h->pws_bytes = 0;
+  h->poll = nullptr;
   *out = h;
   return LOMPC_OK;
 }
 
 int lompc_destroy(lompc_t* h) {
   if (!h) return LOMPC_OK;
-  if (h->ws) {
-    cudaSetDevice(h->device);
-    cudaFree(h->ws);
-  }
+  cudaSetDevice(h->device);
+  if (h->ws) cudaFree(h->ws);
+  if (h->pws) cudaFree(h->pws);
+  if (h->poll) cudaFreeHost(h->poll);
   delete h;
   return LOMPC_OK;
 }
@@ -203,6 +212,12 @@ int lompc_solve_batch_dev(lompc_t* h, int64_t B, const double* lmbd, int64_t lmb
   a.kkt_res = kkt_res;
   a.max_iter = h->max_iter;
   a.tol = h->tol;
+  a.group_of = nullptr;
+  a.skip = nullptr;
+  a.w_ref = nullptr;
+  a.err_out = nullptr;
+  a.w0_out = nullptr;
+  a.price0_out = nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return h->cs.large ? launch_solve<4>(h, a, s) : launch_solve<1>(h, a, s);
 }
@@ -269,6 +284,348 @@ int lompc_solve_batch_host(lompc_t* h, int64_t B, const double* lmbd, int64_t lm
   }
   delete[] st_tmp;
   return rc;
+}
+
+
+// ------------------------------------------------------------------------------
+// Price loop
+// ------------------------------------------------------------------------------
+}  // extern "C" (helpers below are internal)
+
+namespace {
+
+struct Carver {  // carves aligned sub-buffers out of one allocation
+  char* base;
+  size_t off = 0;
+  explicit Carver(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T>
+  T* take(size_t n) {
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += (n * sizeof(T) + 255) & ~(size_t)255;
+    return p;
+  }
+};
+
+int ensure_pws(lompc_handle* h, size_t bytes) {
+  if (!h->poll) CK(cudaMallocHost(&h->poll, 64));
+  if (h->pws_bytes >= bytes) return LOMPC_OK;
+  if (h->pws) CK(cudaFree(h->pws));
+  h->pws = nullptr;
+  h->pws_bytes = 0;
+  const size_t want = bytes + bytes / 8;
+  CK(cudaMalloc(&h->pws, want));
+  h->pws_bytes = want;
+  return LOMPC_OK;
+}
+
+// K1 in group mode (shared prices per group, optional skip mask and fused epilogues).
+int launch_group_solve(const lompc_handle* h, int64_t B, const double* lmbd, const double* lmbd_r,
+                       const double* gamma, const int32_t* group_of, const int32_t* skip,
+                       const double* w_ref, double* w_out, double* cost_out, double* err_out,
+                       double* w0_out, double* price0_out, cudaStream_t s) {
+  if (B == 0) return LOMPC_OK;
+  lompc::SolveArgs a;
+  a.B = B;
+  a.lmbd = lmbd;
+  a.lmbd_stride = 3 * (int64_t)h->cs.N;
+  a.lmbd_r = lmbd_r;
+  a.lmbd_r_stride = 1;
+  a.gamma = gamma;
+  a.w_out = w_out;
+  a.cost_out = cost_out;
+  a.status = nullptr;
+  a.iters = nullptr;
+  a.kkt_res = nullptr;
+  a.max_iter = h->max_iter;
+  a.tol = h->tol;
+  a.group_of = group_of;
+  a.skip = skip;
+  a.w_ref = w_ref;
+  a.err_out = err_out;
+  a.w0_out = w0_out;
+  a.price0_out = price0_out;
+  return h->cs.large ? launch_solve<4>(h, a, s) : launch_solve<1>(h, a, s);
+}
+
+inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+#define COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
+
+}  // namespace
+
+extern "C" {
+
+int price_group_stats_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off,
+                          const double* y0, double* gamma, double* y0_rng, double* gamma_sc,
+                          double* gamma_sm, void* stream) {
+  if (!h || G < 0 || B < 0 || !group_off || !y0 || !gamma || !y0_rng || !gamma_sc || !gamma_sm)
+    return LOMPC_ERR_ARG;
+  if (G == 0) return LOMPC_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int rc = ensure_pws(h, 256);
+  if (rc) return rc;
+  int32_t* bad = static_cast<int32_t*>(h->pws);
+  CK(cudaMemsetAsync(bad, 0, 4, s));
+  lompc::group_stats_kernel<<<nblk(G, 128), 128, 0, s>>>(h->cs, G, group_off, y0, gamma, y0_rng, gamma_sc,
+                                                        gamma_sm, bad);
+  COUNT_LAUNCH();
+  CK(cudaMemcpyAsync(h->poll, bad, 4, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  return h->poll[0] ? LOMPC_ERR_CONSTS : LOMPC_OK;
+}
+
+int price_w_err_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off,
+                    const double* gamma, const double* lmbd, const double* lmbd_r,
+                    const double* w_ref, double* w_avg, double* w_err_max, double* w0_err,
+                    double* w_avg_err, double* w0, void* stream) {
+  if (!h || G < 0 || B < 0 || !group_off || !gamma || !lmbd || !lmbd_r || !w_ref) return LOMPC_ERR_ARG;
+  if (G == 0 || B == 0) return LOMPC_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int N = h->cs.N;
+  Carver sz(nullptr);
+  sz.take<int32_t>(B); sz.take<double>((size_t)B * N); sz.take<double>(B);
+  sz.take<double>((size_t)G * N); sz.take<double>(G); sz.take<double>(G); sz.take<double>(G);
+  sz.take<int32_t>(G); sz.take<int32_t>(G); sz.take<int32_t>(G); sz.take<int32_t>(1); sz.take<double>(G);
+  int rc = ensure_pws(h, sz.off);
+  if (rc) return rc;
+  Carver cv(h->pws);
+  int32_t* group_of = cv.take<int32_t>(B);
+  double* w_ev = cv.take<double>((size_t)B * N);
+  double* err_ev = cv.take<double>(B);
+  double* t_wavg = cv.take<double>((size_t)G * N);
+  double* t_emax = cv.take<double>(G);
+  double* t_e0 = cv.take<double>(G);
+  double* t_eavg = cv.take<double>(G);
+  int32_t* skip = cv.take<int32_t>(G);
+  int32_t* iters = cv.take<int32_t>(G);
+  int32_t* nst = cv.take<int32_t>(G);
+  int32_t* nact = cv.take<int32_t>(1);
+  double* y0r = cv.take<double>(G);
+  lompc::group_of_kernel<<<nblk(B, 256), 256, 0, s>>>(B, G, group_off, group_of);
+  COUNT_LAUNCH();
+  lompc::init_groups_kernel<<<nblk(G, 128), 128, 0, s>>>(G, 1, group_off, skip, iters, nst);
+  COUNT_LAUNCH();
+  rc = launch_group_solve(h, B, lmbd, lmbd_r, gamma, group_of, skip, w_ref, w_ev, nullptr, err_ev, w0,
+                          nullptr, s);
+  if (rc) return rc;
+  double* wa = w_avg ? w_avg : t_wavg;
+  double* em = w_err_max ? w_err_max : t_emax;
+  lompc::colsum_kernel<<<nblk((int64_t)G * N, 128), 128, 0, s>>>(N, G, group_off, skip, w_ev, err_ev, wa, em);
+  COUNT_LAUNCH();
+  // errors via the step kernel's first phase with an infinite tolerance (every group "converges")
+  CK(cudaMemsetAsync(y0r, 0x7f, (size_t)G * 8, s));  // 0x7f7f... = 1.4e306
+  lompc::PriceArgs p{};
+  p.G = G; p.r = 3 * N; p.tol_type_max = 0; p.eps_reg = 0.01; p.eps_tol = 0.0;
+  p.group_off = group_off; p.w_ref = w_ref; p.lmbd_r = lmbd_r; p.y0_rng = y0r;
+  p.w_avg = wa; p.w_err_max = em; p.w_avg_err = w_avg_err ? w_avg_err : t_eavg;
+  p.w0_err = w0_err ? w0_err : t_e0; p.skip = skip; p.iters = iters; p.nnqp_status = nst; p.n_active = nact;
+  lompc::group_step_kernel<<<nblk(G, 64), 64, 0, s>>>(h->cs, p, 0);
+  COUNT_LAUNCH();
+  CK(cudaGetLastError());
+  return LOMPC_OK;
+}
+
+int price_step_dev(lompc_t* h, int32_t G, int r, const double* w_ref, const double* w_k,
+                   const double* lmbd_r, double* lmbd, double* dual_decrease, int32_t* status,
+                   void* stream) {
+  if (!h || G < 0 || !w_ref || !w_k || !lmbd_r || !lmbd) return LOMPC_ERR_ARG;
+  const int N = h->cs.N;
+  if (r != 2 * N && r != 3 * N) return LOMPC_ERR_ARG;
+  if (G == 0) return LOMPC_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Carver sz(nullptr);
+  sz.take<double>((size_t)G * N); sz.take<double>(G); sz.take<double>(G); sz.take<double>(G); sz.take<double>(G);
+  sz.take<double>(G); sz.take<double>(G); sz.take<int32_t>(G); sz.take<int32_t>(G); sz.take<int32_t>(G);
+  sz.take<int32_t>(1); sz.take<double>((size_t)(2 * r + 6 * N) * G); sz.take<unsigned char>((size_t)r * G);
+  int rc = ensure_pws(h, sz.off);
+  if (rc) return rc;
+  Carver cv(h->pws);
+  double* w_avg = cv.take<double>((size_t)G * N);
+  double* y0r = cv.take<double>(G);
+  double* e1 = cv.take<double>(G);
+  double* e2 = cv.take<double>(G);
+  double* e3 = cv.take<double>(G);
+  double* lamdiff = cv.take<double>(G);
+  double* decp = cv.take<double>(G);
+  int32_t* skip = cv.take<int32_t>(G);
+  int32_t* iters = cv.take<int32_t>(G);
+  int32_t* nst = cv.take<int32_t>(G);
+  int32_t* nact = cv.take<int32_t>(1);
+  double* ws = cv.take<double>((size_t)(2 * r + 6 * N) * G);
+  unsigned char* wsb = cv.take<unsigned char>((size_t)r * G);
+  CK(cudaMemsetAsync(skip, 0, (size_t)G * 4, s));
+  // force the step: w_avg = +huge so that the error test never passes
+  CK(cudaMemsetAsync(w_avg, 0x7f, (size_t)G * N * 8, s));
+  CK(cudaMemsetAsync(y0r, 0, (size_t)G * 8, s));
+  lompc::PriceArgs p{};
+  p.G = G; p.r = r; p.tol_type_max = 0; p.eps_reg = 0.01; p.eps_tol = 0.01;
+  p.w_ref = w_ref; p.lmbd_r = lmbd_r; p.y0_rng = y0r; p.lmbd = lmbd; p.w_k = const_cast<double*>(w_k);
+  p.w_avg = w_avg; p.w_err_max = e1; p.w_avg_err = e2; p.w0_err = e3; p.lamdiff_phi = lamdiff;
+  p.dec_pred = dual_decrease ? dual_decrease : decp; p.skip = skip; p.iters = iters;
+  p.nnqp_status = status ? status : nst; p.n_active = nact; p.ws = ws; p.wsb = wsb;
+  lompc::group_step_kernel<<<nblk(G, 64), 64, 0, s>>>(h->cs, p, 1);
+  COUNT_LAUNCH();
+  CK(cudaGetLastError());
+  return LOMPC_OK;
+}
+
+int price_regularize_dev(lompc_t* h, int32_t G, int r, const double* w_k, double* lmbd,
+                         double* price_pre, double* price_post, void* stream) {
+  if (!h || G < 0 || !w_k || !lmbd || !price_pre || !price_post) return LOMPC_ERR_ARG;
+  const int N = h->cs.N;
+  if (r != 2 * N && r != 3 * N) return LOMPC_ERR_ARG;
+  if (G == 0) return LOMPC_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  lompc::regularize_kernel<<<nblk(G, 128), 128, 0, s>>>(h->cs, G, r, w_k, lmbd, price_pre, price_post, nullptr);
+  COUNT_LAUNCH();
+  CK(cudaGetLastError());
+  return LOMPC_OK;
+}
+
+int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, const double* y0,
+                    const double* w_ref, const double* lmbd_r, int r, int max_iter,
+                    int tol_type_max, double eps_reg, double eps_tol, double* prices,
+                    int32_t* iters, double* price_pre, double* price_post, double* w_k_out,
+                    double* hist_ac, double* hist_pred, int hist_cap, int32_t* total_iters,
+                    void* stream) {
+  if (!h || G < 0 || B < 0 || !group_off || !y0 || !w_ref || !lmbd_r || !prices || !iters ||
+      !price_pre || !price_post)
+    return LOMPC_ERR_ARG;
+  const int N = h->cs.N;
+  if ((r != 2 * N && r != 3 * N) || max_iter < 1) return LOMPC_ERR_ARG;
+  if (total_iters) *total_iters = 0;
+  if (G == 0) return LOMPC_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Carver sz(nullptr);
+  auto carve = [&](Carver& cv, int32_t*& group_of, double*& gamma, double*& w_ev, double*& err_ev,
+                   double*& y0_rng, double*& gamma_sc, double*& gamma_sm, double*& w_k, double*& w_avg,
+                   double*& e_max, double*& e_avg, double*& e_0, double*& dual_cost, double*& cost_new,
+                   double*& lamdiff, double*& decp, int32_t*& skip, int32_t*& nst, int32_t*& nact,
+                   double*& ws, unsigned char*& wsb) {
+    group_of = cv.take<int32_t>(B); gamma = cv.take<double>(B); w_ev = cv.take<double>((size_t)B * N);
+    err_ev = cv.take<double>(B); y0_rng = cv.take<double>(G); gamma_sc = cv.take<double>(G);
+    gamma_sm = cv.take<double>(G); w_k = cv.take<double>((size_t)G * N); w_avg = cv.take<double>((size_t)G * N);
+    e_max = cv.take<double>(G); e_avg = cv.take<double>(G); e_0 = cv.take<double>(G);
+    dual_cost = cv.take<double>(G); cost_new = cv.take<double>(G); lamdiff = cv.take<double>(G);
+    decp = cv.take<double>(G); skip = cv.take<int32_t>(G); nst = cv.take<int32_t>(G); nact = cv.take<int32_t>(4);
+    ws = cv.take<double>((size_t)(2 * r + 6 * N) * G); wsb = cv.take<unsigned char>((size_t)r * G);
+  };
+  int32_t *group_of, *skip, *nst, *nact;
+  double *gamma, *w_ev, *err_ev, *y0_rng, *gamma_sc, *gamma_sm, *w_k, *w_avg, *e_max, *e_avg, *e_0, *dual_cost,
+      *cost_new, *lamdiff, *decp, *ws;
+  unsigned char* wsb;
+  carve(sz, group_of, gamma, w_ev, err_ev, y0_rng, gamma_sc, gamma_sm, w_k, w_avg, e_max, e_avg, e_0, dual_cost,
+        cost_new, lamdiff, decp, skip, nst, nact, ws, wsb);
+  int rc = ensure_pws(h, sz.off);
+  if (rc) return rc;
+  Carver cv(h->pws);
+  carve(cv, group_of, gamma, w_ev, err_ev, y0_rng, gamma_sc, gamma_sm, w_k, w_avg, e_max, e_avg, e_0, dual_cost,
+        cost_new, lamdiff, decp, skip, nst, nact, ws, wsb);
+  if (w_k_out) w_k = w_k_out;
+
+  CK(cudaMemsetAsync(nact, 0, 16, s));
+  lompc::group_of_kernel<<<nblk(B, 256), 256, 0, s>>>(B, G, group_off, group_of);
+  COUNT_LAUNCH();
+  lompc::group_stats_kernel<<<nblk(G, 128), 128, 0, s>>>(h->cs, G, group_off, y0, gamma, y0_rng, gamma_sc,
+                                                        gamma_sm, nact + 1);
+  COUNT_LAUNCH();
+  lompc::init_groups_kernel<<<nblk(G, 128), 128, 0, s>>>(G, max_iter, group_off, skip, iters, nst);
+  COUNT_LAUNCH();
+  if (hist_ac && hist_pred && hist_cap > 0) {
+    CK(cudaMemsetAsync(hist_ac, 0, (size_t)G * hist_cap * 8, s));
+    CK(cudaMemsetAsync(hist_pred, 0, (size_t)G * hist_cap * 8, s));
+  }
+  // w_k, dual_cost = solve_lompc(lmbd_k, lmbd_r, gamma_sc)   (price_solver.py:106)
+  rc = launch_group_solve(h, G, prices, lmbd_r, gamma_sc, nullptr, skip, nullptr, w_k, dual_cost, nullptr,
+                          nullptr, nullptr, s);
+  if (rc) return rc;
+  lompc::PriceArgs p{};
+  p.G = G; p.r = r; p.tol_type_max = tol_type_max; p.eps_reg = eps_reg; p.eps_tol = eps_tol;
+  p.group_off = group_off; p.w_ref = w_ref; p.lmbd_r = lmbd_r; p.y0_rng = y0_rng; p.lmbd = prices;
+  p.w_k = w_k; p.w_avg = w_avg; p.w_err_max = e_max; p.w_avg_err = e_avg; p.w0_err = e_0;
+  p.dual_cost = dual_cost; p.cost_new = cost_new; p.lamdiff_phi = lamdiff; p.dec_pred = decp; p.skip = skip;
+  p.iters = iters; p.nnqp_status = nst; p.n_active = nact;
+  p.hist_ac = (hist_ac && hist_pred && hist_cap > 0) ? hist_ac : nullptr;
+  p.hist_pred = hist_pred; p.hist_cap = hist_cap; p.ws = ws; p.wsb = wsb;
+  int it = 0;
+  for (; it < max_iter; ++it) {
+    // _get_w_err (price_solver.py:112,196-214)
+    rc = launch_group_solve(h, B, prices, lmbd_r, gamma, group_of, skip, w_ref, w_ev, nullptr,
+                            tol_type_max ? err_ev : nullptr, nullptr, nullptr, s);
+    if (rc) return rc;
+    lompc::colsum_kernel<<<nblk((int64_t)G * N, 128), 128, 0, s>>>(N, G, group_off, skip, w_ev,
+                                                                    tol_type_max ? err_ev : nullptr, w_avg, e_max);
+    COUNT_LAUNCH();
+    CK(cudaMemsetAsync(nact, 0, 4, s));
+    lompc::group_step_kernel<<<nblk(G, 64), 64, 0, s>>>(h->cs, p, it);
+    COUNT_LAUNCH();
+    CK(cudaMemcpyAsync(h->poll, nact, 8, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h->poll[1]) return LOMPC_ERR_CONSTS;  // y0 outside [0, y_max], price_solver.py:71
+    if (h->poll[0] == 0) break;
+    // w_k, dual_cost_new = solve_lompc(lmbd_k_new, lmbd_r, gamma_sc)   (price_solver.py:132)
+    rc = launch_group_solve(h, G, prices, lmbd_r, gamma_sc, nullptr, skip, nullptr, w_k, cost_new, nullptr,
+                            nullptr, nullptr, s);
+    if (rc) return rc;
+    lompc::bookkeep_kernel<<<nblk(G, 128), 128, 0, s>>>(p, it);
+    COUNT_LAUNCH();
+  }
+  if (total_iters) *total_iters = it;
+  // price_solver.py:145-147
+  lompc::regularize_kernel<<<nblk(G, 128), 128, 0, s>>>(h->cs, G, r, w_k, prices, price_pre, price_post, nullptr);
+  COUNT_LAUNCH();
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));
+  return LOMPC_OK;
+}
+
+int price_lp_rows_dev(int device, int N, int nb, const double* a, const double* b, const double* c,
+                      double* x, void* stream) {
+  if (N < 0 || nb < 1 || !a || !b || !c || !x) return LOMPC_ERR_ARG;
+  if (lompc_device_count() <= device || device < 0) return LOMPC_ERR_NO_DEVICE;
+  if (N == 0) return LOMPC_OK;
+  CK(cudaSetDevice(device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  int32_t* st = nullptr;
+  CK(cudaMalloc(&st, 4));
+  CK(cudaMemsetAsync(st, 0, 4, s));
+  lompc::lp_rows_kernel<<<nblk(N, 128), 128, 0, s>>>(N, nb, a, b, c, x, st);
+  COUNT_LAUNCH();
+  int32_t hst = 0;
+  cudaError_t e = cudaMemcpyAsync(&hst, st, 4, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(st);
+  if (e != cudaSuccess) return cuda_fail(e, "price_lp_rows_dev");
+  return hst ? LOMPC_ERR_ARG : LOMPC_OK;
+}
+
+int price_w0_price0_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off,
+                        const double* gamma, const double* lmbd, const double* lmbd_r,
+                        double* w0, double* price0, void* stream) {
+  if (!h || G < 0 || B < 0 || !group_off || !gamma || !lmbd || !lmbd_r || !w0 || !price0) return LOMPC_ERR_ARG;
+  if (G == 0 || B == 0) return LOMPC_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  Carver sz(nullptr);
+  sz.take<int32_t>(B); sz.take<double>(B);
+  int rc = ensure_pws(h, sz.off);
+  if (rc) return rc;
+  Carver cv(h->pws);
+  int32_t* group_of = cv.take<int32_t>(B);
+  double* p0_ev = cv.take<double>(B);
+  lompc::group_of_kernel<<<nblk(B, 256), 256, 0, s>>>(B, G, group_off, group_of);
+  COUNT_LAUNCH();
+  rc = launch_group_solve(h, B, lmbd, lmbd_r, gamma, group_of, nullptr, nullptr, nullptr, nullptr, nullptr, w0,
+                          p0_ev, s);
+  if (rc) return rc;
+  lompc::mean_kernel<<<nblk(G, 128), 128, 0, s>>>(G, group_off, p0_ev, price0);
+  COUNT_LAUNCH();
+  CK(cudaGetLastError());
+  return LOMPC_OK;
 }
 
 }  // extern "C"

@@ -13,6 +13,7 @@ constexpr int kMaxSeg = 4;  // pieces of the large-EV pwl (lompc.py:111-115)
 struct Consts {
   int N;
   int large;         // 0 small EV, 1 large EV
+  double delta;      // relative weight of the charging cost
   double theta;      // battery capacity
   double w_max;      // box upper bound (lompc.py:93)
   double y_max;      // gamma <= y_max (lompc.py:87)
@@ -41,6 +42,13 @@ struct SolveArgs {
   double* kkt_res;
   int max_iter;
   double tol;
+  // ---- group mode (price loop, price_solver.py:196-214,272-285); all nullable ----
+  const int32_t* group_of;  // [B] row of lmbd / lmbd_r / w_ref used by QP b (NULL: row = b)
+  const int32_t* skip;      // [rows] QPs whose row has skip != 0 are not solved (converged groups)
+  const double* w_ref;      // [rows, N] reference trajectories for err_out
+  double* err_out;          // [B] sqrt((w-w_ref)' (A'A + lmbd_r/delta I) (w-w_ref)), price_solver.py:207
+  double* w0_out;           // [B] first-step charge w[0]
+  double* price0_out;       // [B] LoMPC.get_price0 (lompc.py:164-170)
 };
 
 }  // namespace lompc

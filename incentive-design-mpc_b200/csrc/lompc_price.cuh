@@ -1,0 +1,364 @@
+// K2-K5: the price loop around the LoMPC solve (reference price_solver.py,
+// price_regularizer.py), batched over G independent (station, EV-type, partition)
+// groups.  EVs are sorted by group: group g owns EVs [group_off[g], group_off[g+1]).
+//
+//   group_of_kernel      EV -> group index (binary search in group_off)
+//   group_stats_kernel   PriceSolver.set_charge_levels        price_solver.py:66-77
+//   colsum_kernel        w_avg / w_err_max of _get_w_err      price_solver.py:199-213
+//   group_step_kernel    convergence test + _price_gradient_descent_step
+//                                                             price_solver.py:121-131,216-246
+//   bookkeep_kernel      dual-cost statistics                 price_solver.py:135-140
+//   regularize_kernel    _regularize_prices (closed form of the LP, price_regularizer.py:68-85)
+//   mean_kernel          mean first-step price of get_w0_price0   price_solver.py:281-284
+//
+// All group-level reductions run in a fixed order (the reference's own order:
+// EV 0, 1, ... of the group), so results do not depend on the launch geometry.
+#pragma once
+#include "lompc_common.cuh"
+
+namespace lompc {
+
+struct PriceArgs {
+  int G;
+  int r;               // 2N ("linear") or 3N ("linear-convex"), price_solver.py:44-47
+  int tol_type_max;    // settings.PRICE_SOLVER_TOL_TYPE == "max"
+  double eps_reg;      // settings.PRICE_SOLVER_EPS_REG
+  double eps_tol;      // settings.PRICE_SOLVER_EPS_TOL
+  const int32_t* group_off;  // [G+1]
+  const double* w_ref;       // [G,N]
+  const double* lmbd_r;      // [G]
+  const double* y0_rng;      // [G]
+  double* lmbd;              // [G,3N] current prices (updated in place)
+  double* w_k;               // [G,N]  LoMPC solution at gamma_sc for the current prices
+  double* w_avg;             // [G,N]
+  double* w_err_max;         // [G]
+  double* w_avg_err;         // [G]
+  double* w0_err;            // [G]
+  double* dual_cost;         // [G]
+  double* cost_new;          // [G]
+  double* lamdiff_phi;       // [G] (lmbd_k - lmbd_k_new) @ phi(w_ref), first iteration only (aliasing quirk :140)
+  double* dec_pred;          // [G]
+  int32_t* skip;             // [G] 1 = converged / empty
+  int32_t* iters;            // [G]
+  int32_t* nnqp_status;      // [G] 0 ok, 1 = active-set iteration cap hit
+  int32_t* n_active;         // [1]
+  double* hist_ac;           // [G,hist_cap] or NULL
+  double* hist_pred;         // [G,hist_cap] or NULL
+  int hist_cap;
+  double* ws;                // scratch, (2r + 6N) * G doubles
+  unsigned char* wsb;        // scratch, r * G bytes
+};
+
+__global__ void group_of_kernel(int64_t B, int G, const int32_t* __restrict__ off, int32_t* __restrict__ group_of) {
+  const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= B) return;
+  int lo = 0, hi = G;  // find g with off[g] <= b < off[g+1]
+  while (hi - lo > 1) {
+    const int mid = (lo + hi) >> 1;
+    if ((int64_t)off[mid] <= b) lo = mid; else hi = mid;
+  }
+  group_of[b] = lo;
+}
+
+// price_solver.py:66-77 for every group; also gamma_i = y_max - y0_i (price_solver.py:201,279).
+__global__ void group_stats_kernel(const Consts cs, int G, const int32_t* __restrict__ off,
+                                   const double* __restrict__ y0, double* __restrict__ gamma,
+                                   double* __restrict__ y0_rng, double* __restrict__ gamma_sc,
+                                   double* __restrict__ gamma_sm, int32_t* __restrict__ bad) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const int b0 = off[g], b1 = off[g + 1];
+  if (b1 <= b0) {
+    y0_rng[g] = 0.0; gamma_sc[g] = 0.0; gamma_sm[g] = 0.0;
+    return;
+  }
+  double mn = y0[b0], mx = y0[b0], sum = 0.0;
+  for (int b = b0; b < b1; ++b) {
+    const double y = y0[b];
+    if (!(y >= 0.0 && y <= cs.y_max)) atomicExch(bad, 1);  // assert of price_solver.py:71
+    mn = fmin(mn, y);
+    mx = fmax(mx, y);
+    sum += y;
+    gamma[b] = cs.y_max - y;
+  }
+  y0_rng[g] = (mx - mn) / 2;
+  gamma_sc[g] = cs.y_max - (mx + mn) / 2;
+  gamma_sm[g] = cs.y_max - sum / (b1 - b0);
+}
+
+// One thread per (group, time step): w_avg[g,k] = mean_i w_i[k] in EV order; thread k = 0
+// also takes max_i err_i (price_solver.py:199-210).
+__global__ void colsum_kernel(int N, int G, const int32_t* __restrict__ off, const int32_t* __restrict__ skip,
+                              const double* __restrict__ w_ev, const double* __restrict__ err_ev,
+                              double* __restrict__ w_avg, double* __restrict__ w_err_max) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= (int64_t)G * N) return;
+  const int g = (int)(idx / N), k = (int)(idx % N);
+  if (skip && skip[g]) return;
+  const int b0 = off[g], b1 = off[g + 1];
+  double sum = 0.0;
+  for (int b = b0; b < b1; ++b) sum += w_ev[(int64_t)b * N + k];
+  w_avg[idx] = sum / (b1 - b0);
+  if (k == 0 && err_ev) {
+    double m = 0.0;
+    for (int b = b0; b < b1; ++b) m = fmax(m, err_ev[b]);
+    w_err_max[g] = m;
+  }
+}
+
+// x = (diag(d) + c A'A)^{-1} b by the scalar Riccati recursion (A = tril(ones)).
+// d_k = dvec[k*G] (+ dadd).  K/KAP are scratch; all vectors are strided by G.
+__device__ __forceinline__ void ric_solve(int N, int G, const double* dvec, double dadd, double c,
+                                          const double* bvec, double* x, double* K, double* KAP) {
+  double P = 0.0, r = 0.0;
+  for (int k = N - 1; k >= 0; --k) {
+    const double d = (dvec ? dvec[(size_t)k * G] : 0.0) + dadd;
+    const double Q = c + P;
+    const double inv = 1.0 / (d + Q);
+    const double gk = -bvec[(size_t)k * G];
+    K[(size_t)k * G] = Q * inv;
+    KAP[(size_t)k * G] = (r + gk) * inv;
+    P = Q * d * inv;
+    r = (d * r - Q * gk) * inv;
+  }
+  double s = 0.0;
+  for (int k = 0; k < N; ++k) {
+    const double xk = -fma(K[(size_t)k * G], s, KAP[(size_t)k * G]);
+    x[(size_t)k * G] = xk;
+    s += xk;
+  }
+}
+
+// One thread per group: errors of _get_w_err, the convergence test, and -- for groups
+// that go on -- the exact solution of the non-negative QP of the price step
+//     min_{l >= 0} l'P l + q'l,  P = Dphi A_bar^{-1} Dphi'/(2m) + eps I,  q = -2 P l_k - (phi(w_k) - phi(w_ref))
+// by a primal-dual active-set iteration.  P is never formed: with B = Dphi[:r] (three
+// diagonals) the free-set system is solved through Woodbury,
+//     l_F = (rho_F - B_F z)/eps,   (2 m eps A_bar + B_F'B_F) z = B_F' rho_F,   rho = -q/2,
+// and A_bar = A'A + kappa I makes that an O(N) Riccati solve like the LoMPC's own.
+__global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int G = p.G, N = cs.N, r = p.r;
+  if (g >= G || p.skip[g]) return;
+  const double kappa = p.lmbd_r[g] / cs.delta;
+  // ---- errors (price_solver.py:211-214)
+  {
+    double cum = 0.0, e2 = 0.0;
+    for (int k = 0; k < N; ++k) {
+      const double v = p.w_avg[(size_t)g * N + k] - p.w_ref[(size_t)g * N + k];
+      cum += v;
+      e2 += cum * cum + kappa * v * v;
+    }
+    const double w_avg_err = sqrt(e2);
+    p.w_avg_err[g] = w_avg_err;
+    p.w0_err[g] = fabs(p.w_avg[(size_t)g * N] - p.w_ref[(size_t)g * N]);
+    const double tol = sqrt((double)N) * p.y0_rng[g] + p.eps_tol;  // price_solver.py:184
+    const double w_err = p.tol_type_max ? p.w_err_max[g] : w_avg_err;
+    if (w_err <= tol) {  // price_solver.py:125
+      p.skip[g] = 1;
+      p.iters[g] = it;
+      return;
+    }
+  }
+  atomicAdd(p.n_active, 1);
+  // ---- scratch (strided by G)
+  double* LAM = p.ws + g;                    // [r] new prices
+  double* RHO = LAM + (size_t)r * G;         // [r]
+  double* C3 = RHO + (size_t)r * G;          // [N] third diagonal of Dphi': 2 q w_k
+  double* KS = C3 + (size_t)N * G;           // [N]
+  double* KAPS = KS + (size_t)N * G;         // [N]
+  double* U = KAPS + (size_t)N * G;          // [N]
+  double* V = U + (size_t)N * G;             // [N]
+  double* TD = V + (size_t)N * G;            // [N]
+  unsigned char* FREE = p.wsb + g;           // [r]
+  const int nb = r / N;                      // 2 or 3 price blocks
+  const double th = cs.theta, qs = cs.q_scale, m = cs.c, eps = p.eps_reg;
+  double* lk = p.lmbd + (size_t)g * 3 * N;
+  const double* wk = p.w_k + (size_t)g * N;
+  const double* wr = p.w_ref + (size_t)g * N;
+  // u = B' l_k ; v = A_bar^{-1} u ; rho = P l_k + (phi(w_k) - phi(w_ref))/2
+  for (int k = 0; k < N; ++k) {
+    const double c3 = 2.0 * qs * wk[k];
+    C3[(size_t)k * G] = c3;
+    U[(size_t)k * G] = th * (lk[k] - lk[N + k]) + (nb == 3 ? c3 * lk[2 * N + k] : 0.0);
+  }
+  ric_solve(N, G, nullptr, kappa, 1.0, U, V, KS, KAPS);
+  double gs = 1.0, F0 = 0.0, lamdiff = 0.0;
+  for (int k = 0; k < N; ++k) {
+    const double v = V[(size_t)k * G] / (2.0 * m);
+    const double dw = wk[k] - wr[k];
+    const double dphi[3] = {th * dw, -th * dw, qs * (wk[k] * wk[k] - wr[k] * wr[k])};
+    const double coef[3] = {th, -th, C3[(size_t)k * G]};
+    for (int j = 0; j < nb; ++j) {
+      const double l = lk[j * N + k];
+      const double Pl = eps * l + coef[j] * v;
+      const double rho = Pl + 0.5 * dphi[j];
+      RHO[(size_t)(j * N + k) * G] = rho;
+      gs = fmax(gs, fabs(rho));
+      F0 += l * (Pl - 2.0 * rho);  // l'P l + q'l with q = -2 rho
+      FREE[(size_t)(j * N + k) * G] = (l > 0.0) || (dphi[j] > 0.0);  // half-gradient at l_k is -dphi/2
+    }
+  }
+  // ---- primal-dual active set
+  int st = 1;
+  double F1 = F0;
+  for (int pit = 0; pit < 64; ++pit) {
+    for (int k = 0; k < N; ++k) {
+      const double coef[3] = {th, -th, C3[(size_t)k * G]};
+      double t = 0.0, rhs = 0.0;
+      for (int j = 0; j < nb; ++j)
+        if (FREE[(size_t)(j * N + k) * G]) {
+          t += coef[j] * coef[j];
+          rhs += coef[j] * RHO[(size_t)(j * N + k) * G];
+        }
+      TD[(size_t)k * G] = t;
+      U[(size_t)k * G] = rhs;
+    }
+    ric_solve(N, G, TD, 2.0 * m * eps * kappa, 2.0 * m * eps, U, V, KS, KAPS);  // z
+    for (int k = 0; k < N; ++k) {
+      const double coef[3] = {th, -th, C3[(size_t)k * G]};
+      const double z = V[(size_t)k * G];
+      double u = 0.0;
+      for (int j = 0; j < nb; ++j) {
+        const size_t i = (size_t)(j * N + k) * G;
+        const double l = FREE[i] ? (RHO[i] - coef[j] * z) / eps : 0.0;
+        LAM[i] = l;
+        u += coef[j] * l;
+      }
+      U[(size_t)k * G] = u;
+    }
+    ric_solve(N, G, nullptr, kappa, 1.0, U, V, KS, KAPS);  // v = A_bar^{-1} B' l
+    bool same = true;
+    F1 = 0.0;
+    for (int k = 0; k < N; ++k) {
+      const double coef[3] = {th, -th, C3[(size_t)k * G]};
+      const double v = V[(size_t)k * G] / (2.0 * m);
+      for (int j = 0; j < nb; ++j) {
+        const size_t i = (size_t)(j * N + k) * G;
+        const double l = LAM[i];
+        const double Pl = eps * l + coef[j] * v;
+        const double hg = Pl - RHO[i];  // half gradient
+        F1 += l * (Pl - 2.0 * RHO[i]);
+        const bool fr = FREE[i];
+        const bool nf = fr ? (l > 0.0) : (hg < -1e-12 * gs);
+        if (nf != fr) same = false;
+        FREE[i] = nf;
+      }
+    }
+    if (same) {
+      st = 0;
+      break;
+    }
+  }
+  p.nnqp_status[g] = st;
+  // ---- write back (price_solver.py:129,135-140)
+  const bool first = (it == 0);
+  for (int k = 0; k < N; ++k) {
+    const double phir[3] = {th * wr[k], th * (cs.w_max - wr[k]), qs * wr[k] * wr[k]};
+    for (int j = 0; j < nb; ++j) {
+      const double ln = fmax(LAM[(size_t)(j * N + k) * G], 0.0);
+      if (first) lamdiff += (lk[j * N + k] - ln) * phir[j];
+      lk[j * N + k] = ln;
+    }
+  }
+  p.lamdiff_phi[g] = first ? lamdiff : 0.0;
+  p.dec_pred[g] = F0 - F1;
+}
+
+__global__ void bookkeep_kernel(const PriceArgs p, int it) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= p.G || p.skip[g]) return;
+  const double ac = p.cost_new[g] - p.dual_cost[g] + p.lamdiff_phi[g];  // price_solver.py:135-137
+  p.dual_cost[g] = p.cost_new[g];
+  if (p.hist_ac && it < p.hist_cap) {
+    p.hist_ac[(size_t)g * p.hist_cap + it] = ac;
+    p.hist_pred[(size_t)g * p.hist_cap + it] = p.dec_pred[g];
+  }
+}
+
+// price_solver.py:145-147,248-255 with the LP of price_regularizer.py:68-85 in closed form:
+// row k of Dphi' touches only (x1_k, x2_k, x3_k); b_k = theta(l1-l2) + 2 q w_k l3;
+// b_k < 0: x2 = -b_k/theta;  b_k >= 0: x3 = b_k/(2 q w_k) if r = 3N and w_k > 0 (unit cost
+// w_k/2 beats x1's w_k) else x1 = b_k/theta.
+__global__ void regularize_kernel(const Consts cs, int G, int r, const double* __restrict__ w_k,
+                                  double* __restrict__ lmbd, double* __restrict__ price_pre,
+                                  double* __restrict__ price_post, const int32_t* __restrict__ empty) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  if (empty && empty[g]) return;
+  const int N = cs.N;
+  const double th = cs.theta, qs = cs.q_scale, wm = cs.w_max;
+  double* l = lmbd + (size_t)g * 3 * N;
+  const double* w = w_k + (size_t)g * N;
+  double pre = 0.0, post = 0.0;
+  for (int k = 0; k < N; ++k) {
+    const double wk = w[k];
+    const double ph1 = th * wk, ph2 = th * (wm - wk), ph3 = qs * wk * wk;
+    const double l3 = (r == 3 * N) ? l[2 * N + k] : 0.0;
+    pre += ph1 * l[k] + ph2 * l[N + k] + ph3 * l3;
+    const double bk = th * (l[k] - l[N + k]) + 2.0 * qs * wk * l3;
+    double x1 = 0.0, x2 = 0.0, x3 = 0.0;
+    if (bk < 0.0) x2 = -bk / th;
+    else if (r == 3 * N && wk > 0.0) x3 = bk / (2.0 * qs * wk);
+    else x1 = bk / th;
+    l[k] = x1;
+    l[N + k] = x2;
+    if (r == 3 * N) l[2 * N + k] = x3;
+    post += ph1 * x1 + ph2 * x2 + ph3 * x3;
+  }
+  price_pre[g] = pre;
+  price_post[g] = post;
+}
+
+// PriceRegularizer.solve_price_regularization (price_regularizer.py:68-85) for a constraint
+// matrix with the block-diagonal pattern A = [diag(a_0) ... diag(a_{nb-1})] (every use in the
+// reference: Dphi' and the [I, -I] of test_price_regularizer.py): the LP separates into N
+// one-row LPs  min c'x, a'x = b_k, x >= 0, whose optimum puts all weight on the column with
+// the smallest cost per unit of b_k.  status: 0 ok, 1 infeasible row.
+__global__ void lp_rows_kernel(int N, int nb, const double* __restrict__ a, const double* __restrict__ b,
+                               const double* __restrict__ c, double* __restrict__ x, int32_t* __restrict__ status) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= N) return;
+  for (int j = 0; j < nb; ++j) x[j * N + k] = 0.0;
+  const double bk = b[k];
+  if (bk == 0.0) return;
+  int best = -1;
+  double best_ratio = 0.0;
+  for (int j = 0; j < nb; ++j) {
+    const double aj = a[j * N + k];
+    if (aj * bk > 0.0) {
+      const double ratio = c[j * N + k] / fabs(aj);
+      if (best < 0 || ratio < best_ratio) {
+        best = j;
+        best_ratio = ratio;
+      }
+    }
+  }
+  if (best < 0) {
+    atomicExch(status, 1);
+    return;
+  }
+  x[best * N + k] = bk / a[best * N + k];
+}
+
+__global__ void mean_kernel(int G, const int32_t* __restrict__ off, const double* __restrict__ x_ev,
+                            double* __restrict__ mean) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const int b0 = off[g], b1 = off[g + 1];
+  double s = 0.0;
+  for (int b = b0; b < b1; ++b) s += x_ev[b];
+  mean[g] = b1 > b0 ? s / (b1 - b0) : 0.0;
+}
+
+__global__ void init_groups_kernel(int G, int max_iter, const int32_t* __restrict__ off,
+                                   int32_t* __restrict__ skip, int32_t* __restrict__ iters,
+                                   int32_t* __restrict__ nnqp_status) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  skip[g] = off[g + 1] <= off[g];  // empty groups are never solved (charging_station.py:277,293)
+  iters[g] = max_iter - 1;         // value of `iter` if the loop never breaks (price_solver.py:111)
+  nnqp_status[g] = 0;
+}
+
+}  // namespace lompc

@@ -70,8 +70,10 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
   if (!live) return;  // no block-level sync below
 
   // ---- problem data (lompc.py:101-135 restated) -------------------------------
-  const double* lm = a.lmbd + b * a.lmbd_stride;
-  const double lr = a.lmbd_r[b * a.lmbd_r_stride];
+  const int64_t row = a.group_of ? (int64_t)a.group_of[b] : b;
+  if (a.skip && a.skip[row]) return;
+  const double* lm = a.lmbd + row * a.lmbd_stride;
+  const double lr = a.lmbd_r[row * a.lmbd_r_stride];
   const double gam = a.gamma[b];
   int st = LOMPC_ST_OK;
   if (gam < 0.0 || lr < 0.0) st = LOMPC_ST_NEGATIVE;  // nonneg parameters, lompc.py:78-82
@@ -272,15 +274,31 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
   // ---- outputs: w, cost in the reference's form (lompc.py:155) ----------------
   double cost = cs.theta * wmax * l2sum;  // theta * lmbd2 @ w_max, lompc.py:130
   double s = 0.0;
-  double* wo = a.w_out + b * (int64_t)N;
+  double* wo = a.w_out ? a.w_out + b * (int64_t)N : nullptr;
   for (int k = 0; k < N; ++k) {
     const double x = W[k * T];
-    wo[k] = x;
+    if (wo) wo[k] = x;
     s += x;
     cost += x * fma(0.5 * D[k * T], x, G[k * T]) + 0.5 * c * s * (s - 2.0 * gam);
     if (NSEG > 1) cost += pwl_value<NSEG>(cs, x);
   }
-  a.cost_out[b] = cost;
+  if (a.cost_out) a.cost_out[b] = cost;
+  if (a.err_out) {  // ||w - w_ref|| in the A_bar metric: v'A'Av = ||cumsum(v)||^2 (price_solver.py:188-194,207)
+    const double* wr = a.w_ref + row * (int64_t)N;
+    const double kap = lr / cs.delta;
+    double cum = 0.0, e2 = 0.0;
+    for (int k = 0; k < N; ++k) {
+      const double v = W[k * T] - wr[k];
+      cum += v;
+      e2 += cum * cum + kap * v * v;
+    }
+    a.err_out[b] = sqrt(e2);
+  }
+  const double w0 = W[0];
+  if (a.w0_out) a.w0_out[b] = w0;
+  if (a.price0_out)  // lompc.py:164-170
+    a.price0_out[b] = cs.theta * (w0 * lm[0] + (wmax - w0) * lm[N]) + cs.q_scale * w0 * w0 * lm[2 * N] +
+                      cs.theta2 * w0 * w0 * lr;
   if (a.status) a.status[b] = st;
   if (a.iters) a.iters[b] = it;
   if (a.kkt_res) a.kkt_res[b] = viol / gscale;

@@ -84,6 +84,71 @@ int lompc_solve_batch_host(lompc_t* h, int64_t B, const double* lmbd, int64_t lm
                            double* w_out, double* cost_out, int32_t* status, int32_t* iters,
                            double* kkt_res);
 
+/* ------------------------------------------------------------------------
+ * Price loop (reference price_solver.py / price_regularizer.py), batched over
+ * G independent groups = (station, EV type, partition) triples.  EVs are sorted
+ * by group; group g owns EVs [group_off[g], group_off[g+1]).  All pointers are
+ * DEVICE pointers; prices are stored as G rows of 3N doubles (the last N are
+ * zero for price type "linear", like lmbd_k in price_solver.py:102-104).
+ * ------------------------------------------------------------------------ */
+
+/* PriceSolver.set_charge_levels (price_solver.py:66-77) for every group:
+ * y0_rng, gamma_sc, gamma_sm [G] and gamma_i = y_max - y0_i [B]
+ * (price_solver.py:201).  Synchronises; LOMPC_ERR_CONSTS if some y0 is outside
+ * [0, y_max] (the assert of price_solver.py:71).                             */
+int price_group_stats_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off,
+                          const double* y0, double* gamma, double* y0_rng, double* gamma_sc,
+                          double* gamma_sm, void* stream);
+
+/* PriceSolver._get_w_err (price_solver.py:196-214) for every group: solves the
+ * B LoMPC QPs with their group's prices and reduces.  Outputs (any may be
+ * NULL): w_avg[G,N], w_err_max[G], w0_err[G], w_avg_err[G], w0[B].            */
+int price_w_err_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off,
+                    const double* gamma, const double* lmbd, const double* lmbd_r,
+                    const double* w_ref, double* w_avg, double* w_err_max, double* w0_err,
+                    double* w_avg_err, double* w0, void* stream);
+
+/* PriceSolver._price_gradient_descent_step (price_solver.py:216-246): exact
+ * solution of the non-negative QP for every group.  r = 2N or 3N.  lmbd[G,3N]
+ * is updated in place; dual_decrease[G] = predicted decrease (:244).          */
+int price_step_dev(lompc_t* h, int32_t G, int r, const double* w_ref, const double* w_k,
+                   const double* lmbd_r, double* lmbd, double* dual_decrease, int32_t* status,
+                   void* stream);
+
+/* PriceSolver._regularize_prices -> PriceRegularizer.solve_price_regularization
+ * (price_solver.py:248-255, price_regularizer.py:68-85) in closed form; lmbd is
+ * replaced by the regularised prices; price_pre/post = phi(w_k) @ lmbd before
+ * and after (price_solver.py:145,147).                                        */
+int price_regularize_dev(lompc_t* h, int32_t G, int r, const double* w_k, double* lmbd,
+                         double* price_pre, double* price_post, void* stream);
+
+/* PriceRegularizer.solve_price_regularization (price_regularizer.py:68-85) for a
+ * constraint matrix of the pattern A = [diag(a_0) ... diag(a_{nb-1})] (a, c:
+ * [nb,N]; b: [N]; x out: [nb,N]; DEVICE pointers).  LOMPC_ERR_ARG if a row is
+ * infeasible.  Synchronises.                                                 */
+int price_lp_rows_dev(int device, int N, int nb, const double* a, const double* b, const double* c,
+                      double* x, void* stream);
+
+/* PriceSolver.compute_optimal_prices (price_solver.py:79-174) for every group.
+ * prices[G,3N]: in = warm start (prev_prices), out = regularised prices.
+ * iters[G] = value of `iter` at exit; price_pre/post[G]; optional (NULL ok)
+ * hist_ac/hist_pred[G,hist_cap] = dual_cost_decrease_actual/predicted per
+ * iteration; w_k_out[G,N] = LoMPC solution at gamma_sc for the last
+ * un-regularised prices.  Host loop with one poll per iteration; returns after
+ * the stream has drained.  tol_type_max = 1 for settings "max", 0 for "avg". */
+int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, const double* y0,
+                    const double* w_ref, const double* lmbd_r, int r, int max_iter,
+                    int tol_type_max, double eps_reg, double eps_tol, double* prices,
+                    int32_t* iters, double* price_pre, double* price_post, double* w_k_out,
+                    double* hist_ac, double* hist_pred, int hist_cap, int32_t* total_iters,
+                    void* stream);
+
+/* PriceSolver.get_w0_price0 (price_solver.py:272-285) for every group:
+ * w0[B] = first-step charge of each EV, price0[G] = mean first-step price.    */
+int price_w0_price0_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off,
+                        const double* gamma, const double* lmbd, const double* lmbd_r,
+                        double* w0, double* price0, void* stream);
+
 /* Measures the device's FP64 FMA peak (TFLOP/s, FMA = 2 flops) with a
  * register-resident DFMA chain kernel: the roofline denominator of this
  * FP64-bound path (MEASURED_PEAKS.json has no FP64 figure).                 */

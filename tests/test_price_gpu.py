@@ -1,0 +1,189 @@
+"""GPU parity tests of the price loop (K2-K5) through the C ABI against
+oracle/price_oracle.py.  The loop's break test (price_solver.py:125) is
+discontinuous, so parity is judged per iteration (teacher forcing on the
+oracle's price iterates) and, for whole loops, on iteration counts plus prices
+when the counts agree."""
+import numpy as np
+import pytest
+
+from oracle import lompc_oracle as orc
+from oracle import price_oracle as po
+
+pytestmark = pytest.mark.gpu
+
+
+def _consts(ev):
+    from chargingstation.lompc import LoMPCConstants
+    o = orc.small_ev_consts() if ev == "small" else orc.large_ev_consts()
+    return o, LoMPCConstants(o.delta, o.theta, o.y_max, o.w_max, o.ev_type)
+
+
+@pytest.mark.parametrize("ev", ["small", "large"])
+@pytest.mark.parametrize("price_type", ["linear", "linear-convex"])
+def test_price_step_matches_nnls_oracle(ev, price_type):
+    """_price_gradient_descent_step (price_solver.py:216-246): exact NNQP optimum."""
+    from chargingstation.price_solver import PriceSolver
+    o, c = _consts(ev)
+    rng = np.random.default_rng(21)
+    for N in (12, 24):
+        ps = PriceSolver(N, c, price_type)
+        ora = po.PriceOracle(N, o, price_type)
+        for trial in range(6):
+            lmbd_r = [0.0, 0.0, float(N), 3.0 * N][trial % 4]
+            w = o.w_max * rng.random(N) * (rng.random(N) < 0.8)
+            w_ref = o.w_max * rng.random(N)
+            lam = 0.05 * o.theta * rng.random(ps.r) * (rng.random(ps.r) < 0.6)
+            A_bar, A_bar_inv = ora._metric(lmbd_r)
+            P, q = ora.price_step_matrices(A_bar_inv, w_ref, w, lam)
+            x = po.nnqp_exact(P, q)
+            for kw in ({"lmbd_r": lmbd_r}, {}):  # explicit kappa and kappa recovered from A_bar_inv
+                lam_next, dec = ps._price_gradient_descent_step(A_bar_inv, w_ref, w, lam, **kw)
+                assert np.max(np.abs(lam_next - x)) <= 1e-9 * max(1.0, np.max(np.abs(x)))
+                assert po.nnqp_kkt(P, q, lam_next) <= 1e-8 * max(1.0, np.max(np.abs(q)))
+                dec_o = (lam @ P @ lam + q @ lam) - (x @ P @ x + q @ x)
+                assert abs(dec - dec_o) <= 1e-9 * max(1.0, abs(dec_o))
+
+
+@pytest.mark.parametrize("ev", ["small", "large"])
+@pytest.mark.parametrize("price_type", ["linear", "linear-convex"])
+def test_regularizer_closed_form_vs_highs(ev, price_type):
+    """_regularize_prices: same LP objective as HiGHS, feasible, non-negative (price_regularizer.py:68-85)."""
+    from chargingstation.price_solver import PriceSolver
+    o, c = _consts(ev)
+    N = 12
+    rng = np.random.default_rng(22)
+    ps = PriceSolver(N, c, price_type)
+    ora = po.PriceOracle(N, o, price_type)
+    for trial in range(5):
+        w = o.w_max * rng.random(N) * (rng.random(N) < 0.8)
+        lam = 0.05 * o.theta * rng.random(ps.r)
+        x = ps._regularize_prices(w, lam)
+        x_lp = ora.regularize_prices(w, lam)
+        phi = ora.phi(w)[:ps.r]
+        D = ora.Dphi(w)[:ps.r]
+        assert np.all(x >= 0)
+        assert np.max(np.abs(D.T @ x - D.T @ lam)) <= 1e-10 * max(1, np.max(np.abs(D.T @ lam)))
+        assert abs(phi @ x - phi @ x_lp) <= 1e-9 * max(1, abs(phi @ x_lp))
+        assert np.allclose(x, po.regularize_closed_form(N, o, ps.r, w, lam), rtol=1e-13, atol=1e-15)
+
+
+def test_price_regularizer_class_invariants():
+    """test/test_price_regularizer.py:6-28 turned into assertions: feasibility and complementarity."""
+    from chargingstation.price_regularizer import PriceRegularizer
+    N, r = 12, 24
+    A = np.block([np.eye(N), -np.eye(N)])
+    cvec = np.ones((r,))
+    reg = PriceRegularizer(N, r)
+    rng = np.random.default_rng(23)
+    for _ in range(50):
+        b = 200 * (rng.random((N,)) - 0.5)
+        x = reg.solve_price_regularization(A, b, cvec)
+        assert np.linalg.norm(A @ x - b) <= 1e-12
+        assert x[:N] @ x[N:] == 0.0 and np.all(x >= 0)
+        x_lp = po.solve_price_regularization_lp(A, b, cvec)
+        assert abs(cvec @ x - cvec @ x_lp) <= 1e-9
+    with pytest.raises(NotImplementedError):
+        reg.solve_price_regularization(rng.random((N, r)), np.ones(N), cvec)
+
+
+@pytest.mark.parametrize("ev", ["small", "large"])
+def test_get_w_err_and_w0_price0(ev):
+    from chargingstation.price_solver import PriceSolver
+    o, c = _consts(ev)
+    N, nEVs = 12, 37
+    rng = np.random.default_rng(24)
+    for price_type, lmbd_r in (("linear-convex", 0.0), ("linear", 6.0)):
+        ps = PriceSolver(N, c, price_type)
+        ora = po.PriceOracle(N, o, price_type)
+        y0 = 0.3 + 0.2 * rng.random(nEVs)
+        ps.set_charge_levels(y0)
+        ora.set_charge_levels(y0)
+        assert ps.get_gamma_sc() == ora.gamma_sc and ps.get_gamma_sm() == ora.gamma_sm
+        assert ps.get_robustness_bounds(lmbd_r) == ora.get_robustness_bounds(lmbd_r)
+        lam = np.zeros(3 * N)
+        lam[:ps.r] = 0.05 * o.theta * rng.random(ps.r)
+        w_ref = o.w_max * rng.random(N)
+        A_bar, _ = ora._metric(lmbd_r)
+        e_max, e0, e_avg = ps._get_w_err(lam, lmbd_r, w_ref, A_bar)
+        o_max, o0, o_avg, _ = ora.get_w_err(lam, lmbd_r, w_ref, A_bar)
+        assert abs(e_max - o_max) <= 1e-10 and abs(e0 - o0) <= 1e-10 and abs(e_avg - o_avg) <= 1e-10
+        w0, price0 = ps.get_w0_price0(lam[:ps.r], lmbd_r)
+        w0_o, price0_o = ora.get_w0_price0(lam[:ps.r], lmbd_r)
+        assert np.max(np.abs(w0 - w0_o)) <= 1e-10 * o.w_max and abs(price0 - price0_o) <= 1e-10 * max(1, abs(price0_o))
+    with pytest.raises(AssertionError):
+        ps.set_charge_levels(np.array([0.1, 0.95]))  # price_solver.py:71
+
+
+@pytest.mark.parametrize("ev,price_type,lmbd_r", [("small", "linear-convex", 0.0), ("large", "linear-convex", 0.0),
+                                                  ("small", "linear", 0.0), ("large", "linear", 12.0)])
+def test_compute_optimal_prices_against_oracle(ev, price_type, lmbd_r):
+    """Whole loop (price_solver.py:79-174), inputs as test/test_price_solver.py:23-35."""
+    from chargingstation.price_solver import PriceSolver
+    o, c = _consts(ev)
+    N, nEVs = 12, 10
+    rng = np.random.default_rng(25)
+    ps = PriceSolver(N, c, price_type)
+    ora = po.PriceOracle(N, o, price_type)
+    y0 = (1 / 36.0) * o.y_max * rng.random(nEVs)
+    w_ref = o.w_max * rng.random(N)
+    ps.set_charge_levels(y0)
+    ora.set_charge_levels(y0)
+    trace = []
+    lam_o, st_o = ora.compute_optimal_prices(w_ref, lmbd_r, trace=trace)
+    lam, st = ps.compute_optimal_prices(w_ref, lmbd_r)
+    assert set(st) == {"iter", "price_before_reg", "price_after_reg", "dual_cost_decrease_actual",
+                       "dual_cost_decrease_predicted"}
+    assert lam.shape == (3 * N,) and np.all(lam >= 0)
+    # teacher forcing: at every oracle price iterate the device errors and the next step agree
+    A_bar, A_bar_inv = ora._metric(lmbd_r)
+    for t in trace[:: max(1, len(trace) // 6)]:
+        e_max, e0, e_avg = ps._get_w_err(t["lmbd"], lmbd_r, w_ref, A_bar)
+        assert abs(e_avg - t["w_avg_err"]) <= 1e-9 and abs(e_max - t["w_err_max"]) <= 1e-9
+        nxt, _ = ps._price_gradient_descent_step(A_bar_inv, w_ref, t["w_k"], t["lmbd"][:ps.r], lmbd_r=lmbd_r)
+        nxt_o, _ = ora.price_gradient_descent_step(A_bar_inv, w_ref, t["w_k"], t["lmbd"][:ps.r])
+        assert np.max(np.abs(nxt - nxt_o)) <= 1e-8 * max(1, np.max(np.abs(nxt_o)))
+    # whole loop
+    assert st["iter"] == st_o["iter"]
+    assert np.max(np.abs(lam - lam_o)) <= 1e-6 * max(1, np.max(np.abs(lam_o)))
+    assert abs(st["price_before_reg"] - st_o["price_before_reg"]) <= 1e-6 * max(1, abs(st_o["price_before_reg"]))
+    assert abs(st["price_after_reg"] - st_o["price_after_reg"]) <= 1e-6 * max(1, abs(st_o["price_after_reg"]))
+    n = st["iter"]
+    assert len(st["dual_cost_decrease_actual"]) == n == len(st_o["dual_cost_decrease_actual"])
+    assert np.allclose(st["dual_cost_decrease_actual"], st_o["dual_cost_decrease_actual"], rtol=1e-5, atol=1e-7)
+    assert np.allclose(st["dual_cost_decrease_predicted"], st_o["dual_cost_decrease_predicted"], rtol=1e-5, atol=1e-7)
+    # invariants the reference prints: dual-cost decrease >= 0 (price_solver.py:135-138), response at the
+    # regularised prices unchanged, warm start stored
+    assert np.all(st["dual_cost_decrease_predicted"] >= -1e-9)
+    assert np.array_equal(ps.prev_prices, lam[:ps.r])
+    # second call warm-starts from prev_prices (price_solver.py:103-104,166)
+    lam2, st2 = ps.compute_optimal_prices(w_ref, lmbd_r)
+    lam2_o, st2_o = ora.compute_optimal_prices(w_ref, lmbd_r)
+    assert st2["iter"] == st2_o["iter"]
+    assert np.max(np.abs(lam2 - lam2_o)) <= 1e-6 * max(1, np.max(np.abs(lam2_o)))
+
+
+def test_batch_equals_single_groups():
+    """G groups in one device loop == each group on its own (no cross-group coupling)."""
+    from chargingstation.price_solver import PriceSolver
+    o, c = _consts("large")
+    N = 12
+    rng = np.random.default_rng(26)
+    ps = PriceSolver(N, c, "linear-convex")
+    sizes = [5, 0, 17, 1, 9]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    y0 = 0.3 + 0.05 * rng.random(off[-1])
+    G = len(sizes)
+    w_ref = o.w_max * rng.random((G, N))
+    prev = np.zeros((G, 3 * N))
+    prices, stats = ps.compute_optimal_prices_batch(off, y0, w_ref, np.zeros(G), prev)
+    for g, n in enumerate(sizes):
+        if n == 0:
+            assert np.all(prices[g] == 0)
+            continue
+        single = PriceSolver(N, c, "linear-convex")
+        single.set_charge_levels(y0[off[g]:off[g + 1]])
+        lam, st = single.compute_optimal_prices(w_ref[g], 0.0)
+        assert st["iter"] == stats["iter"][g]
+        assert np.array_equal(lam, prices[g])
+    w0, p0 = ps.get_w0_price0_batch(off, y0, prices, np.zeros(G))
+    assert w0.shape == (off[-1],) and p0.shape == (G,) and p0[1] == 0.0
