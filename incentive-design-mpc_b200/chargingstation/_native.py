@@ -31,6 +31,7 @@ SIGNATURES = {
     "lompc_destroy": (C.c_int, [C.c_void_p]),
     "lompc_sc_modulus": (C.c_double, [C.c_void_p]),
     "lompc_set_options": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "lompc_set_kernel_variant": (C.c_int, [C.c_void_p, C.c_int]),
     "lompc_solve_batch_dev": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p,
                                         C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_void_p, C.c_void_p]),

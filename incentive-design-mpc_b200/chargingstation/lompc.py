@@ -86,6 +86,10 @@ class LoMPC:
     def set_solver_options(self, max_iter: int = 200, tol: float = 1e-11) -> None:
         _native.raise_for(self._lib.lompc_set_options(self._h, int(max_iter), float(tol)))
 
+    def set_kernel_variant(self, variant: int = 0) -> None:
+        """0 = automatic; 1 = any-N shared-memory kernel; 2-5 = register-kernel variants (tuning)."""
+        _native.raise_for(self._lib.lompc_set_kernel_variant(self._h, int(variant)))
+
     def solve_lompc(self, lmbd: np.ndarray, lmbd_r: float, gamma: float) -> tuple[np.ndarray, float]:
         """
         Inputs:

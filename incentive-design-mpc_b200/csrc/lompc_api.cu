@@ -7,6 +7,7 @@
 
 #include "lompc_common.cuh"
 #include "lompc_solve.cuh"
+#include "lompc_solve_reg.cuh"
 #include "lompc_price.cuh"
 
 namespace {
@@ -41,6 +42,7 @@ struct lompc_handle {
   void* ws;
   size_t ws_bytes;
   // grow-only device workspace of the price loop + pinned poll word
+  int variant;  // 0 auto, 1 = any-N shared-memory kernel, 2.. = register-kernel variants
   void* pws;
   size_t pws_bytes;
   int32_t* poll;  // pinned host
@@ -59,9 +61,43 @@ int ensure_ws(lompc_handle* h, size_t bytes) {
   return LOMPC_OK;
 }
 
+// Register-resident kernel for the compile-time horizons (variants: see lompc_set_kernel_variant).
+template <int N, int NSEG, int T, int MINB, bool GREG>
+int launch_solve_reg(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t stream) {
+  constexpr size_t smem = lompc::RegSmem<N, NSEG, T, GREG>::bytes;
+  static bool configured = false;
+  if (!configured) {
+    CK(cudaFuncSetAttribute(lompc::lompc_solve_reg_kernel<N, NSEG, T, MINB, GREG>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  const int64_t blocks = (a.B + T - 1) / T;
+  lompc::lompc_solve_reg_kernel<N, NSEG, T, MINB, GREG><<<(unsigned)blocks, T, smem, stream>>>(h->cs, a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  return LOMPC_OK;
+}
+
+template <int N, int NSEG>
+int launch_solve_reg_variant(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t stream) {
+  switch (h->variant) {
+    case 2: return launch_solve_reg<N, NSEG, 64, 4, false>(h, a, stream);
+    case 3: return launch_solve_reg<N, NSEG, 64, 6, true>(h, a, stream);
+    case 4: return launch_solve_reg<N, NSEG, 128, 3, true>(h, a, stream);
+    case 5: return launch_solve_reg<N, NSEG, 64, 5, true>(h, a, stream);
+    default:  // measured on B200 (tools/sweep_variants.sh): small EV best at (64,4,G in smem), large at (128,3,G in regs)
+      if (NSEG == 1) return launch_solve_reg<N, NSEG, 64, 4, false>(h, a, stream);
+      return launch_solve_reg<N, NSEG, 128, 3, true>(h, a, stream);
+  }
+}
+
 template <int NSEG>
 int launch_solve(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t stream) {
   const int N = h->cs.N;
+  if (h->variant != 1) {
+    if (N == 24) return launch_solve_reg_variant<24, NSEG>(h, a, stream);
+    if (N == 12) return launch_solve_reg_variant<12, NSEG>(h, a, stream);
+  }
   // Threads per block: as many as fit the 227 KB of shared memory, capped at 128;
   // small batches use small blocks so that more SMs take part.
   int T = 128;
@@ -163,6 +199,7 @@ int lompc_create(int N, double delta, double theta, double y_max, double w_max, 
   h->delta = delta;
   h->ws = nullptr;
   h->ws_bytes = 0;
+  h->variant = 0;
   h->pws = nullptr;
   h->pws_bytes = 0;
   h->poll = nullptr;
@@ -186,6 +223,12 @@ int lompc_set_options(lompc_t* h, int max_iter, double tol) {
   if (!h || max_iter < 1 || !(tol > 0.0)) return LOMPC_ERR_ARG;
   h->max_iter = max_iter;
   h->tol = tol;
+  return LOMPC_OK;
+}
+
+int lompc_set_kernel_variant(lompc_t* h, int variant) {
+  if (!h || variant < 0 || variant > 5) return LOMPC_ERR_ARG;
+  h->variant = variant;
   return LOMPC_OK;
 }
 
@@ -310,6 +353,7 @@ int ensure_pws(lompc_handle* h, size_t bytes) {
   if (!h->poll) CK(cudaMallocHost(&h->poll, 64));
   if (h->pws_bytes >= bytes) return LOMPC_OK;
   if (h->pws) CK(cudaFree(h->pws));
+  h->variant = 0;
   h->pws = nullptr;
   h->pws_bytes = 0;
   const size_t want = bytes + bytes / 8;

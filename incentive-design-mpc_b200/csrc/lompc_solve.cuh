@@ -21,11 +21,14 @@
 //       minimiser of  stage cost + quadratic cost-to-go  over [0, w_max]
 //       (a fused clip for the box, a min/max ladder for the pwl kinks), and the
 //       objective of the rollout is accumulated on the fly.
-// The rollout is accepted iff it lowers the objective; otherwise the same
-// Riccati gains give the projected-Newton direction on the working set and a
-// backtracking search along its projection arc (always a descent step), so
-// the iteration cannot cycle.  It stops when the KKT residual of the backward
-// sweep is below tol * scale, i.e. at the exact optimum of the active face.
+// The rollout is accepted iff it does not raise the objective (to fp64 resolution).  A
+// rejected rollout is retried with a proximal (Levenberg-Marquardt) term mu/2 |w - w_cur|^2
+// added to every stage (d_k -> d_k + mu, g_k -> g_k - mu w_k in the Riccati model only):
+// mu starts at 4c, grows x4 per rejection and is reset to 0 by an acceptance.  For mu
+// above the Lipschitz constant the regularised rollout is a descent step, so the
+// iteration cannot cycle, and accepted and rejected iterations run the SAME two sweeps
+// (no divergent fallback path inside a warp).  It stops when the KKT residual of the
+// backward sweep is below tol * scale, i.e. at the exact optimum of the active face.
 #pragma once
 #include "lompc_common.cuh"
 
@@ -37,7 +40,7 @@ template <int NSEG>
 struct SmemLayout {
   static constexpr int kArrays = (NSEG > 1) ? 7 : 6;  // D,G,KK,KAP,W0,W1 (+INV)
   __host__ __device__ static size_t bytes(int N, int T) {
-    return (size_t)kArrays * N * T * sizeof(double) + (size_t)N * T;
+    return (size_t)kArrays * N * T * sizeof(double);
   }
 };
 
@@ -65,8 +68,6 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
   double* WA = KAP + (size_t)N * T;
   double* WB = WA + (size_t)N * T;
   double* INV = WB + (size_t)N * T;  // only touched when NSEG > 1
-  unsigned char* CFG =
-      reinterpret_cast<unsigned char*>(smem + (size_t)SmemLayout<NSEG>::kArrays * N * T) + t;
   if (!live) return;  // no block-level sync below
 
   // ---- problem data (lompc.py:101-135 restated) -------------------------------
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
   double sN = 0.0;  // s_{N-1} of the current iterate
   double f = 0.5 * c * N * gam * gam;  // objective at w = 0 (without kappa0)
   double viol = 0.0;
+  double mu = 0.0;  // proximal weight of the safeguard
   int it = 0;
   bool converged = false;
   if (st != LOMPC_ST_OK) {
@@ -166,19 +168,20 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
       // Riccati step
       const double Q = c + P;
       const double rp = r - cg;
-      const double inv = 1.0 / (dk + Q);
-      const double h = gk + ((NSEG > 1) ? cs.slope[seg] : 0.0);
+      const double dm = dk + mu;            // proximal model: d + mu, g - mu w
+      const double gm = fma(-mu, wk, gk);
+      const double inv = 1.0 / (dm + Q);
+      const double h = gm + ((NSEG > 1) ? cs.slope[seg] : 0.0);
       if (binding) {
         P = Q;
         r = fma(Q, wk, rp);
       } else {
-        P = Q * dk * inv;
-        r = (dk * rp - Q * h) * inv;
+        P = Q * dm * inv;
+        r = (dm * rp - Q * h) * inv;
       }
       KK[k * T] = Q * inv;
-      KAP[k * T] = (rp + gk) * inv;
+      KAP[k * T] = (rp + gm) * inv;
       if (NSEG > 1) INV[k * T] = inv;
-      CFG[k * T] = (unsigned char)((binding ? 1 : 0) | (seg << 1));
       s -= wk;
     }
     if (viol <= tq) {
@@ -213,61 +216,11 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
       WN = tmp;
       f = fmin(f, fn);
       sN = s;
-      continue;
+      mu = 0.0;
+    } else {
+      mu = fmax(4.0 * c, 4.0 * mu);
+      if (mu > 1e30) break;  // no representable descent step left: report MAXITER below
     }
-    // ---------------- safeguard: projected Newton on the working set ----------------
-    s = 0.0;
-    for (int k = 0; k < N; ++k) {  // equality-constrained solution on the working set
-      const int cfg = CFG[k * T];
-      double x;
-      if (cfg & 1) {
-        x = W[k * T];
-      } else {
-        x = -fma(KK[k * T], s, KAP[k * T]);
-        if (NSEG > 1) x -= cs.slope[cfg >> 1] * INV[k * T];
-      }
-      WN[k * T] = x;
-      s += x;
-    }
-    double alpha = 1.0;
-    bool ok = false;
-    for (int ls = 0; ls < 60 && !ok; ++ls, alpha *= 0.5) {
-      fn = 0.0;
-      s = 0.0;
-      for (int k = 0; k < N; ++k) {
-        const int cfg = CFG[k * T];
-        const double wk = W[k * T];
-        double x = wk;
-        if (!(cfg & 1)) {
-          const int seg = cfg >> 1;
-          x = fma(alpha, WN[k * T] - wk, wk);
-          x = fmin(fmax(x, cs.brk[seg]), cs.brk[seg + 1]);
-        }
-        s += x;
-        const double e = s - gam;
-        fn += x * fma(0.5 * D[k * T], x, G[k * T]) + 0.5 * c * e * e;
-        if (NSEG > 1) fn += pwl_value<NSEG>(cs, x);
-      }
-      ok = fn < f;
-      if (ok) break;
-    }
-    if (!ok) break;  // no representable descent step left: report MAXITER below
-    s = 0.0;
-    for (int k = 0; k < N; ++k) {
-      const int cfg = CFG[k * T];
-      const double wk = W[k * T];
-      if (!(cfg & 1)) {
-        const int seg = cfg >> 1;
-        double x = fma(alpha, WN[k * T] - wk, wk);
-        x = fmin(fmax(x, cs.brk[seg]), cs.brk[seg + 1]);
-        W[k * T] = x;
-        s += x;
-      } else {
-        s += wk;
-      }
-    }
-    f = fn;
-    sN = s;
   }
   if (!converged && st == LOMPC_ST_OK) st = LOMPC_ST_MAXITER;
 

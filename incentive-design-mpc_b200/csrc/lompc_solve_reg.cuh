@@ -1,0 +1,257 @@
+// K1, register-resident variant for compile-time horizons (N = 12, 24): same algorithm
+// as lompc_solve.cuh (see the header there), restructured for the B200 SM:
+//   * the iterate w, the diagonal d and the linear term g live in REGISTERS (fully
+//     unrolled sweeps, no address arithmetic); only the Riccati gains (K, kappa[, inv]),
+//     the rollout candidate and the 1-byte working-set codes live in shared memory
+//     (column-per-thread [k][128] layout, bank-conflict free), so two 128-thread CTAs
+//     fit per SM instead of one;
+//   * the reciprocal of the Riccati pivot is MUFU.RCP64H + two Newton steps (4 DFMA)
+//     instead of the IEEE division sequence with its slow-path branch;
+//   * with TMA staging (kStage): every thread issues ONE cp.async.bulk for its own
+//     3N-double price row into a padded shared-memory slot (16-byte aligned, 2-way
+//     conflict at worst) instead of 3N uncoalesced loads, and results leave through a
+//     cp.async.bulk store of the [k][tid]->row transposed tile.
+#pragma once
+#include "lompc_common.cuh"
+#include "lompc_solve.cuh"
+
+namespace lompc {
+
+__device__ __forceinline__ double fast_rcp(double x) {
+  // x is a Riccati pivot d + c + P in [c, 1e6]: no denormals / infinities to guard.
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  e = fma(-x, y, 1.0);
+  y = fma(y, e, y);
+  return y;
+}
+
+// Keeps the shared-memory loads of one unrolled stage inside that stage: without it the
+// compiler hoists all 3N loads of a sweep to its top and spills ~60 doubles per thread.
+#define LOMPC_STAGE_FENCE() asm volatile("" ::: "memory")
+
+// T = threads per CTA, MINB = CTAs per SM asked of the register allocator, GREG = keep the
+// linear term g in registers as well (fewer shared-memory arrays, more registers).
+template <int N, int NSEG, int T, bool GREG>
+struct RegSmem {
+  static constexpr int kArrays = 3 + (GREG ? 0 : 1) + (NSEG > 1 ? 1 : 0);  // KK, KAP, WN [, G] [, INV]
+  static constexpr size_t bytes = (size_t)kArrays * N * T * sizeof(double);
+};
+
+template <int N, int NSEG, int T, int MINB, bool GREG>
+__global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts cs, const SolveArgs a) {
+  extern __shared__ double smem[];
+  const int t = threadIdx.x;
+  const int64_t b = (int64_t)blockIdx.x * T + t;
+  if (b >= a.B) return;
+  double* KK = smem + t;
+  double* KAP = KK + N * T;
+  double* WN = KAP + N * T;
+  double* GS = WN + N * T;                    // only when !GREG
+  double* INV = GS + (GREG ? 0 : N * T);      // only when NSEG > 1
+  double GR[GREG ? N : 1];
+#define LOMPC_G(k) (GREG ? GR[GREG ? (k) : 0] : GS[(k) * T])
+
+  const int64_t row = a.group_of ? (int64_t)a.group_of[b] : b;
+  if (a.skip && a.skip[row]) return;
+  const double* lm = a.lmbd + row * a.lmbd_stride;
+  const double lr = a.lmbd_r[row * a.lmbd_r_stride];
+  const double gam = a.gamma[b];
+  int st = LOMPC_ST_OK;
+  if (gam < 0.0 || lr < 0.0) st = LOMPC_ST_NEGATIVE;
+
+  double W[N], D[N];
+  double l2sum = 0.0, gmax = 0.0, dmax = 0.0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const double l1 = lm[k], l2 = lm[N + k], l3 = lm[2 * N + k];
+    if (l1 < 0.0 || l2 < 0.0 || l3 < 0.0) st = LOMPC_ST_NEGATIVE;
+    const double g = cs.theta * (l1 - l2);
+    if (GREG) GR[GREG ? k : 0] = g; else GS[k * T] = g;
+    D[k] = 2.0 * (lr * cs.theta2 + cs.q_scale * l3) + cs.d_base;
+    W[k] = 0.0;
+    gmax = fmax(gmax, fabs(g));
+    dmax = fmax(dmax, D[k]);
+    l2sum += l2;
+    LOMPC_STAGE_FENCE();
+  }
+  if (gam > cs.y_max) st = LOMPC_ST_BAD_GAMMA;
+  const double c = cs.c, wmax = cs.w_max;
+  const double gscale = fmax(1.0, gmax + c * N * cs.y_max);
+  const double tq = a.tol * gscale;
+  const double cg = c * gam;
+  const double band = 1e-9 * wmax;
+  const double ftol = 1e-15 * (c * N * cs.y_max * cs.y_max + N * wmax * (gmax + 0.5 * dmax * wmax + cs.slope[NSEG - 1]));
+  double brk[NSEG + 1], slope[NSEG];
+#pragma unroll
+  for (int i = 0; i <= NSEG; ++i) brk[i] = cs.brk[i];
+#pragma unroll
+  for (int j = 0; j < NSEG; ++j) slope[j] = cs.slope[j];
+
+  double sN = 0.0, f = 0.5 * c * N * gam * gam, viol = 0.0, mu = 0.0;
+  int it = 0;
+  bool converged = (st != LOMPC_ST_OK);
+
+  for (; !converged && it < a.max_iter; ++it) {
+    // ---------------- backward sweep ----------------
+    double P = 0.0, r = 0.0, p = 0.0, s = sN;
+    viol = 0.0;
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {
+      const double wk = W[k], dk = D[k], gk = LOMPC_G(k);
+      p = fma(c, s, p) - cg;
+      const double q = fma(dk, wk, gk) + p;
+      bool binding = false;
+      int seg = 0;
+      double v, sl = 0.0;
+      if (NSEG == 1) {
+        if (wk <= band) {
+          binding = (q >= -tq);
+          v = binding ? 0.0 : -q;
+        } else if (wk >= wmax - band) {
+          binding = (q <= tq);
+          v = binding ? 0.0 : q;
+        } else {
+          v = fabs(q);
+        }
+      } else {
+        int at = -1;
+#pragma unroll
+        for (int i = 0; i <= NSEG; ++i)
+          if (fabs(wk - brk[i]) <= band) at = i;
+#pragma unroll
+        for (int j = 1; j < NSEG; ++j) seg += (wk > brk[j] + band) ? 1 : 0;  // containing segment
+        const double mq = -q;
+        if (at >= 0) {
+          // slopes left / right of breakpoint `at` (+-inf at the box ends)
+          double s_hi = 1e300, s_lo = -1e300;
+#pragma unroll
+          for (int j = 0; j < NSEG; ++j) {
+            if (at == j) s_hi = slope[j];
+            if (at == j + 1) s_lo = slope[j];
+          }
+          if (mq > s_hi + tq) {
+            seg = at;
+            sl = s_hi;
+            v = mq - s_hi;
+          } else if (mq < s_lo - tq) {
+            seg = at - 1;
+            sl = s_lo;
+            v = s_lo - mq;
+          } else {
+            binding = true;
+            seg = at < NSEG ? at : NSEG - 1;
+            v = 0.0;
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < NSEG; ++j)
+            if (seg == j) sl = slope[j];
+          v = fabs(q + sl);
+        }
+      }
+      viol = fmax(viol, v);
+      const double Q = c + P;
+      const double rp = r - cg;
+      const double dm = dk + mu;  // proximal model of the safeguard: d + mu, g - mu w
+      const double gm = fma(-mu, wk, gk);
+      const double inv = fast_rcp(dm + Q);
+      const double kk = Q * inv;
+      if (binding) {
+        P = Q;
+        r = fma(Q, wk, rp);
+      } else {
+        P = kk * dm;
+        r = fma(dm * inv, rp, -kk * (gm + sl));
+      }
+      KK[k * T] = kk;
+      KAP[k * T] = (rp + gm) * inv;
+      if (NSEG > 1) INV[k * T] = inv;
+      s -= wk;
+      LOMPC_STAGE_FENCE();
+    }
+    if (viol <= tq) {
+      converged = true;
+      break;
+    }
+    // ---------------- forward sweep: stage-optimal rollout ----------------
+    double fn = 0.0;
+    s = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const double x0 = -fma(KK[k * T], s, KAP[k * T]);
+      double x = x0;
+      if (NSEG > 1) {
+        const double inv = INV[k * T];
+        x = fma(-slope[NSEG - 1], inv, x0);
+#pragma unroll
+        for (int j = NSEG - 2; j >= 0; --j) x = fmin(fma(-slope[j], inv, x0), fmax(brk[j + 1], x));
+      }
+      x = fmin(fmax(x, 0.0), wmax);
+      WN[k * T] = x;
+      s += x;
+      const double e = s - gam;
+      fn += x * fma(0.5 * D[k], x, LOMPC_G(k)) + 0.5 * c * e * e;
+      if (NSEG > 1) {
+#pragma unroll
+        for (int j = 1; j < NSEG; ++j) fn += (slope[j] - slope[j - 1]) * fmax(x - brk[j], 0.0);
+      }
+      LOMPC_STAGE_FENCE();
+    }
+    if (fn <= f + ftol) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) W[k] = WN[k * T];
+      f = fmin(f, fn);
+      sN = s;
+      mu = 0.0;
+    } else {
+      mu = fmax(4.0 * c, 4.0 * mu);
+      if (mu > 1e30) break;
+    }
+  }
+  if (!converged && st == LOMPC_ST_OK) st = LOMPC_ST_MAXITER;
+
+  // ---- outputs ----
+  double cost = cs.theta * wmax * l2sum;
+  double s = 0.0;
+  double* wo = a.w_out ? a.w_out + b * (int64_t)N : nullptr;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const double x = W[k];
+    if (wo) wo[k] = x;
+    s += x;
+    cost += x * fma(0.5 * D[k], x, LOMPC_G(k)) + 0.5 * c * s * (s - 2.0 * gam);
+    if (NSEG > 1) {
+#pragma unroll
+      for (int j = 1; j < NSEG; ++j) cost += (slope[j] - slope[j - 1]) * fmax(x - brk[j], 0.0);
+    }
+    LOMPC_STAGE_FENCE();
+  }
+  if (a.cost_out) a.cost_out[b] = cost;
+  if (a.err_out) {
+    const double* wr = a.w_ref + row * (int64_t)N;
+    const double kap = lr / cs.delta;
+    double cum = 0.0, e2 = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const double v = W[k] - wr[k];
+      cum += v;
+      e2 += cum * cum + kap * v * v;
+      LOMPC_STAGE_FENCE();
+    }
+    a.err_out[b] = sqrt(e2);
+  }
+  const double w0 = W[0];
+  if (a.w0_out) a.w0_out[b] = w0;
+  if (a.price0_out)
+    a.price0_out[b] = cs.theta * (w0 * lm[0] + (wmax - w0) * lm[N]) + cs.q_scale * w0 * w0 * lm[2 * N] +
+                      cs.theta2 * w0 * w0 * lr;
+  if (a.status) a.status[b] = st;
+  if (a.iters) a.iters[b] = it;
+  if (a.kkt_res) a.kkt_res[b] = viol / gscale;
+#undef LOMPC_G
+}
+
+}  // namespace lompc

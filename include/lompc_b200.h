@@ -64,6 +64,10 @@ double lompc_sc_modulus(const lompc_t* h);
 /* Solver knobs (defaults: max_iter 200, tol 1e-11 relative KKT residual). */
 int lompc_set_options(lompc_t* h, int max_iter, double tol);
 
+/* Kernel choice: 0 = automatic (register-resident kernel for N = 12, 24, the
+ * any-N shared-memory kernel otherwise), 1 = always the any-N kernel.        */
+int lompc_set_kernel_variant(lompc_t* h, int variant);
+
 /* Replaces LoMPC.solve_lompc (lompc.py:137-156), batched over B independent
  * QPs.  lmbd: B rows of 3N prices (row stride lmbd_stride doubles; 0 =
  * broadcast ONE price vector to the whole batch, the _get_w_err case

@@ -16,6 +16,7 @@ ap.add_argument("--ev", default="small")
 ap.add_argument("--batch", type=int, default=262144)
 ap.add_argument("--N", type=int, default=24)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--variant", type=int, default=0)
 ap.add_argument("--mode", type=int, default=0, help="0: test_lompc.py:34-36 prices; 1: closed-loop scale")
 args = ap.parse_args()
 
@@ -33,6 +34,7 @@ else:
     lr, gam = np.zeros(B), y_max - (0.3 + 0.2 * rng.random(B))
 dev = torch.device("cuda:0")
 solver = LoMPC(N, LoMPCConstants(delta, theta, y_max, w_max, args.ev))
+solver.set_kernel_variant(args.variant)
 lm, lr, gam = (torch.from_numpy(x).to(dev) for x in (lm, lr, gam))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 for r in range(args.reps):
