@@ -1,0 +1,147 @@
+"""Multi-GPU price loop: EVs sharded over ranks, one process per GPU.
+
+The lower-level QPs are independent, so each rank solves its own slice of the
+EV batch.  The only coupling is inside ``_get_w_err`` (reference
+price_solver.py:196-214): the mean response of a (station, EV-type, partition)
+group, ``w_avg = sum_i w_i / nEVs`` (:205,210), and ``set_charge_levels``' group
+statistics (:66-77).  When a group's EVs straddle ranks those become ONE
+``all_reduce`` each: MIN/MAX/SUM of ``[G]`` statistics once per solve, SUM of the
+``[G, N]`` fp64 partial sums once per price iteration (393 KB for BASELINE config 3),
+issued on the same stream as the kernels.  The convergence test, the price step
+and the gamma_sc solve then run replicated on every rank (identical inputs ->
+identical prices, no broadcast).  ``torch.distributed`` is the plumbing (NCCL on
+GPUs); the compute is the C ABI's ``price_shard_*`` phases.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import numpy as np
+
+from chargingstation import _native
+from chargingstation.settings import (MAX_PRICE_SOLVER_ITERATIONS,
+                                      PRICE_SOLVER_TOL_TYPE)
+
+
+def shard_bounds(B: int, rank: int, world: int) -> tuple[int, int]:
+    """Block partition of EV indices [0, B) over ranks (sizes differ by at most one)."""
+    base, rem = divmod(B, world)
+    lo = rank * base + min(rank, rem)
+    return lo, lo + base + (1 if rank < rem else 0)
+
+
+def shard_groups(group_off: np.ndarray, y0: np.ndarray, rank: int, world: int):
+    """Local view of a group-sorted EV batch: (local group_off [G+1], local y0, (lo, hi)).
+    Groups that have no EV on this rank get an empty local range."""
+    group_off = np.asarray(group_off, dtype=np.int64)
+    lo, hi = shard_bounds(int(group_off[-1]), rank, world)
+    local_off = (np.clip(group_off, lo, hi) - lo).astype(np.int32)
+    return local_off, np.ascontiguousarray(y0[lo:hi]), (lo, hi)
+
+
+class CudaShardBackend:
+    """The five phases on one GPU through the C ABI (``price_shard_*``)."""
+
+    def __init__(self, price_solver):
+        import torch
+        self.torch = torch
+        self.ps = price_solver
+        self.lib = _native.load()
+        self.dev = torch.device("cuda", price_solver.device)
+
+    def _t(self, x, dtype=None):
+        t = self.torch.from_numpy(np.ascontiguousarray(x))
+        return (t if dtype is None else t.to(dtype)).to(self.dev).contiguous()
+
+    def _stream(self):
+        return self.torch.cuda.current_stream(self.dev).cuda_stream
+
+    def begin(self, group_off, y0, w_ref, lmbd_r, prev_prices, max_iter, history):
+        torch, ps = self.torch, self.ps
+        N = ps.N
+        G = len(group_off) - 1
+        self.G, self.B = G, int(group_off[-1])
+        f64 = dict(dtype=torch.float64, device=self.dev)
+        self.off = self._t(np.asarray(group_off, dtype=np.int32))
+        self.y0 = self._t(np.asarray(y0, dtype=np.float64)) if self.B > 0 else torch.zeros((1,), **f64)
+        self.w_ref = self._t(np.asarray(w_ref, dtype=np.float64).reshape(G, N))
+        self.lmbd_r = self._t(np.asarray(lmbd_r, dtype=np.float64).reshape(G))
+        self.prices = self._t(np.asarray(prev_prices, dtype=np.float64).reshape(G, 3 * N).copy())
+        self.iters = torch.zeros((G,), dtype=torch.int32, device=self.dev)
+        self.stat_min, self.stat_max = torch.zeros((G,), **f64), torch.zeros((G,), **f64)
+        self.stat_sum, self.stat_cnt = torch.zeros((G,), **f64), torch.zeros((G,), **f64)
+        self.w_sum, self.err_max = torch.zeros((G, N), **f64), torch.zeros((G,), **f64)
+        cap = max_iter if history else 0
+        self.hist_ac = torch.zeros((G, max(cap, 1)), **f64) if history else None
+        self.hist_pred = torch.zeros((G, max(cap, 1)), **f64) if history else None
+        rc = self.lib.price_shard_begin(
+            ps._h, G, self.B, self.off.data_ptr(), self.y0.data_ptr(), self.w_ref.data_ptr(),
+            self.lmbd_r.data_ptr(), ps.r, int(max_iter), 1 if PRICE_SOLVER_TOL_TYPE == "max" else 0,
+            float(ps.eps_reg), float(ps.eps_tol), self.prices.data_ptr(), self.iters.data_ptr(),
+            self.stat_min.data_ptr(), self.stat_max.data_ptr(), self.stat_sum.data_ptr(), self.stat_cnt.data_ptr(),
+            self.w_sum.data_ptr(), self.err_max.data_ptr(),
+            self.hist_ac.data_ptr() if history else None, self.hist_pred.data_ptr() if history else None, cap,
+            self._stream())
+        _native.raise_for(rc)
+        return self.stat_min, self.stat_max, self.stat_sum, self.stat_cnt
+
+    def start(self):
+        _native.raise_for(self.lib.price_shard_start(self.ps._h, self._stream()))
+
+    def ev_phase(self):
+        _native.raise_for(self.lib.price_shard_ev_phase(self.ps._h, self._stream()))
+        return self.w_sum, self.err_max
+
+    def group_phase(self, it: int) -> int:
+        n = C.c_int32(0)
+        _native.raise_for(self.lib.price_shard_group_phase(self.ps._h, int(it), C.byref(n), self._stream()))
+        return int(n.value)
+
+    def finish(self, history):
+        torch = self.torch
+        pre = torch.zeros((self.G,), dtype=torch.float64, device=self.dev)
+        post = torch.zeros((self.G,), dtype=torch.float64, device=self.dev)
+        w_k = torch.zeros((self.G, self.ps.N), dtype=torch.float64, device=self.dev)
+        _native.raise_for(self.lib.price_shard_finish(self.ps._h, pre.data_ptr(), post.data_ptr(), w_k.data_ptr(),
+                                                      self._stream()))
+        stats = {"iter": self.iters.cpu().numpy(), "price_before_reg": pre.cpu().numpy(),
+                 "price_after_reg": post.cpu().numpy(), "w_k": w_k.cpu().numpy()}
+        if history:
+            stats["hist_ac"], stats["hist_pred"] = self.hist_ac.cpu().numpy(), self.hist_pred.cpu().numpy()
+        return self.prices.cpu().numpy(), stats
+
+
+def compute_optimal_prices_sharded(price_solver, group_off_local, y0_local, w_ref, lmbd_r, prev_prices,
+                                   process_group=None, backend=None, history: bool = False,
+                                   max_iter: int = MAX_PRICE_SOLVER_ITERATIONS):
+    """``PriceSolver.compute_optimal_prices`` for G groups whose EVs are sharded over the ranks
+    of ``process_group`` (None: single process, no collective).  Every rank passes the SAME
+    w_ref / lmbd_r / prev_prices and its LOCAL (group_off, y0) from ``shard_groups``; every rank
+    returns the same (prices [G, 3N], stats)."""
+    import torch
+    import torch.distributed as dist
+
+    be = backend if backend is not None else CudaShardBackend(price_solver)
+    distributed = process_group is not None or (dist.is_available() and dist.is_initialized()
+                                                and dist.get_world_size() > 1)
+    smin, smax, ssum, scnt = be.begin(group_off_local, y0_local, w_ref, lmbd_r, prev_prices, max_iter, history)
+    if distributed:  # set_charge_levels across ranks (price_solver.py:66-77)
+        dist.all_reduce(smin, op=dist.ReduceOp.MIN, group=process_group)
+        dist.all_reduce(smax, op=dist.ReduceOp.MAX, group=process_group)
+        dist.all_reduce(ssum, op=dist.ReduceOp.SUM, group=process_group)
+        dist.all_reduce(scnt, op=dist.ReduceOp.SUM, group=process_group)
+    be.start()
+    total = 0
+    for it in range(max_iter):
+        w_sum, err_max = be.ev_phase()
+        if distributed:  # w_avg += w_i over all ranks (price_solver.py:205)
+            dist.all_reduce(w_sum, op=dist.ReduceOp.SUM, group=process_group)
+            if PRICE_SOLVER_TOL_TYPE == "max":
+                dist.all_reduce(err_max, op=dist.ReduceOp.MAX, group=process_group)
+        total = it
+        if be.group_phase(it) == 0:
+            break
+        total = it + 1
+    prices, stats = be.finish(history)
+    stats["total_iters"] = total
+    return prices, stats

@@ -32,6 +32,20 @@ constexpr double kMaxBatChargeRate = 0.25;
 
 }  // namespace
 
+struct PriceSession {  // state of one (possibly sharded) compute_optimal_prices run
+  bool active = false;
+  int G = 0, max_iter = 0;
+  int64_t B = 0;
+  const int32_t* group_off = nullptr;
+  int32_t *group_of = nullptr, *skip = nullptr, *nst = nullptr, *nact = nullptr;
+  double *gamma = nullptr, *w_ev = nullptr, *err_ev = nullptr, *y0_rng = nullptr, *gamma_sc = nullptr,
+         *gamma_sm = nullptr, *w_k = nullptr, *e_avg = nullptr, *e_0 = nullptr, *dual_cost = nullptr,
+         *cost_new = nullptr, *lamdiff = nullptr, *decp = nullptr, *ws = nullptr;
+  unsigned char* wsb = nullptr;
+  double *stat_min = nullptr, *stat_max = nullptr, *stat_sum = nullptr, *stat_cnt = nullptr;
+  lompc::PriceArgs p;
+};
+
 struct lompc_handle {
   lompc::Consts cs;
   int device;
@@ -46,6 +60,9 @@ struct lompc_handle {
   void* pws;
   size_t pws_bytes;
   int32_t* poll;  // pinned host
+  void* rws;      // reduction buffers of the single-GPU price loop
+  size_t rws_bytes;
+  PriceSession ses;
 };
 
 namespace {
@@ -203,6 +220,8 @@ int lompc_create(int N, double delta, double theta, double y_max, double w_max, 
   h->pws = nullptr;
   h->pws_bytes = 0;
   h->poll = nullptr;
+  h->rws = nullptr;
+  h->rws_bytes = 0;
   *out = h;
   return LOMPC_OK;
 }
@@ -213,6 +232,7 @@ int lompc_destroy(lompc_t* h) {
   if (h->ws) cudaFree(h->ws);
   if (h->pws) cudaFree(h->pws);
   if (h->poll) cudaFreeHost(h->poll);
+  if (h->rws) cudaFree(h->rws);
   delete h;
   return LOMPC_OK;
 }
@@ -455,7 +475,7 @@ int price_w_err_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off,
   if (rc) return rc;
   double* wa = w_avg ? w_avg : t_wavg;
   double* em = w_err_max ? w_err_max : t_emax;
-  lompc::colsum_kernel<<<nblk((int64_t)G * N, 128), 128, 0, s>>>(N, G, group_off, skip, w_ev, err_ev, wa, em);
+  lompc::colsum_kernel<<<nblk((int64_t)G * N, 128), 128, 0, s>>>(N, G, group_off, skip, w_ev, err_ev, wa, em, 0);
   COUNT_LAUNCH();
   // errors via the step kernel's first phase with an infinite tolerance (every group "converges")
   CK(cudaMemsetAsync(y0r, 0x7f, (size_t)G * 8, s));  // 0x7f7f... = 1.4e306
@@ -529,6 +549,144 @@ int price_regularize_dev(lompc_t* h, int32_t G, int r, const double* w_k, double
   return LOMPC_OK;
 }
 
+// ---- sharded price loop: the pieces of compute_optimal_prices between which a multi-GPU
+// caller all-reduces (include/lompc_b200.h).  State lives in the handle (one session at a time).
+int price_shard_begin(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, const double* y0,
+                      const double* w_ref, const double* lmbd_r, int r, int max_iter, int tol_type_max,
+                      double eps_reg, double eps_tol, double* prices, int32_t* iters, double* stat_min,
+                      double* stat_max, double* stat_sum, double* stat_cnt, double* w_sum, double* err_max,
+                      double* hist_ac, double* hist_pred, int hist_cap, void* stream) {
+  if (!h || G < 0 || B < 0 || !group_off || (!y0 && B > 0) || !w_ref || !lmbd_r || !prices || !iters ||
+      !stat_min || !stat_max || !stat_sum || !stat_cnt || !w_sum || !err_max)
+    return LOMPC_ERR_ARG;
+  const int N = h->cs.N;
+  if ((r != 2 * N && r != 3 * N) || max_iter < 1) return LOMPC_ERR_ARG;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  PriceSession& S = h->ses;
+  S = PriceSession{};
+  S.G = G; S.B = B; S.group_off = group_off; S.max_iter = max_iter;
+  if (G == 0) { S.active = true; return LOMPC_OK; }
+  auto carve = [&](Carver& cv) {
+    S.group_of = cv.take<int32_t>(B); S.gamma = cv.take<double>(B); S.w_ev = cv.take<double>((size_t)B * N);
+    S.err_ev = cv.take<double>(B); S.y0_rng = cv.take<double>(G); S.gamma_sc = cv.take<double>(G);
+    S.gamma_sm = cv.take<double>(G); S.w_k = cv.take<double>((size_t)G * N);
+    S.e_avg = cv.take<double>(G); S.e_0 = cv.take<double>(G); S.dual_cost = cv.take<double>(G);
+    S.cost_new = cv.take<double>(G); S.lamdiff = cv.take<double>(G); S.decp = cv.take<double>(G);
+    S.skip = cv.take<int32_t>(G); S.nst = cv.take<int32_t>(G); S.nact = cv.take<int32_t>(4);
+    S.ws = cv.take<double>((size_t)(2 * r + 6 * N) * G); S.wsb = cv.take<unsigned char>((size_t)r * G);
+  };
+  Carver sz(nullptr);
+  carve(sz);
+  int rc = ensure_pws(h, sz.off);
+  if (rc) return rc;
+  Carver cv(h->pws);
+  carve(cv);
+  S.stat_min = stat_min; S.stat_max = stat_max; S.stat_sum = stat_sum; S.stat_cnt = stat_cnt;
+  lompc::PriceArgs& p = S.p;
+  p = lompc::PriceArgs{};
+  p.G = G; p.r = r; p.tol_type_max = tol_type_max; p.eps_reg = eps_reg; p.eps_tol = eps_tol;
+  p.group_off = group_off; p.w_ref = w_ref; p.lmbd_r = lmbd_r; p.y0_rng = S.y0_rng; p.lmbd = prices;
+  p.w_k = S.w_k; p.w_avg = w_sum; p.cnt = stat_cnt; p.w_err_max = err_max; p.w_avg_err = S.e_avg; p.w0_err = S.e_0;
+  p.dual_cost = S.dual_cost; p.cost_new = S.cost_new; p.lamdiff_phi = S.lamdiff; p.dec_pred = S.decp;
+  p.skip = S.skip; p.iters = iters; p.nnqp_status = S.nst; p.n_active = S.nact;
+  p.hist_ac = (hist_ac && hist_pred && hist_cap > 0) ? hist_ac : nullptr;
+  p.hist_pred = hist_pred; p.hist_cap = hist_cap; p.ws = S.ws; p.wsb = S.wsb;
+  CK(cudaMemsetAsync(S.nact, 0, 16, s));
+  if (B > 0) {
+    lompc::group_of_kernel<<<nblk(B, 256), 256, 0, s>>>(B, G, group_off, S.group_of);
+    COUNT_LAUNCH();
+  }
+  lompc::group_stats_local_kernel<<<nblk(G, 128), 128, 0, s>>>(h->cs, G, group_off, y0, S.gamma, stat_min, stat_max,
+                                                              stat_sum, stat_cnt, S.nact + 1);
+  COUNT_LAUNCH();
+  if (p.hist_ac) {
+    CK(cudaMemsetAsync(hist_ac, 0, (size_t)G * hist_cap * 8, s));
+    CK(cudaMemsetAsync(hist_pred, 0, (size_t)G * hist_cap * 8, s));
+  }
+  CK(cudaGetLastError());
+  S.active = true;
+  return LOMPC_OK;
+}
+
+int price_shard_start(lompc_t* h, void* stream) {
+  if (!h || !h->ses.active) return LOMPC_ERR_ARG;
+  PriceSession& S = h->ses;
+  if (S.G == 0) return LOMPC_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  lompc::stats_finalize_kernel<<<nblk(S.G, 128), 128, 0, s>>>(h->cs, S.G, S.max_iter, S.stat_min, S.stat_max,
+                                                             S.stat_sum, S.stat_cnt, S.y0_rng, S.gamma_sc,
+                                                             S.gamma_sm, S.skip, S.p.iters, S.nst);
+  COUNT_LAUNCH();
+  // w_k, dual_cost = solve_lompc(lmbd_k, lmbd_r, gamma_sc)   (price_solver.py:106)
+  return launch_group_solve(h, S.G, S.p.lmbd, S.p.lmbd_r, S.gamma_sc, nullptr, S.skip, nullptr, S.w_k,
+                            S.dual_cost, nullptr, nullptr, nullptr, s);
+}
+
+int price_shard_ev_phase(lompc_t* h, void* stream) {
+  if (!h || !h->ses.active) return LOMPC_ERR_ARG;
+  PriceSession& S = h->ses;
+  if (S.G == 0) return LOMPC_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int N = h->cs.N;
+  const bool need_err = S.p.tol_type_max != 0;
+  // _get_w_err (price_solver.py:112,196-214): the EV solves and the per-group column sums
+  int rc = launch_group_solve(h, S.B, S.p.lmbd, S.p.lmbd_r, S.gamma, S.group_of, S.skip, S.p.w_ref, S.w_ev,
+                              nullptr, need_err ? S.err_ev : nullptr, nullptr, nullptr, s);
+  if (rc) return rc;
+  lompc::colsum_kernel<<<nblk((int64_t)S.G * N, 128), 128, 0, s>>>(N, S.G, S.group_off, S.skip, S.w_ev,
+                                                                  need_err ? S.err_ev : nullptr, S.p.w_avg,
+                                                                  S.p.w_err_max, 1);
+  COUNT_LAUNCH();
+  CK(cudaGetLastError());
+  return LOMPC_OK;
+}
+
+int price_shard_group_phase(lompc_t* h, int it, int32_t* n_active, void* stream) {
+  if (!h || !h->ses.active || !n_active) return LOMPC_ERR_ARG;
+  PriceSession& S = h->ses;
+  *n_active = 0;
+  if (S.G == 0) return LOMPC_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  CK(cudaMemsetAsync(S.nact, 0, 4, s));
+  lompc::group_step_kernel<<<nblk(S.G, 64), 64, 0, s>>>(h->cs, S.p, it);
+  COUNT_LAUNCH();
+  CK(cudaMemcpyAsync(h->poll, S.nact, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (h->poll[1]) return LOMPC_ERR_CONSTS;  // y0 outside [0, y_max], price_solver.py:71
+  *n_active = h->poll[0];
+  if (h->poll[0] == 0) return LOMPC_OK;
+  // w_k, dual_cost_new = solve_lompc(lmbd_k_new, lmbd_r, gamma_sc)   (price_solver.py:132)
+  int rc = launch_group_solve(h, S.G, S.p.lmbd, S.p.lmbd_r, S.gamma_sc, nullptr, S.skip, nullptr, S.w_k,
+                              S.cost_new, nullptr, nullptr, nullptr, s);
+  if (rc) return rc;
+  lompc::bookkeep_kernel<<<nblk(S.G, 128), 128, 0, s>>>(S.p, it);
+  COUNT_LAUNCH();
+  CK(cudaGetLastError());
+  return LOMPC_OK;
+}
+
+int price_shard_finish(lompc_t* h, double* price_pre, double* price_post, double* w_k_out, void* stream) {
+  if (!h || !h->ses.active || !price_pre || !price_post) return LOMPC_ERR_ARG;
+  PriceSession& S = h->ses;
+  S.active = false;
+  if (S.G == 0) return LOMPC_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  const int N = h->cs.N;
+  // price_solver.py:145-147
+  lompc::regularize_kernel<<<nblk(S.G, 128), 128, 0, s>>>(h->cs, S.G, S.p.r, S.w_k, S.p.lmbd, price_pre, price_post,
+                                                         nullptr);
+  COUNT_LAUNCH();
+  if (w_k_out) CK(cudaMemcpyAsync(w_k_out, S.w_k, (size_t)S.G * N * 8, cudaMemcpyDeviceToDevice, s));
+  CK(cudaGetLastError());
+  CK(cudaStreamSynchronize(s));
+  return LOMPC_OK;
+}
+
 int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, const double* y0,
                     const double* w_ref, const double* lmbd_r, int r, int max_iter,
                     int tol_type_max, double eps_reg, double eps_tol, double* prices,
@@ -538,93 +696,38 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
   if (!h || G < 0 || B < 0 || !group_off || !y0 || !w_ref || !lmbd_r || !prices || !iters ||
       !price_pre || !price_post)
     return LOMPC_ERR_ARG;
-  const int N = h->cs.N;
-  if ((r != 2 * N && r != 3 * N) || max_iter < 1) return LOMPC_ERR_ARG;
   if (total_iters) *total_iters = 0;
   if (G == 0) return LOMPC_OK;
   CK(cudaSetDevice(h->device));
-  cudaStream_t s = static_cast<cudaStream_t>(stream);
-  Carver sz(nullptr);
-  auto carve = [&](Carver& cv, int32_t*& group_of, double*& gamma, double*& w_ev, double*& err_ev,
-                   double*& y0_rng, double*& gamma_sc, double*& gamma_sm, double*& w_k, double*& w_avg,
-                   double*& e_max, double*& e_avg, double*& e_0, double*& dual_cost, double*& cost_new,
-                   double*& lamdiff, double*& decp, int32_t*& skip, int32_t*& nst, int32_t*& nact,
-                   double*& ws, unsigned char*& wsb) {
-    group_of = cv.take<int32_t>(B); gamma = cv.take<double>(B); w_ev = cv.take<double>((size_t)B * N);
-    err_ev = cv.take<double>(B); y0_rng = cv.take<double>(G); gamma_sc = cv.take<double>(G);
-    gamma_sm = cv.take<double>(G); w_k = cv.take<double>((size_t)G * N); w_avg = cv.take<double>((size_t)G * N);
-    e_max = cv.take<double>(G); e_avg = cv.take<double>(G); e_0 = cv.take<double>(G);
-    dual_cost = cv.take<double>(G); cost_new = cv.take<double>(G); lamdiff = cv.take<double>(G);
-    decp = cv.take<double>(G); skip = cv.take<int32_t>(G); nst = cv.take<int32_t>(G); nact = cv.take<int32_t>(4);
-    ws = cv.take<double>((size_t)(2 * r + 6 * N) * G); wsb = cv.take<unsigned char>((size_t)r * G);
-  };
-  int32_t *group_of, *skip, *nst, *nact;
-  double *gamma, *w_ev, *err_ev, *y0_rng, *gamma_sc, *gamma_sm, *w_k, *w_avg, *e_max, *e_avg, *e_0, *dual_cost,
-      *cost_new, *lamdiff, *decp, *ws;
-  unsigned char* wsb;
-  carve(sz, group_of, gamma, w_ev, err_ev, y0_rng, gamma_sc, gamma_sm, w_k, w_avg, e_max, e_avg, e_0, dual_cost,
-        cost_new, lamdiff, decp, skip, nst, nact, ws, wsb);
-  int rc = ensure_pws(h, sz.off);
-  if (rc) return rc;
-  Carver cv(h->pws);
-  carve(cv, group_of, gamma, w_ev, err_ev, y0_rng, gamma_sc, gamma_sm, w_k, w_avg, e_max, e_avg, e_0, dual_cost,
-        cost_new, lamdiff, decp, skip, nst, nact, ws, wsb);
-  if (w_k_out) w_k = w_k_out;
-
-  CK(cudaMemsetAsync(nact, 0, 16, s));
-  lompc::group_of_kernel<<<nblk(B, 256), 256, 0, s>>>(B, G, group_off, group_of);
-  COUNT_LAUNCH();
-  lompc::group_stats_kernel<<<nblk(G, 128), 128, 0, s>>>(h->cs, G, group_off, y0, gamma, y0_rng, gamma_sc,
-                                                        gamma_sm, nact + 1);
-  COUNT_LAUNCH();
-  lompc::init_groups_kernel<<<nblk(G, 128), 128, 0, s>>>(G, max_iter, group_off, skip, iters, nst);
-  COUNT_LAUNCH();
-  if (hist_ac && hist_pred && hist_cap > 0) {
-    CK(cudaMemsetAsync(hist_ac, 0, (size_t)G * hist_cap * 8, s));
-    CK(cudaMemsetAsync(hist_pred, 0, (size_t)G * hist_cap * 8, s));
+  // single-GPU: the reduction buffers live in a second grow-only allocation of the handle
+  const int N = h->cs.N;
+  const size_t need = ((size_t)G * (N + 5) + 64) * sizeof(double);
+  if (h->rws_bytes < need) {
+    if (h->rws) CK(cudaFree(h->rws));
+    h->rws = nullptr;
+    h->rws_bytes = 0;
+    CK(cudaMalloc(&h->rws, need + need / 8));
+    h->rws_bytes = need + need / 8;
   }
-  // w_k, dual_cost = solve_lompc(lmbd_k, lmbd_r, gamma_sc)   (price_solver.py:106)
-  rc = launch_group_solve(h, G, prices, lmbd_r, gamma_sc, nullptr, skip, nullptr, w_k, dual_cost, nullptr,
-                          nullptr, nullptr, s);
+  double* rb = static_cast<double*>(h->rws);
+  double *smin = rb, *smax = rb + G, *ssum = rb + 2 * (size_t)G, *scnt = rb + 3 * (size_t)G,
+         *emax = rb + 4 * (size_t)G, *wsum = rb + 5 * (size_t)G;
+  int rc = price_shard_begin(h, G, B, group_off, y0, w_ref, lmbd_r, r, max_iter, tol_type_max, eps_reg, eps_tol,
+                             prices, iters, smin, smax, ssum, scnt, wsum, emax, hist_ac, hist_pred, hist_cap, stream);
   if (rc) return rc;
-  lompc::PriceArgs p{};
-  p.G = G; p.r = r; p.tol_type_max = tol_type_max; p.eps_reg = eps_reg; p.eps_tol = eps_tol;
-  p.group_off = group_off; p.w_ref = w_ref; p.lmbd_r = lmbd_r; p.y0_rng = y0_rng; p.lmbd = prices;
-  p.w_k = w_k; p.w_avg = w_avg; p.w_err_max = e_max; p.w_avg_err = e_avg; p.w0_err = e_0;
-  p.dual_cost = dual_cost; p.cost_new = cost_new; p.lamdiff_phi = lamdiff; p.dec_pred = decp; p.skip = skip;
-  p.iters = iters; p.nnqp_status = nst; p.n_active = nact;
-  p.hist_ac = (hist_ac && hist_pred && hist_cap > 0) ? hist_ac : nullptr;
-  p.hist_pred = hist_pred; p.hist_cap = hist_cap; p.ws = ws; p.wsb = wsb;
+  rc = price_shard_start(h, stream);
+  if (rc) return rc;
   int it = 0;
   for (; it < max_iter; ++it) {
-    // _get_w_err (price_solver.py:112,196-214)
-    rc = launch_group_solve(h, B, prices, lmbd_r, gamma, group_of, skip, w_ref, w_ev, nullptr,
-                            tol_type_max ? err_ev : nullptr, nullptr, nullptr, s);
+    rc = price_shard_ev_phase(h, stream);
     if (rc) return rc;
-    lompc::colsum_kernel<<<nblk((int64_t)G * N, 128), 128, 0, s>>>(N, G, group_off, skip, w_ev,
-                                                                    tol_type_max ? err_ev : nullptr, w_avg, e_max);
-    COUNT_LAUNCH();
-    CK(cudaMemsetAsync(nact, 0, 4, s));
-    lompc::group_step_kernel<<<nblk(G, 64), 64, 0, s>>>(h->cs, p, it);
-    COUNT_LAUNCH();
-    CK(cudaMemcpyAsync(h->poll, nact, 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaStreamSynchronize(s));
-    if (h->poll[1]) return LOMPC_ERR_CONSTS;  // y0 outside [0, y_max], price_solver.py:71
-    if (h->poll[0] == 0) break;
-    // w_k, dual_cost_new = solve_lompc(lmbd_k_new, lmbd_r, gamma_sc)   (price_solver.py:132)
-    rc = launch_group_solve(h, G, prices, lmbd_r, gamma_sc, nullptr, skip, nullptr, w_k, cost_new, nullptr,
-                            nullptr, nullptr, s);
+    int32_t nact = 0;
+    rc = price_shard_group_phase(h, it, &nact, stream);
     if (rc) return rc;
-    lompc::bookkeep_kernel<<<nblk(G, 128), 128, 0, s>>>(p, it);
-    COUNT_LAUNCH();
+    if (nact == 0) break;
   }
   if (total_iters) *total_iters = it;
-  // price_solver.py:145-147
-  lompc::regularize_kernel<<<nblk(G, 128), 128, 0, s>>>(h->cs, G, r, w_k, prices, price_pre, price_post, nullptr);
-  COUNT_LAUNCH();
-  CK(cudaGetLastError());
-  CK(cudaStreamSynchronize(s));
-  return LOMPC_OK;
+  return price_shard_finish(h, price_pre, price_post, w_k_out, stream);
 }
 
 int price_lp_rows_dev(int device, int N, int nb, const double* a, const double* b, const double* c,

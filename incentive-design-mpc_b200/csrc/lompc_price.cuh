@@ -30,7 +30,8 @@ struct PriceArgs {
   const double* y0_rng;      // [G]
   double* lmbd;              // [G,3N] current prices (updated in place)
   double* w_k;               // [G,N]  LoMPC solution at gamma_sc for the current prices
-  double* w_avg;             // [G,N]
+  double* w_avg;             // [G,N] mean of w over the group's EVs, or the SUM when cnt != NULL
+  const double* cnt;         // [G] number of EVs per group over all ranks (NULL: w_avg already is the mean)
   double* w_err_max;         // [G]
   double* w_avg_err;         // [G]
   double* w0_err;            // [G]
@@ -86,11 +87,50 @@ __global__ void group_stats_kernel(const Consts cs, int G, const int32_t* __rest
   gamma_sm[g] = cs.y_max - sum / (b1 - b0);
 }
 
+// Sharded variant of set_charge_levels: per-group LOCAL min / max / sum / count of y0 (the
+// caller all-reduces them with MIN / MAX / SUM / SUM), then stats_finalize_kernel.
+__global__ void group_stats_local_kernel(const Consts cs, int G, const int32_t* __restrict__ off,
+                                         const double* __restrict__ y0, double* __restrict__ gamma,
+                                         double* __restrict__ smin, double* __restrict__ smax,
+                                         double* __restrict__ ssum, double* __restrict__ scnt,
+                                         int32_t* __restrict__ bad) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const int b0 = off[g], b1 = off[g + 1];
+  double mn = 1e300, mx = -1e300, sum = 0.0;
+  for (int b = b0; b < b1; ++b) {
+    const double y = y0[b];
+    if (!(y >= 0.0 && y <= cs.y_max)) atomicExch(bad, 1);
+    mn = fmin(mn, y);
+    mx = fmax(mx, y);
+    sum += y;
+    gamma[b] = cs.y_max - y;
+  }
+  smin[g] = mn; smax[g] = mx; ssum[g] = sum; scnt[g] = (double)(b1 - b0);
+}
+
+__global__ void stats_finalize_kernel(const Consts cs, int G, int max_iter, const double* __restrict__ smin,
+                                      const double* __restrict__ smax, const double* __restrict__ ssum,
+                                      const double* __restrict__ scnt, double* __restrict__ y0_rng,
+                                      double* __restrict__ gamma_sc, double* __restrict__ gamma_sm,
+                                      int32_t* __restrict__ skip, int32_t* __restrict__ iters,
+                                      int32_t* __restrict__ nnqp_status) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  const bool empty = !(scnt[g] > 0.0);
+  y0_rng[g] = empty ? 0.0 : (smax[g] - smin[g]) / 2;
+  gamma_sc[g] = empty ? 0.0 : cs.y_max - (smax[g] + smin[g]) / 2;
+  gamma_sm[g] = empty ? 0.0 : cs.y_max - ssum[g] / scnt[g];
+  skip[g] = empty;
+  iters[g] = max_iter - 1;
+  nnqp_status[g] = 0;
+}
+
 // One thread per (group, time step): w_avg[g,k] = mean_i w_i[k] in EV order; thread k = 0
 // also takes max_i err_i (price_solver.py:199-210).
 __global__ void colsum_kernel(int N, int G, const int32_t* __restrict__ off, const int32_t* __restrict__ skip,
                               const double* __restrict__ w_ev, const double* __restrict__ err_ev,
-                              double* __restrict__ w_avg, double* __restrict__ w_err_max) {
+                              double* __restrict__ w_avg, double* __restrict__ w_err_max, int sum_only) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)G * N) return;
   const int g = (int)(idx / N), k = (int)(idx % N);
@@ -98,7 +138,7 @@ __global__ void colsum_kernel(int N, int G, const int32_t* __restrict__ off, con
   const int b0 = off[g], b1 = off[g + 1];
   double sum = 0.0;
   for (int b = b0; b < b1; ++b) sum += w_ev[(int64_t)b * N + k];
-  w_avg[idx] = sum / (b1 - b0);
+  w_avg[idx] = sum_only ? sum : sum / (b1 - b0);  // sum_only: the caller all-reduces, then divides by the global count
   if (k == 0 && err_ev) {
     double m = 0.0;
     for (int b = b0; b < b1; ++b) m = fmax(m, err_ev[b]);
@@ -143,15 +183,16 @@ __global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
   const double kappa = p.lmbd_r[g] / cs.delta;
   // ---- errors (price_solver.py:211-214)
   {
+    const double n = p.cnt ? p.cnt[g] : 1.0;
     double cum = 0.0, e2 = 0.0;
     for (int k = 0; k < N; ++k) {
-      const double v = p.w_avg[(size_t)g * N + k] - p.w_ref[(size_t)g * N + k];
+      const double v = p.w_avg[(size_t)g * N + k] / n - p.w_ref[(size_t)g * N + k];
       cum += v;
       e2 += cum * cum + kappa * v * v;
     }
     const double w_avg_err = sqrt(e2);
     p.w_avg_err[g] = w_avg_err;
-    p.w0_err[g] = fabs(p.w_avg[(size_t)g * N] - p.w_ref[(size_t)g * N]);
+    p.w0_err[g] = fabs(p.w_avg[(size_t)g * N] / n - p.w_ref[(size_t)g * N]);
     const double tol = sqrt((double)N) * p.y0_rng[g] + p.eps_tol;  // price_solver.py:184
     const double w_err = p.tol_type_max ? p.w_err_max[g] : w_avg_err;
     if (w_err <= tol) {  // price_solver.py:125

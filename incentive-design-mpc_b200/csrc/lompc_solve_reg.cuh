@@ -20,12 +20,10 @@ namespace lompc {
 __device__ __forceinline__ double fast_rcp(double x) {
   // x is a Riccati pivot d + c + P in [c, 1e6]: no denormals / infinities to guard.
   double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
-  double e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  e = fma(-x, y, 1.0);
-  y = fma(y, e, y);
-  return y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // ~2^-23 relative error
+  const double e = fma(-x, y, 1.0);
+  const double t = fma(e, e, e);  // one cubic step: error e^3 ~ 2^-69
+  return fma(y, t, y);
 }
 
 // Keeps the shared-memory loads of one unrolled stage inside that stage: without it the
@@ -96,7 +94,10 @@ __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts c
 
   for (; !converged && it < a.max_iter; ++it) {
     // ---------------- backward sweep ----------------
-    double P = 0.0, r = 0.0, p = 0.0, s = sN;
+    // Riccati recursion in homogeneous form: P = pa/pb, r = pr/pb.  The numerators and
+    // the denominator obey a LINEAR recurrence (2 dependent FMAs per stage); the one
+    // reciprocal per stage (1/pb_new, needed only for the gains) is off the dependency chain.
+    double pa = 0.0, pb = 1.0, pr = 0.0, p = 0.0, s = sN;
     viol = 0.0;
 #pragma unroll
     for (int k = N - 1; k >= 0; --k) {
@@ -153,22 +154,28 @@ __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts c
         }
       }
       viol = fmax(viol, v);
-      const double Q = c + P;
-      const double rp = r - cg;
       const double dm = dk + mu;  // proximal model of the safeguard: d + mu, g - mu w
       const double gm = fma(-mu, wk, gk);
-      const double inv = fast_rcp(dm + Q);
-      const double kk = Q * inv;
-      if (binding) {
-        P = Q;
-        r = fma(Q, wk, rp);
-      } else {
-        P = kk * dm;
-        r = fma(dm * inv, rp, -kk * (gm + sl));
+      const double tq_ = fma(c, pb, pa);     // Q * pb,  Q = c + P
+      const double tu = fma(-cg, pb, pr);    // (r - c gamma) * pb
+      const double bn = fma(dm, pb, tq_);    // (dm + Q) * pb
+      const double ib = fast_rcp(bn);
+      KK[k * T] = tq_ * ib;                  // Q / (dm + Q)
+      KAP[k * T] = fma(gm, pb, tu) * ib;     // (r - c gamma + gm) / (dm + Q)
+      if (NSEG > 1) INV[k * T] = pb * ib;    // 1 / (dm + Q)
+      if (binding) {  // P <- Q, r <- Q w + r - c gamma (denominator unchanged)
+        pa = tq_;
+        pr = fma(tq_, wk, tu);
+      } else {        // P <- Q dm/(dm+Q), r <- (dm (r - c gamma) - Q h)/(dm+Q)
+        pa = dm * tq_;
+        pr = fma(dm, tu, -tq_ * (gm + sl));
+        pb = bn;
       }
-      KK[k * T] = kk;
-      KAP[k * T] = (rp + gm) * inv;
-      if (NSEG > 1) INV[k * T] = inv;
+      if ((k & 7) == 0 && pb > 0x1p600) {  // keep the homogeneous triple in range (exact rescale)
+        pa *= 0x1p-600;
+        pb *= 0x1p-600;
+        pr *= 0x1p-600;
+      }
       s -= wk;
       LOMPC_STAGE_FENCE();
     }

@@ -147,6 +147,27 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
                     double* hist_ac, double* hist_pred, int hist_cap, int32_t* total_iters,
                     void* stream);
 
+/* The same loop cut into the phases between which a multi-GPU caller
+ * all-reduces, for EVs sharded over ranks (each rank passes its LOCAL EVs and
+ * LOCAL group_off; a group may be empty on a rank).  Per handle one session at
+ * a time.  Caller-owned DEVICE buffers carry the cross-rank quantities:
+ *   stat_min/max/sum/cnt[G]  after price_shard_begin : all-reduce MIN/MAX/SUM/SUM
+ *   w_sum[G,N]               after price_shard_ev_phase : all-reduce SUM
+ *   err_max[G]               after price_shard_ev_phase : all-reduce MAX ("max" tolerance type only)
+ * (price_solver.py:66-77 and :199-210 are the reductions being distributed).
+ * price_shard_group_phase runs the convergence test, the price step and the
+ * gamma_sc solve on every rank identically (replicated, deterministic) and
+ * returns the number of still-active groups; stop when it is 0.              */
+int price_shard_begin(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, const double* y0,
+                      const double* w_ref, const double* lmbd_r, int r, int max_iter, int tol_type_max,
+                      double eps_reg, double eps_tol, double* prices, int32_t* iters, double* stat_min,
+                      double* stat_max, double* stat_sum, double* stat_cnt, double* w_sum, double* err_max,
+                      double* hist_ac, double* hist_pred, int hist_cap, void* stream);
+int price_shard_start(lompc_t* h, void* stream);
+int price_shard_ev_phase(lompc_t* h, void* stream);
+int price_shard_group_phase(lompc_t* h, int it, int32_t* n_active, void* stream);
+int price_shard_finish(lompc_t* h, double* price_pre, double* price_post, double* w_k_out, void* stream);
+
 /* PriceSolver.get_w0_price0 (price_solver.py:272-285) for every group:
  * w0[B] = first-step charge of each EV, price0[G] = mean first-step price.    */
 int price_w0_price0_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off,

@@ -187,3 +187,52 @@ def test_batch_equals_single_groups():
         assert np.array_equal(lam, prices[g])
     w0, p0 = ps.get_w0_price0_batch(off, y0, prices, np.zeros(G))
     assert w0.shape == (off[-1],) and p0.shape == (G,) and p0[1] == 0.0
+
+
+@pytest.mark.parametrize("ev", ["small", "large"])
+def test_sharded_phases_two_emulated_ranks(ev):
+    """The price_shard_* phases with EVs split over two 'ranks' (two handles on one GPU; the
+    all-reduces are emulated by summing the ranks' buffers) reproduce the unsharded loop."""
+    import torch
+    from chargingstation.price_solver import PriceSolver
+    from chargingstation.sharded import CudaShardBackend, shard_groups
+    o, c = _consts(ev)
+    N = 12
+    rng = np.random.default_rng(27)
+    sizes = [9, 0, 14, 1, 6, 11]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    G = len(sizes)
+    y0 = 0.3 + 0.05 * rng.random(off[-1])
+    w_ref = o.w_max * rng.random((G, N))
+    prev = np.zeros((G, 3 * N))
+    ref = PriceSolver(N, c, "linear-convex")
+    prices_ref, stats_ref = ref.compute_optimal_prices_batch(off, y0, w_ref, np.zeros(G), prev, max_iter=300)
+    world = 2
+    bes = []
+    for rank in range(world):
+        ps = PriceSolver(N, c, "linear-convex")
+        be = CudaShardBackend(ps)
+        loc_off, loc_y0, _ = shard_groups(off, y0, rank, world)
+        be.begin(loc_off, loc_y0, w_ref, np.zeros(G), prev, 300, False)
+        bes.append(be)
+    # all-reduce MIN / MAX / SUM / SUM of the group statistics
+    smin = torch.minimum(bes[0].stat_min, bes[1].stat_min)
+    smax = torch.maximum(bes[0].stat_max, bes[1].stat_max)
+    ssum, scnt = bes[0].stat_sum + bes[1].stat_sum, bes[0].stat_cnt + bes[1].stat_cnt
+    for be in bes:
+        be.stat_min.copy_(smin); be.stat_max.copy_(smax); be.stat_sum.copy_(ssum); be.stat_cnt.copy_(scnt)
+        be.start()
+    for it in range(300):
+        sums = [be.ev_phase()[0] for be in bes]
+        tot = sums[0] + sums[1]
+        for be in bes:
+            be.w_sum.copy_(tot)
+        act = [be.group_phase(it) for be in bes]
+        assert act[0] == act[1]
+        if act[0] == 0:
+            break
+    outs = [be.finish(False) for be in bes]
+    assert np.array_equal(outs[0][0], outs[1][0])  # replicated group phase: bit-identical on both ranks
+    assert np.array_equal(outs[0][1]["iter"], stats_ref["iter"])
+    # different summation order across ranks: last-bit differences only
+    assert np.max(np.abs(outs[0][0] - prices_ref)) <= 1e-8 * max(1.0, np.max(np.abs(prices_ref)))

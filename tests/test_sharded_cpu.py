@@ -1,0 +1,104 @@
+"""CPU tests of the multi-rank host logic (world_size 2, gloo): sharding of a group-sorted EV
+batch, the placement of the all-reduces in the price loop and loop termination.  The compute
+phases are played by an oracle-backed stand-in (tests/fake_shard_backend.py); the CUDA phases
+themselves are covered by tests/test_price_gpu.py::test_sharded_*."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from chargingstation.sharded import (compute_optimal_prices_sharded,
+                                     shard_bounds, shard_groups)
+from oracle import lompc_oracle as orc
+from oracle import price_oracle as po
+
+
+def test_shard_bounds_partition():
+    for B in (0, 1, 7, 64, 65537):
+        for world in (1, 2, 3, 8):
+            cuts = [shard_bounds(B, r, world) for r in range(world)]
+            assert cuts[0][0] == 0 and cuts[-1][1] == B
+            assert all(cuts[i][1] == cuts[i + 1][0] for i in range(world - 1))
+            sizes = [hi - lo for lo, hi in cuts]
+            assert max(sizes) - min(sizes) <= 1
+
+
+def test_shard_groups_local_offsets():
+    off = np.array([0, 5, 5, 22, 23, 32])
+    y0 = np.arange(32, dtype=np.float64)
+    seen = np.zeros(32, dtype=int)
+    for world in (1, 2, 4):
+        seen[:] = 0
+        counts = np.zeros(5, dtype=int)
+        for r in range(world):
+            loc, y_loc, (lo, hi) = shard_groups(off, y0, r, world)
+            assert loc[0] == 0 and loc[-1] == hi - lo and np.all(np.diff(loc) >= 0)
+            assert np.array_equal(y_loc, y0[lo:hi])
+            counts += np.diff(loc)
+            for g in range(5):  # local group g really is the global group's slice on this rank
+                assert np.array_equal(y_loc[loc[g]:loc[g + 1]], y0[max(off[g], lo):max(min(off[g + 1], hi), max(off[g], lo))])
+            seen[lo:hi] += 1
+        assert np.all(seen == 1) and np.array_equal(counts, np.diff(off))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    return port
+
+
+def _problem():
+    o = orc.small_ev_consts()
+    N = 6
+    rng = np.random.default_rng(31)
+    sizes = [3, 0, 4, 2]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int64)
+    y0 = 0.3 + 0.05 * rng.random(off[-1])
+    w_ref = o.w_max * rng.random((len(sizes), N))
+    return o, N, off, y0, w_ref
+
+
+def _worker(rank, world, port, out):
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    for p in (root, os.path.join(root, "incentive-design-mpc_b200"), os.path.join(root, "tests")):
+        if p not in sys.path:
+            sys.path.insert(0, p)
+    from fake_shard_backend import OracleShardBackend
+    dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
+    o, N, off, y0, w_ref = _problem()
+    loc_off, loc_y0, _ = shard_groups(off, y0, rank, world)
+    G = len(off) - 1
+    be = OracleShardBackend(N, o, "linear-convex")
+    prices, stats = compute_optimal_prices_sharded(None, loc_off, loc_y0, w_ref, np.zeros(G), np.zeros((G, 3 * N)),
+                                                   backend=be, max_iter=60)
+    if rank == 0:
+        out["prices"], out["iter"], out["total"] = prices, np.asarray(stats["iter"]), stats["total_iters"]
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_gloo_price_loop_matches_single_process():
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+        prices, iters = np.array(out["prices"]), np.array(out["iter"])
+    # reference: every group on its own, single process, the oracle's own loop
+    o, N, off, y0, w_ref = _problem()
+    for g in range(len(off) - 1):
+        if off[g + 1] == off[g]:
+            assert np.all(prices[g] == 0)
+            continue
+        ora = po.PriceOracle(N, o, "linear-convex")
+        ora.set_charge_levels(y0[off[g]:off[g + 1]])
+        lam, st = ora.compute_optimal_prices(w_ref[g], 0.0, max_iter=60)
+        assert st["iter"] == iters[g]
+        assert np.max(np.abs(lam - prices[g])) <= 1e-9 * max(1.0, np.max(np.abs(lam)))
