@@ -1,4 +1,5 @@
-"""ctypes binding of ``liblompc_b200.so`` (C ABI: ``include/lompc_b200.h``).
+"""ctypes binding of ``liblompc_b200.so`` (C ABI: ``include/lompc_b200.h``,
+``include/bimpc_b200.h``).
 
 The library is built in-tree by ``__graft_entry__.build()`` (or ``make -C
 incentive-design-mpc_b200/csrc``).  Loading fails loudly if it is missing:
@@ -57,6 +58,13 @@ SIGNATURES = {
     "price_shard_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "price_w0_price0_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 7),
     "lompc_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, _dp, _dp]),
+    # include/bimpc_b200.h
+    "bimpc_create": (C.c_int, [C.c_int, C.c_int] + [C.c_double] * 5 + [C.c_int] + [C.c_double] * 5 +
+                     [C.c_int, C.POINTER(C.c_void_p)]),
+    "bimpc_destroy": (C.c_int, [C.c_void_p]),
+    "bimpc_set_options": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
+    "bimpc_solve_batch_dev": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 15),
+    "bimpc_solve_batch_host": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 14),
 }
 
 _lib = None

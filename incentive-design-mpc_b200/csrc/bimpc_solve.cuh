@@ -1,0 +1,710 @@
+// K6: batched upper-level BiMPC (reference chargingstation/bimpc.py:142-292), one station
+// per CTA.  The convex program
+//
+//   min  c_g sum_k u[k]^1.7 + delta sum_q sum_k omega_k a_q (cumsum(w_q)_k - gamma_q)^2
+//   s.t. 0 <= w_q <= wmax_q,  0 <= u <= u_g_max,                               (bimpc.py:143-186)
+//        v = u - demand - sum_q m_q w_q,   |v -+ d e1| <= u_b_max,             (bimpc.py:188-203)
+//        d <= x0 + cumsum(v) <= x_max - d                                      (bimpc.py:205-218)
+//
+// (q = 0..2P-1: P small-EV then P large-EV partitions, m_q = theta_q Mp_q) is solved with a
+// Mehrotra predictor-corrector interior-point method (cvxpy hands the same program to
+// CLARABEL's interior point, bimpc.py:114,287).  The (2P+1)N x (2P+1)N Newton matrix
+//     K = diag(E) + blockdiag_q(A' D_q A) + Ub' (diag(D1) + A' diag(D2) A) Ub,
+//     A = tril(ones),  Ub = [-m_0 I .. -m_{2P-1} I,  I]
+// is dense, but in CUMULATIVE coordinates xi_k = (cumsum(w_0)_k .. cumsum(w_{2P-1})_k, cumsum(u)_k)
+// (the MPC states: energy delivered per partition and generated so far) it is block
+// TRIDIAGONAL over the horizon with (2P+1) x (2P+1) blocks
+//     Diag_k = diag(E_k + E_{k+1} + D_k) + (D2_k + D1_k + D1_{k+1}) a a',   a = (-m, 1)
+//     Off_k  = -diag(E_k) - D1_k a a'
+// and is factorised by a block Cholesky sweep over the stages (backward stable: with the
+// reference's exponential stage weights 5^(k-N+1) the blocks H_q span 11 decades and a
+// Woodbury / dual-decomposition solve through H_q^{-1} loses the Newton direction).  Only the
+// inverse triangular factors of the diagonal blocks are stored (packed); the off-diagonal
+// blocks are diagonal + rank one and are applied on the fly.
+//
+// The body is written as thread-strided loops separated by block barriers and uses no warp
+// intrinsics, so that tests/hostsim can compile this very file for the host with one
+// "thread" (BIMPC_HOSTSIM) and check the algorithm against the dense oracle without a GPU.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+#ifdef BIMPC_TRACE
+#include <stdio.h>
+#endif
+
+#ifdef BIMPC_HOSTSIM
+#define BI_FN inline
+#define BI_HD inline
+#define BI_SYNC() ((void)0)
+#else
+#define BI_FN __device__ __forceinline__
+#define BI_HD __host__ __device__ inline
+#define BI_SYNC() __syncthreads()
+#endif
+
+namespace bimpc {
+
+constexpr int kRefine = 1; // refinement steps of every Newton solve
+constexpr int kMaxN = 48;  // horizon cap (scratch of one station must fit 227 KB of shared memory)
+
+struct BiConsts {
+  int N, P;
+  double delta, c_g, u_g_max, u_b_max, x_max;
+  int cost_type;  // 0 WEIGHTED, 1 UNWEIGHTED, 2 EXP_UNWEIGHTED (bimpc.py:12-15)
+  double theta_s, theta_l, w_max_s, w_max_l;
+};
+
+struct BiArgs {
+  int S;                  // stations
+  const double* omega;    // [N] stage weights of the charging cost (bimpc.py:255-257)
+  const double* Mp_s;     // [S,P] normalised partition sizes (BiMPCParameters, bimpc.py:44-58)
+  const double* Mp_l;
+  const double* beta_s;   // [S,P]
+  const double* beta_l;
+  const double* gamma_sm; // [S,P]
+  const double* gamma_lm;
+  const double* x0;       // [S]
+  const double* demand;   // [S,N]
+  double* w_hat_s;        // [S,P,N]
+  double* w_hat_l;        // [S,P,N]
+  double* u_g;            // [S,N]
+  int32_t* status;        // [S] 0 ok, 1 iteration cap, 2 numerical breakdown
+  int32_t* iters;         // [S]
+  double* objective;      // [S] or NULL
+  double tol;
+  int max_iter;
+};
+
+// Number of doubles of scratch one station needs (shared memory on the device).
+BI_HD size_t scratch_doubles(int N, int P, int T) {
+  const int Q2 = 2 * P, QN = Q2 * N, nb = Q2 + 1;
+  return (size_t)11 * QN + (size_t)(QN + N) + (size_t)N * (nb * (nb + 1) / 2) + (size_t)nb * nb +
+         (size_t)40 * N + 8 * (size_t)nb + 3 * (size_t)T + 4 * Q2 + 16;
+}
+
+// Deterministic block reduction of (sum, max, min): partials in tid order.
+BI_FN void block_reduce(double* RED, int tid, int T, double& sum, double& mx, double& mn) {
+  RED[tid] = sum;
+  RED[T + tid] = mx;
+  RED[2 * T + tid] = mn;
+  BI_SYNC();
+  double s = 0.0, a = RED[T], b = RED[2 * T];
+  for (int i = 0; i < T; ++i) {
+    s += RED[i];
+    a = fmax(a, RED[T + i]);
+    b = fmin(b, RED[2 * T + i]);
+  }
+  BI_SYNC();
+  sum = s;
+  mx = a;
+  mn = b;
+}
+
+// In-place Cholesky of the SPD matrix Mx (row-major N x N, lower triangle used/produced),
+// left-looking, columns in order; DIAG is an N-vector of scratch.  Returns false on breakdown.
+BI_FN bool block_cholesky(double* Mx, double* DIAG, int N, int tid, int T) {
+  bool ok = true;
+  for (int j = 0; j < N; ++j) {
+    for (int i = j + tid; i < N; i += T) {
+      double v = Mx[i * N + j];
+      for (int k = 0; k < j; ++k) v -= Mx[i * N + k] * Mx[j * N + k];
+      DIAG[i] = v;
+    }
+    BI_SYNC();
+    const double djj = DIAG[j];
+    if (!(djj > 0.0)) ok = false;
+    const double rs = 1.0 / sqrt(djj > 0.0 ? djj : 1.0);
+    for (int i = j + tid; i < N; i += T) Mx[i * N + j] = DIAG[i] * rs;
+    BI_SYNC();
+  }
+  return ok;
+}
+
+// One station.  `sm` = scratch_doubles(N, P, T) doubles private to this CTA.
+BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double* sm, int tid, int T) {
+  const int N = c.N, P = c.P, Q2 = 2 * P, QN = Q2 * N;
+  const int nb = Q2 + 1, np = nb * (nb + 1) / 2;
+  // ---- carve
+  double* W = sm;             // [Q2,N] iterate
+  double* S1 = W + QN;        // slack / multiplier of w >= 0
+  double* Z1 = S1 + QN;
+  double* S2 = Z1 + QN;       // slack / multiplier of w <= wmax
+  double* Z2 = S2 + QN;
+  double* RDW = Z2 + QN;      // dual residual, w block
+  double* DXA = RDW + QN;     // affine direction, w block
+  double* DX = DXA + QN;      // current direction, w block
+  double* EW = DX + QN;       // barrier diagonal z1/s1 + z2/s2
+  double* RB = EW + QN;       // Newton right-hand side, w block
+  double* RR = RB + QN;       // refinement residual / correction, w block
+  double* XI = RR + QN;       // [N,nb] block-tridiagonal solve vector (cumulative coordinates)
+  double* LI = XI + QN + N;   // [N,np] packed inverse Cholesky factors of the diagonal blocks
+  double* SW = LI + (size_t)N * np;  // [nb,nb] Schur complement of the current stage -> its factor
+  double* pk = SW + nb * nb;  // per-k vectors
+  double* U = pk;             pk += N;
+  double* S3 = pk;            pk += N;
+  double* Z3 = pk;            pk += N;
+  double* S4 = pk;            pk += N;
+  double* Z4 = pk;            pk += N;
+  double* S5 = pk;            pk += N;
+  double* Z5 = pk;            pk += N;
+  double* S6 = pk;            pk += N;
+  double* Z6 = pk;            pk += N;
+  double* S7 = pk;            pk += N;
+  double* Z7 = pk;            pk += N;
+  double* S8 = pk;            pk += N;
+  double* Z8 = pk;            pk += N;
+  double* V = pk;             pk += N;  // u_b
+  double* XX = pk;            pk += N;  // battery state
+  double* RDU = pk;           pk += N;
+  double* HU = pk;            pk += N;
+  double* D1 = pk;            pk += N;
+  double* D2 = pk;            pk += N;
+  double* BU = pk;            pk += N;  // current direction, u block
+  double* DXUA = pk;          pk += N;
+  double* DV = pk;            pk += N;
+  double* DVA = pk;           pk += N;
+  double* DXX = pk;           pk += N;
+  double* DXXA = pk;          pk += N;
+  double* NU = pk;            pk += N;
+  double* YV = pk;            pk += N;
+  double* T56 = pk;           pk += N;
+  double* T78 = pk;           pk += N;
+  double* DEM = pk;           pk += N;
+  double* OM = pk;            pk += N;
+  double* RBU = pk;           pk += N;
+  double* RRU = pk;           pk += N;
+  pk += 7 * N;                          // (spare, keeps the 40 N budget)
+  double* AV = pk;            pk += nb;  // a = (-m, 1)
+  double* LA = pk;            pk += nb;  // Linv_{k-1} a
+  double* TL = pk;            pk += nb;  // T' la
+  double* DIAG = pk;          pk += nb;
+  double* TV1 = pk;           pk += nb;
+  double* TV2 = pk;           pk += nb;
+  pk += 2 * nb;
+  double* RED = pk;           pk += 3 * T;
+  double* MQ = pk;            pk += Q2;   // m_q
+  double* AQ = pk;            pk += Q2;   // a_q
+  double* GQ = pk;            pk += Q2;   // gamma_q
+  double* WMX = pk;           pk += Q2;   // wmax_q
+
+  // ---- station data
+  const double x0 = a.x0[st_idx];
+  // d = theta_s (Mp_s . beta_s) + theta_l (Mp_l . beta_l)   (bimpc.py:195-197); every thread
+  // evaluates the scalar itself, in the same order
+  double dot_s = 0.0, dot_l = 0.0;
+  for (int p = 0; p < P; ++p) {
+    dot_s += a.Mp_s[(size_t)st_idx * P + p] * a.beta_s[(size_t)st_idx * P + p];
+    dot_l += a.Mp_l[(size_t)st_idx * P + p] * a.beta_l[(size_t)st_idx * P + p];
+  }
+  const double derr = c.theta_s * dot_s + c.theta_l * dot_l;
+  for (int q = tid; q < Q2; q += T) {
+    const bool small = q < P;
+    const int p = small ? q : q - P;
+    const double mp = small ? a.Mp_s[(size_t)st_idx * P + p] : a.Mp_l[(size_t)st_idx * P + p];
+    const double th = small ? c.theta_s : c.theta_l;
+    MQ[q] = th * mp;
+    AQ[q] = c.cost_type == 0 ? (th * mp) * (th * mp) : 1.0;
+    GQ[q] = small ? a.gamma_sm[(size_t)st_idx * P + p] : a.gamma_lm[(size_t)st_idx * P + p];
+    WMX[q] = small ? c.w_max_s : c.w_max_l;
+    AV[q] = -th * mp;
+  }
+  if (tid == 0) AV[Q2] = 1.0;
+  for (int k = tid; k < N; k += T) {
+    DEM[k] = a.demand[(size_t)st_idx * N + k];
+    OM[k] = a.omega[k];
+  }
+  BI_SYNC();
+  double om_sum = 0.0;
+  for (int k = 0; k < N; ++k) om_sum += OM[k];
+  double scale_g = 1.0;
+  for (int q = 0; q < Q2; ++q) scale_g = fmax(scale_g, 2.0 * c.delta * AQ[q] * fabs(GQ[q]) * om_sum);
+  const double mtot = (double)(2 * QN + 6 * N);
+
+  // ---- starting point: box centre, slacks max(h - Gx, 1e-2), multipliers 1
+  for (int i = tid; i < QN; i += T) {
+    const int q = i / N;
+    W[i] = 0.5 * WMX[q];
+    S1[i] = fmax(0.5 * WMX[q], 1e-2);
+    S2[i] = fmax(0.5 * WMX[q], 1e-2);
+    Z1[i] = 1.0;
+    Z2[i] = 1.0;
+  }
+  for (int k = tid; k < N; k += T) {
+    U[k] = 0.5 * c.u_g_max;
+    S3[k] = fmax(0.5 * c.u_g_max, 1e-2);
+    S4[k] = fmax(0.5 * c.u_g_max, 1e-2);
+    Z3[k] = Z4[k] = Z5[k] = Z6[k] = Z7[k] = Z8[k] = 1.0;
+  }
+  BI_SYNC();
+  for (int k = tid; k < N; k += T) {
+    double v = U[k] - DEM[k];
+    for (int q = 0; q < Q2; ++q) v -= MQ[q] * W[q * N + k];
+    V[k] = v;
+  }
+  BI_SYNC();
+  for (int k = tid; k < N; k += T) {
+    double x = x0;
+    for (int j = 0; j <= k; ++j) x += V[j];
+    const double e1 = (k == 0) ? derr : 0.0;
+    S5[k] = fmax(V[k] + c.u_b_max - e1, 1e-2);
+    S6[k] = fmax(c.u_b_max - e1 - V[k], 1e-2);
+    S7[k] = fmax(x - derr, 1e-2);
+    S8[k] = fmax(c.x_max - derr - x, 1e-2);
+  }
+  BI_SYNC();
+
+  int it = 0, status = 1;
+  double mu = 0.0;
+  for (;; ++it) {
+    // ---- A. primal quantities and the gradient of the charging cost
+    for (int q = tid; q < Q2; q += T) {
+      // grad_q = 2 delta a_q A' (omega .* (A w_q - gamma_q)):  forward cumsum, then reverse
+      double s = 0.0;
+      for (int k = 0; k < N; ++k) {
+        s += W[q * N + k];
+        RDW[q * N + k] = OM[k] * (s - GQ[q]);
+      }
+      double r = 0.0;
+      const double f = 2.0 * c.delta * AQ[q];
+      for (int k = N - 1; k >= 0; --k) {
+        r += RDW[q * N + k];
+        RDW[q * N + k] = f * r;
+      }
+    }
+    for (int k = tid; k < N; k += T) {
+      double v = U[k] - DEM[k];
+      for (int q = 0; q < Q2; ++q) v -= MQ[q] * W[q * N + k];
+      V[k] = v;
+      T56[k] = Z6[k] - Z5[k];
+      T78[k] = Z8[k] - Z7[k];
+    }
+    BI_SYNC();
+    for (int k = tid; k < N; k += T) {
+      double x = x0;
+      for (int j = 0; j <= k; ++j) x += V[j];
+      XX[k] = x;
+      double y = T56[k];
+      for (int j = N - 1; j >= k; --j) y += T78[j];
+      YV[k] = y;
+    }
+    BI_SYNC();
+    // ---- B. residuals
+    double r_sz = 0.0, r_max = 0.0, r_dummy = 0.0, rp_max = 0.0;
+    for (int i = tid; i < QN; i += T) {
+      const int q = i / N, k = i - q * N;
+      const double rd = RDW[i] - Z1[i] + Z2[i] - MQ[q] * YV[k];
+      RDW[i] = rd;
+      r_max = fmax(r_max, fabs(rd));
+      rp_max = fmax(rp_max, fmax(fabs(S1[i] - W[i]), fabs(W[i] + S2[i] - WMX[q])));
+      r_sz += S1[i] * Z1[i] + S2[i] * Z2[i];
+    }
+    for (int k = tid; k < N; k += T) {
+      const double u = fmax(U[k], 1e-300);
+      const double rd = 1.7 * c.c_g * pow(u, 0.7) - Z3[k] + Z4[k] + YV[k];
+      RDU[k] = rd;
+      r_max = fmax(r_max, fabs(rd));
+      const double e1 = (k == 0) ? derr : 0.0;
+      double m = fmax(fabs(S3[k] - U[k]), fabs(U[k] + S4[k] - c.u_g_max));
+      m = fmax(m, fabs(-V[k] + S5[k] - (c.u_b_max - e1)));
+      m = fmax(m, fabs(V[k] + S6[k] - (c.u_b_max - e1)));
+      m = fmax(m, fabs(-XX[k] + S7[k] + derr));
+      m = fmax(m, fabs(XX[k] + S8[k] - (c.x_max - derr)));
+      rp_max = fmax(rp_max, m);
+      r_sz += S3[k] * Z3[k] + S4[k] * Z4[k] + S5[k] * Z5[k] + S6[k] * Z6[k] + S7[k] * Z7[k] + S8[k] * Z8[k];
+    }
+    // two maxima travel through one reduction: (sum, max, min) = (s'z, max|rd|, -max|rp|)
+    r_dummy = -rp_max;
+    block_reduce(RED, tid, T, r_sz, r_max, r_dummy);
+    rp_max = -r_dummy;
+    mu = r_sz / mtot;
+#ifdef BIMPC_TRACE
+    printf("it %d rd %.3e rp %.3e mu %.3e\n", it, r_max, rp_max, mu);
+#endif
+    if (r_max <= a.tol * scale_g && rp_max <= a.tol && mu <= a.tol) {
+      status = 0;
+      break;
+    }
+    if (it >= a.max_iter) break;
+    if (!(mu == mu) || !(r_max == r_max)) {  // NaN
+      status = 2;
+      break;
+    }
+
+    // ---- C. factorisation: block Cholesky of the stage-ordered Newton matrix
+    for (int i = tid; i < QN; i += T) EW[i] = Z1[i] / S1[i] + Z2[i] / S2[i];
+    for (int k = tid; k < N; k += T) {
+      const double u = fmax(U[k], 1e-300);
+      HU[k] = 1.7 * 0.7 * c.c_g * pow(u, -0.3) + Z3[k] / S3[k] + Z4[k] / S4[k];
+      D1[k] = Z5[k] / S5[k] + Z6[k] / S6[k];
+      D2[k] = Z7[k] / S7[k] + Z8[k] / S8[k];
+    }
+    BI_SYNC();
+    // E_k[i]: barrier diagonal of stage k in block order (partitions, then u)
+    auto Ek = [&](int k, int i) { return k >= N ? 0.0 : (i < Q2 ? EW[i * N + k] : HU[k]); };
+    bool ok = true;
+    for (int k = 0; k < N; ++k) {
+      const double* Lp = LI + (size_t)(k - 1) * np;  // previous stage (k >= 1)
+      const double d1k = D1[k], d1n = (k + 1 < N) ? D1[k + 1] : 0.0;
+      if (k >= 1) {
+        for (int i = tid; i < nb; i += T) {  // la = Linv_{k-1} a
+          double v = 0.0;
+          for (int j = 0; j <= i; ++j) v += Lp[i * (i + 1) / 2 + j] * AV[j];
+          LA[i] = v;
+        }
+        BI_SYNC();
+        for (int i = tid; i < nb; i += T) {  // tl = T' la,  T = Linv_{k-1} diag(E_k)
+          double v = 0.0;
+          for (int l = i; l < nb; ++l) v += Lp[l * (l + 1) / 2 + i] * LA[l];
+          TL[i] = v * Ek(k, i);
+        }
+        BI_SYNC();
+      }
+      double ll = 0.0;
+      if (k >= 1)
+        for (int i = 0; i < nb; ++i) ll += LA[i] * LA[i];
+      const double rho = D2[k] + d1k + d1n;
+      for (int e = tid; e < np; e += T) {  // lower triangle of the Schur complement
+        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
+        while (i * (i + 1) / 2 > e) --i;
+        while ((i + 1) * (i + 2) / 2 <= e) ++i;
+        const int j = e - i * (i + 1) / 2;
+        double v = rho * AV[i] * AV[j];
+        if (i == j) v += Ek(k, i) + Ek(k + 1, i) + (i < Q2 ? 2.0 * c.delta * AQ[i] * OM[k] : 0.0);
+        if (k >= 1) {
+          double tt = 0.0;
+          for (int l = i; l < nb; ++l) tt += Lp[l * (l + 1) / 2 + i] * Lp[l * (l + 1) / 2 + j];
+          tt *= Ek(k, i) * Ek(k, j);
+          const double di = d1k * AV[i], dj = d1k * AV[j];
+          v -= tt + TL[i] * dj + di * TL[j] + ll * di * dj;
+        }
+        SW[i * nb + j] = v;
+      }
+      BI_SYNC();
+      ok = block_cholesky(SW, DIAG, nb, tid, T) && ok;
+      // Linv_k: column j by thread j (forward substitution on e_j), packed
+      double* Lk = LI + (size_t)k * np;
+      for (int j = tid; j < nb; j += T) {
+        for (int i = j; i < nb; ++i) {
+          double v = (i == j) ? 1.0 : 0.0;
+          for (int l = j; l < i; ++l) v -= SW[i * nb + l] * Lk[l * (l + 1) / 2 + j];
+          Lk[i * (i + 1) / 2 + j] = v / SW[i * nb + i];
+        }
+      }
+      BI_SYNC();
+    }
+    if (!ok) {
+      status = 2;
+      break;
+    }
+
+    // (outW, outU) = K^{-1} (inW, inU) through the block factorisation; in and out may alias.
+    auto lin_solve = [&](const double* inW, const double* inU, double* outW, double* outU) {
+      // right-hand side in cumulative coordinates: b~_k = b_k - b_{k+1}
+      for (int e = tid; e < N * nb; e += T) {
+        const int k = e / nb, i = e - k * nb;
+        const double b0 = i < Q2 ? inW[i * N + k] : inU[k];
+        const double b1 = (k + 1 < N) ? (i < Q2 ? inW[i * N + k + 1] : inU[k + 1]) : 0.0;
+        XI[e] = b0 - b1;
+      }
+      BI_SYNC();
+      // forward: y_k = Linv_k (b~_k - Off_k Linv_{k-1}' y_{k-1})
+      for (int k = 0; k < N; ++k) {
+        double* x = XI + k * nb;
+        if (k >= 1) {
+          const double* Lp = LI + (size_t)(k - 1) * np;
+          const double* yp = XI + (k - 1) * nb;
+          for (int i = tid; i < nb; i += T) {
+            double v = 0.0;
+            for (int l = i; l < nb; ++l) v += Lp[l * (l + 1) / 2 + i] * yp[l];
+            TV1[i] = v;
+          }
+          BI_SYNC();
+          double at = 0.0;
+          for (int i = 0; i < nb; ++i) at += AV[i] * TV1[i];
+          for (int i = tid; i < nb; i += T) TV2[i] = x[i] + Ek(k, i) * TV1[i] + D1[k] * AV[i] * at;
+        } else {
+          for (int i = tid; i < nb; i += T) TV2[i] = x[i];
+        }
+        BI_SYNC();
+        const double* Lk = LI + (size_t)k * np;
+        for (int i = tid; i < nb; i += T) {
+          double v = 0.0;
+          for (int j = 0; j <= i; ++j) v += Lk[i * (i + 1) / 2 + j] * TV2[j];
+          x[i] = v;
+        }
+        BI_SYNC();
+      }
+      // backward: xi_k = Linv_k' (y_k - Linv_k Off_{k+1} xi_{k+1})
+      for (int k = N - 1; k >= 0; --k) {
+        double* x = XI + k * nb;
+        const double* Lk = LI + (size_t)k * np;
+        if (k + 1 < N) {
+          const double* xn = XI + (k + 1) * nb;
+          double ax = 0.0;
+          for (int i = 0; i < nb; ++i) ax += AV[i] * xn[i];
+          for (int i = tid; i < nb; i += T) TV1[i] = -(Ek(k + 1, i) * xn[i] + D1[k + 1] * AV[i] * ax);
+          BI_SYNC();
+          for (int i = tid; i < nb; i += T) {
+            double v = 0.0;
+            for (int j = 0; j <= i; ++j) v += Lk[i * (i + 1) / 2 + j] * TV1[j];
+            TV2[i] = x[i] - v;
+          }
+        } else {
+          for (int i = tid; i < nb; i += T) TV2[i] = x[i];
+        }
+        BI_SYNC();
+        for (int i = tid; i < nb; i += T) {
+          double v = 0.0;
+          for (int l = i; l < nb; ++l) v += Lk[l * (l + 1) / 2 + i] * TV2[l];
+          x[i] = v;
+        }
+        BI_SYNC();
+      }
+      // back to stage increments: dx_k = xi_k - xi_{k-1}
+      for (int e = tid; e < N * nb; e += T) {
+        const int k = e / nb, i = e - k * nb;
+        const double v = XI[e] - (k >= 1 ? XI[e - nb] : 0.0);
+        if (i < Q2) outW[i * N + k] = v;
+        else outU[k] = v;
+      }
+      BI_SYNC();
+    };
+
+    // ---- D..G: predictor (pass 0) and corrector (pass 1)
+    double sigma_mu = 0.0, alpha = 1.0;
+    for (int pass = 0; pass < 2; ++pass) {
+      // complementarity target rc_i = s z [+ ds_a dz_a - sigma mu]; xi_i = (z rp - rc)/s
+      auto rc_of = [&](double s, double z, double rp, double ga) {
+        double rc = s * z;
+        if (pass == 1) {
+          const double dsa = -rp - ga;
+          const double dza = (-s * z - z * dsa) / s;
+          rc += dsa * dza - sigma_mu;
+        }
+        return rc;
+      };
+      for (int k = tid; k < N; k += T) {
+        const double e1 = (k == 0) ? derr : 0.0;
+        const double rp5 = -V[k] + S5[k] - (c.u_b_max - e1), rp6 = V[k] + S6[k] - (c.u_b_max - e1);
+        const double rp7 = -XX[k] + S7[k] + derr, rp8 = XX[k] + S8[k] - (c.x_max - derr);
+        const double x5 = (Z5[k] * rp5 - rc_of(S5[k], Z5[k], rp5, -DVA[k])) / S5[k];
+        const double x6 = (Z6[k] * rp6 - rc_of(S6[k], Z6[k], rp6, DVA[k])) / S6[k];
+        const double x7 = (Z7[k] * rp7 - rc_of(S7[k], Z7[k], rp7, -DXXA[k])) / S7[k];
+        const double x8 = (Z8[k] * rp8 - rc_of(S8[k], Z8[k], rp8, DXXA[k])) / S8[k];
+        T56[k] = x6 - x5;
+        T78[k] = x8 - x7;
+      }
+      BI_SYNC();
+      for (int k = tid; k < N; k += T) {
+        double y = T56[k];
+        for (int j = N - 1; j >= k; --j) y += T78[j];
+        NU[k] = y;  // y_xi (NU is free until tau has been formed)
+      }
+      BI_SYNC();
+      for (int i = tid; i < QN; i += T) {
+        const int q = i / N, k = i - q * N;
+        const double rp1 = S1[i] - W[i], rp2 = W[i] + S2[i] - WMX[q];
+        const double x1 = (Z1[i] * rp1 - rc_of(S1[i], Z1[i], rp1, -DXA[i])) / S1[i];
+        const double x2 = (Z2[i] * rp2 - rc_of(S2[i], Z2[i], rp2, DXA[i])) / S2[i];
+        RB[i] = -RDW[i] + x1 - x2 + MQ[q] * NU[k];
+      }
+      for (int k = tid; k < N; k += T) {
+        const double rp3 = S3[k] - U[k], rp4 = U[k] + S4[k] - c.u_g_max;
+        const double x3 = (Z3[k] * rp3 - rc_of(S3[k], Z3[k], rp3, -DXUA[k])) / S3[k];
+        const double x4 = (Z4[k] * rp4 - rc_of(S4[k], Z4[k], rp4, DXUA[k])) / S4[k];
+        RBU[k] = -RDU[k] + x3 - x4 - NU[k];
+      }
+      BI_SYNC();
+      // dx = K^{-1} b, then iterative refinement with the operator in its original coordinates
+      lin_solve(RB, RBU, DX, BU);
+      for (int ref = 0; ref < kRefine; ++ref) {
+        for (int k = tid; k < N; k += T) {
+          double v = BU[k];
+          for (int q = 0; q < Q2; ++q) v -= MQ[q] * DX[q * N + k];
+          DV[k] = v;
+        }
+        BI_SYNC();
+        for (int k = tid; k < N; k += T) {  // D2 .* cumsum(dv)
+          double x = 0.0;
+          for (int j = 0; j <= k; ++j) x += DV[j];
+          T78[k] = D2[k] * x;
+        }
+        BI_SYNC();
+        for (int k = tid; k < N; k += T) {  // y = S dv = D1 .* dv + A' (D2 .* A dv)
+          double v = D1[k] * DV[k];
+          for (int j = N - 1; j >= k; --j) v += T78[j];
+          YV[k] = v;
+        }
+        BI_SYNC();
+        for (int q = tid; q < Q2; q += T) {  // r_q = b_q - (e .* dx + A' D_q A dx) + m_q y
+          const int o = q * N;
+          const double f = 2.0 * c.delta * AQ[q], mq = MQ[q];
+          double cs = 0.0;
+          for (int k = 0; k < N; ++k) {
+            cs += DX[o + k];
+            RR[o + k] = f * OM[k] * cs;
+          }
+          double g = 0.0;
+          for (int k = N - 1; k >= 0; --k) {
+            g += RR[o + k];
+            RR[o + k] = RB[o + k] - (EW[o + k] * DX[o + k] + g) + mq * YV[k];
+          }
+        }
+        for (int k = tid; k < N; k += T) RRU[k] = RBU[k] - HU[k] * BU[k] - YV[k];
+        BI_SYNC();
+        lin_solve(RR, RRU, RR, RRU);
+        for (int i = tid; i < QN; i += T) DX[i] += RR[i];
+        for (int k = tid; k < N; k += T) BU[k] += RRU[k];
+        BI_SYNC();
+      }
+      for (int k = tid; k < N; k += T) {
+        double v = BU[k];
+        for (int q = 0; q < Q2; ++q) v -= MQ[q] * DX[q * N + k];
+        DV[k] = v;
+      }
+      BI_SYNC();
+      for (int k = tid; k < N; k += T) {
+        double x = 0.0;
+        for (int j = 0; j <= k; ++j) x += DV[j];
+        DXX[k] = x;
+      }
+      BI_SYNC();
+      // ---- ratio test (and, on the predictor pass, mu_aff)
+      double amin = 1e300, dummy_s = 0.0, dummy_m = 0.0;
+      auto ratio = [&](double s, double z, double rp, double g, double ga) {
+        const double rc = rc_of(s, z, rp, ga);
+        const double ds = -rp - g;
+        const double dz = (-rc - z * ds) / s;
+        if (ds < 0.0) amin = fmin(amin, -s / ds);
+        if (dz < 0.0) amin = fmin(amin, -z / dz);
+      };
+      for (int i = tid; i < QN; i += T) {
+        const int q = i / N;
+        const double rp1 = S1[i] - W[i], rp2 = W[i] + S2[i] - WMX[q];
+        ratio(S1[i], Z1[i], rp1, -DX[i], -DXA[i]);
+        ratio(S2[i], Z2[i], rp2, DX[i], DXA[i]);
+      }
+      for (int k = tid; k < N; k += T) {
+        const double e1 = (k == 0) ? derr : 0.0;
+        ratio(S3[k], Z3[k], S3[k] - U[k], -BU[k], -DXUA[k]);
+        ratio(S4[k], Z4[k], U[k] + S4[k] - c.u_g_max, BU[k], DXUA[k]);
+        ratio(S5[k], Z5[k], -V[k] + S5[k] - (c.u_b_max - e1), -DV[k], -DVA[k]);
+        ratio(S6[k], Z6[k], V[k] + S6[k] - (c.u_b_max - e1), DV[k], DVA[k]);
+        ratio(S7[k], Z7[k], -XX[k] + S7[k] + derr, -DXX[k], -DXXA[k]);
+        ratio(S8[k], Z8[k], XX[k] + S8[k] - (c.x_max - derr), DXX[k], DXXA[k]);
+      }
+      block_reduce(RED, tid, T, dummy_s, dummy_m, amin);
+      if (pass == 0) {
+        const double a_aff = fmin(1.0, amin);
+        double acc = 0.0, d1 = 0.0, d2 = 0.0;
+        auto muaff = [&](double s, double z, double rp, double g) {
+          const double ds = -rp - g;
+          const double dz = (-s * z - z * ds) / s;
+          acc += (s + a_aff * ds) * (z + a_aff * dz);
+        };
+        for (int i = tid; i < QN; i += T) {
+          const int q = i / N;
+          muaff(S1[i], Z1[i], S1[i] - W[i], -DX[i]);
+          muaff(S2[i], Z2[i], W[i] + S2[i] - WMX[q], DX[i]);
+          DXA[i] = DX[i];
+        }
+        for (int k = tid; k < N; k += T) {
+          const double e1 = (k == 0) ? derr : 0.0;
+          muaff(S3[k], Z3[k], S3[k] - U[k], -BU[k]);
+          muaff(S4[k], Z4[k], U[k] + S4[k] - c.u_g_max, BU[k]);
+          muaff(S5[k], Z5[k], -V[k] + S5[k] - (c.u_b_max - e1), -DV[k]);
+          muaff(S6[k], Z6[k], V[k] + S6[k] - (c.u_b_max - e1), DV[k]);
+          muaff(S7[k], Z7[k], -XX[k] + S7[k] + derr, -DXX[k]);
+          muaff(S8[k], Z8[k], XX[k] + S8[k] - (c.x_max - derr), DXX[k]);
+          DXUA[k] = BU[k];
+          DVA[k] = DV[k];
+          DXXA[k] = DXX[k];
+        }
+        block_reduce(RED, tid, T, acc, d1, d2);
+        const double mu_aff = acc / mtot;
+        const double sg = mu_aff / mu;
+        sigma_mu = sg * sg * sg * mu;
+      } else {
+        alpha = fmin(1.0, 0.99 * amin);
+#ifdef BIMPC_TRACE
+        printf("   alpha %.4f sigma_mu %.3e\n", alpha, sigma_mu);
+#endif
+      }
+    }
+    // ---- G. step (pass == 1 semantics for rc: DXA etc. still hold the affine direction)
+    {
+      auto upd = [&](double& s, double& z, double rp, double g, double ga) {
+        const double dsa = -rp - ga;
+        const double dza = (-s * z - z * dsa) / s;
+        const double rc = s * z + dsa * dza - sigma_mu;
+        const double ds = -rp - g;
+        const double dz = (-rc - z * ds) / s;
+        s += alpha * ds;
+        z += alpha * dz;
+      };
+      for (int i = tid; i < QN; i += T) {
+        const int q = i / N;
+        const double rp1 = S1[i] - W[i], rp2 = W[i] + S2[i] - WMX[q];
+        upd(S1[i], Z1[i], rp1, -DX[i], -DXA[i]);
+        upd(S2[i], Z2[i], rp2, DX[i], DXA[i]);
+        W[i] += alpha * DX[i];
+      }
+      for (int k = tid; k < N; k += T) {
+        const double e1 = (k == 0) ? derr : 0.0;
+        const double rp3 = S3[k] - U[k], rp4 = U[k] + S4[k] - c.u_g_max;
+        const double rp5 = -V[k] + S5[k] - (c.u_b_max - e1), rp6 = V[k] + S6[k] - (c.u_b_max - e1);
+        const double rp7 = -XX[k] + S7[k] + derr, rp8 = XX[k] + S8[k] - (c.x_max - derr);
+        upd(S3[k], Z3[k], rp3, -BU[k], -DXUA[k]);
+        upd(S4[k], Z4[k], rp4, BU[k], DXUA[k]);
+        upd(S5[k], Z5[k], rp5, -DV[k], -DVA[k]);
+        upd(S6[k], Z6[k], rp6, DV[k], DVA[k]);
+        upd(S7[k], Z7[k], rp7, -DXX[k], -DXXA[k]);
+        upd(S8[k], Z8[k], rp8, DXX[k], DXXA[k]);
+        U[k] += alpha * BU[k];
+      }
+      BI_SYNC();
+    }
+  }
+
+  // ---- outputs (clipped into the box like the oracle)
+  for (int i = tid; i < QN; i += T) {
+    const int q = i / N, k = i - q * N;
+    const double x = fmin(fmax(W[i], 0.0), WMX[q]);
+    if (q < P) a.w_hat_s[((size_t)st_idx * P + q) * N + k] = x;
+    else a.w_hat_l[((size_t)st_idx * P + (q - P)) * N + k] = x;
+  }
+  for (int k = tid; k < N; k += T) a.u_g[(size_t)st_idx * N + k] = fmin(fmax(U[k], 0.0), c.u_g_max);
+  if (tid == 0) {
+    a.status[st_idx] = status;
+    a.iters[st_idx] = it;
+  }
+  if (a.objective) {
+    // c_g sum u^1.7 + delta sum_q a_q sum_k omega_k (cumsum(w_q)_k - gamma_q)^2, by thread 0
+    BI_SYNC();
+    if (tid == 0) {
+      double f = 0.0;
+      for (int k = 0; k < N; ++k) f += c.c_g * pow(fmax(U[k], 0.0), 1.7);
+      for (int q = 0; q < Q2; ++q) {
+        double s = 0.0;
+        for (int k = 0; k < N; ++k) {
+          s += W[q * N + k];
+          f += c.delta * AQ[q] * OM[k] * (s - GQ[q]) * (s - GQ[q]);
+        }
+      }
+      a.objective[st_idx] = f;
+    }
+  }
+
+}
+
+#ifndef BIMPC_HOSTSIM
+__global__ void __launch_bounds__(128) bimpc_solve_kernel(const BiConsts c, const BiArgs a) {
+  extern __shared__ double bimpc_smem[];
+  for (int s = blockIdx.x; s < a.S; s += gridDim.x) {
+    solve_station(c, a, s, bimpc_smem, threadIdx.x, blockDim.x);
+    __syncthreads();
+  }
+}
+#endif
+
+}  // namespace bimpc

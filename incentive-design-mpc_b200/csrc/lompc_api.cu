@@ -32,6 +32,11 @@ constexpr double kMaxBatChargeRate = 0.25;
 
 }  // namespace
 
+namespace lompc_detail {
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
+int cuda_fail(cudaError_t e, const char* what) { return ::cuda_fail(e, what); }
+}  // namespace lompc_detail
+
 struct PriceSession {  // state of one (possibly sharded) compute_optimal_prices run
   bool active = false;
   int G = 0, max_iter = 0;

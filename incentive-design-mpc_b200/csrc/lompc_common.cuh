@@ -5,6 +5,12 @@
 
 #include "lompc_b200.h"
 
+// Shared by the translation units of the library (defined in lompc_api.cu).
+namespace lompc_detail {
+void count_launch();                              // feeds lompc_launch_count()
+int cuda_fail(cudaError_t e, const char* what);   // records the message, returns LOMPC_ERR_CUDA
+}  // namespace lompc_detail
+
 namespace lompc {
 
 constexpr int kMaxSeg = 4;  // pieces of the large-EV pwl (lompc.py:111-115)

@@ -9,13 +9,18 @@ import pytest
 from chargingstation import _native
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-HEADER = os.path.join(ROOT, "include", "lompc_b200.h")
+INCLUDE = os.path.join(ROOT, "include")
 
 
 def _declared_functions():
-    src = open(HEADER).read()
-    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
-    return sorted(set(re.findall(r"\b(lompc_[a-z0-9_]+|price_[a-z0-9_]+)\s*\(", src)))
+    names = set()
+    for f in sorted(os.listdir(INCLUDE)):
+        if not f.endswith(".h"):
+            continue
+        src = open(os.path.join(INCLUDE, f)).read()
+        src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+        names |= set(re.findall(r"\b((?:lompc|price|bimpc|fleet)_[a-z0-9_]+)\s*\(", src))
+    return sorted(names)
 
 
 def test_library_exports_every_declared_symbol():
@@ -23,7 +28,7 @@ def test_library_exports_every_declared_symbol():
     names = _declared_functions()
     assert len(names) >= 10
     for n in names:
-        assert hasattr(lib, n), f"{n} declared in include/lompc_b200.h but not exported"
+        assert hasattr(lib, n), f"{n} declared in include/*.h but not exported"
         assert n in _native.SIGNATURES, f"{n} has no ctypes signature in _native.py"
 
 
