@@ -1,0 +1,75 @@
+"""Mirror of the reference's ``chargingstation/example/real_time_price_control.py``
+(BASELINE.json configs[0]): one station, 500 + 500 EVs, 12 partitions, LoMPC horizon 12,
+BiMPC horizon 16, 49 hours, "linear-convex" prices, the bundled demand profile scaled by
+1/4 (real_time_price_control.py:11-79).  Run from ``incentive-design-mpc_b200/``:
+
+    python -m chargingstation.example.real_time_price_control [--steps T] [--out logs.pkl]
+"""
+from __future__ import annotations
+
+import argparse
+import pickle
+import time
+
+import numpy as np
+
+from chargingstation.bimpc import BiMPCChargingCostType, BiMPCConstants
+from chargingstation.charging_station import ChargingStation, ChargingStationConstants
+from chargingstation.demand_data import medium_term_demand_forecast
+from chargingstation.lompc import LoMPCConstants
+
+## Simulation parameters.
+SIMULATION_LENGTH = 49  # [hours].
+
+HORIZON_LOMPC = 12
+HORIZON_BIMPC = 16
+
+NUM_EVS_PER_EV_TYPE = 500
+NUM_PARTITIONS = 12
+
+PRICE_TYPE = "linear-convex"
+# PRICE_TYPE = "linear"
+
+DEMAND_SCALE = 1 / 4  # {1 / 4, 1 / 3}.
+
+
+def _get_lompc_consts() -> tuple[LoMPCConstants, LoMPCConstants]:
+    consts_s = LoMPCConstants(delta=0.05, theta=10, y_max=0.9, w_max=0.25, ev_type="small")
+    consts_l = LoMPCConstants(delta=0.025, theta=50, y_max=0.9, w_max=0.15, ev_type="large")
+    return consts_s, consts_l
+
+
+def _get_normalized_bimpc_consts() -> BiMPCConstants:
+    return BiMPCConstants(delta=1e3, c_g=1, u_g_max=1, u_b_max=0.3, x_max=0.3,
+                          charging_cost_type=BiMPCChargingCostType.EXP_UNWEIGHTED, exp_rate=5)
+
+
+def _get_unnormalized_external_demand(simulation_length: int = SIMULATION_LENGTH) -> np.ndarray:
+    return medium_term_demand_forecast(simulation_length + HORIZON_BIMPC + 1, DEMAND_SCALE, interpolate=False)
+
+
+def get_chargingstation_consts(simulation_length: int = SIMULATION_LENGTH) -> ChargingStationConstants:
+    consts_s, consts_l = _get_lompc_consts()
+    return ChargingStationConstants(simulation_length, HORIZON_BIMPC, HORIZON_LOMPC, NUM_EVS_PER_EV_TYPE,
+                                    NUM_PARTITIONS, _get_unnormalized_external_demand(simulation_length),
+                                    _get_normalized_bimpc_consts(), consts_s, consts_l, PRICE_TYPE)
+
+
+def main() -> None:
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--steps", type=int, default=SIMULATION_LENGTH)
+    ap.add_argument("--seed", type=int, default=None)
+    ap.add_argument("--out", default="real-time-price-control_logs_" + PRICE_TYPE + ".pkl")
+    args = ap.parse_args()
+    if args.seed is not None:
+        np.random.seed(args.seed)
+    cs = ChargingStation(get_chargingstation_consts(args.steps))
+    t0 = time.time()
+    logs = cs.simulate()
+    print(f"{args.steps} closed-loop steps in {time.time() - t0:.2f} s")
+    with open(args.out, "wb") as file:
+        pickle.dump(logs, file)
+
+
+if __name__ == "__main__":
+    main()

@@ -19,7 +19,8 @@ from chargingstation.price_regularizer import PriceRegularizer
 from chargingstation.settings import (MAX_PRICE_SOLVER_ITERATIONS,
                                       PRICE_SOLVER_EPS_REG,
                                       PRICE_SOLVER_EPS_TOL,
-                                      PRICE_SOLVER_TOL_TYPE, PRINT_LEVEL)
+                                      PRICE_SOLVER_TOL_TYPE)
+from chargingstation import settings
 
 
 class PriceSolver:
@@ -119,7 +120,7 @@ class PriceSolver:
             prev, history=True)
         lmbd_k = prices[0]
         it = int(stats["iter"][0])
-        if PRINT_LEVEL >= 1:  # price_solver.py:150-164
+        if settings.PRINT_LEVEL >= 1:  # price_solver.py:150-164
             _, w0_err_bound = self.get_robustness_bounds(lmbd_r)
             _, w0_err, _ = self._get_w_err(lmbd_k, lmbd_r, w_ref, None)
             print(f"w0-error      : {w0_err:13.8f} | w0 error bound: {w0_err_bound:13.8f}")

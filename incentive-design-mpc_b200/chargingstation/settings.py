@@ -21,7 +21,7 @@ PRICE_SOLVER_EPS_TOL = 0.01
 PRICE_SOLVER_SOLVER = "B200_NNQP"
 
 # BiMPC settings.
-BIMPC_SOLVER = "HOST_BARRIER_NEWTON"
+BIMPC_SOLVER = "B200_BLOCK_TRIDIAGONAL_IPM"
 
 # ChargingStation settings.
 MIN_INITIAL_SOC = 0.3  # y_{min, 1}.
