@@ -42,7 +42,7 @@ def test_closed_loop_matches_oracle(cost_type, price_type):
     # under the exponential stage weights w_hat is only weakly determined (tests/test_bimpc_cpu.py),
     # and so is everything downstream of it; the unweighted cost pins the whole loop
     tight = cost_type != bo.EXP_UNWEIGHTED
-    tol = 1e-6 if tight else 5e-3
+    tol = 1e-5 if tight else 5e-3
     for t, rec in enumerate(so.trace):
         assert np.array_equal(logs["statistics"]["Mp_s"][:, t], rec["Mp_s"])
         assert np.array_equal(logs["statistics"]["Mp_l"][:, t], rec["Mp_l"])
@@ -57,8 +57,8 @@ def test_closed_loop_matches_oracle(cost_type, price_type):
                 assert np.max(np.abs(logs["prices"]["avg_price_" + key][:, t] - rec["price0_" + key])) <= 1e-5 * 50
             assert np.all(logs["statistics"]["niter_" + key][~idx_nonempty, t] == -1)
     if tight:
-        assert np.max(np.abs(cs.y_s - so.y["s"])) <= 1e-6 and np.max(np.abs(cs.y_l - so.y["l"])) <= 1e-6
-        assert abs(cs.x - so.x) <= 1e-6
+        assert np.max(np.abs(cs.y_s - so.y["s"])) <= 1e-5 and np.max(np.abs(cs.y_l - so.y["l"])) <= 1e-5
+        assert abs(cs.x - so.x) <= 1e-5
 
 
 def test_example_configuration_two_steps():
