@@ -1,5 +1,5 @@
 """ctypes binding of ``liblompc_b200.so`` (C ABI: ``include/lompc_b200.h``,
-``include/bimpc_b200.h``).
+``include/bimpc_b200.h``, ``include/fleet_b200.h``).
 
 The library is built in-tree by ``__graft_entry__.build()`` (or ``make -C
 incentive-design-mpc_b200/csrc``).  Loading fails loudly if it is missing:
@@ -65,6 +65,16 @@ SIGNATURES = {
     "bimpc_set_options": (C.c_int, [C.c_void_p, C.c_int, C.c_double]),
     "bimpc_solve_batch_dev": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 15),
     "bimpc_solve_batch_host": (C.c_int, [C.c_void_p, C.c_int32] + [C.c_void_p] * 14),
+    # include/fleet_b200.h
+    "fleet_partition_dev": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 9),
+    "fleet_bimpc_params_dev": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [C.c_double] * 5 +
+                               [C.c_void_p] * 8 + [C.c_int32, C.c_int32] + [C.c_void_p] * 9),
+    "fleet_wref_dev": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 3),
+    "fleet_keep_prices_dev": (C.c_int, [C.c_int, C.c_int32, C.c_int32] + [C.c_void_p] * 7),
+    "fleet_apply_charge_dev": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_int32, C.c_double, C.c_double,
+                                         C.c_double, C.c_int64, C.c_int32, C.c_int32] + [C.c_void_p] * 9),
+    "fleet_battery_dev": (C.c_int, [C.c_int, C.c_int32, C.c_int32, C.c_double, C.c_double, C.c_double] +
+                          [C.c_void_p] * 4 + [C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None

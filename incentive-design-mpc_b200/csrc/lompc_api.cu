@@ -42,7 +42,7 @@ struct PriceSession {  // state of one (possibly sharded) compute_optimal_prices
   int G = 0, max_iter = 0;
   int64_t B = 0;
   const int32_t* group_off = nullptr;
-  int32_t *group_of = nullptr, *skip = nullptr, *nst = nullptr, *nact = nullptr;
+  int32_t *group_of = nullptr, *skip = nullptr, *nst = nullptr, *nact = nullptr, *empty = nullptr;
   double *gamma = nullptr, *w_ev = nullptr, *err_ev = nullptr, *y0_rng = nullptr, *gamma_sc = nullptr,
          *gamma_sm = nullptr, *w_k = nullptr, *e_avg = nullptr, *e_0 = nullptr, *dual_cost = nullptr,
          *cost_new = nullptr, *lamdiff = nullptr, *decp = nullptr, *ws = nullptr;
@@ -579,6 +579,7 @@ int price_shard_begin(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off
     S.e_avg = cv.take<double>(G); S.e_0 = cv.take<double>(G); S.dual_cost = cv.take<double>(G);
     S.cost_new = cv.take<double>(G); S.lamdiff = cv.take<double>(G); S.decp = cv.take<double>(G);
     S.skip = cv.take<int32_t>(G); S.nst = cv.take<int32_t>(G); S.nact = cv.take<int32_t>(4);
+    S.empty = cv.take<int32_t>(G);
     S.ws = cv.take<double>((size_t)(2 * r + 6 * N) * G); S.wsb = cv.take<unsigned char>((size_t)r * G);
   };
   Carver sz(nullptr);
@@ -622,7 +623,7 @@ int price_shard_start(lompc_t* h, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   lompc::stats_finalize_kernel<<<nblk(S.G, 128), 128, 0, s>>>(h->cs, S.G, S.max_iter, S.stat_min, S.stat_max,
                                                              S.stat_sum, S.stat_cnt, S.y0_rng, S.gamma_sc,
-                                                             S.gamma_sm, S.skip, S.p.iters, S.nst);
+                                                             S.gamma_sm, S.skip, S.p.iters, S.nst, S.empty);
   COUNT_LAUNCH();
   // w_k, dual_cost = solve_lompc(lmbd_k, lmbd_r, gamma_sc)   (price_solver.py:106)
   return launch_group_solve(h, S.G, S.p.lmbd, S.p.lmbd_r, S.gamma_sc, nullptr, S.skip, nullptr, S.w_k,
@@ -683,8 +684,9 @@ int price_shard_finish(lompc_t* h, double* price_pre, double* price_post, double
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   const int N = h->cs.N;
   // price_solver.py:145-147
+  // (empty groups keep their price row: no EV, no solve - charging_station.py:277,293)
   lompc::regularize_kernel<<<nblk(S.G, 128), 128, 0, s>>>(h->cs, S.G, S.p.r, S.w_k, S.p.lmbd, price_pre, price_post,
-                                                         nullptr);
+                                                         S.empty);
   COUNT_LAUNCH();
   if (w_k_out) CK(cudaMemcpyAsync(w_k_out, S.w_k, (size_t)S.G * N * 8, cudaMemcpyDeviceToDevice, s));
   CK(cudaGetLastError());

@@ -114,15 +114,16 @@ __global__ void stats_finalize_kernel(const Consts cs, int G, int max_iter, cons
                                       const double* __restrict__ scnt, double* __restrict__ y0_rng,
                                       double* __restrict__ gamma_sc, double* __restrict__ gamma_sm,
                                       int32_t* __restrict__ skip, int32_t* __restrict__ iters,
-                                      int32_t* __restrict__ nnqp_status) {
+                                      int32_t* __restrict__ nnqp_status, int32_t* __restrict__ empty_out) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
   const bool empty = !(scnt[g] > 0.0);
+  empty_out[g] = empty;
   y0_rng[g] = empty ? 0.0 : (smax[g] - smin[g]) / 2;
   gamma_sc[g] = empty ? 0.0 : cs.y_max - (smax[g] + smin[g]) / 2;
   gamma_sm[g] = empty ? 0.0 : cs.y_max - ssum[g] / scnt[g];
   skip[g] = empty;
-  iters[g] = max_iter - 1;
+  iters[g] = empty ? -1 : max_iter - 1;  // -1: the reference logs niter = -1 for an empty partition (charging_station.py:404-411)
   nnqp_status[g] = 0;
 }
 
