@@ -113,6 +113,7 @@ class ChargingStationFleet:
                 self.log[f"{name}_{k}"] = z(Tf, P, S)
             self.log[f"niter_{k}"] = z(Tf, P, S, dtype=i32)
             self.log[f"Mp_{k}"] = z(Tf, P, S, dtype=i32)
+        self.ncharged_logged = {k: z(S, dtype=i32) for k in ("s", "l")}
         self.price_loop_iters = []  # per step: total device-loop iterations of the price loops
         self.qp_solves = 0
 
@@ -208,6 +209,8 @@ class ChargingStationFleet:
         L["x"][t].copy_(self.x)
         L["bimpc_iters"][t].copy_(bi["iters"])
         L["bimpc_status"][t].copy_(bi["status"])
+        # the reference logs the departure counters BEFORE this step's plant update (:399-400)
+        self.ncharged_logged = {k: self.ncharged[k].clone() for k in ("s", "l")}
         # ---- plant
         for ti, k in enumerate(("s", "l")):
             w = self.w[k]
@@ -265,7 +268,8 @@ class ChargingStationFleet:
                        "u_g": L["u_g"]},
             "states": {"x": L["x"]},
             "bounds": {"beta_s": T(L["beta_s"]), "beta_l": T(L["beta_l"])},
-            "statistics": {"ncharged_s": int(self.ncharged["s"][s]), "ncharged_l": int(self.ncharged["l"][s]),
+            "statistics": {"ncharged_s": int(self.ncharged_logged["s"][s]),
+                           "ncharged_l": int(self.ncharged_logged["l"][s]),
                            "gamma_sm": T(L["gamma_m_s"]), "gamma_lm": T(L["gamma_m_l"]),
                            "niter_s": T(L["niter_s"]).astype(int), "niter_l": T(L["niter_l"]).astype(int),
                            "Mp_s": T(L["Mp_s"]).astype(int), "Mp_l": T(L["Mp_l"]).astype(int)},

@@ -9,6 +9,7 @@
 #include "lompc_solve.cuh"
 #include "lompc_solve_reg.cuh"
 #include "lompc_price.cuh"
+#include "lompc_price_fused.cuh"
 
 namespace {
 
@@ -62,6 +63,8 @@ struct lompc_handle {
   size_t ws_bytes;
   // grow-only device workspace of the price loop + pinned poll word
   int variant;  // 0 auto, 1 = any-N shared-memory kernel, 2.. = register-kernel variants
+  int loop_mode;  // price loop: 0 auto (fused one-CTA-per-group kernel when compiled for N), 1 = phase-split host loop
+  unsigned long long last_qp_solves;  // LoMPC QPs solved by the last fused price loop
   void* pws;
   size_t pws_bytes;
   int32_t* poll;  // pinned host
@@ -222,6 +225,8 @@ int lompc_create(int N, double delta, double theta, double y_max, double w_max, 
   h->ws = nullptr;
   h->ws_bytes = 0;
   h->variant = 0;
+  h->loop_mode = 0;
+  h->last_qp_solves = 0;
   h->pws = nullptr;
   h->pws_bytes = 0;
   h->poll = nullptr;
@@ -256,6 +261,14 @@ int lompc_set_kernel_variant(lompc_t* h, int variant) {
   h->variant = variant;
   return LOMPC_OK;
 }
+
+int price_set_loop_mode(lompc_t* h, int mode) {
+  if (!h || mode < 0 || mode > 1) return LOMPC_ERR_ARG;
+  h->loop_mode = mode;
+  return LOMPC_OK;
+}
+
+int64_t price_last_qp_solves(const lompc_t* h) { return h ? (int64_t)h->last_qp_solves : 0; }
 
 int lompc_solve_batch_dev(lompc_t* h, int64_t B, const double* lmbd, int64_t lmbd_stride,
                           const double* lmbd_r, int64_t lmbd_r_stride, const double* gamma,
@@ -379,6 +392,8 @@ int ensure_pws(lompc_handle* h, size_t bytes) {
   if (h->pws_bytes >= bytes) return LOMPC_OK;
   if (h->pws) CK(cudaFree(h->pws));
   h->variant = 0;
+  h->loop_mode = 0;
+  h->last_qp_solves = 0;
   h->pws = nullptr;
   h->pws_bytes = 0;
   const size_t want = bytes + bytes / 8;
@@ -694,6 +709,42 @@ int price_shard_finish(lompc_t* h, double* price_pre, double* price_post, double
   return LOMPC_OK;
 }
 
+}  // extern "C"
+
+namespace {
+
+template <int N, int NSEG, int T, int MINB, bool GREG>
+int launch_fused(lompc_handle* h, const lompc::FusedArgs& a, cudaStream_t s) {
+  constexpr size_t smem = lompc::FusedSmem<N, NSEG, T, GREG>::bytes;
+  static bool configured = false;
+  if (!configured) {
+    CK(cudaFuncSetAttribute(lompc::price_group_loop_kernel<N, NSEG, T, MINB, GREG>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    configured = true;
+  }
+  lompc::price_group_loop_kernel<N, NSEG, T, MINB, GREG><<<(unsigned)a.G, T, smem, s>>>(h->cs, a);
+  COUNT_LAUNCH();
+  CK(cudaGetLastError());
+  return LOMPC_OK;
+}
+
+// compute_optimal_prices for whole groups resident on this GPU: one CTA per group, no host loop.
+int price_solve_fused(lompc_handle* h, const lompc::FusedArgs& a, cudaStream_t s) {
+  const int N = h->cs.N;
+  if (h->cs.large) {
+    if (N == 24) return launch_fused<24, 4, 64, 4, true>(h, a, s);
+    if (N == 12) return launch_fused<12, 4, 64, 4, true>(h, a, s);
+  } else {
+    if (N == 24) return launch_fused<24, 1, 64, 4, false>(h, a, s);
+    if (N == 12) return launch_fused<12, 1, 64, 4, false>(h, a, s);
+  }
+  return LOMPC_ERR_ARG;
+}
+
+}  // namespace
+
+extern "C" {
+
 int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, const double* y0,
                     const double* w_ref, const double* lmbd_r, int r, int max_iter,
                     int tol_type_max, double eps_reg, double eps_tol, double* prices,
@@ -706,7 +757,37 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
   if (total_iters) *total_iters = 0;
   if (G == 0) return LOMPC_OK;
   CK(cudaSetDevice(h->device));
-  // single-GPU: the reduction buffers live in a second grow-only allocation of the handle
+  if ((h->cs.N == 24 || h->cs.N == 12) && h->variant != 1 && h->loop_mode != 1) {
+    // fused, device-resident loop: one CTA per group (lompc_price_fused.cuh)
+    if ((r != 2 * h->cs.N && r != 3 * h->cs.N) || max_iter < 1) return LOMPC_ERR_ARG;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    int rc = ensure_pws(h, 256);
+    if (rc) return rc;
+    int32_t* flags = static_cast<int32_t*>(h->pws);
+    CK(cudaMemsetAsync(flags, 0, 32, s));
+    const bool hist = hist_ac && hist_pred && hist_cap > 0;
+    if (hist) {
+      CK(cudaMemsetAsync(hist_ac, 0, (size_t)G * hist_cap * 8, s));
+      CK(cudaMemsetAsync(hist_pred, 0, (size_t)G * hist_cap * 8, s));
+    }
+    lompc::FusedArgs a{};
+    a.G = G; a.r = r; a.tol_type_max = tol_type_max; a.eps_reg = eps_reg; a.eps_tol = eps_tol;
+    a.max_iter = max_iter; a.qp_tol = h->tol; a.qp_max_iter = h->max_iter; a.group_off = group_off; a.y0 = y0;
+    a.w_ref = w_ref; a.lmbd_r = lmbd_r; a.prices = prices; a.iters = iters; a.price_pre = price_pre;
+    a.price_post = price_post; a.w_k_out = w_k_out; a.hist_ac = hist ? hist_ac : nullptr; a.hist_pred = hist_pred;
+    a.hist_cap = hist_cap; a.flags = flags;
+    a.qp_count = reinterpret_cast<unsigned long long*>(flags + 4);
+    rc = price_solve_fused(h, a, s);
+    if (rc) return rc;
+    CK(cudaMemcpyAsync(h->poll, flags, 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (total_iters) *total_iters = h->poll[2];
+    h->last_qp_solves = *reinterpret_cast<unsigned long long*>(h->poll + 4);
+    if (h->poll[1]) return LOMPC_ERR_CONSTS;  // y0 outside [0, y_max], price_solver.py:71
+    return LOMPC_OK;
+  }
+  // phase-split loop (any horizon; also the path a multi-GPU caller drives, see price_shard_*):
+  // the reduction buffers live in a second grow-only allocation of the handle
   const int N = h->cs.N;
   const size_t need = ((size_t)G * (N + 5) + 64) * sizeof(double);
   if (h->rws_bytes < need) {

@@ -170,41 +170,21 @@ __device__ __forceinline__ void ric_solve(int N, int G, const double* dvec, doub
   }
 }
 
-// One thread per group: errors of _get_w_err, the convergence test, and -- for groups
-// that go on -- the exact solution of the non-negative QP of the price step
+// The exact solution of the non-negative QP of the price step
 //     min_{l >= 0} l'P l + q'l,  P = Dphi A_bar^{-1} Dphi'/(2m) + eps I,  q = -2 P l_k - (phi(w_k) - phi(w_ref))
-// by a primal-dual active-set iteration.  P is never formed: with B = Dphi[:r] (three
-// diagonals) the free-set system is solved through Woodbury,
+// (price_solver.py:216-246) by a primal-dual active-set iteration, for ONE group by ONE thread.
+// P is never formed: with B = Dphi[:r] (three diagonals) the free-set system is solved through
+// Woodbury,
 //     l_F = (rho_F - B_F z)/eps,   (2 m eps A_bar + B_F'B_F) z = B_F' rho_F,   rho = -q/2,
 // and A_bar = A'A + kappa I makes that an O(N) Riccati solve like the LoMPC's own.
-__global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  const int G = p.G, N = cs.N, r = p.r;
-  if (g >= G || p.skip[g]) return;
-  const double kappa = p.lmbd_r[g] / cs.delta;
-  // ---- errors (price_solver.py:211-214)
-  {
-    const double n = p.cnt ? p.cnt[g] : 1.0;
-    double cum = 0.0, e2 = 0.0;
-    for (int k = 0; k < N; ++k) {
-      const double v = p.w_avg[(size_t)g * N + k] / n - p.w_ref[(size_t)g * N + k];
-      cum += v;
-      e2 += cum * cum + kappa * v * v;
-    }
-    const double w_avg_err = sqrt(e2);
-    p.w_avg_err[g] = w_avg_err;
-    p.w0_err[g] = fabs(p.w_avg[(size_t)g * N] / n - p.w_ref[(size_t)g * N]);
-    const double tol = sqrt((double)N) * p.y0_rng[g] + p.eps_tol;  // price_solver.py:184
-    const double w_err = p.tol_type_max ? p.w_err_max[g] : w_avg_err;
-    if (w_err <= tol) {  // price_solver.py:125
-      p.skip[g] = 1;
-      p.iters[g] = it;
-      return;
-    }
-  }
-  atomicAdd(p.n_active, 1);
-  // ---- scratch (strided by G)
-  double* LAM = p.ws + g;                    // [r] new prices
+// lk[3N] (contiguous) is updated in place; ws / wsb = scratch of (2r + 6N) doubles / r bytes
+// with element stride `G` (global scratch interleaved over groups, or G = 1 in shared memory).
+__device__ __forceinline__ void price_step_core(const Consts& cs, int r, double kappa, double eps, double* lk,
+                                                const double* wk, const double* wr, double* ws,
+                                                unsigned char* wsb, size_t G, bool first, double& lamdiff_out,
+                                                double& dec_pred_out, int& status_out) {
+  const int N = cs.N;
+  double* LAM = ws;                          // [r] new prices
   double* RHO = LAM + (size_t)r * G;         // [r]
   double* C3 = RHO + (size_t)r * G;          // [N] third diagonal of Dphi': 2 q w_k
   double* KS = C3 + (size_t)N * G;           // [N]
@@ -212,12 +192,9 @@ __global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
   double* U = KAPS + (size_t)N * G;          // [N]
   double* V = U + (size_t)N * G;             // [N]
   double* TD = V + (size_t)N * G;            // [N]
-  unsigned char* FREE = p.wsb + g;           // [r]
+  unsigned char* FREE = wsb;                 // [r]
   const int nb = r / N;                      // 2 or 3 price blocks
-  const double th = cs.theta, qs = cs.q_scale, m = cs.c, eps = p.eps_reg;
-  double* lk = p.lmbd + (size_t)g * 3 * N;
-  const double* wk = p.w_k + (size_t)g * N;
-  const double* wr = p.w_ref + (size_t)g * N;
+  const double th = cs.theta, qs = cs.q_scale, m = cs.c;
   // u = B' l_k ; v = A_bar^{-1} u ; rho = P l_k + (phi(w_k) - phi(w_ref))/2
   for (int k = 0; k < N; ++k) {
     const double c3 = 2.0 * qs * wk[k];
@@ -292,9 +269,7 @@ __global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
       break;
     }
   }
-  p.nnqp_status[g] = st;
   // ---- write back (price_solver.py:129,135-140)
-  const bool first = (it == 0);
   for (int k = 0; k < N; ++k) {
     const double phir[3] = {th * wr[k], th * (cs.w_max - wr[k]), qs * wr[k] * wr[k]};
     for (int j = 0; j < nb; ++j) {
@@ -303,8 +278,53 @@ __global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
       lk[j * N + k] = ln;
     }
   }
-  p.lamdiff_phi[g] = first ? lamdiff : 0.0;
-  p.dec_pred[g] = F0 - F1;
+  lamdiff_out = first ? lamdiff : 0.0;
+  dec_pred_out = F0 - F1;
+  status_out = st;
+}
+
+// Errors of _get_w_err (price_solver.py:211-214) for a mean trajectory w_sum / n.
+__device__ __forceinline__ void price_errors(int N, double kappa, const double* w_sum, double n, const double* w_ref,
+                                             double& w_avg_err, double& w0_err) {
+  double cum = 0.0, e2 = 0.0;
+  for (int k = 0; k < N; ++k) {
+    const double v = w_sum[k] / n - w_ref[k];
+    cum += v;
+    e2 += cum * cum + kappa * v * v;
+  }
+  w_avg_err = sqrt(e2);
+  w0_err = fabs(w_sum[0] / n - w_ref[0]);
+}
+
+// One thread per group: errors, the convergence test (price_solver.py:121-127) and -- for
+// groups that go on -- the price step.
+__global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  const int G = p.G, N = cs.N, r = p.r;
+  if (g >= G || p.skip[g]) return;
+  const double kappa = p.lmbd_r[g] / cs.delta;
+  {
+    double w_avg_err, w0_err;
+    price_errors(N, kappa, p.w_avg + (size_t)g * N, p.cnt ? p.cnt[g] : 1.0, p.w_ref + (size_t)g * N, w_avg_err,
+                 w0_err);
+    p.w_avg_err[g] = w_avg_err;
+    p.w0_err[g] = w0_err;
+    const double tol = sqrt((double)N) * p.y0_rng[g] + p.eps_tol;  // price_solver.py:184
+    const double w_err = p.tol_type_max ? p.w_err_max[g] : w_avg_err;
+    if (w_err <= tol) {  // price_solver.py:125
+      p.skip[g] = 1;
+      p.iters[g] = it;
+      return;
+    }
+  }
+  atomicAdd(p.n_active, 1);
+  double lamdiff, dec;
+  int st;
+  price_step_core(cs, r, kappa, p.eps_reg, p.lmbd + (size_t)g * 3 * N, p.w_k + (size_t)g * N,
+                  p.w_ref + (size_t)g * N, p.ws + g, p.wsb + g, (size_t)G, it == 0, lamdiff, dec, st);
+  p.nnqp_status[g] = st;
+  p.lamdiff_phi[g] = lamdiff;
+  p.dec_pred[g] = dec;
 }
 
 __global__ void bookkeep_kernel(const PriceArgs p, int it) {
@@ -322,16 +342,10 @@ __global__ void bookkeep_kernel(const PriceArgs p, int it) {
 // row k of Dphi' touches only (x1_k, x2_k, x3_k); b_k = theta(l1-l2) + 2 q w_k l3;
 // b_k < 0: x2 = -b_k/theta;  b_k >= 0: x3 = b_k/(2 q w_k) if r = 3N and w_k > 0 (unit cost
 // w_k/2 beats x1's w_k) else x1 = b_k/theta.
-__global__ void regularize_kernel(const Consts cs, int G, int r, const double* __restrict__ w_k,
-                                  double* __restrict__ lmbd, double* __restrict__ price_pre,
-                                  double* __restrict__ price_post, const int32_t* __restrict__ empty) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= G) return;
-  if (empty && empty[g]) return;
+__device__ __forceinline__ void regularize_core(const Consts& cs, int r, const double* w, double* l, double& pre_out,
+                                                double& post_out) {
   const int N = cs.N;
   const double th = cs.theta, qs = cs.q_scale, wm = cs.w_max;
-  double* l = lmbd + (size_t)g * 3 * N;
-  const double* w = w_k + (size_t)g * N;
   double pre = 0.0, post = 0.0;
   for (int k = 0; k < N; ++k) {
     const double wk = w[k];
@@ -348,6 +362,18 @@ __global__ void regularize_kernel(const Consts cs, int G, int r, const double* _
     if (r == 3 * N) l[2 * N + k] = x3;
     post += ph1 * x1 + ph2 * x2 + ph3 * x3;
   }
+  pre_out = pre;
+  post_out = post;
+}
+
+__global__ void regularize_kernel(const Consts cs, int G, int r, const double* __restrict__ w_k,
+                                  double* __restrict__ lmbd, double* __restrict__ price_pre,
+                                  double* __restrict__ price_post, const int32_t* __restrict__ empty) {
+  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= G) return;
+  if (empty && empty[g]) return;
+  double pre, post;
+  regularize_core(cs, r, w_k + (size_t)g * cs.N, lmbd + (size_t)g * 3 * cs.N, pre, post);
   price_pre[g] = pre;
   price_post[g] = post;
 }

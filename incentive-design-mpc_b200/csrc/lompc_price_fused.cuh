@@ -1,0 +1,223 @@
+// K5: the whole of PriceSolver.compute_optimal_prices (reference price_solver.py:79-174) for
+// one group (station, EV type, partition) in ONE CTA, device-resident from the warm start to
+// the regularised prices: no host round trip, no kernel launch and no global-memory traffic
+// per iteration.  Groups are independent (they couple only through the BiMPC plan they
+// track), so every CTA runs its own group to convergence; the grid is the set of groups.
+//
+// Per iteration (price_solver.py:111-140):
+//   * every thread solves the LoMPC QP of one EV of the group at the current prices (K1 as a
+//     device function, iterate in registers); one extra "virtual EV" solves the QP at
+//     gamma_sc (price_solver.py:106,132) in the same pass;
+//   * thread k < N adds up w_i[k] over the EVs IN EV ORDER (the reference's own summation
+//     order, price_solver.py:205 - bit-identical to the phase-split kernels);
+//   * thread 0 runs the convergence test, the exact non-negative QP of the price step
+//     (price_step_core) on shared-memory scratch, and the dual-cost bookkeeping.
+// The current price row lives in shared memory; EV data (one SoC per EV) is read once.
+#pragma once
+#include "lompc_common.cuh"
+#include "lompc_price.cuh"
+#include "lompc_solve_reg.cuh"
+
+namespace lompc {
+
+struct FusedArgs {
+  int G;
+  int r;
+  int tol_type_max;
+  double eps_reg, eps_tol;
+  int max_iter;            // MAX_PRICE_SOLVER_ITERATIONS
+  double qp_tol;           // K1 knobs
+  int qp_max_iter;
+  const int32_t* group_off;  // [G+1]
+  const double* y0;          // [B] SoCs, EVs sorted by group
+  const double* w_ref;       // [G,N]
+  const double* lmbd_r;      // [G]
+  double* prices;            // [G,3N] in: warm start, out: regularised prices
+  int32_t* iters;            // [G] value of `iter` at exit, -1 for an empty group
+  double* price_pre;         // [G]
+  double* price_post;        // [G]
+  double* w_k_out;           // [G,N] or NULL
+  double* hist_ac;           // [G,hist_cap] or NULL
+  double* hist_pred;
+  int hist_cap;
+  int32_t* flags;            // [0] += groups whose NNQP hit its iteration cap, [1] = some y0 outside [0, y_max],
+                             // [2] = max over groups of the LoMPC passes run (loop length of the slowest group)
+  unsigned long long* qp_count;  // total LoMPC QP solves (or NULL)
+};
+
+template <int N, int NSEG, int T, bool GREG>
+struct FusedSmem {
+  static constexpr int kK1 = RegSmem<N, NSEG, T, GREG>::kArrays * N * T;
+  // LM[3N] WREF[N] WK[N] WSUM[N] + NNQP scratch (2*3N + 6N) + ERR[T] + 8 scalars
+  static constexpr int kDoubles = kK1 + 3 * N + 3 * N + (6 * N + 6 * N) + T + 8;
+  static constexpr size_t bytes = (size_t)kDoubles * sizeof(double) + 3 * N + 16;
+};
+
+template <int N, int NSEG, int T, int MINB, bool GREG>
+__global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts cs, const FusedArgs a) {
+  extern __shared__ double smem[];
+  const int tid = threadIdx.x;
+  const int g = blockIdx.x;
+  const int b0 = a.group_off[g], b1 = a.group_off[g + 1];
+  const int n = b1 - b0;
+  if (n <= 0) {  // empty partition: never solved (charging_station.py:277,293); prices stay
+    if (tid == 0) a.iters[g] = -1;
+    return;
+  }
+  constexpr int kK1 = FusedSmem<N, NSEG, T, GREG>::kK1;
+  double* LM = smem + kK1;          // [3N] current prices
+  double* WREF = LM + 3 * N;        // [N]
+  double* WK = WREF + N;            // [N] LoMPC solution at gamma_sc for LM
+  double* WSUM = WK + N;            // [N]
+  double* WS = WSUM + N;            // NNQP scratch, 2r + 6N <= 12N doubles
+  double* ERR = WS + 12 * N;        // [T]
+  double* SC = ERR + T;             // scalars: 0 cost_sc, 1 flag
+  unsigned char* WSB = reinterpret_cast<unsigned char*>(SC + 8);  // [r]
+  double* WN = smem + 2 * N * T;    // K1's candidate array doubles as the [k][tid] transpose buffer
+
+  // ---- set_charge_levels (price_solver.py:66-77): exact min / max over the group
+  double mn = 1e300, mx = -1e300;
+  bool bad = false;
+  for (int i = tid; i < n; i += T) {
+    const double y = a.y0[b0 + i];
+    if (!(y >= 0.0 && y <= cs.y_max)) bad = true;
+    mn = fmin(mn, y);
+    mx = fmax(mx, y);
+  }
+  ERR[tid] = mn;
+  __syncthreads();
+  if (tid == 0) {
+    double v = ERR[0];
+    for (int i = 1; i < T; ++i) v = fmin(v, ERR[i]);
+    SC[2] = v;
+  }
+  __syncthreads();
+  ERR[tid] = mx;
+  __syncthreads();
+  if (tid == 0) {
+    double v = ERR[0];
+    for (int i = 1; i < T; ++i) v = fmax(v, ERR[i]);
+    SC[3] = v;
+  }
+  if (bad) atomicExch(a.flags + 1, 1);
+  for (int k = tid; k < 3 * N; k += T) LM[k] = a.prices[(size_t)g * 3 * N + k];
+  for (int k = tid; k < N; k += T) WREF[k] = a.w_ref[(size_t)g * N + k];
+  __syncthreads();
+  mn = SC[2];
+  mx = SC[3];
+  const double y0_rng = (mx - mn) / 2;
+  const double gamma_sc = cs.y_max - (mx + mn) / 2;
+  const double lr = a.lmbd_r[g];
+  const double kappa = lr / cs.delta;
+  const double tolg = sqrt((double)N) * y0_rng + a.eps_tol;  // price_solver.py:184
+
+  double dual_cost = 0.0, lamdiff = 0.0, dec_pred = 0.0;  // thread 0 only
+  int it = 0, nnqp_bad = 0;
+  unsigned long long solves = 0;
+  for (;; ++it) {
+    // ---- LoMPC pass at the current prices: EVs 0..n-1 and the virtual EV n (gamma_sc)
+    double wsum = 0.0, emax = 0.0;
+    for (int c0 = 0; c0 <= n; c0 += T) {
+      const int i = c0 + tid;
+      if (i <= n) {
+        const double gam = (i < n) ? cs.y_max - a.y0[b0 + i] : gamma_sc;
+        double W[N], D[N], GR[GREG ? N : 1];
+        double l2sum, gscale, viol;
+        int st, qit;
+        solve_reg<N, NSEG, T, GREG>(cs, LM, lr, gam, a.qp_tol, a.qp_max_iter, smem + tid, W, D, GR, l2sum, gscale,
+                                    viol, st, qit);
+        if (i < n) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) WN[k * T + tid] = W[k];
+          if (a.tol_type_max) {  // price_solver.py:207
+            double cum = 0.0, e2 = 0.0;
+#pragma unroll
+            for (int k = 0; k < N; ++k) {
+              const double v = W[k] - WREF[k];
+              cum += v;
+              e2 += cum * cum + kappa * v * v;
+            }
+            ERR[tid] = sqrt(e2);
+          }
+        } else {
+          // cost at gamma_sc = the dual cost (lompc.py:155: full objective incl. theta w_max sum(lmbd2))
+          const double* GS = smem + tid + 3 * N * T;
+          double cost = cs.theta * cs.w_max * l2sum, s = 0.0;
+#pragma unroll
+          for (int k = 0; k < N; ++k) {
+            const double x = W[k];
+            WK[k] = x;
+            s += x;
+            const double gk = GREG ? GR[GREG ? k : 0] : GS[k * T];
+            cost += x * fma(0.5 * D[k], x, gk) + 0.5 * cs.c * s * (s - 2.0 * gam);
+            if (NSEG > 1) {
+#pragma unroll
+              for (int j = 1; j < NSEG; ++j) cost += (cs.slope[j] - cs.slope[j - 1]) * fmax(x - cs.brk[j], 0.0);
+            }
+            LOMPC_STAGE_FENCE();
+          }
+          SC[0] = cost;
+        }
+      }
+      __syncthreads();
+      const int cnt = min(T, n - c0);  // real EVs in this chunk (may be <= 0 for the chunk holding only the virtual EV)
+      if (tid < N) {
+        const double* col = WN + tid * T;
+        for (int j = 0; j < cnt; ++j) wsum += col[j];
+      } else if (tid == N && a.tol_type_max) {
+        for (int j = 0; j < cnt; ++j) emax = fmax(emax, ERR[j]);
+        SC[4] = (c0 == 0) ? emax : fmax(SC[4], emax);
+      }
+      __syncthreads();
+    }
+    if (tid < N) WSUM[tid] = wsum;
+    solves += (unsigned long long)(tid == 0 ? n + 1 : 0);
+    __syncthreads();
+    // ---- thread 0: bookkeeping of the previous step, convergence test, price step
+    if (tid == 0) {
+      const double cost_sc = SC[0];
+      if (it > 0) {  // price_solver.py:135-139
+        if (a.hist_ac && it - 1 < a.hist_cap) {
+          a.hist_ac[(size_t)g * a.hist_cap + it - 1] = cost_sc - dual_cost + lamdiff;
+          a.hist_pred[(size_t)g * a.hist_cap + it - 1] = dec_pred;
+        }
+      }
+      dual_cost = cost_sc;
+      int flag = 0;
+      if (it >= a.max_iter) {
+        flag = 2;  // the loop ran out: `iter` ends at max_iter - 1 (price_solver.py:111)
+      } else {
+        double w_avg_err, w0_err;
+        price_errors(N, kappa, WSUM, (double)n, WREF, w_avg_err, w0_err);
+        const double w_err = a.tol_type_max ? SC[4] : w_avg_err;
+        if (w_err <= tolg) {
+          flag = 1;  // price_solver.py:125
+        } else {
+          int st;
+          price_step_core(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, 1, it == 0, lamdiff, dec_pred, st);
+          nnqp_bad |= st;
+        }
+      }
+      SC[1] = (double)flag;
+    }
+    __syncthreads();
+    if (SC[1] != 0.0) break;
+  }
+  // ---- regularisation (price_solver.py:145-147) and outputs
+  if (tid == 0) {
+    a.iters[g] = (SC[1] == 2.0) ? a.max_iter - 1 : it;
+    double pre, post;
+    regularize_core(cs, a.r, WK, LM, pre, post);
+    a.price_pre[g] = pre;
+    a.price_post[g] = post;
+    if (nnqp_bad) atomicAdd(a.flags, 1);
+    atomicMax(a.flags + 2, it);
+    if (a.qp_count) atomicAdd(a.qp_count, solves);
+  }
+  __syncthreads();
+  for (int k = tid; k < 3 * N; k += T) a.prices[(size_t)g * 3 * N + k] = LM[k];
+  if (a.w_k_out)
+    for (int k = tid; k < N; k += T) a.w_k_out[(size_t)g * N + k] = WK[k];
+}
+
+}  // namespace lompc

@@ -38,29 +38,23 @@ struct RegSmem {
   static constexpr size_t bytes = (size_t)kArrays * N * T * sizeof(double);
 };
 
-template <int N, int NSEG, int T, int MINB, bool GREG>
-__global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts cs, const SolveArgs a) {
-  extern __shared__ double smem[];
-  const int t = threadIdx.x;
-  const int64_t b = (int64_t)blockIdx.x * T + t;
-  if (b >= a.B) return;
-  double* KK = smem + t;
+// The solve itself: one QP per thread, iterate / diagonal / linear term in the caller's
+// registers.  `smem_t` = this thread's column of the CTA's shared-memory arrays (base + t).
+// `lm` may point to global or shared memory (the fused price loop keeps the group's price
+// row in shared memory).
+template <int N, int NSEG, int T, bool GREG>
+__device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, const double lr, const double gam,
+                                          const double tol, const int max_iter, double* smem_t, double (&W)[N],
+                                          double (&D)[N], double (&GR)[GREG ? N : 1], double& l2sum_out,
+                                          double& gscale_out, double& viol_out, int& st_out, int& it_out) {
+  double* KK = smem_t;
   double* KAP = KK + N * T;
   double* WN = KAP + N * T;
   double* GS = WN + N * T;                    // only when !GREG
   double* INV = GS + (GREG ? 0 : N * T);      // only when NSEG > 1
-  double GR[GREG ? N : 1];
 #define LOMPC_G(k) (GREG ? GR[GREG ? (k) : 0] : GS[(k) * T])
-
-  const int64_t row = a.group_of ? (int64_t)a.group_of[b] : b;
-  if (a.skip && a.skip[row]) return;
-  const double* lm = a.lmbd + row * a.lmbd_stride;
-  const double lr = a.lmbd_r[row * a.lmbd_r_stride];
-  const double gam = a.gamma[b];
   int st = LOMPC_ST_OK;
   if (gam < 0.0 || lr < 0.0) st = LOMPC_ST_NEGATIVE;
-
-  double W[N], D[N];
   double l2sum = 0.0, gmax = 0.0, dmax = 0.0;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
@@ -78,7 +72,7 @@ __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts c
   if (gam > cs.y_max) st = LOMPC_ST_BAD_GAMMA;
   const double c = cs.c, wmax = cs.w_max;
   const double gscale = fmax(1.0, gmax + c * N * cs.y_max);
-  const double tq = a.tol * gscale;
+  const double tq = tol * gscale;
   const double cg = c * gam;
   const double band = 1e-9 * wmax;
   const double ftol = 1e-15 * (c * N * cs.y_max * cs.y_max + N * wmax * (gmax + 0.5 * dmax * wmax + cs.slope[NSEG - 1]));
@@ -92,7 +86,7 @@ __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts c
   int it = 0;
   bool converged = (st != LOMPC_ST_OK);
 
-  for (; !converged && it < a.max_iter; ++it) {
+  for (; !converged && it < max_iter; ++it) {
     // ---------------- backward sweep ----------------
     // Riccati recursion in homogeneous form: P = pa/pb, r = pr/pb.  The numerators and
     // the denominator obey a LINEAR recurrence (2 dependent FMAs per stage); the one
@@ -219,6 +213,37 @@ __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts c
     }
   }
   if (!converged && st == LOMPC_ST_OK) st = LOMPC_ST_MAXITER;
+  l2sum_out = l2sum;
+  gscale_out = gscale;
+  viol_out = viol;
+  st_out = st;
+  it_out = it;
+#undef LOMPC_G
+}
+
+template <int N, int NSEG, int T, int MINB, bool GREG>
+__global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts cs, const SolveArgs a) {
+  extern __shared__ double smem[];
+  const int t = threadIdx.x;
+  const int64_t b = (int64_t)blockIdx.x * T + t;
+  if (b >= a.B) return;
+  const int64_t row = a.group_of ? (int64_t)a.group_of[b] : b;
+  if (a.skip && a.skip[row]) return;
+  const double* lm = a.lmbd + row * a.lmbd_stride;
+  const double lr = a.lmbd_r[row * a.lmbd_r_stride];
+  const double gam = a.gamma[b];
+  double W[N], D[N], GR[GREG ? N : 1];
+  double l2sum, gscale, viol;
+  int st, it;
+  solve_reg<N, NSEG, T, GREG>(cs, lm, lr, gam, a.tol, a.max_iter, smem + t, W, D, GR, l2sum, gscale, viol, st, it);
+  const double* GS = smem + t + 3 * N * T;
+#define LOMPC_G(k) (GREG ? GR[GREG ? (k) : 0] : GS[(k) * T])
+  const double c = cs.c, wmax = cs.w_max;
+  double slope[NSEG], brk[NSEG + 1];
+#pragma unroll
+  for (int i = 0; i <= NSEG; ++i) brk[i] = cs.brk[i];
+#pragma unroll
+  for (int j = 0; j < NSEG; ++j) slope[j] = cs.slope[j];
 
   // ---- outputs ----
   double cost = cs.theta * wmax * l2sum;

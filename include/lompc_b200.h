@@ -138,14 +138,20 @@ int price_lp_rows_dev(int device, int N, int nb, const double* a, const double* 
  * iters[G] = value of `iter` at exit; price_pre/post[G]; optional (NULL ok)
  * hist_ac/hist_pred[G,hist_cap] = dual_cost_decrease_actual/predicted per
  * iteration; w_k_out[G,N] = LoMPC solution at gamma_sc for the last
- * un-regularised prices.  Host loop with one poll per iteration; returns after
- * the stream has drained.  tol_type_max = 1 for settings "max", 0 for "avg". */
+ * un-regularised prices.  Returns after the stream has drained.  tol_type_max = 1 for settings "max", 0 for "avg". */
 int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, const double* y0,
                     const double* w_ref, const double* lmbd_r, int r, int max_iter,
                     int tol_type_max, double eps_reg, double eps_tol, double* prices,
                     int32_t* iters, double* price_pre, double* price_post, double* w_k_out,
                     double* hist_ac, double* hist_pred, int hist_cap, int32_t* total_iters,
                     void* stream);
+
+/* price_solve_dev runs, for the compiled horizons (N = 12, 24), ONE fused kernel with one
+ * CTA per group that iterates its group to convergence on the device (mode 0, default);
+ * mode 1 forces the phase-split loop below (any N; one host poll per iteration).  Both give
+ * bit-identical prices.  price_last_qp_solves = LoMPC QPs solved by the last fused call.  */
+int price_set_loop_mode(lompc_t* h, int mode);
+int64_t price_last_qp_solves(const lompc_t* h);
 
 /* The same loop cut into the phases between which a multi-GPU caller
  * all-reduces, for EVs sharded over ranks (each rank passes its LOCAL EVs and

@@ -1,0 +1,95 @@
+#!/usr/bin/env python
+"""BASELINE.json configs[3]: closed loop over S stations, device-resident (chargingstation.fleet).
+Prints one JSON line: per-step latency (CUDA events), p50/p95, price-loop iterations.
+
+    python tools/run_fleet.py --stations 4096 --steps 96 --chain reference
+"""
+import argparse
+import json
+import os
+import sys
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+for p in (ROOT, os.path.join(ROOT, "incentive-design-mpc_b200")):
+    if p not in sys.path:
+        sys.path.insert(0, p)
+
+
+def fleet_consts(steps, N_lo, N_bi, M, P):
+    from chargingstation import settings
+    from chargingstation.bimpc import BiMPCChargingCostType, BiMPCConstants
+    from chargingstation.charging_station import ChargingStationConstants
+    from chargingstation.demand_data import medium_term_demand_forecast
+    from chargingstation.lompc import LoMPCConstants
+    settings.PRINT_LEVEL = 0
+    dem = medium_term_demand_forecast(steps + N_bi + 1 + 24, 0.25) * (M / 500)
+    cb = BiMPCConstants(1e3, 1, 1, 0.3, 0.3, BiMPCChargingCostType.EXP_UNWEIGHTED, 5)
+    cs = LoMPCConstants(0.05, 10, 0.9, 0.25, "small")
+    cl = LoMPCConstants(0.025, 50, 0.9, 0.15, "large")
+    return ChargingStationConstants(steps, N_bi, N_lo, M, P, dem, cb, cs, cl, "linear-convex")
+
+
+def fleet_demand(consts, S, steps, N_bi, seed=4):
+    """per-station demand = the bundled profile scaled by U(0.22,0.28)/0.25
+    and circularly shifted by U{0..23} hours."""
+    rng = np.random.default_rng(seed)
+    L = steps + N_bi + 1
+    out = np.empty((S, L))
+    for s in range(S):
+        sh = int(rng.integers(24))
+        out[s] = consts.demand[sh:sh + L] * (rng.uniform(0.22, 0.28) / 0.25)
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--stations", type=int, default=64)
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--evs", type=int, default=500)
+    ap.add_argument("--partitions", type=int, default=12)
+    ap.add_argument("--n-lo", type=int, default=24)
+    ap.add_argument("--n-bi", type=int, default=24)
+    ap.add_argument("--chain", default="reference")
+    ap.add_argument("--max-price-iter", type=int, default=1000)
+    args = ap.parse_args()
+    import torch
+    from chargingstation.fleet import ChargingStationFleet
+    consts = fleet_consts(args.steps, args.n_lo, args.n_bi, args.evs, args.partitions)
+    demand = fleet_demand(consts, args.stations, args.steps, args.n_bi)
+    fleet = ChargingStationFleet(consts, args.stations, demand=demand, seed=4, rng="device", chain=args.chain,
+                                 max_price_iter=args.max_price_iter)
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    wall = []
+    for t in range(args.steps):
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        ev0[t].record()
+        fleet.step()
+        ev1[t].record()
+        torch.cuda.synchronize()
+        wall.append((time.perf_counter() - t0) * 1e3)
+    ms = np.array([a.elapsed_time(b) for a, b in zip(ev0, ev1)])
+    log = fleet.log
+    out = {"config": f"{args.stations} stations x ({args.evs}+{args.evs}) EVs, P={args.partitions}, N_lo={args.n_lo}, "
+                     f"N_bi={args.n_bi}, {args.steps} closed-loop steps, chain={args.chain}",
+           "step_ms_p50": float(np.median(ms)), "step_ms_p95": float(np.percentile(ms, 95)),
+           "step_ms_first": float(ms[0]), "step_ms_mean": float(ms.mean()), "wall_ms_p50": float(np.median(wall)),
+           "price_loop_iters_per_step": fleet.price_loop_iters,
+           "bimpc_iters_mean": float(log["bimpc_iters"].double().mean()),
+           "bimpc_failed": int((log["bimpc_status"] != 0).sum())}
+    for k in ("s", "l"):
+        ni = log[f"niter_{k}"].cpu().numpy()
+        mp = log[f"Mp_{k}"].cpu().numpy()
+        v = ni[mp > 0]
+        out[f"niter_{k}"] = {"mean": float(v.mean()), "p50": float(np.median(v)), "p95": float(np.percentile(v, 95)),
+                             "max": int(v.max()), "capped": int((v >= args.max_price_iter - 1).sum()),
+                             "groups": int(v.size)}
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()
