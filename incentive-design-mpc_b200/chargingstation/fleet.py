@@ -115,7 +115,8 @@ class ChargingStationFleet:
             self.log[f"Mp_{k}"] = z(Tf, P, S, dtype=i32)
         self.ncharged_logged = {k: z(S, dtype=i32) for k in ("s", "l")}
         self.price_loop_iters = []  # per step: total device-loop iterations of the price loops
-        self.qp_solves = 0
+        self.qp_solves = 0   # LoMPC QPs solved inside the price loops so far
+        self.cycles = [0, 0]  # SM cycles (summed over groups) in the LoMPC passes / the price steps
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -123,6 +124,11 @@ class ChargingStationFleet:
 
     def _ck(self, rc):
         _native.raise_for(rc)
+
+    def _account(self, h) -> None:
+        self.qp_solves += self._lib.price_last_qp_solves(h)
+        self.cycles[0] += self._lib.price_last_cycles(h, 0)
+        self.cycles[1] += self._lib.price_last_cycles(h, 1)
 
     # ------------------------------------------------------------------ one closed-loop step
     def step(self) -> None:
@@ -175,6 +181,7 @@ class ChargingStationFleet:
                             w["iters"][g0:].data_ptr(), w["pre"][g0:].data_ptr(), w["post"][g0:].data_ptr(), None,
                             None, None, 0, C.byref(total), st))
                         loop_iters += total.value
+                        self._account(h)
                     else:
                         w["iters"][g0:g0 + S].fill_(-1)
                     self._ck(lib.fleet_keep_prices_dev(
@@ -190,6 +197,7 @@ class ChargingStationFleet:
                     float(self.solver[k].eps_tol), self.prices[k].data_ptr(), w["iters"].data_ptr(),
                     w["pre"].data_ptr(), w["post"].data_ptr(), None, None, None, 0, C.byref(total), st))
                 loop_iters += total.value
+                self._account(h)
                 for p in range(P):  # price reduction / NaN for empty groups (prices keep the warm start)
                     g0 = p * S
                     self._ck(lib.fleet_keep_prices_dev(

@@ -65,6 +65,7 @@ struct lompc_handle {
   int variant;  // 0 auto, 1 = any-N shared-memory kernel, 2.. = register-kernel variants
   int loop_mode;  // price loop: 0 auto (fused one-CTA-per-group kernel when compiled for N), 1 = phase-split host loop
   unsigned long long last_qp_solves;  // LoMPC QPs solved by the last fused price loop
+  unsigned long long last_cycles[2];  // its SM cycles in the LoMPC passes / the price steps (summed over groups)
   void* pws;
   size_t pws_bytes;
   int32_t* poll;  // pinned host
@@ -227,6 +228,7 @@ int lompc_create(int N, double delta, double theta, double y_max, double w_max, 
   h->variant = 0;
   h->loop_mode = 0;
   h->last_qp_solves = 0;
+  h->last_cycles[0] = h->last_cycles[1] = 0;
   h->pws = nullptr;
   h->pws_bytes = 0;
   h->poll = nullptr;
@@ -269,6 +271,10 @@ int price_set_loop_mode(lompc_t* h, int mode) {
 }
 
 int64_t price_last_qp_solves(const lompc_t* h) { return h ? (int64_t)h->last_qp_solves : 0; }
+
+int64_t price_last_cycles(const lompc_t* h, int which) {
+  return (h && which >= 0 && which < 2) ? (int64_t)h->last_cycles[which] : 0;
+}
 
 int lompc_solve_batch_dev(lompc_t* h, int64_t B, const double* lmbd, int64_t lmbd_stride,
                           const double* lmbd_r, int64_t lmbd_r_stride, const double* gamma,
@@ -394,6 +400,7 @@ int ensure_pws(lompc_handle* h, size_t bytes) {
   h->variant = 0;
   h->loop_mode = 0;
   h->last_qp_solves = 0;
+  h->last_cycles[0] = h->last_cycles[1] = 0;
   h->pws = nullptr;
   h->pws_bytes = 0;
   const size_t want = bytes + bytes / 8;
@@ -548,7 +555,7 @@ int price_step_dev(lompc_t* h, int32_t G, int r, const double* w_ref, const doub
   p.w_ref = w_ref; p.lmbd_r = lmbd_r; p.y0_rng = y0r; p.lmbd = lmbd; p.w_k = const_cast<double*>(w_k);
   p.w_avg = w_avg; p.w_err_max = e1; p.w_avg_err = e2; p.w0_err = e3; p.lamdiff_phi = lamdiff;
   p.dec_pred = dual_decrease ? dual_decrease : decp; p.skip = skip; p.iters = iters;
-  p.nnqp_status = status ? status : nst; p.n_active = nact; p.ws = ws; p.wsb = wsb;
+  p.nnqp_status = status ? status : nst; p.n_active = nact; p.ws = ws; p.wsb = wsb; p.cold = 1;
   lompc::group_step_kernel<<<nblk(G, 64), 64, 0, s>>>(h->cs, p, 1);
   COUNT_LAUNCH();
   CK(cudaGetLastError());
@@ -764,7 +771,7 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
     int rc = ensure_pws(h, 256);
     if (rc) return rc;
     int32_t* flags = static_cast<int32_t*>(h->pws);
-    CK(cudaMemsetAsync(flags, 0, 32, s));
+    CK(cudaMemsetAsync(flags, 0, 64, s));
     const bool hist = hist_ac && hist_pred && hist_cap > 0;
     if (hist) {
       CK(cudaMemsetAsync(hist_ac, 0, (size_t)G * hist_cap * 8, s));
@@ -779,10 +786,12 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
     a.qp_count = reinterpret_cast<unsigned long long*>(flags + 4);
     rc = price_solve_fused(h, a, s);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h->poll, flags, 32, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->poll, flags, 64, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (total_iters) *total_iters = h->poll[2];
     h->last_qp_solves = *reinterpret_cast<unsigned long long*>(h->poll + 4);
+    h->last_cycles[0] = *reinterpret_cast<unsigned long long*>(h->poll + 6);
+    h->last_cycles[1] = *reinterpret_cast<unsigned long long*>(h->poll + 8);
     if (h->poll[1]) return LOMPC_ERR_CONSTS;  // y0 outside [0, y_max], price_solver.py:71
     return LOMPC_OK;
   }

@@ -34,6 +34,16 @@ struct Consts {
   double slope[kMaxSeg];
 };
 
+// Reciprocal of a positive, well-scaled double (Riccati pivots): MUFU.RCP64H seed + one cubic
+// Newton step, off the IEEE division's slow path.
+__device__ __forceinline__ double fast_rcp(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // ~2^-23 relative error
+  const double e = fma(-x, y, 1.0);
+  const double t = fma(e, e, e);  // one cubic step: error e^3 ~ 2^-69
+  return fma(y, t, y);
+}
+
 struct SolveArgs {
   int64_t B;
   const double* lmbd;

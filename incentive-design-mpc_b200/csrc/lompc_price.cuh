@@ -47,7 +47,8 @@ struct PriceArgs {
   double* hist_pred;         // [G,hist_cap] or NULL
   int hist_cap;
   double* ws;                // scratch, (2r + 6N) * G doubles
-  unsigned char* wsb;        // scratch, r * G bytes
+  unsigned char* wsb;        // scratch, r * G bytes (keeps the free set between iterations)
+  int cold;                  // 1: never warm-start the free set (stand-alone price_step_dev)
 };
 
 __global__ void group_of_kernel(int64_t B, int G, const int32_t* __restrict__ off, int32_t* __restrict__ group_of) {
@@ -155,7 +156,7 @@ __device__ __forceinline__ void ric_solve(int N, int G, const double* dvec, doub
   for (int k = N - 1; k >= 0; --k) {
     const double d = (dvec ? dvec[(size_t)k * G] : 0.0) + dadd;
     const double Q = c + P;
-    const double inv = 1.0 / (d + Q);
+    const double inv = fast_rcp(d + Q);
     const double gk = -bvec[(size_t)k * G];
     K[(size_t)k * G] = Q * inv;
     KAP[(size_t)k * G] = (r + gk) * inv;
@@ -181,7 +182,7 @@ __device__ __forceinline__ void ric_solve(int N, int G, const double* dvec, doub
 // with element stride `G` (global scratch interleaved over groups, or G = 1 in shared memory).
 __device__ __forceinline__ void price_step_core(const Consts& cs, int r, double kappa, double eps, double* lk,
                                                 const double* wk, const double* wr, double* ws,
-                                                unsigned char* wsb, size_t G, bool first, double& lamdiff_out,
+                                                unsigned char* wsb, size_t G, bool first, bool warm, double& lamdiff_out,
                                                 double& dec_pred_out, int& status_out) {
   const int N = cs.N;
   double* LAM = ws;                          // [r] new prices
@@ -215,13 +216,22 @@ __device__ __forceinline__ void price_step_core(const Consts& cs, int r, double 
       RHO[(size_t)(j * N + k) * G] = rho;
       gs = fmax(gs, fabs(rho));
       F0 += l * (Pl - 2.0 * rho);  // l'P l + q'l with q = -2 rho
-      FREE[(size_t)(j * N + k) * G] = (l > 0.0) || (dphi[j] > 0.0);  // half-gradient at l_k is -dphi/2
+      // cold start of the free set: half-gradient at l_k is -dphi/2; a warm start keeps the
+      // final free set of the previous price iteration (it rarely changes: one verification pass)
+      if (!warm) FREE[(size_t)(j * N + k) * G] = (l > 0.0) || (dphi[j] > 0.0);
     }
   }
-  // ---- primal-dual active set
+  // ---- primal-dual active set (the result depends only on the final free set, not on the start)
   int st = 1;
   double F1 = F0;
-  for (int pit = 0; pit < 64; ++pit) {
+  for (int pit = 0; pit < 96; ++pit) {
+    if (pit == 32 && warm) {  // a warm start that does not settle: restart cold
+      for (int k = 0; k < N; ++k) {
+        const double dw = wk[k] - wr[k];
+        const double dphi[3] = {th * dw, -th * dw, qs * (wk[k] * wk[k] - wr[k] * wr[k])};
+        for (int j = 0; j < nb; ++j) FREE[(size_t)(j * N + k) * G] = (lk[j * N + k] > 0.0) || (dphi[j] > 0.0);
+      }
+    }
     for (int k = 0; k < N; ++k) {
       const double coef[3] = {th, -th, C3[(size_t)k * G]};
       double t = 0.0, rhs = 0.0;
@@ -321,7 +331,7 @@ __global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
   double lamdiff, dec;
   int st;
   price_step_core(cs, r, kappa, p.eps_reg, p.lmbd + (size_t)g * 3 * N, p.w_k + (size_t)g * N,
-                  p.w_ref + (size_t)g * N, p.ws + g, p.wsb + g, (size_t)G, it == 0, lamdiff, dec, st);
+                  p.w_ref + (size_t)g * N, p.ws + g, p.wsb + g, (size_t)G, it == 0, it > 0 && !p.cold, lamdiff, dec, st);
   p.nnqp_status[g] = st;
   p.lamdiff_phi[g] = lamdiff;
   p.dec_pred[g] = dec;

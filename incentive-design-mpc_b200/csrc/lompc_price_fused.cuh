@@ -42,7 +42,8 @@ struct FusedArgs {
   int hist_cap;
   int32_t* flags;            // [0] += groups whose NNQP hit its iteration cap, [1] = some y0 outside [0, y_max],
                              // [2] = max over groups of the LoMPC passes run (loop length of the slowest group)
-  unsigned long long* qp_count;  // total LoMPC QP solves (or NULL)
+  unsigned long long* qp_count;  // [0] total LoMPC QP solves, [1] / [2] SM cycles summed over groups spent in
+                                 // the LoMPC passes / in thread 0's price step (or NULL)
 };
 
 template <int N, int NSEG, int T, bool GREG>
@@ -114,7 +115,9 @@ __global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts 
   double dual_cost = 0.0, lamdiff = 0.0, dec_pred = 0.0;  // thread 0 only
   int it = 0, nnqp_bad = 0;
   unsigned long long solves = 0;
+  long long cyc_qp = 0, cyc_step = 0;  // thread 0: cycles in the LoMPC passes / in the price step
   for (;; ++it) {
+    const long long t_a = clock64();
     // ---- LoMPC pass at the current prices: EVs 0..n-1 and the virtual EV n (gamma_sc)
     double wsum = 0.0, emax = 0.0;
     for (int c0 = 0; c0 <= n; c0 += T) {
@@ -175,6 +178,8 @@ __global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts 
     __syncthreads();
     // ---- thread 0: bookkeeping of the previous step, convergence test, price step
     if (tid == 0) {
+      const long long t_b = clock64();
+      cyc_qp += t_b - t_a;
       const double cost_sc = SC[0];
       if (it > 0) {  // price_solver.py:135-139
         if (a.hist_ac && it - 1 < a.hist_cap) {
@@ -194,11 +199,12 @@ __global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts 
           flag = 1;  // price_solver.py:125
         } else {
           int st;
-          price_step_core(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, 1, it == 0, lamdiff, dec_pred, st);
+          price_step_core(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, 1, it == 0, it > 0, lamdiff, dec_pred, st);
           nnqp_bad |= st;
         }
       }
       SC[1] = (double)flag;
+      cyc_step += clock64() - t_b;
     }
     __syncthreads();
     if (SC[1] != 0.0) break;
@@ -212,7 +218,11 @@ __global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts 
     a.price_post[g] = post;
     if (nnqp_bad) atomicAdd(a.flags, 1);
     atomicMax(a.flags + 2, it);
-    if (a.qp_count) atomicAdd(a.qp_count, solves);
+    if (a.qp_count) {
+      atomicAdd(a.qp_count, solves);
+      atomicAdd(a.qp_count + 1, (unsigned long long)cyc_qp);
+      atomicAdd(a.qp_count + 2, (unsigned long long)cyc_step);
+    }
   }
   __syncthreads();
   for (int k = tid; k < 3 * N; k += T) a.prices[(size_t)g * 3 * N + k] = LM[k];

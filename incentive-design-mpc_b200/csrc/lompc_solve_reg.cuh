@@ -17,15 +17,6 @@
 
 namespace lompc {
 
-__device__ __forceinline__ double fast_rcp(double x) {
-  // x is a Riccati pivot d + c + P in [c, 1e6]: no denormals / infinities to guard.
-  double y;
-  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));  // ~2^-23 relative error
-  const double e = fma(-x, y, 1.0);
-  const double t = fma(e, e, e);  // one cubic step: error e^3 ~ 2^-69
-  return fma(y, t, y);
-}
-
 // Keeps the shared-memory loads of one unrolled stage inside that stage: without it the
 // compiler hoists all 3N loads of a sweep to its top and spills ~60 doubles per thread.
 #define LOMPC_STAGE_FENCE() asm volatile("" ::: "memory")

@@ -152,6 +152,8 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
  * bit-identical prices.  price_last_qp_solves = LoMPC QPs solved by the last fused call.  */
 int price_set_loop_mode(lompc_t* h, int mode);
 int64_t price_last_qp_solves(const lompc_t* h);
+/* SM cycles of the last fused call summed over groups: which = 0 LoMPC passes, 1 price steps. */
+int64_t price_last_cycles(const lompc_t* h, int which);
 
 /* The same loop cut into the phases between which a multi-GPU caller
  * all-reduces, for EVs sharded over ranks (each rank passes its LOCAL EVs and

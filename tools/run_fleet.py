@@ -80,7 +80,9 @@ def main():
            "step_ms_first": float(ms[0]), "step_ms_mean": float(ms.mean()), "wall_ms_p50": float(np.median(wall)),
            "price_loop_iters_per_step": fleet.price_loop_iters,
            "bimpc_iters_mean": float(log["bimpc_iters"].double().mean()),
-           "bimpc_failed": int((log["bimpc_status"] != 0).sum())}
+           "bimpc_failed": int((log["bimpc_status"] != 0).sum()),
+           "price_loop_qp_solves": int(fleet.qp_solves), "qp_solves_per_s": fleet.qp_solves / (ms.sum() * 1e-3),
+           "cycles_lompc_passes": fleet.cycles[0], "cycles_price_steps": fleet.cycles[1]}
     for k in ("s", "l"):
         ni = log[f"niter_{k}"].cpu().numpy()
         mp = log[f"Mp_{k}"].cpu().numpy()
