@@ -40,13 +40,13 @@ int cuda_fail(cudaError_t e, const char* what) { return ::cuda_fail(e, what); }
 
 struct PriceSession {  // state of one (possibly sharded) compute_optimal_prices run
   bool active = false;
-  int G = 0, max_iter = 0;
+  int G = 0, max_iter = 0, ev_passes = 0;
   int64_t B = 0;
   const int32_t* group_off = nullptr;
   int32_t *group_of = nullptr, *skip = nullptr, *nst = nullptr, *nact = nullptr, *empty = nullptr;
   double *gamma = nullptr, *w_ev = nullptr, *err_ev = nullptr, *y0_rng = nullptr, *gamma_sc = nullptr,
          *gamma_sm = nullptr, *w_k = nullptr, *e_avg = nullptr, *e_0 = nullptr, *dual_cost = nullptr,
-         *cost_new = nullptr, *lamdiff = nullptr, *decp = nullptr, *ws = nullptr;
+         *cost_new = nullptr, *lamdiff = nullptr, *decp = nullptr;
   unsigned char* wsb = nullptr;
   double *stat_min = nullptr, *stat_max = nullptr, *stat_sum = nullptr, *stat_cnt = nullptr;
   lompc::PriceArgs p;
@@ -305,6 +305,7 @@ int lompc_solve_batch_dev(lompc_t* h, int64_t B, const double* lmbd, int64_t lmb
   a.err_out = nullptr;
   a.w0_out = nullptr;
   a.price0_out = nullptr;
+  a.w_init = nullptr;
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   return h->cs.large ? launch_solve<4>(h, a, s) : launch_solve<1>(h, a, s);
 }
@@ -413,7 +414,7 @@ int ensure_pws(lompc_handle* h, size_t bytes) {
 int launch_group_solve(const lompc_handle* h, int64_t B, const double* lmbd, const double* lmbd_r,
                        const double* gamma, const int32_t* group_of, const int32_t* skip,
                        const double* w_ref, double* w_out, double* cost_out, double* err_out,
-                       double* w0_out, double* price0_out, cudaStream_t s) {
+                       double* w0_out, double* price0_out, cudaStream_t s, const double* w_init = nullptr) {
   if (B == 0) return LOMPC_OK;
   lompc::SolveArgs a;
   a.B = B;
@@ -435,10 +436,24 @@ int launch_group_solve(const lompc_handle* h, int64_t B, const double* lmbd, con
   a.err_out = err_out;
   a.w0_out = w0_out;
   a.price0_out = price0_out;
+  a.w_init = w_init;
   return h->cs.large ? launch_solve<4>(h, a, s) : launch_solve<1>(h, a, s);
 }
 
 inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
+
+// group_step_kernel: one warp per group, 2 warps per CTA, scratch in dynamic shared memory
+int launch_group_step(const lompc_handle* h, const lompc::PriceArgs& p, int it, cudaStream_t s) {
+  const int N = h->cs.N, wpc = 2;
+  const size_t smem = (size_t)wpc * (lompc::price_step_scratch_doubles(N, p.r) + (p.r + 7) / 8) * sizeof(double);
+  if (smem > 48 * 1024) {
+    CK(cudaFuncSetAttribute(lompc::group_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  }
+  lompc::group_step_kernel<<<nblk(p.G, wpc), 32 * wpc, smem, s>>>(h->cs, p, it);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  return LOMPC_OK;
+}
 #define COUNT_LAUNCH() g_launches.fetch_add(1, std::memory_order_relaxed)
 
 }  // namespace
@@ -511,10 +526,7 @@ int price_w_err_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off,
   p.group_off = group_off; p.w_ref = w_ref; p.lmbd_r = lmbd_r; p.y0_rng = y0r;
   p.w_avg = wa; p.w_err_max = em; p.w_avg_err = w_avg_err ? w_avg_err : t_eavg;
   p.w0_err = w0_err ? w0_err : t_e0; p.skip = skip; p.iters = iters; p.nnqp_status = nst; p.n_active = nact;
-  lompc::group_step_kernel<<<nblk(G, 64), 64, 0, s>>>(h->cs, p, 0);
-  COUNT_LAUNCH();
-  CK(cudaGetLastError());
-  return LOMPC_OK;
+  return launch_group_step(h, p, 0, s);
 }
 
 int price_step_dev(lompc_t* h, int32_t G, int r, const double* w_ref, const double* w_k,
@@ -529,7 +541,7 @@ int price_step_dev(lompc_t* h, int32_t G, int r, const double* w_ref, const doub
   Carver sz(nullptr);
   sz.take<double>((size_t)G * N); sz.take<double>(G); sz.take<double>(G); sz.take<double>(G); sz.take<double>(G);
   sz.take<double>(G); sz.take<double>(G); sz.take<int32_t>(G); sz.take<int32_t>(G); sz.take<int32_t>(G);
-  sz.take<int32_t>(1); sz.take<double>((size_t)(2 * r + 6 * N) * G); sz.take<unsigned char>((size_t)r * G);
+  sz.take<int32_t>(1); sz.take<unsigned char>((size_t)r * G);
   int rc = ensure_pws(h, sz.off);
   if (rc) return rc;
   Carver cv(h->pws);
@@ -544,7 +556,6 @@ int price_step_dev(lompc_t* h, int32_t G, int r, const double* w_ref, const doub
   int32_t* iters = cv.take<int32_t>(G);
   int32_t* nst = cv.take<int32_t>(G);
   int32_t* nact = cv.take<int32_t>(1);
-  double* ws = cv.take<double>((size_t)(2 * r + 6 * N) * G);
   unsigned char* wsb = cv.take<unsigned char>((size_t)r * G);
   CK(cudaMemsetAsync(skip, 0, (size_t)G * 4, s));
   // force the step: w_avg = +huge so that the error test never passes
@@ -555,11 +566,8 @@ int price_step_dev(lompc_t* h, int32_t G, int r, const double* w_ref, const doub
   p.w_ref = w_ref; p.lmbd_r = lmbd_r; p.y0_rng = y0r; p.lmbd = lmbd; p.w_k = const_cast<double*>(w_k);
   p.w_avg = w_avg; p.w_err_max = e1; p.w_avg_err = e2; p.w0_err = e3; p.lamdiff_phi = lamdiff;
   p.dec_pred = dual_decrease ? dual_decrease : decp; p.skip = skip; p.iters = iters;
-  p.nnqp_status = status ? status : nst; p.n_active = nact; p.ws = ws; p.wsb = wsb; p.cold = 1;
-  lompc::group_step_kernel<<<nblk(G, 64), 64, 0, s>>>(h->cs, p, 1);
-  COUNT_LAUNCH();
-  CK(cudaGetLastError());
-  return LOMPC_OK;
+  p.nnqp_status = status ? status : nst; p.n_active = nact; p.wsb = wsb; p.cold = 1; p.want_dec = 1;
+  return launch_group_step(h, p, 1, s);
 }
 
 int price_regularize_dev(lompc_t* h, int32_t G, int r, const double* w_k, double* lmbd,
@@ -602,7 +610,7 @@ int price_shard_begin(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off
     S.cost_new = cv.take<double>(G); S.lamdiff = cv.take<double>(G); S.decp = cv.take<double>(G);
     S.skip = cv.take<int32_t>(G); S.nst = cv.take<int32_t>(G); S.nact = cv.take<int32_t>(4);
     S.empty = cv.take<int32_t>(G);
-    S.ws = cv.take<double>((size_t)(2 * r + 6 * N) * G); S.wsb = cv.take<unsigned char>((size_t)r * G);
+    S.wsb = cv.take<unsigned char>((size_t)r * G);
   };
   Carver sz(nullptr);
   carve(sz);
@@ -619,7 +627,7 @@ int price_shard_begin(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off
   p.dual_cost = S.dual_cost; p.cost_new = S.cost_new; p.lamdiff_phi = S.lamdiff; p.dec_pred = S.decp;
   p.skip = S.skip; p.iters = iters; p.nnqp_status = S.nst; p.n_active = S.nact;
   p.hist_ac = (hist_ac && hist_pred && hist_cap > 0) ? hist_ac : nullptr;
-  p.hist_pred = hist_pred; p.hist_cap = hist_cap; p.ws = S.ws; p.wsb = S.wsb;
+  p.hist_pred = hist_pred; p.hist_cap = hist_cap; p.wsb = S.wsb;
   CK(cudaMemsetAsync(S.nact, 0, 16, s));
   if (B > 0) {
     lompc::group_of_kernel<<<nblk(B, 256), 256, 0, s>>>(B, G, group_off, S.group_of);
@@ -661,9 +669,12 @@ int price_shard_ev_phase(lompc_t* h, void* stream) {
   const int N = h->cs.N;
   const bool need_err = S.p.tol_type_max != 0;
   // _get_w_err (price_solver.py:112,196-214): the EV solves and the per-group column sums
+  // (from the second pass on every QP starts from its solution at the previous prices)
   int rc = launch_group_solve(h, S.B, S.p.lmbd, S.p.lmbd_r, S.gamma, S.group_of, S.skip, S.p.w_ref, S.w_ev,
-                              nullptr, need_err ? S.err_ev : nullptr, nullptr, nullptr, s);
+                              nullptr, need_err ? S.err_ev : nullptr, nullptr, nullptr, s,
+                              S.ev_passes > 0 ? S.w_ev : nullptr);
   if (rc) return rc;
+  ++S.ev_passes;
   lompc::colsum_kernel<<<nblk((int64_t)S.G * N, 128), 128, 0, s>>>(N, S.G, S.group_off, S.skip, S.w_ev,
                                                                   need_err ? S.err_ev : nullptr, S.p.w_avg,
                                                                   S.p.w_err_max, 1);
@@ -680,8 +691,10 @@ int price_shard_group_phase(lompc_t* h, int it, int32_t* n_active, void* stream)
   CK(cudaSetDevice(h->device));
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   CK(cudaMemsetAsync(S.nact, 0, 4, s));
-  lompc::group_step_kernel<<<nblk(S.G, 64), 64, 0, s>>>(h->cs, S.p, it);
-  COUNT_LAUNCH();
+  {
+    int rc0 = launch_group_step(h, S.p, it, s);
+    if (rc0) return rc0;
+  }
   CK(cudaMemcpyAsync(h->poll, S.nact, 8, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
   if (h->poll[1]) return LOMPC_ERR_CONSTS;  // y0 outside [0, y_max], price_solver.py:71
@@ -689,7 +702,7 @@ int price_shard_group_phase(lompc_t* h, int it, int32_t* n_active, void* stream)
   if (h->poll[0] == 0) return LOMPC_OK;
   // w_k, dual_cost_new = solve_lompc(lmbd_k_new, lmbd_r, gamma_sc)   (price_solver.py:132)
   int rc = launch_group_solve(h, S.G, S.p.lmbd, S.p.lmbd_r, S.gamma_sc, nullptr, S.skip, nullptr, S.w_k,
-                              S.cost_new, nullptr, nullptr, nullptr, s);
+                              S.cost_new, nullptr, nullptr, nullptr, s, S.w_k);
   if (rc) return rc;
   lompc::bookkeep_kernel<<<nblk(S.G, 128), 128, 0, s>>>(S.p, it);
   COUNT_LAUNCH();
@@ -768,7 +781,7 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
     // fused, device-resident loop: one CTA per group (lompc_price_fused.cuh)
     if ((r != 2 * h->cs.N && r != 3 * h->cs.N) || max_iter < 1) return LOMPC_ERR_ARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int rc = ensure_pws(h, 256);
+    int rc = ensure_pws(h, 256 + (size_t)(B + G) * h->cs.N * sizeof(double));
     if (rc) return rc;
     int32_t* flags = static_cast<int32_t*>(h->pws);
     CK(cudaMemsetAsync(flags, 0, 64, s));
@@ -784,6 +797,8 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
     a.price_post = price_post; a.w_k_out = w_k_out; a.hist_ac = hist ? hist_ac : nullptr; a.hist_pred = hist_pred;
     a.hist_cap = hist_cap; a.flags = flags;
     a.qp_count = reinterpret_cast<unsigned long long*>(flags + 4);
+    a.w_scratch = reinterpret_cast<double*>(static_cast<char*>(h->pws) + 256);
+    a.B = B;
     rc = price_solve_fused(h, a, s);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->poll, flags, 64, cudaMemcpyDeviceToHost, s));

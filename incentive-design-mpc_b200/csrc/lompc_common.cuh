@@ -65,6 +65,8 @@ struct SolveArgs {
   double* err_out;          // [B] sqrt((w-w_ref)' (A'A + lmbd_r/delta I) (w-w_ref)), price_solver.py:207
   double* w0_out;           // [B] first-step charge w[0]
   double* price0_out;       // [B] LoMPC.get_price0 (lompc.py:164-170)
+  const double* w_init;     // [B,N] feasible starting points (the previous solutions of the price loop;
+                            // register kernel only) or NULL: start from w = 0
 };
 
 }  // namespace lompc

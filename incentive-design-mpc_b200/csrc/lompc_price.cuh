@@ -46,9 +46,9 @@ struct PriceArgs {
   double* hist_ac;           // [G,hist_cap] or NULL
   double* hist_pred;         // [G,hist_cap] or NULL
   int hist_cap;
-  double* ws;                // scratch, (2r + 6N) * G doubles
   unsigned char* wsb;        // scratch, r * G bytes (keeps the free set between iterations)
   int cold;                  // 1: never warm-start the free set (stand-alone price_step_dev)
+  int want_dec;              // 1: compute dec_pred even without a history buffer
 };
 
 __global__ void group_of_kernel(int64_t B, int G, const int32_t* __restrict__ off, int32_t* __restrict__ group_of) {
@@ -148,149 +148,186 @@ __global__ void colsum_kernel(int N, int G, const int32_t* __restrict__ off, con
   }
 }
 
-// x = (diag(d) + c A'A)^{-1} b by the scalar Riccati recursion (A = tril(ones)).
-// d_k = dvec[k*G] (+ dadd).  K/KAP are scratch; all vectors are strided by G.
-__device__ __forceinline__ void ric_solve(int N, int G, const double* dvec, double dadd, double c,
-                                          const double* bvec, double* x, double* K, double* KAP) {
-  double P = 0.0, r = 0.0;
+// x = (diag(d) + c A'A)^{-1} b by the scalar Riccati recursion (A = tril(ones)), by ONE thread
+// on contiguous vectors.  d_k = dvec[k] (+ dadd).  K/KAP are scratch.  Homogeneous form of the
+// recursion (P = pa/pb, r = pr/pb): two dependent FMAs per stage, the reciprocal off the chain.
+__device__ __forceinline__ void ric_solve(int N, const double* dvec, double dadd, double c, const double* bvec,
+                                          double* x, double* K, double* KAP) {
+  double pa = 0.0, pb = 1.0, pr = 0.0;
   for (int k = N - 1; k >= 0; --k) {
-    const double d = (dvec ? dvec[(size_t)k * G] : 0.0) + dadd;
-    const double Q = c + P;
-    const double inv = fast_rcp(d + Q);
-    const double gk = -bvec[(size_t)k * G];
-    K[(size_t)k * G] = Q * inv;
-    KAP[(size_t)k * G] = (r + gk) * inv;
-    P = Q * d * inv;
-    r = (d * r - Q * gk) * inv;
+    const double d = (dvec ? dvec[k] : 0.0) + dadd;
+    const double gk = -bvec[k];
+    const double tq = fma(c, pb, pa);   // Q pb,  Q = c + P
+    const double bn = fma(d, pb, tq);   // (d + Q) pb
+    const double ib = fast_rcp(bn);
+    K[k] = tq * ib;                     // Q / (d + Q)
+    KAP[k] = fma(gk, pb, pr) * ib;      // (r + g_k) / (d + Q)
+    pa = d * tq;                        // P <- Q d / (d + Q)
+    pr = fma(d, pr, -tq * gk);          // r <- (d r - Q g_k) / (d + Q)
+    pb = bn;
+    if ((k & 7) == 0 && pb > 0x1p600) {  // keep the homogeneous triple in range (exact rescale)
+      pa *= 0x1p-600;
+      pb *= 0x1p-600;
+      pr *= 0x1p-600;
+    }
   }
   double s = 0.0;
   for (int k = 0; k < N; ++k) {
-    const double xk = -fma(K[(size_t)k * G], s, KAP[(size_t)k * G]);
-    x[(size_t)k * G] = xk;
+    const double xk = -fma(K[k], s, KAP[k]);
+    x[k] = xk;
     s += xk;
   }
 }
 
+// Scratch of one price step: (3r + 6N) doubles.
+__host__ __device__ inline int price_step_scratch_doubles(int N, int r) { return 3 * r + 6 * N; }
+
 // The exact solution of the non-negative QP of the price step
 //     min_{l >= 0} l'P l + q'l,  P = Dphi A_bar^{-1} Dphi'/(2m) + eps I,  q = -2 P l_k - (phi(w_k) - phi(w_ref))
-// (price_solver.py:216-246) by a primal-dual active-set iteration, for ONE group by ONE thread.
-// P is never formed: with B = Dphi[:r] (three diagonals) the free-set system is solved through
-// Woodbury,
+// (price_solver.py:216-246) by a primal-dual active-set iteration, for ONE group by ONE WARP
+// (every lane of the warp must call; lanes stride over the horizon, lane 0 runs the O(N)
+// Riccati recursions).  P is never formed: with B = Dphi[:r] (three diagonals) the free-set
+// system is solved through Woodbury,
 //     l_F = (rho_F - B_F z)/eps,   (2 m eps A_bar + B_F'B_F) z = B_F' rho_F,   rho = -q/2,
 // and A_bar = A'A + kappa I makes that an O(N) Riccati solve like the LoMPC's own.
-// lk[3N] (contiguous) is updated in place; ws / wsb = scratch of (2r + 6N) doubles / r bytes
-// with element stride `G` (global scratch interleaved over groups, or G = 1 in shared memory).
-__device__ __forceinline__ void price_step_core(const Consts& cs, int r, double kappa, double eps, double* lk,
+// lk[3N] is updated in place; ws = price_step_scratch_doubles() doubles and FREE = r bytes of
+// (shared-memory) scratch private to the warp.  FREE carries the free set from one price
+// iteration to the next (`warm`): the result depends only on the FINAL free set, and that
+// rarely changes between iterations, so a warm start costs one verification pass.  Sums that
+// feed statistics are taken by lane 0 in (k, j) order, so the result does not depend on the
+// number of lanes.
+__device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double kappa, double eps, double* lk,
                                                 const double* wk, const double* wr, double* ws,
-                                                unsigned char* wsb, size_t G, bool first, bool warm, double& lamdiff_out,
-                                                double& dec_pred_out, int& status_out) {
+                                                unsigned char* FREE, int lane, bool first, bool warm,
+                                                bool need_dec, double& lamdiff_out, double& dec_pred_out,
+                                                int& status_out) {
   const int N = cs.N;
-  double* LAM = ws;                          // [r] new prices
-  double* RHO = LAM + (size_t)r * G;         // [r]
-  double* C3 = RHO + (size_t)r * G;          // [N] third diagonal of Dphi': 2 q w_k
-  double* KS = C3 + (size_t)N * G;           // [N]
-  double* KAPS = KS + (size_t)N * G;         // [N]
-  double* U = KAPS + (size_t)N * G;          // [N]
-  double* V = U + (size_t)N * G;             // [N]
-  double* TD = V + (size_t)N * G;            // [N]
-  unsigned char* FREE = wsb;                 // [r]
-  const int nb = r / N;                      // 2 or 3 price blocks
+  double* LAM = ws;        // [r] new prices
+  double* RHO = LAM + r;   // [r]
+  double* TERM = RHO + r;  // [r] summands of the ordered sums
+  double* C3 = TERM + r;   // [N] third diagonal of Dphi': 2 q w_k
+  double* KS = C3 + N;     // [N]
+  double* KAPS = KS + N;   // [N]
+  double* U = KAPS + N;    // [N]
+  double* V = U + N;       // [N]
+  double* TD = V + N;      // [N]
+  const int nb = r / N;    // 2 or 3 price blocks
   const double th = cs.theta, qs = cs.q_scale, m = cs.c;
+  const unsigned full = 0xffffffffu;
+  auto ordered_sum = [&](void) {  // lane 0: sum of TERM in (k, j) order
+    double acc = 0.0;
+    if (lane == 0)
+      for (int k = 0; k < N; ++k)
+        for (int j = 0; j < nb; ++j) acc += TERM[j * N + k];
+    return acc;
+  };
   // u = B' l_k ; v = A_bar^{-1} u ; rho = P l_k + (phi(w_k) - phi(w_ref))/2
-  for (int k = 0; k < N; ++k) {
+  for (int k = lane; k < N; k += 32) {
     const double c3 = 2.0 * qs * wk[k];
-    C3[(size_t)k * G] = c3;
-    U[(size_t)k * G] = th * (lk[k] - lk[N + k]) + (nb == 3 ? c3 * lk[2 * N + k] : 0.0);
+    C3[k] = c3;
+    U[k] = th * (lk[k] - lk[N + k]) + (nb == 3 ? c3 * lk[2 * N + k] : 0.0);
   }
-  ric_solve(N, G, nullptr, kappa, 1.0, U, V, KS, KAPS);
-  double gs = 1.0, F0 = 0.0, lamdiff = 0.0;
-  for (int k = 0; k < N; ++k) {
-    const double v = V[(size_t)k * G] / (2.0 * m);
+  __syncwarp();
+  if (lane == 0) ric_solve(N, nullptr, kappa, 1.0, U, V, KS, KAPS);
+  __syncwarp();
+  double gs = 1.0;
+  for (int k = lane; k < N; k += 32) {
+    const double v = V[k] / (2.0 * m);
     const double dw = wk[k] - wr[k];
     const double dphi[3] = {th * dw, -th * dw, qs * (wk[k] * wk[k] - wr[k] * wr[k])};
-    const double coef[3] = {th, -th, C3[(size_t)k * G]};
+    const double coef[3] = {th, -th, C3[k]};
     for (int j = 0; j < nb; ++j) {
       const double l = lk[j * N + k];
       const double Pl = eps * l + coef[j] * v;
       const double rho = Pl + 0.5 * dphi[j];
-      RHO[(size_t)(j * N + k) * G] = rho;
+      RHO[j * N + k] = rho;
       gs = fmax(gs, fabs(rho));
-      F0 += l * (Pl - 2.0 * rho);  // l'P l + q'l with q = -2 rho
-      // cold start of the free set: half-gradient at l_k is -dphi/2; a warm start keeps the
-      // final free set of the previous price iteration (it rarely changes: one verification pass)
-      if (!warm) FREE[(size_t)(j * N + k) * G] = (l > 0.0) || (dphi[j] > 0.0);
+      TERM[j * N + k] = l * (Pl - 2.0 * rho);  // l'P l + q'l with q = -2 rho
+      // cold start of the free set: the half-gradient at l_k is -dphi/2
+      if (!warm) FREE[j * N + k] = (l > 0.0) || (dphi[j] > 0.0);
     }
   }
-  // ---- primal-dual active set (the result depends only on the final free set, not on the start)
+  for (int o = 16; o > 0; o >>= 1) gs = fmax(gs, __shfl_xor_sync(full, gs, o));
+  __syncwarp();
+  const double F0 = need_dec ? ordered_sum() : 0.0;
+  // ---- primal-dual active set
   int st = 1;
-  double F1 = F0;
   for (int pit = 0; pit < 96; ++pit) {
     if (pit == 32 && warm) {  // a warm start that does not settle: restart cold
-      for (int k = 0; k < N; ++k) {
+      for (int k = lane; k < N; k += 32) {
         const double dw = wk[k] - wr[k];
         const double dphi[3] = {th * dw, -th * dw, qs * (wk[k] * wk[k] - wr[k] * wr[k])};
-        for (int j = 0; j < nb; ++j) FREE[(size_t)(j * N + k) * G] = (lk[j * N + k] > 0.0) || (dphi[j] > 0.0);
+        for (int j = 0; j < nb; ++j) FREE[j * N + k] = (lk[j * N + k] > 0.0) || (dphi[j] > 0.0);
       }
     }
-    for (int k = 0; k < N; ++k) {
-      const double coef[3] = {th, -th, C3[(size_t)k * G]};
+    for (int k = lane; k < N; k += 32) {
+      const double coef[3] = {th, -th, C3[k]};
       double t = 0.0, rhs = 0.0;
       for (int j = 0; j < nb; ++j)
-        if (FREE[(size_t)(j * N + k) * G]) {
+        if (FREE[j * N + k]) {
           t += coef[j] * coef[j];
-          rhs += coef[j] * RHO[(size_t)(j * N + k) * G];
+          rhs += coef[j] * RHO[j * N + k];
         }
-      TD[(size_t)k * G] = t;
-      U[(size_t)k * G] = rhs;
+      TD[k] = t;
+      U[k] = rhs;
     }
-    ric_solve(N, G, TD, 2.0 * m * eps * kappa, 2.0 * m * eps, U, V, KS, KAPS);  // z
-    for (int k = 0; k < N; ++k) {
-      const double coef[3] = {th, -th, C3[(size_t)k * G]};
-      const double z = V[(size_t)k * G];
+    __syncwarp();
+    if (lane == 0) ric_solve(N, TD, 2.0 * m * eps * kappa, 2.0 * m * eps, U, V, KS, KAPS);  // z
+    __syncwarp();
+    for (int k = lane; k < N; k += 32) {
+      const double coef[3] = {th, -th, C3[k]};
+      const double z = V[k];
       double u = 0.0;
       for (int j = 0; j < nb; ++j) {
-        const size_t i = (size_t)(j * N + k) * G;
+        const int i = j * N + k;
         const double l = FREE[i] ? (RHO[i] - coef[j] * z) / eps : 0.0;
         LAM[i] = l;
         u += coef[j] * l;
       }
-      U[(size_t)k * G] = u;
+      U[k] = u;
     }
-    ric_solve(N, G, nullptr, kappa, 1.0, U, V, KS, KAPS);  // v = A_bar^{-1} B' l
+    __syncwarp();
+    if (lane == 0) ric_solve(N, nullptr, kappa, 1.0, U, V, KS, KAPS);  // v = A_bar^{-1} B' l
+    __syncwarp();
     bool same = true;
-    F1 = 0.0;
-    for (int k = 0; k < N; ++k) {
-      const double coef[3] = {th, -th, C3[(size_t)k * G]};
-      const double v = V[(size_t)k * G] / (2.0 * m);
+    for (int k = lane; k < N; k += 32) {
+      const double coef[3] = {th, -th, C3[k]};
+      const double v = V[k] / (2.0 * m);
       for (int j = 0; j < nb; ++j) {
-        const size_t i = (size_t)(j * N + k) * G;
+        const int i = j * N + k;
         const double l = LAM[i];
         const double Pl = eps * l + coef[j] * v;
         const double hg = Pl - RHO[i];  // half gradient
-        F1 += l * (Pl - 2.0 * RHO[i]);
+        TERM[i] = l * (Pl - 2.0 * RHO[i]);
         const bool fr = FREE[i];
         const bool nf = fr ? (l > 0.0) : (hg < -1e-12 * gs);
         if (nf != fr) same = false;
         FREE[i] = nf;
       }
     }
+    same = __all_sync(full, same);
+    __syncwarp();
     if (same) {
       st = 0;
       break;
     }
   }
+  const double F1 = need_dec ? ordered_sum() : 0.0;
+  __syncwarp();
   // ---- write back (price_solver.py:129,135-140)
-  for (int k = 0; k < N; ++k) {
+  for (int k = lane; k < N; k += 32) {
     const double phir[3] = {th * wr[k], th * (cs.w_max - wr[k]), qs * wr[k] * wr[k]};
     for (int j = 0; j < nb; ++j) {
-      const double ln = fmax(LAM[(size_t)(j * N + k) * G], 0.0);
-      if (first) lamdiff += (lk[j * N + k] - ln) * phir[j];
+      const double ln = fmax(LAM[j * N + k], 0.0);
+      if (first) TERM[j * N + k] = (lk[j * N + k] - ln) * phir[j];
       lk[j * N + k] = ln;
     }
   }
-  lamdiff_out = first ? lamdiff : 0.0;
-  dec_pred_out = F0 - F1;
+  __syncwarp();
+  lamdiff_out = first ? ordered_sum() : 0.0;  // valid on lane 0
+  dec_pred_out = F0 - F1;                      // valid on lane 0
   status_out = st;
+  __syncwarp();
 }
 
 // Errors of _get_w_err (price_solver.py:211-214) for a mean trajectory w_sum / n.
@@ -306,14 +343,21 @@ __device__ __forceinline__ void price_errors(int N, double kappa, const double* 
   w0_err = fabs(w_sum[0] / n - w_ref[0]);
 }
 
-// One thread per group: errors, the convergence test (price_solver.py:121-127) and -- for
-// groups that go on -- the price step.
+// One WARP per group: errors, the convergence test (price_solver.py:121-127) and -- for
+// groups that go on -- the price step.  Dynamic shared memory: per warp
+// price_step_scratch_doubles() doubles + r bytes (rounded up to 8).
 __global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
-  const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  extern __shared__ double gs_smem[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int g = blockIdx.x * (blockDim.x >> 5) + wib;
   const int G = p.G, N = cs.N, r = p.r;
-  if (g >= G || p.skip[g]) return;
+  if (g >= G || p.skip[g]) return;  // warp-uniform
+  const int per_warp = price_step_scratch_doubles(N, r) + (r + 7) / 8;
+  double* ws = gs_smem + (size_t)wib * per_warp;
+  unsigned char* FREE = reinterpret_cast<unsigned char*>(ws + price_step_scratch_doubles(N, r));
   const double kappa = p.lmbd_r[g] / cs.delta;
-  {
+  int done = 0;
+  if (lane == 0) {
     double w_avg_err, w0_err;
     price_errors(N, kappa, p.w_avg + (size_t)g * N, p.cnt ? p.cnt[g] : 1.0, p.w_ref + (size_t)g * N, w_avg_err,
                  w0_err);
@@ -324,17 +368,29 @@ __global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
     if (w_err <= tol) {  // price_solver.py:125
       p.skip[g] = 1;
       p.iters[g] = it;
-      return;
+      done = 1;
+    } else {
+      atomicAdd(p.n_active, 1);
     }
   }
-  atomicAdd(p.n_active, 1);
+  done = __shfl_sync(0xffffffffu, done, 0);
+  if (done) return;
+  const bool warm = it > 0 && !p.cold;
+  unsigned char* gfree = p.wsb + (size_t)g * r;  // the free set lives in global memory between launches
+  if (warm)
+    for (int i = lane; i < r; i += 32) FREE[i] = gfree[i];
+  __syncwarp();
   double lamdiff, dec;
   int st;
-  price_step_core(cs, r, kappa, p.eps_reg, p.lmbd + (size_t)g * 3 * N, p.w_k + (size_t)g * N,
-                  p.w_ref + (size_t)g * N, p.ws + g, p.wsb + g, (size_t)G, it == 0, it > 0 && !p.cold, lamdiff, dec, st);
-  p.nnqp_status[g] = st;
-  p.lamdiff_phi[g] = lamdiff;
-  p.dec_pred[g] = dec;
+  price_step_warp(cs, r, kappa, p.eps_reg, p.lmbd + (size_t)g * 3 * N, p.w_k + (size_t)g * N,
+                  p.w_ref + (size_t)g * N, ws, FREE, lane, it == 0, warm, p.hist_ac != nullptr || p.want_dec, lamdiff,
+                  dec, st);
+  for (int i = lane; i < r; i += 32) gfree[i] = FREE[i];
+  if (lane == 0) {
+    p.nnqp_status[g] = st;
+    p.lamdiff_phi[g] = lamdiff;
+    p.dec_pred[g] = dec;
+  }
 }
 
 __global__ void bookkeep_kernel(const PriceArgs p, int it) {

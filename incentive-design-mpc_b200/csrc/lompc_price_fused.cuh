@@ -10,8 +10,8 @@
 //     gamma_sc (price_solver.py:106,132) in the same pass;
 //   * thread k < N adds up w_i[k] over the EVs IN EV ORDER (the reference's own summation
 //     order, price_solver.py:205 - bit-identical to the phase-split kernels);
-//   * thread 0 runs the convergence test, the exact non-negative QP of the price step
-//     (price_step_core) on shared-memory scratch, and the dual-cost bookkeeping.
+//   * warp 0 runs the convergence test, the exact non-negative QP of the price step
+//     (price_step_warp) on shared-memory scratch, and the dual-cost bookkeeping.
 // The current price row lives in shared memory; EV data (one SoC per EV) is read once.
 #pragma once
 #include "lompc_common.cuh"
@@ -42,6 +42,9 @@ struct FusedArgs {
   int hist_cap;
   int32_t* flags;            // [0] += groups whose NNQP hit its iteration cap, [1] = some y0 outside [0, y_max],
                              // [2] = max over groups of the LoMPC passes run (loop length of the slowest group)
+  double* w_scratch;         // [B + G, N] LoMPC iterates of groups with more than T - 1 EVs (rows b0 + i; the
+                             // virtual EV of group g in row B + g); smaller groups keep them in registers
+  int64_t B;
   unsigned long long* qp_count;  // [0] total LoMPC QP solves, [1] / [2] SM cycles summed over groups spent in
                                  // the LoMPC passes / in thread 0's price step (or NULL)
 };
@@ -49,8 +52,8 @@ struct FusedArgs {
 template <int N, int NSEG, int T, bool GREG>
 struct FusedSmem {
   static constexpr int kK1 = RegSmem<N, NSEG, T, GREG>::kArrays * N * T;
-  // LM[3N] WREF[N] WK[N] WSUM[N] + NNQP scratch (2*3N + 6N) + ERR[T] + 8 scalars
-  static constexpr int kDoubles = kK1 + 3 * N + 3 * N + (6 * N + 6 * N) + T + 8;
+  // LM[3N] WREF[N] WK[N] WSUM[N] + price-step scratch (3*3N + 6N) + ERR[T] + 8 scalars
+  static constexpr int kDoubles = kK1 + 3 * N + 3 * N + 15 * N + T + 8;
   static constexpr size_t bytes = (size_t)kDoubles * sizeof(double) + 3 * N + 16;
 };
 
@@ -70,8 +73,8 @@ __global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts 
   double* WREF = LM + 3 * N;        // [N]
   double* WK = WREF + N;            // [N] LoMPC solution at gamma_sc for LM
   double* WSUM = WK + N;            // [N]
-  double* WS = WSUM + N;            // NNQP scratch, 2r + 6N <= 12N doubles
-  double* ERR = WS + 12 * N;        // [T]
+  double* WS = WSUM + N;            // price-step scratch, 3r + 6N <= 15N doubles
+  double* ERR = WS + 15 * N;        // [T]
   double* SC = ERR + T;             // scalars: 0 cost_sc, 1 flag
   unsigned char* WSB = reinterpret_cast<unsigned char*>(SC + 8);  // [r]
   double* WN = smem + 2 * N * T;    // K1's candidate array doubles as the [k][tid] transpose buffer
@@ -115,6 +118,8 @@ __global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts 
   double dual_cost = 0.0, lamdiff = 0.0, dec_pred = 0.0;  // thread 0 only
   int it = 0, nnqp_bad = 0;
   unsigned long long solves = 0;
+  const bool single = n + 1 <= T;  // one LoMPC pass covers the group: iterates stay in registers
+  double W[N];
   long long cyc_qp = 0, cyc_step = 0;  // thread 0: cycles in the LoMPC passes / in the price step
   for (;; ++it) {
     const long long t_a = clock64();
@@ -124,11 +129,23 @@ __global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts 
       const int i = c0 + tid;
       if (i <= n) {
         const double gam = (i < n) ? cs.y_max - a.y0[b0 + i] : gamma_sc;
-        double W[N], D[N], GR[GREG ? N : 1];
+        double D[N], GR[GREG ? N : 1];
         double l2sum, gscale, viol;
         int st, qit;
-        solve_reg<N, NSEG, T, GREG>(cs, LM, lr, gam, a.qp_tol, a.qp_max_iter, smem + tid, W, D, GR, l2sum, gscale,
-                                    viol, st, qit);
+        // every QP starts from its own solution at the previous prices (registers, or the
+        // scratch rows when the group needs more than one pass of T threads)
+        const bool warm = it > 0;
+        double* wrow = a.w_scratch + (size_t)(i < n ? (int64_t)b0 + i : a.B + g) * N;
+        if (!single && warm) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) W[k] = wrow[k];
+        }
+        solve_reg<N, NSEG, T, GREG>(cs, LM, lr, gam, a.qp_tol, a.qp_max_iter, warm, smem + tid, W, D, GR, l2sum,
+                                    gscale, viol, st, qit);
+        if (!single) {
+#pragma unroll
+          for (int k = 0; k < N; ++k) wrow[k] = W[k];
+        }
         if (i < n) {
 #pragma unroll
           for (int k = 0; k < N; ++k) WN[k * T + tid] = W[k];
@@ -176,35 +193,36 @@ __global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts 
     if (tid < N) WSUM[tid] = wsum;
     solves += (unsigned long long)(tid == 0 ? n + 1 : 0);
     __syncthreads();
-    // ---- thread 0: bookkeeping of the previous step, convergence test, price step
-    if (tid == 0) {
+    // ---- warp 0: bookkeeping of the previous step, convergence test (lane 0), price step (all lanes)
+    if (tid < 32) {
       const long long t_b = clock64();
-      cyc_qp += t_b - t_a;
-      const double cost_sc = SC[0];
-      if (it > 0) {  // price_solver.py:135-139
-        if (a.hist_ac && it - 1 < a.hist_cap) {
+      int flag = 0;
+      if (tid == 0) {
+        cyc_qp += t_b - t_a;
+        const double cost_sc = SC[0];
+        if (it > 0 && a.hist_ac && it - 1 < a.hist_cap) {  // price_solver.py:135-139
           a.hist_ac[(size_t)g * a.hist_cap + it - 1] = cost_sc - dual_cost + lamdiff;
           a.hist_pred[(size_t)g * a.hist_cap + it - 1] = dec_pred;
         }
-      }
-      dual_cost = cost_sc;
-      int flag = 0;
-      if (it >= a.max_iter) {
-        flag = 2;  // the loop ran out: `iter` ends at max_iter - 1 (price_solver.py:111)
-      } else {
-        double w_avg_err, w0_err;
-        price_errors(N, kappa, WSUM, (double)n, WREF, w_avg_err, w0_err);
-        const double w_err = a.tol_type_max ? SC[4] : w_avg_err;
-        if (w_err <= tolg) {
-          flag = 1;  // price_solver.py:125
+        dual_cost = cost_sc;
+        if (it >= a.max_iter) {
+          flag = 2;  // the loop ran out: `iter` ends at max_iter - 1 (price_solver.py:111)
         } else {
-          int st;
-          price_step_core(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, 1, it == 0, it > 0, lamdiff, dec_pred, st);
-          nnqp_bad |= st;
+          double w_avg_err, w0_err;
+          price_errors(N, kappa, WSUM, (double)n, WREF, w_avg_err, w0_err);
+          const double w_err = a.tol_type_max ? SC[4] : w_avg_err;
+          if (w_err <= tolg) flag = 1;  // price_solver.py:125
         }
+        SC[1] = (double)flag;
       }
-      SC[1] = (double)flag;
-      cyc_step += clock64() - t_b;
+      flag = __shfl_sync(0xffffffffu, flag, 0);
+      if (flag == 0) {
+        int st;
+        price_step_warp(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, tid, it == 0, it > 0, a.hist_ac != nullptr,
+                        lamdiff, dec_pred, st);
+        nnqp_bad |= st;
+      }
+      if (tid == 0) cyc_step += clock64() - t_b;
     }
     __syncthreads();
     if (SC[1] != 0.0) break;

@@ -32,10 +32,11 @@ struct RegSmem {
 // The solve itself: one QP per thread, iterate / diagonal / linear term in the caller's
 // registers.  `smem_t` = this thread's column of the CTA's shared-memory arrays (base + t).
 // `lm` may point to global or shared memory (the fused price loop keeps the group's price
-// row in shared memory).
+// row in shared memory).  `warm`: W holds a feasible starting point on entry (else W = 0).
 template <int N, int NSEG, int T, bool GREG>
 __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, const double lr, const double gam,
-                                          const double tol, const int max_iter, double* smem_t, double (&W)[N],
+                                          const double tol, const int max_iter, const bool warm,
+                                          double* smem_t, double (&W)[N],
                                           double (&D)[N], double (&GR)[GREG ? N : 1], double& l2sum_out,
                                           double& gscale_out, double& viol_out, int& st_out, int& it_out) {
   double* KK = smem_t;
@@ -54,7 +55,7 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
     const double g = cs.theta * (l1 - l2);
     if (GREG) GR[GREG ? k : 0] = g; else GS[k * T] = g;
     D[k] = 2.0 * (lr * cs.theta2 + cs.q_scale * l3) + cs.d_base;
-    W[k] = 0.0;
+    if (!warm) W[k] = 0.0;
     gmax = fmax(gmax, fabs(g));
     dmax = fmax(dmax, D[k]);
     l2sum += l2;
@@ -74,6 +75,26 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
   for (int j = 0; j < NSEG; ++j) slope[j] = cs.slope[j];
 
   double sN = 0.0, f = 0.5 * c * N * gam * gam, viol = 0.0, mu = 0.0;
+  if (warm) {
+    // start from the caller's feasible W (the solution at the previous prices of the price
+    // loop): the active set is usually already right and one verification sweep remains
+    double s0 = 0.0, f0 = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const double x = fmin(fmax(W[k], 0.0), wmax);
+      W[k] = x;
+      s0 += x;
+      const double e = s0 - gam;
+      f0 += x * fma(0.5 * D[k], x, LOMPC_G(k)) + 0.5 * c * e * e;
+      if (NSEG > 1) {
+#pragma unroll
+        for (int j = 1; j < NSEG; ++j) f0 += (slope[j] - slope[j - 1]) * fmax(x - brk[j], 0.0);
+      }
+      LOMPC_STAGE_FENCE();
+    }
+    sN = s0;
+    f = f0;
+  }
   int it = 0;
   bool converged = (st != LOMPC_ST_OK);
 
@@ -226,7 +247,14 @@ __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts c
   double W[N], D[N], GR[GREG ? N : 1];
   double l2sum, gscale, viol;
   int st, it;
-  solve_reg<N, NSEG, T, GREG>(cs, lm, lr, gam, a.tol, a.max_iter, smem + t, W, D, GR, l2sum, gscale, viol, st, it);
+  const bool warm = a.w_init != nullptr;
+  if (warm) {
+    const double* wi = a.w_init + b * (int64_t)N;
+#pragma unroll
+    for (int k = 0; k < N; ++k) W[k] = wi[k];
+  }
+  solve_reg<N, NSEG, T, GREG>(cs, lm, lr, gam, a.tol, a.max_iter, warm, smem + t, W, D, GR, l2sum, gscale, viol, st,
+                              it);
   const double* GS = smem + t + 3 * N * T;
 #define LOMPC_G(k) (GREG ? GR[GREG ? (k) : 0] : GS[(k) * T])
   const double c = cs.c, wmax = cs.w_max;
