@@ -117,6 +117,8 @@ class ChargingStationFleet:
         self.price_loop_iters = []  # per step: total device-loop iterations of the price loops
         self.qp_solves = 0   # LoMPC QPs solved inside the price loops so far
         self.cycles = [0, 0]  # SM cycles (summed over groups) in the LoMPC passes / the price steps
+        self.profile = False  # True: record CUDA events at the phase boundaries of every step
+        self.phase_ms = []    # per step: {phase: ms}
 
     # ------------------------------------------------------------------ helpers
     def _stream(self):
@@ -137,6 +139,15 @@ class ChargingStationFleet:
         G, B = P * S, S * M
         lmbd_r = 0.0  # charging_station.py:162
         tol_max = 1 if PRICE_SOLVER_TOL_TYPE == "max" else 0
+        marks = []
+
+        def mark(name):
+            if self.profile:
+                e = torch.cuda.Event(enable_timing=True)
+                e.record()
+                marks.append((name, e))
+
+        mark("start")
         # ---- partitions, group statistics
         for k in ("s", "l"):
             w, h = self.w[k], self.solver[k]._h
@@ -146,6 +157,7 @@ class ChargingStationFleet:
             self._ck(lib.price_group_stats_dev(h, G, B, w["off"].data_ptr(), w["ysort"].data_ptr(),
                                                w["gamma"].data_ptr(), w["y0_rng"].data_ptr(),
                                                w["gamma_sc"].data_ptr(), w["gamma_sm"].data_ptr(), st))
+        mark("partition+stats")
         # ---- upper level
         ws, wl, bi = self.w["s"], self.w["l"], self.bi
         self._ck(lib.fleet_bimpc_params_dev(
@@ -163,6 +175,7 @@ class ChargingStationFleet:
         for k in ("s", "l"):
             self._ck(lib.fleet_wref_dev(self.device, S, P, N_bi, N_lo, bi["w_hat_" + k].data_ptr(),
                                         self.w[k]["w_ref"].data_ptr(), st))
+        mark("bimpc")
         # ---- price loops
         total = C.c_int32(0)
         loop_iters = 0
@@ -205,12 +218,14 @@ class ChargingStationFleet:
                         self.prices[k][g0:].data_ptr(), w["pre"][g0:].data_ptr(), w["post"][g0:].data_ptr(),
                         w["red"][g0:].data_ptr(), st))
         self.price_loop_iters.append(loop_iters)
+        mark("price_loops")
         # ---- EV responses at the final prices
         for k in ("s", "l"):
             w, h = self.w[k], self.solver[k]._h
             self._ck(lib.price_w0_price0_dev(h, G, B, w["off"].data_ptr(), w["gamma"].data_ptr(),
                                              self.prices[k].data_ptr(), self.lmbd_r0.data_ptr(), w["w0"].data_ptr(),
                                              w["price0"].data_ptr(), st))
+        mark("ev_response")
         # ---- logs of this step (charging_station.py:371-433; x is logged before the update)
         L = self.log
         L["u_g"][t].copy_(bi["u_g"][:, 0])
@@ -244,6 +259,10 @@ class ChargingStationFleet:
             L[f"price_red_{k}"][t].copy_(w["red"].view(P, S))
             L[f"niter_{k}"][t].copy_(w["iters"].view(P, S))
             L[f"Mp_{k}"][t].copy_(w["counts"].view(P, S))
+        mark("plant+logs")
+        if self.profile:
+            torch.cuda.synchronize(self.dev)
+            self.phase_ms.append({n1: e0.elapsed_time(e1) for (_, e0), (n1, e1) in zip(marks[:-1], marks[1:])})
         self.t += 1
 
     def _host_arrivals(self) -> None:

@@ -54,6 +54,7 @@ def main():
     ap.add_argument("--n-bi", type=int, default=24)
     ap.add_argument("--chain", default="reference")
     ap.add_argument("--max-price-iter", type=int, default=1000)
+    ap.add_argument("--profile", action="store_true", help="CUDA-event timing of the phases of every step")
     args = ap.parse_args()
     import torch
     from chargingstation.fleet import ChargingStationFleet
@@ -61,6 +62,7 @@ def main():
     demand = fleet_demand(consts, args.stations, args.steps, args.n_bi)
     fleet = ChargingStationFleet(consts, args.stations, demand=demand, seed=4, rng="device", chain=args.chain,
                                  max_price_iter=args.max_price_iter)
+    fleet.profile = args.profile
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     wall = []
@@ -83,6 +85,8 @@ def main():
            "bimpc_failed": int((log["bimpc_status"] != 0).sum()),
            "price_loop_qp_solves": int(fleet.qp_solves), "qp_solves_per_s": fleet.qp_solves / (ms.sum() * 1e-3),
            "cycles_lompc_passes": fleet.cycles[0], "cycles_price_steps": fleet.cycles[1]}
+    if args.profile:
+        out["phase_ms_median"] = {k: float(np.median([d[k] for d in fleet.phase_ms])) for k in fleet.phase_ms[0]}
     for k in ("s", "l"):
         ni = log[f"niter_{k}"].cpu().numpy()
         mp = log[f"Mp_{k}"].cpu().numpy()
