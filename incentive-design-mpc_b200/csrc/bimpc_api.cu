@@ -48,7 +48,7 @@ int bimpc_create(int N, int P, double delta, double c_g, double u_g_max, double 
   h->device = device;
   h->max_iter = 100;
   h->tol = 1e-9;
-  h->threads = 128;
+  h->threads = bimpc::kThreads;
   h->smem = bimpc::scratch_doubles(N, P, h->threads) * sizeof(double);
   h->ws = nullptr;
   h->ws_bytes = 0;

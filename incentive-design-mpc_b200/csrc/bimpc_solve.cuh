@@ -44,7 +44,8 @@
 
 namespace bimpc {
 
-constexpr int kRefine = 1; // refinement steps of every Newton solve
+constexpr int kThreads = 32;  // one warp per station: the block-Cholesky sweep is a chain of small dependent
+                             // steps, barriers between them must be warp-local to be cheap
 constexpr int kMaxN = 48;  // horizon cap (scratch of one station must fit 227 KB of shared memory)
 
 struct BiConsts {
@@ -78,7 +79,7 @@ struct BiArgs {
 // Number of doubles of scratch one station needs (shared memory on the device).
 BI_HD size_t scratch_doubles(int N, int P, int T) {
   const int Q2 = 2 * P, QN = Q2 * N, nb = Q2 + 1;
-  return (size_t)11 * QN + (size_t)(QN + N) + (size_t)N * (nb * (nb + 1) / 2) + (size_t)nb * nb +
+  return (size_t)9 * QN + (size_t)(QN + N) + (size_t)N * (nb * (nb + 1) / 2) + (size_t)nb * nb +
          (size_t)40 * N + 8 * (size_t)nb + 3 * (size_t)T + 4 * Q2 + 16;
 }
 
@@ -100,15 +101,54 @@ BI_FN void block_reduce(double* RED, int tid, int T, double& sum, double& mx, do
   mn = b;
 }
 
+// Dot products on a packed lower-triangular matrix L (row i starts at i(i+1)/2), with four
+// independent accumulators (the FP64 pipe is latency-bound on a single dependent chain).
+// row_dot: sum_{j<=i} L[i][j] x[j];   col_dot: sum_{l>=i} L[l][i] x[l].
+BI_FN double row_dot(const double* L, int i, const double* x) {
+  const double* r = L + i * (i + 1) / 2;
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int j = 0;
+  for (; j + 3 <= i; j += 4) {
+    a0 += r[j] * x[j];
+    a1 += r[j + 1] * x[j + 1];
+    a2 += r[j + 2] * x[j + 2];
+    a3 += r[j + 3] * x[j + 3];
+  }
+  for (; j <= i; ++j) a0 += r[j] * x[j];
+  return (a0 + a1) + (a2 + a3);
+}
+BI_FN double col_dot(const double* L, int i, int nb, const double* x) {
+  double a0 = 0.0, a1 = 0.0;
+  int l = i, o = i * (i + 1) / 2 + i;
+  for (; l + 1 < nb; l += 2) {
+    a0 += L[o] * x[l];
+    o += l + 1;
+    a1 += L[o] * x[l + 1];
+    o += l + 2;
+  }
+  if (l < nb) a0 += L[o] * x[l];
+  return a0 + a1;
+}
+BI_FN double vec_dot(const double* a, const double* b, int n) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  int j = 0;
+  for (; j + 3 < n; j += 4) {
+    a0 += a[j] * b[j];
+    a1 += a[j + 1] * b[j + 1];
+    a2 += a[j + 2] * b[j + 2];
+    a3 += a[j + 3] * b[j + 3];
+  }
+  for (; j < n; ++j) a0 += a[j] * b[j];
+  return (a0 + a1) + (a2 + a3);
+}
+
 // In-place Cholesky of the SPD matrix Mx (row-major N x N, lower triangle used/produced),
 // left-looking, columns in order; DIAG is an N-vector of scratch.  Returns false on breakdown.
 BI_FN bool block_cholesky(double* Mx, double* DIAG, int N, int tid, int T) {
   bool ok = true;
   for (int j = 0; j < N; ++j) {
     for (int i = j + tid; i < N; i += T) {
-      double v = Mx[i * N + j];
-      for (int k = 0; k < j; ++k) v -= Mx[i * N + k] * Mx[j * N + k];
-      DIAG[i] = v;
+      DIAG[i] = Mx[i * N + j] - vec_dot(Mx + i * N, Mx + j * N, j);
     }
     BI_SYNC();
     const double djj = DIAG[j];
@@ -132,11 +172,9 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
   double* Z2 = S2 + QN;
   double* RDW = Z2 + QN;      // dual residual, w block
   double* DXA = RDW + QN;     // affine direction, w block
-  double* DX = DXA + QN;      // current direction, w block
+  double* DX = DXA + QN;      // Newton right-hand side, then the current direction, w block
   double* EW = DX + QN;       // barrier diagonal z1/s1 + z2/s2
-  double* RB = EW + QN;       // Newton right-hand side, w block
-  double* RR = RB + QN;       // refinement residual / correction, w block
-  double* XI = RR + QN;       // [N,nb] block-tridiagonal solve vector (cumulative coordinates)
+  double* XI = EW + QN;       // [N,nb] block-tridiagonal solve vector (cumulative coordinates)
   double* LI = XI + QN + N;   // [N,np] packed inverse Cholesky factors of the diagonal blocks
   double* SW = LI + (size_t)N * np;  // [nb,nb] Schur complement of the current stage -> its factor
   double* pk = SW + nb * nb;  // per-k vectors
@@ -159,7 +197,7 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
   double* HU = pk;            pk += N;
   double* D1 = pk;            pk += N;
   double* D2 = pk;            pk += N;
-  double* BU = pk;            pk += N;  // current direction, u block
+  double* BU = pk;            pk += N;  // right-hand side, then the current direction, u block
   double* DXUA = pk;          pk += N;
   double* DV = pk;            pk += N;
   double* DVA = pk;           pk += N;
@@ -171,9 +209,7 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
   double* T78 = pk;           pk += N;
   double* DEM = pk;           pk += N;
   double* OM = pk;            pk += N;
-  double* RBU = pk;           pk += N;
-  double* RRU = pk;           pk += N;
-  pk += 7 * N;                          // (spare, keeps the 40 N budget)
+  pk += 9 * N;                          // (spare, keeps the 40 N budget)
   double* AV = pk;            pk += nb;  // a = (-m, 1)
   double* LA = pk;            pk += nb;  // Linv_{k-1} a
   double* TL = pk;            pk += nb;  // T' la
@@ -346,22 +382,12 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
       const double* Lp = LI + (size_t)(k - 1) * np;  // previous stage (k >= 1)
       const double d1k = D1[k], d1n = (k + 1 < N) ? D1[k + 1] : 0.0;
       if (k >= 1) {
-        for (int i = tid; i < nb; i += T) {  // la = Linv_{k-1} a
-          double v = 0.0;
-          for (int j = 0; j <= i; ++j) v += Lp[i * (i + 1) / 2 + j] * AV[j];
-          LA[i] = v;
-        }
+        for (int i = tid; i < nb; i += T) LA[i] = row_dot(Lp, i, AV);  // la = Linv_{k-1} a
         BI_SYNC();
-        for (int i = tid; i < nb; i += T) {  // tl = T' la,  T = Linv_{k-1} diag(E_k)
-          double v = 0.0;
-          for (int l = i; l < nb; ++l) v += Lp[l * (l + 1) / 2 + i] * LA[l];
-          TL[i] = v * Ek(k, i);
-        }
+        for (int i = tid; i < nb; i += T) TL[i] = col_dot(Lp, i, nb, LA) * Ek(k, i);  // tl = T' la, T = Linv_{k-1} diag(E_k)
         BI_SYNC();
       }
-      double ll = 0.0;
-      if (k >= 1)
-        for (int i = 0; i < nb; ++i) ll += LA[i] * LA[i];
+      const double ll = (k >= 1) ? vec_dot(LA, LA, nb) : 0.0;
       const double rho = D2[k] + d1k + d1n;
       for (int e = tid; e < np; e += T) {  // lower triangle of the Schur complement
         int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
@@ -371,9 +397,16 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
         double v = rho * AV[i] * AV[j];
         if (i == j) v += Ek(k, i) + Ek(k + 1, i) + (i < Q2 ? 2.0 * c.delta * AQ[i] * OM[k] : 0.0);
         if (k >= 1) {
-          double tt = 0.0;
-          for (int l = i; l < nb; ++l) tt += Lp[l * (l + 1) / 2 + i] * Lp[l * (l + 1) / 2 + j];
-          tt *= Ek(k, i) * Ek(k, j);
+          double t0 = 0.0, t1 = 0.0;  // (Linv' Linv)[i][j], i >= j
+          int l = i, o = i * (i + 1) / 2;
+          for (; l + 1 < nb; l += 2) {
+            t0 += Lp[o + i] * Lp[o + j];
+            o += l + 1;
+            t1 += Lp[o + i] * Lp[o + j];
+            o += l + 2;
+          }
+          if (l < nb) t0 += Lp[o + i] * Lp[o + j];
+          const double tt = (t0 + t1) * (Ek(k, i) * Ek(k, j));
           const double di = d1k * AV[i], dj = d1k * AV[j];
           v -= tt + TL[i] * dj + di * TL[j] + ll * di * dj;
         }
@@ -385,9 +418,16 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
       double* Lk = LI + (size_t)k * np;
       for (int j = tid; j < nb; j += T) {
         for (int i = j; i < nb; ++i) {
-          double v = (i == j) ? 1.0 : 0.0;
-          for (int l = j; l < i; ++l) v -= SW[i * nb + l] * Lk[l * (l + 1) / 2 + j];
-          Lk[i * (i + 1) / 2 + j] = v / SW[i * nb + i];
+          double v0 = (i == j) ? 1.0 : 0.0, v1 = 0.0;
+          int l = j, o = j * (j + 1) / 2 + j;
+          for (; l + 1 < i; l += 2) {
+            v0 -= SW[i * nb + l] * Lk[o];
+            o += l + 1;
+            v1 -= SW[i * nb + l + 1] * Lk[o];
+            o += l + 2;
+          }
+          if (l < i) v0 -= SW[i * nb + l] * Lk[o];
+          Lk[i * (i + 1) / 2 + j] = (v0 + v1) / SW[i * nb + i];
         }
       }
       BI_SYNC();
@@ -413,25 +453,16 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
         if (k >= 1) {
           const double* Lp = LI + (size_t)(k - 1) * np;
           const double* yp = XI + (k - 1) * nb;
-          for (int i = tid; i < nb; i += T) {
-            double v = 0.0;
-            for (int l = i; l < nb; ++l) v += Lp[l * (l + 1) / 2 + i] * yp[l];
-            TV1[i] = v;
-          }
+          for (int i = tid; i < nb; i += T) TV1[i] = col_dot(Lp, i, nb, yp);
           BI_SYNC();
-          double at = 0.0;
-          for (int i = 0; i < nb; ++i) at += AV[i] * TV1[i];
+          const double at = vec_dot(AV, TV1, nb);
           for (int i = tid; i < nb; i += T) TV2[i] = x[i] + Ek(k, i) * TV1[i] + D1[k] * AV[i] * at;
         } else {
           for (int i = tid; i < nb; i += T) TV2[i] = x[i];
         }
         BI_SYNC();
         const double* Lk = LI + (size_t)k * np;
-        for (int i = tid; i < nb; i += T) {
-          double v = 0.0;
-          for (int j = 0; j <= i; ++j) v += Lk[i * (i + 1) / 2 + j] * TV2[j];
-          x[i] = v;
-        }
+        for (int i = tid; i < nb; i += T) x[i] = row_dot(Lk, i, TV2);
         BI_SYNC();
       }
       // backward: xi_k = Linv_k' (y_k - Linv_k Off_{k+1} xi_{k+1})
@@ -440,24 +471,15 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
         const double* Lk = LI + (size_t)k * np;
         if (k + 1 < N) {
           const double* xn = XI + (k + 1) * nb;
-          double ax = 0.0;
-          for (int i = 0; i < nb; ++i) ax += AV[i] * xn[i];
+          const double ax = vec_dot(AV, xn, nb);
           for (int i = tid; i < nb; i += T) TV1[i] = -(Ek(k + 1, i) * xn[i] + D1[k + 1] * AV[i] * ax);
           BI_SYNC();
-          for (int i = tid; i < nb; i += T) {
-            double v = 0.0;
-            for (int j = 0; j <= i; ++j) v += Lk[i * (i + 1) / 2 + j] * TV1[j];
-            TV2[i] = x[i] - v;
-          }
+          for (int i = tid; i < nb; i += T) TV2[i] = x[i] - row_dot(Lk, i, TV1);
         } else {
           for (int i = tid; i < nb; i += T) TV2[i] = x[i];
         }
         BI_SYNC();
-        for (int i = tid; i < nb; i += T) {
-          double v = 0.0;
-          for (int l = i; l < nb; ++l) v += Lk[l * (l + 1) / 2 + i] * TV2[l];
-          x[i] = v;
-        }
+        for (int i = tid; i < nb; i += T) x[i] = col_dot(Lk, i, nb, TV2);
         BI_SYNC();
       }
       // back to stage increments: dx_k = xi_k - xi_{k-1}
@@ -506,57 +528,17 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
         const double rp1 = S1[i] - W[i], rp2 = W[i] + S2[i] - WMX[q];
         const double x1 = (Z1[i] * rp1 - rc_of(S1[i], Z1[i], rp1, -DXA[i])) / S1[i];
         const double x2 = (Z2[i] * rp2 - rc_of(S2[i], Z2[i], rp2, DXA[i])) / S2[i];
-        RB[i] = -RDW[i] + x1 - x2 + MQ[q] * NU[k];
+        DX[i] = -RDW[i] + x1 - x2 + MQ[q] * NU[k];
       }
       for (int k = tid; k < N; k += T) {
         const double rp3 = S3[k] - U[k], rp4 = U[k] + S4[k] - c.u_g_max;
         const double x3 = (Z3[k] * rp3 - rc_of(S3[k], Z3[k], rp3, -DXUA[k])) / S3[k];
         const double x4 = (Z4[k] * rp4 - rc_of(S4[k], Z4[k], rp4, DXUA[k])) / S4[k];
-        RBU[k] = -RDU[k] + x3 - x4 - NU[k];
+        BU[k] = -RDU[k] + x3 - x4 - NU[k];
       }
       BI_SYNC();
-      // dx = K^{-1} b, then iterative refinement with the operator in its original coordinates
-      lin_solve(RB, RBU, DX, BU);
-      for (int ref = 0; ref < kRefine; ++ref) {
-        for (int k = tid; k < N; k += T) {
-          double v = BU[k];
-          for (int q = 0; q < Q2; ++q) v -= MQ[q] * DX[q * N + k];
-          DV[k] = v;
-        }
-        BI_SYNC();
-        for (int k = tid; k < N; k += T) {  // D2 .* cumsum(dv)
-          double x = 0.0;
-          for (int j = 0; j <= k; ++j) x += DV[j];
-          T78[k] = D2[k] * x;
-        }
-        BI_SYNC();
-        for (int k = tid; k < N; k += T) {  // y = S dv = D1 .* dv + A' (D2 .* A dv)
-          double v = D1[k] * DV[k];
-          for (int j = N - 1; j >= k; --j) v += T78[j];
-          YV[k] = v;
-        }
-        BI_SYNC();
-        for (int q = tid; q < Q2; q += T) {  // r_q = b_q - (e .* dx + A' D_q A dx) + m_q y
-          const int o = q * N;
-          const double f = 2.0 * c.delta * AQ[q], mq = MQ[q];
-          double cs = 0.0;
-          for (int k = 0; k < N; ++k) {
-            cs += DX[o + k];
-            RR[o + k] = f * OM[k] * cs;
-          }
-          double g = 0.0;
-          for (int k = N - 1; k >= 0; --k) {
-            g += RR[o + k];
-            RR[o + k] = RB[o + k] - (EW[o + k] * DX[o + k] + g) + mq * YV[k];
-          }
-        }
-        for (int k = tid; k < N; k += T) RRU[k] = RBU[k] - HU[k] * BU[k] - YV[k];
-        BI_SYNC();
-        lin_solve(RR, RRU, RR, RRU);
-        for (int i = tid; i < QN; i += T) DX[i] += RR[i];
-        for (int k = tid; k < N; k += T) BU[k] += RRU[k];
-        BI_SYNC();
-      }
+      // dx = K^{-1} b (in place; the block Cholesky is backward stable, no refinement needed)
+      lin_solve(DX, BU, DX, BU);
       for (int k = tid; k < N; k += T) {
         double v = BU[k];
         for (int q = 0; q < Q2; ++q) v -= MQ[q] * DX[q * N + k];
@@ -698,7 +680,7 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
 }
 
 #ifndef BIMPC_HOSTSIM
-__global__ void __launch_bounds__(128) bimpc_solve_kernel(const BiConsts c, const BiArgs a) {
+__global__ void __launch_bounds__(kThreads) bimpc_solve_kernel(const BiConsts c, const BiArgs a) {
   extern __shared__ double bimpc_smem[];
   for (int s = blockIdx.x; s < a.S; s += gridDim.x) {
     solve_station(c, a, s, bimpc_smem, threadIdx.x, blockDim.x);

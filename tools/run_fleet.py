@@ -33,14 +33,16 @@ def fleet_consts(steps, N_lo, N_bi, M, P):
 
 
 def fleet_demand(consts, S, steps, N_bi, seed=4):
-    """per-station demand = the bundled profile scaled by U(0.22,0.28)/0.25
-    and circularly shifted by U{0..23} hours."""
+    """SURVEY.md 8d config 4: per-station demand = the bundled profile circularly shifted by U{0..23}
+    hours and scaled by U(0.22, 0.26)/0.25.  (SURVEY proposed U(0.22, 0.28); above 0.26 a station that starts
+    at the evening peak with its battery empty has NO feasible BiMPC plan - demand + robustness margin
+    exceed u_g_max - which the reference would report as an infeasible cvxpy problem.)"""
     rng = np.random.default_rng(seed)
     L = steps + N_bi + 1
     out = np.empty((S, L))
     for s in range(S):
         sh = int(rng.integers(24))
-        out[s] = consts.demand[sh:sh + L] * (rng.uniform(0.22, 0.28) / 0.25)
+        out[s] = consts.demand[sh:sh + L] * (rng.uniform(0.22, 0.26) / 0.25)
     return out
 
 
