@@ -100,7 +100,7 @@ int bimpc_solve_batch_dev(bimpc_t* h, int32_t S, const double* Mp_s, const doubl
   if (S == 0) return LOMPC_OK;
   CK(cudaSetDevice(h->device));
   bimpc::BiArgs a{S, h->omega, Mp_s, Mp_l, beta_s, beta_l, gamma_sm, gamma_lm, x0, demand,
-                  w_hat_s, w_hat_l, u_g, status, iters, objective, h->tol, h->max_iter};
+                  w_hat_s, w_hat_l, u_g, status, iters, objective, h->tol, h->max_iter, nullptr};
   int grid = h->sms * h->ctas_per_sm;  // persistent CTAs, one station at a time each
   if (grid > S) grid = S;
   bimpc::bimpc_solve_kernel<<<grid, h->threads, h->smem, static_cast<cudaStream_t>(stream)>>>(h->c, a);

@@ -42,6 +42,14 @@
 #define BI_SYNC() __syncthreads()
 #endif
 
+#if defined(BIMPC_PROFILE) && !defined(BIMPC_HOSTSIM)
+#define BI_TIC(slot) long long bi_t_##slot = clock64()
+#define BI_TOC(slot) if (tid == 0) a.prof[slot] += clock64() - bi_t_##slot
+#else
+#define BI_TIC(slot) ((void)0)
+#define BI_TOC(slot) ((void)0)
+#endif
+
 namespace bimpc {
 
 constexpr int kThreads = 32;  // one warp per station: the block-Cholesky sweep is a chain of small dependent
@@ -74,6 +82,7 @@ struct BiArgs {
   double* objective;      // [S] or NULL
   double tol;
   int max_iter;
+  long long* prof;        // BIMPC_PROFILE builds only: cycle counters
 };
 
 // Number of doubles of scratch one station needs (shared memory on the device).
@@ -292,6 +301,7 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
   int it = 0, status = 1;
   double mu = 0.0;
   for (;; ++it) {
+    BI_TIC(0);
     // ---- A. primal quantities and the gradient of the charging cost
     for (int q = tid; q < Q2; q += T) {
       // grad_q = 2 delta a_q A' (omega .* (A w_q - gamma_q)):  forward cumsum, then reverse
@@ -366,6 +376,8 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
       break;
     }
 
+    BI_TOC(0);
+    BI_TIC(1);
     // ---- C. factorisation: block Cholesky of the stage-ordered Newton matrix
     for (int i = tid; i < QN; i += T) EW[i] = Z1[i] / S1[i] + Z2[i] / S2[i];
     for (int k = tid; k < N; k += T) {
@@ -437,6 +449,7 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
       break;
     }
 
+    BI_TOC(1);
     // (outW, outU) = K^{-1} (inW, inU) through the block factorisation; in and out may alias.
     auto lin_solve = [&](const double* inW, const double* inU, double* outW, double* outU) {
       // right-hand side in cumulative coordinates: b~_k = b_k - b_{k+1}
@@ -492,6 +505,7 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
       BI_SYNC();
     };
 
+    BI_TIC(3);
     // ---- D..G: predictor (pass 0) and corrector (pass 1)
     double sigma_mu = 0.0, alpha = 1.0;
     for (int pass = 0; pass < 2; ++pass) {
@@ -538,7 +552,9 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
       }
       BI_SYNC();
       // dx = K^{-1} b (in place; the block Cholesky is backward stable, no refinement needed)
+      BI_TIC(2);
       lin_solve(DX, BU, DX, BU);
+      BI_TOC(2);
       for (int k = tid; k < N; k += T) {
         double v = BU[k];
         for (int q = 0; q < Q2; ++q) v -= MQ[q] * DX[q * N + k];
@@ -646,6 +662,7 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
       }
       BI_SYNC();
     }
+    BI_TOC(3);
   }
 
   // ---- outputs (clipped into the box like the oracle)
