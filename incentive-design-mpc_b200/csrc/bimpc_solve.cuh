@@ -36,10 +36,21 @@
 #define BI_FN inline
 #define BI_HD inline
 #define BI_SYNC() ((void)0)
+#define BI_SUBSUM(v, nsub) ((void)0)
+#define BI_RCP(x) (1.0 / (x))
 #else
 #define BI_FN __device__ __forceinline__
 #define BI_HD __host__ __device__ inline
 #define BI_SYNC() __syncthreads()
+#define BI_RCP(x) bimpc::fast_rcp_dev(x)
+// sum over the `nsub` (1 or 4) adjacent lanes that share one matrix row
+#define BI_SUBSUM(v, nsub)                        \
+  do {                                            \
+    if ((nsub) == 4) {                            \
+      v += __shfl_xor_sync(0xffffffffu, v, 1);    \
+      v += __shfl_xor_sync(0xffffffffu, v, 2);    \
+    }                                             \
+  } while (0)
 #endif
 
 #if defined(BIMPC_PROFILE) && !defined(BIMPC_HOSTSIM)
@@ -52,8 +63,18 @@
 
 namespace bimpc {
 
-constexpr int kThreads = 32;  // one warp per station: the block-Cholesky sweep is a chain of small dependent
-                             // steps, barriers between them must be warp-local to be cheap
+#ifndef BIMPC_HOSTSIM
+// reciprocal of a positive, well-scaled double: MUFU seed + one cubic Newton step (~1 ulp)
+__device__ __forceinline__ double fast_rcp_dev(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  const double e = fma(-x, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y, t, y);
+}
+#endif
+
+constexpr int kThreads = 128;
 constexpr int kMaxN = 48;  // horizon cap (scratch of one station must fit 227 KB of shared memory)
 
 struct BiConsts {
@@ -88,7 +109,7 @@ struct BiArgs {
 // Number of doubles of scratch one station needs (shared memory on the device).
 BI_HD size_t scratch_doubles(int N, int P, int T) {
   const int Q2 = 2 * P, QN = Q2 * N, nb = Q2 + 1;
-  return (size_t)9 * QN + (size_t)(QN + N) + (size_t)N * (nb * (nb + 1) / 2) + (size_t)nb * nb +
+  return (size_t)9 * QN + (size_t)(QN + N) + (size_t)N * (nb * (nb + 1) / 2) + 2 * (size_t)nb * nb +
          (size_t)40 * N + 8 * (size_t)nb + 3 * (size_t)T + 4 * Q2 + 16;
 }
 
@@ -110,32 +131,28 @@ BI_FN void block_reduce(double* RED, int tid, int T, double& sum, double& mx, do
   mn = b;
 }
 
-// Dot products on a packed lower-triangular matrix L (row i starts at i(i+1)/2), with four
-// independent accumulators (the FP64 pipe is latency-bound on a single dependent chain).
-// row_dot: sum_{j<=i} L[i][j] x[j];   col_dot: sum_{l>=i} L[l][i] x[l].
-BI_FN double row_dot(const double* L, int i, const double* x) {
+// Partial dot products on a packed lower-triangular matrix L (row i starts at i(i+1)/2): the
+// `nsub` lanes that share row i take the terms part, part + nsub, ... and are summed with
+// BI_SUBSUM.  row: sum_{j<=i} L[i][j] x[j];   col: sum_{l>=i} L[l][i] x[l].
+BI_FN double row_part(const double* L, int i, const double* x, int part, int nsub) {
   const double* r = L + i * (i + 1) / 2;
-  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
-  int j = 0;
-  for (; j + 3 <= i; j += 4) {
-    a0 += r[j] * x[j];
-    a1 += r[j + 1] * x[j + 1];
-    a2 += r[j + 2] * x[j + 2];
-    a3 += r[j + 3] * x[j + 3];
-  }
-  for (; j <= i; ++j) a0 += r[j] * x[j];
-  return (a0 + a1) + (a2 + a3);
-}
-BI_FN double col_dot(const double* L, int i, int nb, const double* x) {
   double a0 = 0.0, a1 = 0.0;
-  int l = i, o = i * (i + 1) / 2 + i;
-  for (; l + 1 < nb; l += 2) {
-    a0 += L[o] * x[l];
-    o += l + 1;
-    a1 += L[o] * x[l + 1];
-    o += l + 2;
+  int j = part;
+  for (; j + nsub <= i; j += 2 * nsub) {
+    a0 += r[j] * x[j];
+    a1 += r[j + nsub] * x[j + nsub];
   }
-  if (l < nb) a0 += L[o] * x[l];
+  if (j <= i) a0 += r[j] * x[j];
+  return a0 + a1;
+}
+BI_FN double col_part(const double* L, int i, int nb, const double* x, int part, int nsub) {
+  double a0 = 0.0, a1 = 0.0;
+  int l = i + part;
+  for (; l + nsub < nb; l += 2 * nsub) {
+    a0 += L[l * (l + 1) / 2 + i] * x[l];
+    a1 += L[(l + nsub) * (l + nsub + 1) / 2 + i] * x[l + nsub];
+  }
+  if (l < nb) a0 += L[l * (l + 1) / 2 + i] * x[l];
   return a0 + a1;
 }
 BI_FN double vec_dot(const double* a, const double* b, int n) {
@@ -151,28 +168,14 @@ BI_FN double vec_dot(const double* a, const double* b, int n) {
   return (a0 + a1) + (a2 + a3);
 }
 
-// In-place Cholesky of the SPD matrix Mx (row-major N x N, lower triangle used/produced),
-// left-looking, columns in order; DIAG is an N-vector of scratch.  Returns false on breakdown.
-BI_FN bool block_cholesky(double* Mx, double* DIAG, int N, int tid, int T) {
-  bool ok = true;
-  for (int j = 0; j < N; ++j) {
-    for (int i = j + tid; i < N; i += T) {
-      DIAG[i] = Mx[i * N + j] - vec_dot(Mx + i * N, Mx + j * N, j);
-    }
-    BI_SYNC();
-    const double djj = DIAG[j];
-    if (!(djj > 0.0)) ok = false;
-    const double rs = 1.0 / sqrt(djj > 0.0 ? djj : 1.0);
-    for (int i = j + tid; i < N; i += T) Mx[i * N + j] = DIAG[i] * rs;
-    BI_SYNC();
-  }
-  return ok;
-}
-
 // One station.  `sm` = scratch_doubles(N, P, T) doubles private to this CTA.
 BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double* sm, int tid, int T) {
   const int N = c.N, P = c.P, Q2 = 2 * P, QN = Q2 * N;
   const int nb = Q2 + 1, np = nb * (nb + 1) / 2;
+  // matrix-vector products: `nsub` adjacent lanes share one row (T >= 128), else one thread per row
+  const int nsub = (T >= 128) ? 4 : 1, row = tid / nsub, part = tid - row * nsub, rows_pp = T / nsub;
+  // dense block operations: thread (tx, ty) = (column, row group)
+  const int nx = T < 32 ? T : 32, tx = tid % nx, ty = tid / nx, ny = T / nx;
   // ---- carve
   double* W = sm;             // [Q2,N] iterate
   double* S1 = W + QN;        // slack / multiplier of w >= 0
@@ -186,7 +189,8 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
   double* XI = EW + QN;       // [N,nb] block-tridiagonal solve vector (cumulative coordinates)
   double* LI = XI + QN + N;   // [N,np] packed inverse Cholesky factors of the diagonal blocks
   double* SW = LI + (size_t)N * np;  // [nb,nb] Schur complement of the current stage -> its factor
-  double* pk = SW + nb * nb;  // per-k vectors
+  double* XW = SW + nb * nb;  // [nb,nb] the identity the elimination turns into the inverse factor
+  double* pk = XW + nb * nb;  // per-k vectors
   double* U = pk;             pk += N;
   double* S3 = pk;            pk += N;
   double* Z3 = pk;            pk += N;
@@ -222,7 +226,7 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
   double* AV = pk;            pk += nb;  // a = (-m, 1)
   double* LA = pk;            pk += nb;  // Linv_{k-1} a
   double* TL = pk;            pk += nb;  // T' la
-  double* DIAG = pk;          pk += nb;
+  pk += nb;
   double* TV1 = pk;           pk += nb;
   double* TV2 = pk;           pk += nb;
   pk += 2 * nb;
@@ -393,56 +397,84 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
     for (int k = 0; k < N; ++k) {
       const double* Lp = LI + (size_t)(k - 1) * np;  // previous stage (k >= 1)
       const double d1k = D1[k], d1n = (k + 1 < N) ? D1[k + 1] : 0.0;
+      BI_TIC(4);
       if (k >= 1) {
-        for (int i = tid; i < nb; i += T) LA[i] = row_dot(Lp, i, AV);  // la = Linv_{k-1} a
+        for (int i0 = 0; i0 < nb; i0 += rows_pp) {  // la = Linv_{k-1} a
+          const int i = i0 + row;
+          double v = (i < nb) ? row_part(Lp, i, AV, part, nsub) : 0.0;
+          BI_SUBSUM(v, nsub);
+          if (i < nb && part == 0) LA[i] = v;
+        }
         BI_SYNC();
-        for (int i = tid; i < nb; i += T) TL[i] = col_dot(Lp, i, nb, LA) * Ek(k, i);  // tl = T' la, T = Linv_{k-1} diag(E_k)
+        for (int i0 = 0; i0 < nb; i0 += rows_pp) {  // tl = T' la,  T = Linv_{k-1} diag(E_k)
+          const int i = i0 + row;
+          double v = (i < nb) ? col_part(Lp, i, nb, LA, part, nsub) : 0.0;
+          BI_SUBSUM(v, nsub);
+          if (i < nb && part == 0) TL[i] = v * Ek(k, i);
+        }
         BI_SYNC();
       }
+      BI_TOC(4);
+      BI_TIC(5);
       const double ll = (k >= 1) ? vec_dot(LA, LA, nb) : 0.0;
       const double rho = D2[k] + d1k + d1n;
-      for (int e = tid; e < np; e += T) {  // lower triangle of the Schur complement
-        int i = (int)((sqrt(8.0 * e + 1.0) - 1.0) * 0.5);
-        while (i * (i + 1) / 2 > e) --i;
-        while ((i + 1) * (i + 2) / 2 <= e) ++i;
-        const int j = e - i * (i + 1) / 2;
-        double v = rho * AV[i] * AV[j];
-        if (i == j) v += Ek(k, i) + Ek(k + 1, i) + (i < Q2 ? 2.0 * c.delta * AQ[i] * OM[k] : 0.0);
-        if (k >= 1) {
-          double t0 = 0.0, t1 = 0.0;  // (Linv' Linv)[i][j], i >= j
-          int l = i, o = i * (i + 1) / 2;
-          for (; l + 1 < nb; l += 2) {
-            t0 += Lp[o + i] * Lp[o + j];
-            o += l + 1;
-            t1 += Lp[o + i] * Lp[o + j];
-            o += l + 2;
+      // Schur complement S_k = Diag_k - Off_k Linv' Linv Off_k (full symmetric storage) and X = I;
+      // thread (tx, ty): column tx (+32, ...), rows ty, ty + ny, ...
+      for (int i = ty; i < nb; i += ny) {
+        const double eki = Ek(k, i), di = d1k * AV[i];
+        for (int j = tx; j < nb; j += nx) {
+          XW[i * nb + j] = (i == j) ? 1.0 : 0.0;
+          if (j > i) continue;
+          double v = rho * AV[i] * AV[j];
+          if (i == j) v += eki + Ek(k + 1, i) + (i < Q2 ? 2.0 * c.delta * AQ[i] * OM[k] : 0.0);
+          if (k >= 1) {
+            double t0 = 0.0, t1 = 0.0;  // (Linv' Linv)[i][j], i >= j
+            int l = i, o = i * (i + 1) / 2;
+            for (; l + 1 < nb; l += 2) {
+              t0 += Lp[o + i] * Lp[o + j];
+              o += l + 1;
+              t1 += Lp[o + i] * Lp[o + j];
+              o += l + 2;
+            }
+            if (l < nb) t0 += Lp[o + i] * Lp[o + j];
+            const double tt = (t0 + t1) * (eki * Ek(k, j));
+            const double dj = d1k * AV[j];
+            v -= tt + TL[i] * dj + di * TL[j] + ll * di * dj;
           }
-          if (l < nb) t0 += Lp[o + i] * Lp[o + j];
-          const double tt = (t0 + t1) * (Ek(k, i) * Ek(k, j));
-          const double di = d1k * AV[i], dj = d1k * AV[j];
-          v -= tt + TL[i] * dj + di * TL[j] + ll * di * dj;
+          SW[i * nb + j] = v;
+          SW[j * nb + i] = v;
         }
-        SW[i * nb + j] = v;
       }
       BI_SYNC();
-      ok = block_cholesky(SW, DIAG, nb, tid, T) && ok;
-      // Linv_k: column j by thread j (forward substitution on e_j), packed
+      BI_TOC(5);
+      BI_TIC(6);
+      // Gaussian elimination of [S | I] without pivoting (S is SPD): the row operations that
+      // triangularise S turn I into the unit-lower inverse factor; scaling row i by
+      // 1/sqrt(pivot_i) gives Linv = chol(S)^{-1}.  One barrier per pivot; in step j thread
+      // (tx, ty) updates column tx of rows j+1+ty, j+1+ty+ny, ... (columns <= j belong to X,
+      // the others to S).
+      for (int j = 0; j < nb; ++j) {
+        const double piv = SW[j * nb + j];
+        if (!(piv > 0.0)) ok = false;
+        const double rp = BI_RCP(piv > 0.0 ? piv : 1.0);
+        for (int cidx = tx; cidx < nb; cidx += nx) {
+          double* M = (cidx <= j) ? XW : SW;
+          const double pr = M[j * nb + cidx];
+          for (int i = j + 1 + ty; i < nb; i += ny) M[i * nb + cidx] -= (SW[i * nb + j] * rp) * pr;
+        }
+        BI_SYNC();
+      }
+      BI_TOC(6);
+      BI_TIC(7);
+      for (int i = tid; i < nb; i += T) TV1[i] = 1.0 / sqrt(SW[i * nb + i]);
+      BI_SYNC();
       double* Lk = LI + (size_t)k * np;
-      for (int j = tid; j < nb; j += T) {
-        for (int i = j; i < nb; ++i) {
-          double v0 = (i == j) ? 1.0 : 0.0, v1 = 0.0;
-          int l = j, o = j * (j + 1) / 2 + j;
-          for (; l + 1 < i; l += 2) {
-            v0 -= SW[i * nb + l] * Lk[o];
-            o += l + 1;
-            v1 -= SW[i * nb + l + 1] * Lk[o];
-            o += l + 2;
-          }
-          if (l < i) v0 -= SW[i * nb + l] * Lk[o];
-          Lk[i * (i + 1) / 2 + j] = (v0 + v1) / SW[i * nb + i];
-        }
+      for (int i = ty; i < nb; i += ny) {
+        const double rs = TV1[i];
+        for (int j = tx; j <= i; j += nx) Lk[i * (i + 1) / 2 + j] = XW[i * nb + j] * rs;
       }
       BI_SYNC();
+      BI_TOC(7);
     }
     if (!ok) {
       status = 2;
@@ -466,7 +498,12 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
         if (k >= 1) {
           const double* Lp = LI + (size_t)(k - 1) * np;
           const double* yp = XI + (k - 1) * nb;
-          for (int i = tid; i < nb; i += T) TV1[i] = col_dot(Lp, i, nb, yp);
+          for (int i0 = 0; i0 < nb; i0 += rows_pp) {
+            const int i = i0 + row;
+            double v = (i < nb) ? col_part(Lp, i, nb, yp, part, nsub) : 0.0;
+            BI_SUBSUM(v, nsub);
+            if (i < nb && part == 0) TV1[i] = v;
+          }
           BI_SYNC();
           const double at = vec_dot(AV, TV1, nb);
           for (int i = tid; i < nb; i += T) TV2[i] = x[i] + Ek(k, i) * TV1[i] + D1[k] * AV[i] * at;
@@ -475,7 +512,12 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
         }
         BI_SYNC();
         const double* Lk = LI + (size_t)k * np;
-        for (int i = tid; i < nb; i += T) x[i] = row_dot(Lk, i, TV2);
+        for (int i0 = 0; i0 < nb; i0 += rows_pp) {
+          const int i = i0 + row;
+          double v = (i < nb) ? row_part(Lk, i, TV2, part, nsub) : 0.0;
+          BI_SUBSUM(v, nsub);
+          if (i < nb && part == 0) x[i] = v;
+        }
         BI_SYNC();
       }
       // backward: xi_k = Linv_k' (y_k - Linv_k Off_{k+1} xi_{k+1})
@@ -487,12 +529,22 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
           const double ax = vec_dot(AV, xn, nb);
           for (int i = tid; i < nb; i += T) TV1[i] = -(Ek(k + 1, i) * xn[i] + D1[k + 1] * AV[i] * ax);
           BI_SYNC();
-          for (int i = tid; i < nb; i += T) TV2[i] = x[i] - row_dot(Lk, i, TV1);
+          for (int i0 = 0; i0 < nb; i0 += rows_pp) {
+            const int i = i0 + row;
+            double v = (i < nb) ? row_part(Lk, i, TV1, part, nsub) : 0.0;
+            BI_SUBSUM(v, nsub);
+            if (i < nb && part == 0) TV2[i] = x[i] - v;
+          }
         } else {
           for (int i = tid; i < nb; i += T) TV2[i] = x[i];
         }
         BI_SYNC();
-        for (int i = tid; i < nb; i += T) x[i] = col_dot(Lk, i, nb, TV2);
+        for (int i0 = 0; i0 < nb; i0 += rows_pp) {
+          const int i = i0 + row;
+          double v = (i < nb) ? col_part(Lk, i, nb, TV2, part, nsub) : 0.0;
+          BI_SUBSUM(v, nsub);
+          if (i < nb && part == 0) x[i] = v;
+        }
         BI_SYNC();
       }
       // back to stage increments: dx_k = xi_k - xi_{k-1}
