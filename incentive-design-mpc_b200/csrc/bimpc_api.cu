@@ -23,6 +23,7 @@ struct bimpc_handle {
   int threads;
   size_t smem;
   int ctas_per_sm, sms;
+  double* li;     // [grid, N, np] inverse-factor scratch of the kernel
   void* ws;       // grow-only device workspace of the _host entry point
   size_t ws_bytes;
 };
@@ -52,6 +53,8 @@ int bimpc_create(int N, int P, double delta, double c_g, double u_g_max, double 
   h->smem = bimpc::scratch_doubles(N, P, h->threads) * sizeof(double);
   h->ws = nullptr;
   h->ws_bytes = 0;
+  h->li = nullptr;
+  h->omega = nullptr;
   cudaDeviceProp prop;
   CK(cudaGetDeviceProperties(&prop, device));
   h->sms = prop.multiProcessorCount;
@@ -63,6 +66,10 @@ int bimpc_create(int N, int P, double delta, double c_g, double u_g_max, double 
   int occ = 1;
   CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bimpc::bimpc_solve_kernel, h->threads, h->smem));
   h->ctas_per_sm = occ < 1 ? 1 : occ;
+  {
+    const size_t nb = 2 * (size_t)P + 1, np = nb * (nb + 1) / 2;
+    CK(cudaMalloc(&h->li, (size_t)h->sms * h->ctas_per_sm * N * np * sizeof(double)));
+  }
   // stage weights of the charging cost: exp_rate^(k-N+1) (bimpc.py:255-257), ones otherwise
   std::vector<double> om(N, 1.0);
   if (cost_type == BIMPC_COST_EXP_UNWEIGHTED)
@@ -77,6 +84,7 @@ int bimpc_destroy(bimpc_t* h) {
   if (!h) return LOMPC_OK;
   cudaSetDevice(h->device);
   if (h->omega) cudaFree(h->omega);
+  if (h->li) cudaFree(h->li);
   if (h->ws) cudaFree(h->ws);
   delete h;
   return LOMPC_OK;
@@ -100,7 +108,7 @@ int bimpc_solve_batch_dev(bimpc_t* h, int32_t S, const double* Mp_s, const doubl
   if (S == 0) return LOMPC_OK;
   CK(cudaSetDevice(h->device));
   bimpc::BiArgs a{S, h->omega, Mp_s, Mp_l, beta_s, beta_l, gamma_sm, gamma_lm, x0, demand,
-                  w_hat_s, w_hat_l, u_g, status, iters, objective, h->tol, h->max_iter, nullptr};
+                  w_hat_s, w_hat_l, u_g, status, iters, objective, h->tol, h->max_iter, nullptr, h->li};
   int grid = h->sms * h->ctas_per_sm;  // persistent CTAs, one station at a time each
   if (grid > S) grid = S;
   bimpc::bimpc_solve_kernel<<<grid, h->threads, h->smem, static_cast<cudaStream_t>(stream)>>>(h->c, a);

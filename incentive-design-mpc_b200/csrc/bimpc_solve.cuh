@@ -104,12 +104,14 @@ struct BiArgs {
   double tol;
   int max_iter;
   long long* prof;        // BIMPC_PROFILE builds only: cycle counters
+  double* li_scratch;     // [CTAs, N, nb(nb+1)/2] packed inverse factors of the diagonal blocks (global memory,
+                          // L2-resident: keeping them out of shared memory lets 3 stations share an SM)
 };
 
 // Number of doubles of scratch one station needs (shared memory on the device).
 BI_HD size_t scratch_doubles(int N, int P, int T) {
   const int Q2 = 2 * P, QN = Q2 * N, nb = Q2 + 1;
-  return (size_t)9 * QN + (size_t)(QN + N) + (size_t)N * (nb * (nb + 1) / 2) + 2 * (size_t)nb * nb +
+  return (size_t)9 * QN + (size_t)(QN + N) + 2 * (size_t)(nb * (nb + 1) / 2) + 2 * (size_t)nb * nb +
          (size_t)40 * N + 8 * (size_t)nb + 3 * (size_t)T + 4 * Q2 + 16;
 }
 
@@ -169,7 +171,7 @@ BI_FN double vec_dot(const double* a, const double* b, int n) {
 }
 
 // One station.  `sm` = scratch_doubles(N, P, T) doubles private to this CTA.
-BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double* sm, int tid, int T) {
+BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double* sm, double* LI, int tid, int T) {
   const int N = c.N, P = c.P, Q2 = 2 * P, QN = Q2 * N;
   const int nb = Q2 + 1, np = nb * (nb + 1) / 2;
   // matrix-vector products: `nsub` adjacent lanes share one row (T >= 128), else one thread per row
@@ -187,8 +189,8 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
   double* DX = DXA + QN;      // Newton right-hand side, then the current direction, w block
   double* EW = DX + QN;       // barrier diagonal z1/s1 + z2/s2
   double* XI = EW + QN;       // [N,nb] block-tridiagonal solve vector (cumulative coordinates)
-  double* LI = XI + QN + N;   // [N,np] packed inverse Cholesky factors of the diagonal blocks
-  double* SW = LI + (size_t)N * np;  // [nb,nb] Schur complement of the current stage -> its factor
+  double* LPS = XI + QN + N;  // [2,np] shared-memory copy of the inverse factor of the last two stages
+  double* SW = LPS + 2 * (size_t)np;  // [nb,nb] Schur complement of the current stage
   double* XW = SW + nb * nb;  // [nb,nb] the identity the elimination turns into the inverse factor
   double* pk = XW + nb * nb;  // per-k vectors
   double* U = pk;             pk += N;
@@ -395,7 +397,7 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
     auto Ek = [&](int k, int i) { return k >= N ? 0.0 : (i < Q2 ? EW[i * N + k] : HU[k]); };
     bool ok = true;
     for (int k = 0; k < N; ++k) {
-      const double* Lp = LI + (size_t)(k - 1) * np;  // previous stage (k >= 1)
+      const double* Lp = LPS + (size_t)((k - 1) & 1) * np;  // previous stage (k >= 1), shared-memory copy
       const double d1k = D1[k], d1n = (k + 1 < N) ? D1[k + 1] : 0.0;
       BI_TIC(4);
       if (k >= 1) {
@@ -469,9 +471,14 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
       for (int i = tid; i < nb; i += T) TV1[i] = 1.0 / sqrt(SW[i * nb + i]);
       BI_SYNC();
       double* Lk = LI + (size_t)k * np;
+      double* Lks = LPS + (size_t)(k & 1) * np;
       for (int i = ty; i < nb; i += ny) {
         const double rs = TV1[i];
-        for (int j = tx; j <= i; j += nx) Lk[i * (i + 1) / 2 + j] = XW[i * nb + j] * rs;
+        for (int j = tx; j <= i; j += nx) {
+          const double v = XW[i * nb + j] * rs;
+          Lk[i * (i + 1) / 2 + j] = v;
+          Lks[i * (i + 1) / 2 + j] = v;
+        }
       }
       BI_SYNC();
       BI_TOC(7);
@@ -752,7 +759,8 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
 __global__ void __launch_bounds__(kThreads) bimpc_solve_kernel(const BiConsts c, const BiArgs a) {
   extern __shared__ double bimpc_smem[];
   for (int s = blockIdx.x; s < a.S; s += gridDim.x) {
-    solve_station(c, a, s, bimpc_smem, threadIdx.x, blockDim.x);
+    solve_station(c, a, s, bimpc_smem, a.li_scratch + (size_t)blockIdx.x * c.N * ((2 * c.P + 1) * (2 * c.P + 2) / 2),
+                  threadIdx.x, blockDim.x);
     __syncthreads();
   }
 }

@@ -17,11 +17,14 @@ extern "C" int bimpc_hostsim_solve(int N, int P, double delta, double c_g, doubl
   if (N > bimpc::kMaxN) return -2;
   bimpc::BiConsts c{N, P, delta, c_g, u_g_max, u_b_max, x_max, cost_type, theta_s, theta_l, w_max_s, w_max_l};
   bimpc::BiArgs a{S, omega, Mp_s, Mp_l, beta_s, beta_l, gamma_sm, gamma_lm, x0, demand,
-                  w_hat_s, w_hat_l, u_g, status, iters, objective, tol, max_iter, nullptr};
+                  w_hat_s, w_hat_l, u_g, status, iters, objective, tol, max_iter, nullptr, nullptr};
   const size_t n = bimpc::scratch_doubles(N, P, 1);
   double* sm = (double*)malloc(n * sizeof(double));
-  if (!sm) return -1;
-  for (int s = 0; s < S; ++s) bimpc::solve_station(c, a, s, sm, 0, 1);
+  const size_t nb = 2 * (size_t)P + 1;
+  double* li = (double*)malloc((size_t)N * (nb * (nb + 1) / 2) * sizeof(double));
+  if (!sm || !li) return -1;
+  for (int s = 0; s < S; ++s) bimpc::solve_station(c, a, s, sm, li, 0, 1);
   free(sm);
+  free(li);
   return 0;
 }
