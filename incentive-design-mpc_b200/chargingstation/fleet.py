@@ -117,6 +117,10 @@ class ChargingStationFleet:
         self.price_loop_iters = []  # per step: total device-loop iterations of the price loops
         self.qp_solves = 0   # LoMPC QPs solved inside the price loops so far
         self.cycles = [0, 0]  # SM cycles (summed over groups) in the LoMPC passes / the price steps
+        from concurrent.futures import ThreadPoolExecutor
+        self._pool = ThreadPoolExecutor(max_workers=2)
+        self.streams = {k: torch.cuda.Stream(self.dev) for k in ("s", "l")}
+        self._lock = __import__("threading").Lock()
         self.profile = False  # True: record CUDA events at the phase boundaries of every step
         self.phase_ms = []    # per step: {phase: ms}
 
@@ -128,9 +132,10 @@ class ChargingStationFleet:
         _native.raise_for(rc)
 
     def _account(self, h) -> None:
-        self.qp_solves += self._lib.price_last_qp_solves(h)
-        self.cycles[0] += self._lib.price_last_cycles(h, 0)
-        self.cycles[1] += self._lib.price_last_cycles(h, 1)
+        with self._lock:
+            self.qp_solves += self._lib.price_last_qp_solves(h)
+            self.cycles[0] += self._lib.price_last_cycles(h, 0)
+            self.cycles[1] += self._lib.price_last_cycles(h, 1)
 
     # ------------------------------------------------------------------ one closed-loop step
     def step(self) -> None:
@@ -176,47 +181,66 @@ class ChargingStationFleet:
             self._ck(lib.fleet_wref_dev(self.device, S, P, N_bi, N_lo, bi["w_hat_" + k].data_ptr(),
                                         self.w[k]["w_ref"].data_ptr(), st))
         mark("bimpc")
-        # ---- price loops
-        total = C.c_int32(0)
-        loop_iters = 0
+        # ---- price loops: the two EV types are independent chains (separate PriceSolver objects in the
+        # reference, charging_station.py:58-59) -> one host thread and one CUDA stream per type
+        main = torch.cuda.current_stream(self.dev)
+        ready = torch.cuda.Event()
+        ready.record(main)
         if self.chain == "reference":
             base = {k: self.w[k]["off"][::S].cpu().numpy() for k in ("s", "l")}  # P+1 slice starts (one sync)
-            for p in range(P):
-                for k in ("s", "l"):
-                    w, h = self.w[k], self.solver[k]._h
-                    b0, b1 = int(base[k][p]), int(base[k][p + 1])
-                    g0 = p * S
-                    if b1 > b0:
-                        self._ck(lib.price_solve_dev(
-                            h, S, b1 - b0, w["reb"][p].data_ptr(), w["ysort"][b0:].data_ptr(),
-                            w["w_ref"][g0:].data_ptr(), self.lmbd_r0.data_ptr(), self.r, self.max_price_iter, tol_max,
-                            float(self.solver[k].eps_reg), float(self.solver[k].eps_tol), self.prev[k].data_ptr(),
-                            w["iters"][g0:].data_ptr(), w["pre"][g0:].data_ptr(), w["post"][g0:].data_ptr(), None,
-                            None, None, 0, C.byref(total), st))
-                        loop_iters += total.value
-                        self._account(h)
-                    else:
-                        w["iters"][g0:g0 + S].fill_(-1)
-                    self._ck(lib.fleet_keep_prices_dev(
-                        self.device, S, 3 * N_lo, w["counts"][g0:].data_ptr(), self.prev[k].data_ptr(),
-                        self.prices[k][g0:].data_ptr(), w["pre"][g0:].data_ptr(), w["post"][g0:].data_ptr(),
-                        w["red"][g0:].data_ptr(), st))
         else:
-            for k in ("s", "l"):
-                w, h = self.w[k], self.solver[k]._h
-                self._ck(lib.price_solve_dev(
-                    h, G, B, w["off"].data_ptr(), w["ysort"].data_ptr(), w["w_ref"].data_ptr(),
-                    self.lmbd_r0.data_ptr(), self.r, self.max_price_iter, tol_max, float(self.solver[k].eps_reg),
-                    float(self.solver[k].eps_tol), self.prices[k].data_ptr(), w["iters"].data_ptr(),
-                    w["pre"].data_ptr(), w["post"].data_ptr(), None, None, None, 0, C.byref(total), st))
-                loop_iters += total.value
-                self._account(h)
-                for p in range(P):  # price reduction / NaN for empty groups (prices keep the warm start)
-                    g0 = p * S
-                    self._ck(lib.fleet_keep_prices_dev(
-                        self.device, S, 3 * N_lo, w["counts"][g0:].data_ptr(), self.prices[k][g0:].data_ptr(),
-                        self.prices[k][g0:].data_ptr(), w["pre"][g0:].data_ptr(), w["post"][g0:].data_ptr(),
-                        w["red"][g0:].data_ptr(), st))
+            base = None
+
+        def run_type(k):
+            w, h = self.w[k], self.solver[k]._h
+            stream = self.streams[k]
+            stream.wait_event(ready)
+            sp = stream.cuda_stream
+            total = C.c_int32(0)
+            iters_sum = 0
+            with torch.cuda.stream(stream):
+                if self.chain == "reference":
+                    for p in range(P):
+                        b0, b1 = int(base[k][p]), int(base[k][p + 1])
+                        g0 = p * S
+                        if b1 > b0:
+                            self._ck(lib.price_solve_dev(
+                                h, S, b1 - b0, w["reb"][p].data_ptr(), w["ysort"][b0:].data_ptr(),
+                                w["w_ref"][g0:].data_ptr(), self.lmbd_r0.data_ptr(), self.r, self.max_price_iter,
+                                tol_max, float(self.solver[k].eps_reg), float(self.solver[k].eps_tol),
+                                self.prev[k].data_ptr(), w["iters"][g0:].data_ptr(), w["pre"][g0:].data_ptr(),
+                                w["post"][g0:].data_ptr(), None, None, None, 0, C.byref(total), sp))
+                            iters_sum += total.value
+                            self._account(h)
+                        else:
+                            w["iters"][g0:g0 + S].fill_(-1)
+                        self._ck(lib.fleet_keep_prices_dev(
+                            self.device, S, 3 * N_lo, w["counts"][g0:].data_ptr(), self.prev[k].data_ptr(),
+                            self.prices[k][g0:].data_ptr(), w["pre"][g0:].data_ptr(), w["post"][g0:].data_ptr(),
+                            w["red"][g0:].data_ptr(), sp))
+                else:
+                    self._ck(lib.price_solve_dev(
+                        h, G, B, w["off"].data_ptr(), w["ysort"].data_ptr(), w["w_ref"].data_ptr(),
+                        self.lmbd_r0.data_ptr(), self.r, self.max_price_iter, tol_max, float(self.solver[k].eps_reg),
+                        float(self.solver[k].eps_tol), self.prices[k].data_ptr(), w["iters"].data_ptr(),
+                        w["pre"].data_ptr(), w["post"].data_ptr(), None, None, None, 0, C.byref(total), sp))
+                    iters_sum += total.value
+                    self._account(h)
+                    for p in range(P):  # price reduction / NaN for empty groups (prices keep the warm start)
+                        g0 = p * S
+                        self._ck(lib.fleet_keep_prices_dev(
+                            self.device, S, 3 * N_lo, w["counts"][g0:].data_ptr(), self.prices[k][g0:].data_ptr(),
+                            self.prices[k][g0:].data_ptr(), w["pre"][g0:].data_ptr(), w["post"][g0:].data_ptr(),
+                            w["red"][g0:].data_ptr(), sp))
+            done = torch.cuda.Event()
+            done.record(stream)
+            return iters_sum, done
+
+        results = list(self._pool.map(run_type, ("s", "l")))
+        loop_iters = 0
+        for iters_sum, done in results:
+            loop_iters += iters_sum
+            main.wait_event(done)
         self.price_loop_iters.append(loop_iters)
         mark("price_loops")
         # ---- EV responses at the final prices
