@@ -266,6 +266,9 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     if not args.no_saturated:
         sat = saturated_run(solvers, dev, rank, fp64_peak)
     clocks = sampler.stop()
+    closed = None
+    if args.closed_loop_stations > 0:
+        closed = closed_loop_leg(args, rank, world, dev)
 
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -314,6 +317,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             "gpu_launches": int(launches),
             "clocks": clocks,
             "saturated": sat,
+            "closed_loop": closed,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_leg(args)
@@ -365,6 +369,62 @@ def saturated_run(solvers, dev, rank, fp64_peak):
     return res
 
 
+def closed_loop_leg(args, rank, world, dev):
+    """BASELINE.json's second metric, "closed-loop price-step p50 latency", on configs[3]'s shape: S stations
+    per GPU (500 + 500 EVs, 12 partitions, N_lo = N_bi = 24), device-resident closed loop
+    (chargingstation.fleet), CUDA events around every step.  Stations are independent, so ranks hold whole
+    stations (no data-path collective inside the price loop); the one exchange per step is the fleet's
+    aggregate planned grid load, an all-reduce of N_bi doubles over NCCL."""
+    import torch
+    import torch.distributed as dist
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    from run_fleet import fleet_consts, fleet_demand
+    from chargingstation.fleet import ChargingStationFleet
+    S, T = args.closed_loop_stations, args.closed_loop_steps
+    consts = fleet_consts(T, 24, 24, 500, 12)
+    demand = fleet_demand(consts, S, T, 24, seed=4 + rank)
+    fleet = ChargingStationFleet(consts, S, demand=demand, seed=4 + rank, rng="device", chain=args.closed_loop_chain,
+                                 device=dev.index)
+    ms, agg_ms = [], []
+    agg = torch.zeros(24, dtype=torch.float64, device=dev)
+    for t in range(T):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1, e2 = (torch.cuda.Event(enable_timing=True) for _ in range(3))
+        e0.record()
+        fleet.step()
+        e1.record()
+        agg.copy_(fleet.bi["u_g"].sum(dim=0))  # aggregate planned generation of this rank's stations
+        if world > 1:
+            dist.all_reduce(agg)
+        e2.record()
+        torch.cuda.synchronize()
+        ms.append(e0.elapsed_time(e2))
+        agg_ms.append(e1.elapsed_time(e2))
+    t = torch.tensor(ms, dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)  # a step ends when the slowest rank has finished it
+    ms = t.cpu().numpy()
+    solves = torch.tensor([float(fleet.qp_solves)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(solves)
+    niter = torch.cat([fleet.log["niter_s"].flatten(), fleet.log["niter_l"].flatten()]).double()
+    niter = niter[niter >= 0]
+    steady = ms[min(8, T // 2):]  # the first steps start from the all-EVs-in-4-partitions initial condition
+    return {"metric": "closed_loop_price_step_latency_ms", "p50_ms": float(np.median(ms)),
+            "p95_ms": float(np.percentile(ms, 95)), "p50_ms_after_warmup": float(np.median(steady)),
+            "stations_per_gpu": S, "stations_total": S * world, "steps": T, "chain": args.closed_loop_chain,
+            "evs_total": 1000 * S * world, "qp_solves_in_price_loops": int(solves.item()),
+            "qp_solves_per_s": float(solves.item() / (ms.sum() * 1e-3)),
+            "price_iters_mean": float(niter.mean()), "price_iters_p95": float(np.percentile(niter.cpu().numpy(), 95)),
+            "bimpc_not_converged": int((fleet.log["bimpc_status"] != 0).sum()),
+            "aggregate_allreduce_ms_p50": float(np.median(agg_ms)),
+            "config": "BASELINE.json configs[3] shape (SURVEY.md 8d config 4): stations of 500+500 EVs, P=12, "
+                      "N_lo=N_bi=24, demand profile shifted U{0..23} h and scaled U(0.22,0.26)/0.25 per station, "
+                      "device RNG; full size = 4096 stations x 96 steps (tools/run_fleet.py, profiles/)"}
+
+
 def cpu_baseline_leg(args):
     work = draw_workload(args.batch, N_HORIZON, 2)
     used = cpu_pass(work, N_HORIZON)  # warm-up
@@ -390,6 +450,10 @@ def main():
     ap.add_argument("--batch", type=int, default=1024, help="QPs per GPU per step (configs[1]: 1024)")
     ap.add_argument("--no-saturated", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--closed-loop-stations", type=int, default=1024,
+                    help="stations per GPU of the closed-loop latency leg (0 = skip; configs[3] is 4096)")
+    ap.add_argument("--closed-loop-steps", type=int, default=24, help="closed-loop steps (configs[3]: 96)")
+    ap.add_argument("--closed-loop-chain", default="reference", choices=["reference", "partition"])
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
