@@ -44,6 +44,11 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return fma(y, t, y);
 }
 
+// max / min of two non-NaN doubles: one DSETP + a select.  (fmax / fmin quiet NaNs, which costs
+// ~8 SASS instructions per call in FP64; a NaN here propagates and ends as LOMPC_ST_MAXITER.)
+__device__ __forceinline__ double dmax2(double a, double b) { return a > b ? a : b; }
+__device__ __forceinline__ double dmin2(double a, double b) { return a < b ? a : b; }
+
 struct SolveArgs {
   int64_t B;
   const double* lmbd;

@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts 
             cost += x * fma(0.5 * D[k], x, gk) + 0.5 * cs.c * s * (s - 2.0 * gam);
             if (NSEG > 1) {
 #pragma unroll
-              for (int j = 1; j < NSEG; ++j) cost += (cs.slope[j] - cs.slope[j - 1]) * fmax(x - cs.brk[j], 0.0);
+              for (int j = 1; j < NSEG; ++j) cost += (cs.slope[j] - cs.slope[j - 1]) * dmax2(x - cs.brk[j], 0.0);
             }
             LOMPC_STAGE_FENCE();
           }

@@ -56,8 +56,8 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
     if (GREG) GR[GREG ? k : 0] = g; else GS[k * T] = g;
     D[k] = 2.0 * (lr * cs.theta2 + cs.q_scale * l3) + cs.d_base;
     if (!warm) W[k] = 0.0;
-    gmax = fmax(gmax, fabs(g));
-    dmax = fmax(dmax, D[k]);
+    gmax = dmax2(gmax, fabs(g));
+    dmax = dmax2(dmax, D[k]);
     l2sum += l2;
     LOMPC_STAGE_FENCE();
   }
@@ -73,6 +73,12 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
   for (int i = 0; i <= NSEG; ++i) brk[i] = cs.brk[i];
 #pragma unroll
   for (int j = 0; j < NSEG; ++j) slope[j] = cs.slope[j];
+  double blo[NSEG + 1], bhi[NSEG + 1];  // breakpoints -+ band
+#pragma unroll
+  for (int i = 0; i <= NSEG; ++i) {
+    blo[i] = brk[i] - band;
+    bhi[i] = brk[i] + band;
+  }
 
   double sN = 0.0, f = 0.5 * c * N * gam * gam, viol = 0.0, mu = 0.0;
   if (warm) {
@@ -81,14 +87,14 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
     double s0 = 0.0, f0 = 0.0;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      const double x = fmin(fmax(W[k], 0.0), wmax);
+      const double x = dmin2(dmax2(W[k], 0.0), wmax);
       W[k] = x;
       s0 += x;
       const double e = s0 - gam;
       f0 += x * fma(0.5 * D[k], x, LOMPC_G(k)) + 0.5 * c * e * e;
       if (NSEG > 1) {
 #pragma unroll
-        for (int j = 1; j < NSEG; ++j) f0 += (slope[j] - slope[j - 1]) * fmax(x - brk[j], 0.0);
+        for (int j = 1; j < NSEG; ++j) f0 += (slope[j] - slope[j - 1]) * dmax2(x - brk[j], 0.0);
       }
       LOMPC_STAGE_FENCE();
     }
@@ -110,56 +116,24 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
       const double wk = W[k], dk = D[k], gk = LOMPC_G(k);
       p = fma(c, s, p) - cg;
       const double q = fma(dk, wk, gk) + p;
-      bool binding = false;
-      int seg = 0;
-      double v, sl = 0.0;
-      if (NSEG == 1) {
-        if (wk <= band) {
-          binding = (q >= -tq);
-          v = binding ? 0.0 : -q;
-        } else if (wk >= wmax - band) {
-          binding = (q <= tq);
-          v = binding ? 0.0 : q;
-        } else {
-          v = fabs(q);
-        }
-      } else {
-        int at = -1;
+      // Subdifferential [s_lo, s_hi] of the separable term at w_k, a coordinate within `band` of
+      // a breakpoint counting as sitting on it (+-1e300 at the box ends).  Interior of a piece:
+      // s_lo == s_hi = its slope.  -q outside the interval (by more than the tolerance) moves
+      // the coordinate onto the neighbouring piece, inside it the coordinate stays put (binding).
+      const double mq = -q;
+      double s_hi = slope[0], s_lo = slope[0];
 #pragma unroll
-        for (int i = 0; i <= NSEG; ++i)
-          if (fabs(wk - brk[i]) <= band) at = i;
-#pragma unroll
-        for (int j = 1; j < NSEG; ++j) seg += (wk > brk[j] + band) ? 1 : 0;  // containing segment
-        const double mq = -q;
-        if (at >= 0) {
-          // slopes left / right of breakpoint `at` (+-inf at the box ends)
-          double s_hi = 1e300, s_lo = -1e300;
-#pragma unroll
-          for (int j = 0; j < NSEG; ++j) {
-            if (at == j) s_hi = slope[j];
-            if (at == j + 1) s_lo = slope[j];
-          }
-          if (mq > s_hi + tq) {
-            seg = at;
-            sl = s_hi;
-            v = mq - s_hi;
-          } else if (mq < s_lo - tq) {
-            seg = at - 1;
-            sl = s_lo;
-            v = s_lo - mq;
-          } else {
-            binding = true;
-            seg = at < NSEG ? at : NSEG - 1;
-            v = 0.0;
-          }
-        } else {
-#pragma unroll
-          for (int j = 0; j < NSEG; ++j)
-            if (seg == j) sl = slope[j];
-          v = fabs(q + sl);
-        }
+      for (int j = 1; j < NSEG; ++j) {
+        if (wk >= blo[j]) s_hi = slope[j];
+        if (wk > bhi[j]) s_lo = slope[j];
       }
-      viol = fmax(viol, v);
+      if (wk >= blo[NSEG]) s_hi = 1e300;
+      if (wk <= band) s_lo = -1e300;
+      const bool right = mq > s_hi + tq, left = mq < s_lo - tq, atbp = s_lo < s_hi;
+      const bool binding = atbp && !right && !left;
+      const double sl = left ? s_lo : s_hi;  // slope of the working piece (unused when binding)
+      const double v = right ? mq - s_hi : (left ? s_lo - mq : (atbp ? 0.0 : fabs(mq - s_hi)));
+      viol = dmax2(viol, v);
       const double dm = dk + mu;  // proximal model of the safeguard: d + mu, g - mu w
       const double gm = fma(-mu, wk, gk);
       const double tq_ = fma(c, pb, pa);     // Q * pb,  Q = c + P
@@ -200,23 +174,23 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
         const double inv = INV[k * T];
         x = fma(-slope[NSEG - 1], inv, x0);
 #pragma unroll
-        for (int j = NSEG - 2; j >= 0; --j) x = fmin(fma(-slope[j], inv, x0), fmax(brk[j + 1], x));
+        for (int j = NSEG - 2; j >= 0; --j) x = dmin2(fma(-slope[j], inv, x0), dmax2(brk[j + 1], x));
       }
-      x = fmin(fmax(x, 0.0), wmax);
+      x = dmin2(dmax2(x, 0.0), wmax);
       WN[k * T] = x;
       s += x;
       const double e = s - gam;
       fn += x * fma(0.5 * D[k], x, LOMPC_G(k)) + 0.5 * c * e * e;
       if (NSEG > 1) {
 #pragma unroll
-        for (int j = 1; j < NSEG; ++j) fn += (slope[j] - slope[j - 1]) * fmax(x - brk[j], 0.0);
+        for (int j = 1; j < NSEG; ++j) fn += (slope[j] - slope[j - 1]) * dmax2(x - brk[j], 0.0);
       }
       LOMPC_STAGE_FENCE();
     }
     if (fn <= f + ftol) {
 #pragma unroll
       for (int k = 0; k < N; ++k) W[k] = WN[k * T];
-      f = fmin(f, fn);
+      f = dmin2(f, fn);
       sN = s;
       mu = 0.0;
     } else {
@@ -276,7 +250,7 @@ __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts c
     cost += x * fma(0.5 * D[k], x, LOMPC_G(k)) + 0.5 * c * s * (s - 2.0 * gam);
     if (NSEG > 1) {
 #pragma unroll
-      for (int j = 1; j < NSEG; ++j) cost += (slope[j] - slope[j - 1]) * fmax(x - brk[j], 0.0);
+      for (int j = 1; j < NSEG; ++j) cost += (slope[j] - slope[j - 1]) * dmax2(x - brk[j], 0.0);
     }
     LOMPC_STAGE_FENCE();
   }
