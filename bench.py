@@ -288,9 +288,13 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         except Exception:
             pass
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
-        traffic = None
-        try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json"))).get("bytes_per_launch")
+        traffic, traffic_src = None, None
+        try:  # DRAM bytes of the dominant kernel from the committed ncu --set full capture, per launch
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
+            per_qp = 0.5 * (tj["small"]["bytes_per_qp"] + tj["large"]["bytes_per_qp"])
+            traffic = per_qp * (args.batch // 2)
+            traffic_src = (f"{per_qp:.0f} B/QP (dram__bytes_read+write of {tj['source']}) x {args.batch // 2} QPs per "
+                           f"launch; algorithmic {bytes_per_qp(N)} B/QP")
         except Exception:
             pass
         h2d = bytes_per_qp(N) * 0 + 8 * (3 * N + 2) * args.batch
@@ -302,7 +306,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             "config": workload_config(args),
             "roofline": {
                 "bound": "fp64", "achieved": achieved_tf, "peak": fp64_peak, "unit": "TFLOP/s",
-                "frac": achieved_tf / fp64_peak, "traffic": traffic,
+                "frac": achieved_tf / fp64_peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": "DFMA chain microbenchmark measured in this run (MEASURED_PEAKS.json has no FP64 figure)",
                 "mean_iters": iters_mean, "flops_per_step": flops_step,
                 "hbm": {"achieved": bytes_step / (ms_per_step * 1e-3) / 1e9, "peak": hbm_peak, "unit": "GB/s",
