@@ -6,7 +6,7 @@ simulates ONE station with Python loops over partitions and EVs
     partition the EVs by SoC      charging_station.py:111-116   fleet_partition_dev
     group statistics              price_solver.py:66-77          price_group_stats_dev
     BiMPC parameters + solve      charging_station.py:187-227    fleet_bimpc_params_dev, bimpc_solve_batch_dev
-    price loop per partition      charging_station.py:265-305    price_solve_dev (S groups per call)
+    price loop per partition      charging_station.py:265-305    price_solve_chain_dev / price_solve_dev
     EV responses                  charging_station.py:307-327    price_w0_price0_dev
     plant update                  charging_station.py:329-365    fleet_apply_charge_dev, fleet_battery_dev
 
@@ -15,8 +15,9 @@ host only sequences kernel launches and reads P+1 slice sizes per EV type and st
 
 ``chain="reference"`` keeps the reference's warm-start chain: the PriceSolver of an EV type
 is shared by its P partitions, so partition p starts from the prices of the last non-empty
-partition solved before it (``prev_prices``, price_solver.py:56,104,166) - here: one
-``price_solve_dev`` per partition over the S stations, 2P sequential device loops per step.
+partition solved before it (``prev_prices``, price_solver.py:56,104,166) - here
+``price_solve_chain_dev``: one CTA per station walks its P partitions in that order, stations
+never wait for each other.
 ``chain="partition"`` solves all P*S groups of a type in ONE device loop, each group
 warm-started from its own prices of the previous step (different iterates, same fixed-point
 conditions; P times fewer sequential loops).
@@ -186,10 +187,6 @@ class ChargingStationFleet:
         main = torch.cuda.current_stream(self.dev)
         ready = torch.cuda.Event()
         ready.record(main)
-        if self.chain == "reference":
-            base = {k: self.w[k]["off"][::S].cpu().numpy() for k in ("s", "l")}  # P+1 slice starts (one sync)
-        else:
-            base = None
 
         def run_type(k):
             w, h = self.w[k], self.solver[k]._h
@@ -200,24 +197,17 @@ class ChargingStationFleet:
             iters_sum = 0
             with torch.cuda.stream(stream):
                 if self.chain == "reference":
-                    for p in range(P):
-                        b0, b1 = int(base[k][p]), int(base[k][p + 1])
-                        g0 = p * S
-                        if b1 > b0:
-                            self._ck(lib.price_solve_dev(
-                                h, S, b1 - b0, w["reb"][p].data_ptr(), w["ysort"][b0:].data_ptr(),
-                                w["w_ref"][g0:].data_ptr(), self.lmbd_r0.data_ptr(), self.r, self.max_price_iter,
-                                tol_max, float(self.solver[k].eps_reg), float(self.solver[k].eps_tol),
-                                self.prev[k].data_ptr(), w["iters"][g0:].data_ptr(), w["pre"][g0:].data_ptr(),
-                                w["post"][g0:].data_ptr(), None, None, None, 0, C.byref(total), sp))
-                            iters_sum += total.value
-                            self._account(h)
-                        else:
-                            w["iters"][g0:g0 + S].fill_(-1)
-                        self._ck(lib.fleet_keep_prices_dev(
-                            self.device, S, 3 * N_lo, w["counts"][g0:].data_ptr(), self.prev[k].data_ptr(),
-                            self.prices[k][g0:].data_ptr(), w["pre"][g0:].data_ptr(), w["post"][g0:].data_ptr(),
-                            w["red"][g0:].data_ptr(), sp))
+                    # one CTA per station walks its P partitions in order (price_station_chain_kernel)
+                    self._ck(lib.price_solve_chain_dev(
+                        h, S, P, B, w["off"].data_ptr(), w["ysort"].data_ptr(), w["w_ref"].data_ptr(),
+                        self.lmbd_r0.data_ptr(), self.r, self.max_price_iter, tol_max, float(self.solver[k].eps_reg),
+                        float(self.solver[k].eps_tol), self.prev[k].data_ptr(), self.prices[k].data_ptr(),
+                        w["iters"].data_ptr(), w["pre"].data_ptr(), w["post"].data_ptr(), C.byref(total), sp))
+                    iters_sum += total.value
+                    self._account(h)
+                    self._ck(lib.fleet_keep_prices_dev(
+                        self.device, G, 3 * N_lo, w["counts"].data_ptr(), self.prices[k].data_ptr(),
+                        self.prices[k].data_ptr(), w["pre"].data_ptr(), w["post"].data_ptr(), w["red"].data_ptr(), sp))
                 else:
                     self._ck(lib.price_solve_dev(
                         h, G, B, w["off"].data_ptr(), w["ysort"].data_ptr(), w["w_ref"].data_ptr(),
@@ -226,12 +216,10 @@ class ChargingStationFleet:
                         w["pre"].data_ptr(), w["post"].data_ptr(), None, None, None, 0, C.byref(total), sp))
                     iters_sum += total.value
                     self._account(h)
-                    for p in range(P):  # price reduction / NaN for empty groups (prices keep the warm start)
-                        g0 = p * S
-                        self._ck(lib.fleet_keep_prices_dev(
-                            self.device, S, 3 * N_lo, w["counts"][g0:].data_ptr(), self.prices[k][g0:].data_ptr(),
-                            self.prices[k][g0:].data_ptr(), w["pre"][g0:].data_ptr(), w["post"][g0:].data_ptr(),
-                            w["red"][g0:].data_ptr(), sp))
+                    # price reduction / NaN for empty groups
+                    self._ck(lib.fleet_keep_prices_dev(
+                        self.device, G, 3 * N_lo, w["counts"].data_ptr(), self.prices[k].data_ptr(),
+                        self.prices[k].data_ptr(), w["pre"].data_ptr(), w["post"].data_ptr(), w["red"].data_ptr(), sp))
             done = torch.cuda.Event()
             done.record(stream)
             return iters_sum, done

@@ -740,9 +740,14 @@ int launch_fused(lompc_handle* h, const lompc::FusedArgs& a, cudaStream_t s) {
   if (!configured) {
     CK(cudaFuncSetAttribute(lompc::price_group_loop_kernel<N, NSEG, T, MINB, GREG>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(lompc::price_station_chain_kernel<N, NSEG, T, MINB, GREG>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     configured = true;
   }
-  lompc::price_group_loop_kernel<N, NSEG, T, MINB, GREG><<<(unsigned)a.G, T, smem, s>>>(h->cs, a);
+  if (a.chain_P > 0)
+    lompc::price_station_chain_kernel<N, NSEG, T, MINB, GREG><<<(unsigned)a.chain_S, T, smem, s>>>(h->cs, a);
+  else
+    lompc::price_group_loop_kernel<N, NSEG, T, MINB, GREG><<<(unsigned)a.G, T, smem, s>>>(h->cs, a);
   COUNT_LAUNCH();
   CK(cudaGetLastError());
   return LOMPC_OK;
@@ -761,24 +766,14 @@ int price_solve_fused(lompc_handle* h, const lompc::FusedArgs& a, cudaStream_t s
   return LOMPC_ERR_ARG;
 }
 
-}  // namespace
-
-extern "C" {
-
-int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, const double* y0,
-                    const double* w_ref, const double* lmbd_r, int r, int max_iter,
-                    int tol_type_max, double eps_reg, double eps_tol, double* prices,
-                    int32_t* iters, double* price_pre, double* price_post, double* w_k_out,
-                    double* hist_ac, double* hist_pred, int hist_cap, int32_t* total_iters,
-                    void* stream) {
-  if (!h || G < 0 || B < 0 || !group_off || !y0 || !w_ref || !lmbd_r || !prices || !iters ||
-      !price_pre || !price_post)
-    return LOMPC_ERR_ARG;
-  if (total_iters) *total_iters = 0;
-  if (G == 0) return LOMPC_OK;
-  CK(cudaSetDevice(h->device));
-  if ((h->cs.N == 24 || h->cs.N == 12) && h->variant != 1 && h->loop_mode != 1) {
-    // fused, device-resident loop: one CTA per group (lompc_price_fused.cuh)
+// Fused, device-resident loop (lompc_price_fused.cuh): one CTA per group, or - chain_P > 0 - one CTA
+// per station running its chain_P partitions in the reference's warm-start order.
+int price_solve_fused_entry(lompc_handle* h, int32_t G, int64_t B, const int32_t* group_off, const double* y0,
+                            const double* w_ref, const double* lmbd_r, int r, int max_iter, int tol_type_max,
+                            double eps_reg, double eps_tol, double* prices, int32_t* iters, double* price_pre,
+                            double* price_post, double* w_k_out, double* hist_ac, double* hist_pred, int hist_cap,
+                            int32_t* total_iters, int chain_S, int chain_P, double* chain_prev, void* stream) {
+  {
     if ((r != 2 * h->cs.N && r != 3 * h->cs.N) || max_iter < 1) return LOMPC_ERR_ARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     int rc = ensure_pws(h, 256 + (size_t)(B + G) * h->cs.N * sizeof(double));
@@ -799,6 +794,7 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
     a.qp_count = reinterpret_cast<unsigned long long*>(flags + 4);
     a.w_scratch = reinterpret_cast<double*>(static_cast<char*>(h->pws) + 256);
     a.B = B;
+    a.chain_S = chain_S; a.chain_P = chain_P; a.chain_prev = chain_prev;
     rc = price_solve_fused(h, a, s);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->poll, flags, 64, cudaMemcpyDeviceToHost, s));
@@ -810,6 +806,28 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
     if (h->poll[1]) return LOMPC_ERR_CONSTS;  // y0 outside [0, y_max], price_solver.py:71
     return LOMPC_OK;
   }
+}
+
+}  // namespace
+
+extern "C" {
+
+int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, const double* y0,
+                    const double* w_ref, const double* lmbd_r, int r, int max_iter,
+                    int tol_type_max, double eps_reg, double eps_tol, double* prices,
+                    int32_t* iters, double* price_pre, double* price_post, double* w_k_out,
+                    double* hist_ac, double* hist_pred, int hist_cap, int32_t* total_iters,
+                    void* stream) {
+  if (!h || G < 0 || B < 0 || !group_off || !y0 || !w_ref || !lmbd_r || !prices || !iters ||
+      !price_pre || !price_post)
+    return LOMPC_ERR_ARG;
+  if (total_iters) *total_iters = 0;
+  if (G == 0) return LOMPC_OK;
+  CK(cudaSetDevice(h->device));
+  if ((h->cs.N == 24 || h->cs.N == 12) && h->variant != 1 && h->loop_mode != 1)
+    return price_solve_fused_entry(h, G, B, group_off, y0, w_ref, lmbd_r, r, max_iter, tol_type_max, eps_reg, eps_tol,
+                                   prices, iters, price_pre, price_post, w_k_out, hist_ac, hist_pred, hist_cap,
+                                   total_iters, 0, 0, nullptr, stream);
   // phase-split loop (any horizon; also the path a multi-GPU caller drives, see price_shard_*):
   // the reduction buffers live in a second grow-only allocation of the handle
   const int N = h->cs.N;
@@ -840,6 +858,21 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
   }
   if (total_iters) *total_iters = it;
   return price_shard_finish(h, price_pre, price_post, w_k_out, stream);
+}
+
+int price_solve_chain_dev(lompc_t* h, int32_t S, int32_t P, int64_t B, const int32_t* group_off, const double* y0,
+                          const double* w_ref, const double* lmbd_r, int r, int max_iter, int tol_type_max,
+                          double eps_reg, double eps_tol, double* prev_prices, double* prices, int32_t* iters,
+                          double* price_pre, double* price_post, int32_t* max_group_iters, void* stream) {
+  if (!h || S < 1 || P < 1 || B < 0 || !group_off || !y0 || !w_ref || !lmbd_r || !prev_prices || !prices || !iters ||
+      !price_pre || !price_post)
+    return LOMPC_ERR_ARG;
+  if (max_group_iters) *max_group_iters = 0;
+  if (!((h->cs.N == 24 || h->cs.N == 12))) return LOMPC_ERR_ARG;  // compiled horizons of the fused kernel
+  CK(cudaSetDevice(h->device));
+  return price_solve_fused_entry(h, S * P, B, group_off, y0, w_ref, lmbd_r, r, max_iter, tol_type_max, eps_reg, eps_tol,
+                                 prices, iters, price_pre, price_post, nullptr, nullptr, nullptr, 0, max_group_iters, S,
+                                 P, prev_prices, stream);
 }
 
 int price_lp_rows_dev(int device, int N, int nb, const double* a, const double* b, const double* c,

@@ -45,6 +45,8 @@ struct FusedArgs {
   double* w_scratch;         // [B + G, N] LoMPC iterates of groups with more than T - 1 EVs (rows b0 + i; the
                              // virtual EV of group g in row B + g); smaller groups keep them in registers
   int64_t B;
+  int chain_S, chain_P;      // price_station_chain_kernel: stations, partitions (G = chain_P * chain_S)
+  double* chain_prev;        // [chain_S, 3N] warm start carried along the chain (in/out)
   unsigned long long* qp_count;  // [0] total LoMPC QP solves, [1] / [2] SM cycles summed over groups spent in
                                  // the LoMPC passes / in thread 0's price step (or NULL)
 };
@@ -57,16 +59,18 @@ struct FusedSmem {
   static constexpr size_t bytes = (size_t)kDoubles * sizeof(double) + 3 * N + 16;
 };
 
-template <int N, int NSEG, int T, int MINB, bool GREG>
-__global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts cs, const FusedArgs a) {
-  extern __shared__ double smem[];
+// The loop of ONE group, run by the whole CTA.  `p_in` = warm start (3N doubles), the regularised
+// prices go to `p_out` and, if not NULL, to `p_out2`.  Returns false for an empty group (never
+// solved, charging_station.py:277,293; nothing is written but iters = -1).
+template <int N, int NSEG, int T, bool GREG>
+__device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArgs& a, const int g, double* smem,
+                                                const double* p_in, double* p_out, double* p_out2) {
   const int tid = threadIdx.x;
-  const int g = blockIdx.x;
   const int b0 = a.group_off[g], b1 = a.group_off[g + 1];
   const int n = b1 - b0;
-  if (n <= 0) {  // empty partition: never solved (charging_station.py:277,293); prices stay
+  if (n <= 0) {
     if (tid == 0) a.iters[g] = -1;
-    return;
+    return false;
   }
   constexpr int kK1 = FusedSmem<N, NSEG, T, GREG>::kK1;
   double* LM = smem + kK1;          // [3N] current prices
@@ -104,7 +108,7 @@ __global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts 
     SC[3] = v;
   }
   if (bad) atomicExch(a.flags + 1, 1);
-  for (int k = tid; k < 3 * N; k += T) LM[k] = a.prices[(size_t)g * 3 * N + k];
+  for (int k = tid; k < 3 * N; k += T) LM[k] = p_in[k];
   for (int k = tid; k < N; k += T) WREF[k] = a.w_ref[(size_t)g * N + k];
   __syncthreads();
   mn = SC[2];
@@ -243,9 +247,44 @@ __global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts 
     }
   }
   __syncthreads();
-  for (int k = tid; k < 3 * N; k += T) a.prices[(size_t)g * 3 * N + k] = LM[k];
+  for (int k = tid; k < 3 * N; k += T) {
+    p_out[k] = LM[k];
+    if (p_out2) p_out2[k] = LM[k];
+  }
   if (a.w_k_out)
     for (int k = tid; k < N; k += T) a.w_k_out[(size_t)g * N + k] = WK[k];
+  return true;
+}
+
+// Grid = the groups: every CTA runs its own group.
+template <int N, int NSEG, int T, int MINB, bool GREG>
+__global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts cs, const FusedArgs a) {
+  extern __shared__ double smem[];
+  const int g = blockIdx.x;
+  double* row = a.prices + (size_t)g * 3 * N;
+  group_loop_body<N, NSEG, T, GREG>(cs, a, g, smem, row, row, nullptr);
+}
+
+// Grid = the stations: every CTA runs the P partitions of ITS station one after the other, each
+// warm-started from the prices of the last non-empty partition before it - the warm-start chain of
+// the reference, whose PriceSolver object (and its prev_prices) is shared by the partitions of an EV
+// type (price_solver.py:56,104,166; charging_station.py:273-304).  Groups are partition-major
+// (g = p S + s); chain_prev[S,3N] is the carried warm start (in/out), a.prices[G,3N] receives every
+// group's prices (zeros for an empty group, charging_station.py:270).  Stations never wait for each
+// other: the step ends when the slowest STATION is done, not after the sum of the slowest groups.
+template <int N, int NSEG, int T, int MINB, bool GREG>
+__global__ void __launch_bounds__(T, MINB) price_station_chain_kernel(const Consts cs, const FusedArgs a) {
+  extern __shared__ double smem[];
+  const int s = blockIdx.x, S = a.chain_S;
+  double* prev = a.chain_prev + (size_t)s * 3 * N;
+  for (int p = 0; p < a.chain_P; ++p) {
+    const int g = p * S + s;
+    double* row = a.prices + (size_t)g * 3 * N;
+    const bool solved = group_loop_body<N, NSEG, T, GREG>(cs, a, g, smem, prev, prev, row);
+    if (!solved)
+      for (int k = threadIdx.x; k < 3 * N; k += T) row[k] = 0.0;
+    __syncthreads();  // prev (global) is re-read by the next group; shared memory is reused
+  }
 }
 
 }  // namespace lompc

@@ -146,6 +146,20 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
                     double* hist_ac, double* hist_pred, int hist_cap, int32_t* total_iters,
                     void* stream);
 
+/* compute_optimal_prices along the reference's WARM-START CHAIN, for S stations with P partitions
+ * each: the PriceSolver object of an EV type is shared by its partitions, so partition p starts from
+ * the prices of the last non-empty partition solved before it (price_solver.py:56,104,166;
+ * charging_station.py:273-304).  Groups are numbered partition-major, g = p*S + s; group_off[P*S+1],
+ * w_ref[P*S,N], lmbd_r[P*S], iters / price_pre / price_post[P*S].  prev_prices[S,3N] is the carried
+ * warm start (in: PriceSolver.prev_prices of every station, out: the same after the step);
+ * prices[P*S,3N] receives every group's regularised prices (zeros for an empty group,
+ * charging_station.py:270; its iters = -1).  One CTA per station runs its P loops back to back, so
+ * stations do not wait for each other.  N = 12 or 24.  Synchronises; max_group_iters = longest loop. */
+int price_solve_chain_dev(lompc_t* h, int32_t S, int32_t P, int64_t B, const int32_t* group_off, const double* y0,
+                          const double* w_ref, const double* lmbd_r, int r, int max_iter, int tol_type_max,
+                          double eps_reg, double eps_tol, double* prev_prices, double* prices, int32_t* iters,
+                          double* price_pre, double* price_post, int32_t* max_group_iters, void* stream);
+
 /* price_solve_dev runs, for the compiled horizons (N = 12, 24), ONE fused kernel with one
  * CTA per group that iterates its group to convergence on the device (mode 0, default);
  * mode 1 forces the phase-split loop below (any N; one host poll per iteration).  Both give
