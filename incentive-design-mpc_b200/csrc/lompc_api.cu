@@ -868,8 +868,42 @@ int price_solve_chain_dev(lompc_t* h, int32_t S, int32_t P, int64_t B, const int
       !price_pre || !price_post)
     return LOMPC_ERR_ARG;
   if (max_group_iters) *max_group_iters = 0;
-  if (!((h->cs.N == 24 || h->cs.N == 12))) return LOMPC_ERR_ARG;  // compiled horizons of the fused kernel
   CK(cudaSetDevice(h->device));
+  if (!((h->cs.N == 24 || h->cs.N == 12) && h->variant != 1 && h->loop_mode != 1)) {
+    // no fused kernel for this horizon: the same chain as P phase-split loops, one per partition slice
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int N = h->cs.N;
+    int32_t* reb = nullptr;
+    CK(cudaMalloc(&reb, (size_t)(S + 1) * sizeof(int32_t)));
+    int rc = LOMPC_OK;
+    for (int p = 0; p < P && rc == LOMPC_OK; ++p) {
+      const int32_t* off_p = group_off + (size_t)p * S;
+      int32_t ends[2] = {0, 0};
+      cudaError_t e = cudaMemcpyAsync(&ends[0], off_p, 4, cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(&ends[1], off_p + S, 4, cudaMemcpyDeviceToHost, s);
+      if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+      if (e != cudaSuccess) { rc = cuda_fail(e, "price_solve_chain_dev"); break; }
+      const size_t g0 = (size_t)p * S;
+      if (ends[1] > ends[0]) {
+        lompc::rebase_offsets_kernel<<<nblk(S + 1, 128), 128, 0, s>>>(S, off_p, reb);
+        COUNT_LAUNCH();
+        int32_t tot = 0;
+        rc = price_solve_dev(h, S, ends[1] - ends[0], reb, y0 + ends[0], w_ref + g0 * N, lmbd_r + g0, r, max_iter,
+                             tol_type_max, eps_reg, eps_tol, prev_prices, iters + g0, price_pre + g0, price_post + g0,
+                             nullptr, nullptr, nullptr, 0, &tot, stream);
+        if (max_group_iters && tot > *max_group_iters) *max_group_iters = tot;
+      } else {
+        e = cudaMemsetAsync(iters + g0, 0xff, (size_t)S * 4, s);  // -1: empty partition
+        if (e != cudaSuccess) { rc = cuda_fail(e, "price_solve_chain_dev"); break; }
+      }
+      lompc::chain_rows_kernel<<<nblk((int64_t)S * 3 * N, 256), 256, 0, s>>>(S, 3 * N, off_p, prev_prices,
+                                                                             prices + g0 * 3 * N);
+      COUNT_LAUNCH();
+    }
+    cudaStreamSynchronize(s);
+    cudaFree(reb);
+    return rc;
+  }
   return price_solve_fused_entry(h, S * P, B, group_off, y0, w_ref, lmbd_r, r, max_iter, tol_type_max, eps_reg, eps_tol,
                                  prices, iters, price_pre, price_post, nullptr, nullptr, nullptr, 0, max_group_iters, S,
                                  P, prev_prices, stream);

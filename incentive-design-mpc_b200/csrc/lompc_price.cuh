@@ -485,6 +485,21 @@ __global__ void mean_kernel(int G, const int32_t* __restrict__ off, const double
   mean[g] = b1 > b0 ? s / (b1 - b0) : 0.0;
 }
 
+// Helpers of the per-partition fallback of price_solve_chain_dev (horizons without a fused kernel).
+__global__ void rebase_offsets_kernel(int S, const int32_t* __restrict__ off_abs, int32_t* __restrict__ off_reb) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i <= S) off_reb[i] = off_abs[i] - off_abs[0];
+}
+
+// rows[s,:] = the group is non-empty ? prev[s,:] : 0   (charging_station.py:270,286)
+__global__ void chain_rows_kernel(int S, int row, const int32_t* __restrict__ off_abs, const double* __restrict__ prev,
+                                  double* __restrict__ rows) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (int64_t)S * row) return;
+  const int s = (int)(i / row);
+  rows[i] = off_abs[s + 1] > off_abs[s] ? prev[i] : 0.0;
+}
+
 __global__ void init_groups_kernel(int G, int max_iter, const int32_t* __restrict__ off,
                                    int32_t* __restrict__ skip, int32_t* __restrict__ iters,
                                    int32_t* __restrict__ nnqp_status) {

@@ -154,7 +154,8 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
  * warm start (in: PriceSolver.prev_prices of every station, out: the same after the step);
  * prices[P*S,3N] receives every group's regularised prices (zeros for an empty group,
  * charging_station.py:270; its iters = -1).  One CTA per station runs its P loops back to back, so
- * stations do not wait for each other.  N = 12 or 24.  Synchronises; max_group_iters = longest loop. */
+ * stations do not wait for each other (N = 12, 24; other horizons run the same chain as P phase-split
+ * loops, one per partition slice).  Synchronises; max_group_iters = length of the longest loop.      */
 int price_solve_chain_dev(lompc_t* h, int32_t S, int32_t P, int64_t B, const int32_t* group_off, const double* y0,
                           const double* w_ref, const double* lmbd_r, int r, int max_iter, int tol_type_max,
                           double eps_reg, double eps_tol, double* prev_prices, double* prices, int32_t* iters,

@@ -22,11 +22,13 @@ def _consts(Tf, N_bi, N_lo, M2, P, cost_type, price_type="linear-convex"):
 
 
 @pytest.mark.parametrize("price_type", ["linear-convex", "linear"])
-def test_fleet_reference_chain_equals_single_station_runs(price_type):
+@pytest.mark.parametrize("sizes", [(8, 4, 40, 6), (16, 12, 120, 12)])  # (N_bi, N_lo, M, P); N_lo = 12 runs the fused chain kernel
+def test_fleet_reference_chain_equals_single_station_runs(price_type, sizes):
     from chargingstation.charging_station import ChargingStation
     from chargingstation.fleet import ChargingStationFleet
     Tf, S = 4, 3
-    consts = _consts(Tf, 8, 4, 40, 6, 1, price_type)
+    N_bi, N_lo, M, P = sizes
+    consts = _consts(Tf, N_bi, N_lo, M, P, 1, price_type)
     scale = np.array([1.0, 0.97, 1.04])
     demand = scale[:, None] * consts.demand[None, :]
     fleet = ChargingStationFleet(consts, S, demand=demand, seed=100, rng="numpy", chain="reference")
