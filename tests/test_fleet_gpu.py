@@ -51,11 +51,11 @@ def test_fleet_reference_chain_equals_single_station_runs(price_type, sizes):
                          ("inputs", "w_s"), ("inputs", "w_l"), ("bounds", "beta_s"), ("bounds", "beta_l"),
                          ("statistics", "gamma_sm"), ("statistics", "gamma_lm"), ("prices", "avg_price_s"),
                          ("prices", "avg_price_l")):
-            assert np.max(np.abs(got[grp][key] - ref[grp][key])) <= 1e-8, (grp, key)
+            assert np.max(np.abs(got[grp][key] - ref[grp][key]) / np.maximum(1.0, np.abs(ref[grp][key]))) <= 1e-8, (grp, key)
         for key in ("price_red_s", "price_red_l"):
             a, b = got["prices"][key], ref["prices"][key]
             assert np.array_equal(np.isnan(a), np.isnan(b))
-            assert np.nanmax(np.abs(a - b)) <= 1e-8
+            assert np.nanmax(np.abs(a - b) / np.maximum(1.0, np.abs(b))) <= 1e-8
         assert np.max(np.abs(fleet.y["s"][s].cpu().numpy() - one.y_s)) <= 1e-9
         assert abs(float(fleet.x[s]) - one.x) <= 1e-9
 
