@@ -110,7 +110,7 @@ class LoMPC:
                                          np.array([gamma], dtype=np.float64))
         return w[0], float(cost[0])
 
-    def solve_lompc_batch(self, lmbd, lmbd_r, gamma, return_info: bool = False, out=None):
+    def solve_lompc_batch(self, lmbd, lmbd_r, gamma, return_info: bool = False, out=None, wait: bool = True):
         """Batched ``solve_lompc``.
 
         lmbd:   [B, 3N] or [3N] (one price vector broadcast to the batch, the
@@ -121,7 +121,9 @@ class LoMPC:
         asynchronous on the current torch stream, no status check).
         Returns (w[B, N], cost[B]) and, with ``return_info``, a dict with
         ``status``, ``iters`` and ``kkt_res`` per QP.  ``out=(w, cost)`` reuses
-        preallocated (e.g. pinned) output buffers."""
+        preallocated (e.g. pinned) output buffers.  ``wait=False`` (numpy path) only
+        enqueues the copies and the kernel on this object's stream - call ``wait()``
+        before reading the outputs; independent LoMPC objects overlap that way."""
         if _is_torch_cuda(gamma):
             return self._solve_batch_torch(lmbd, lmbd_r, gamma, return_info, out)
         N = self.N
@@ -154,10 +156,12 @@ class LoMPC:
             ptrs = (status.ctypes.data, iters.ctypes.data, kkt.ctypes.data)
         else:
             ptrs = (None, None, None)  # the C side still fetches and checks the status
-        rc = self._lib.lompc_solve_batch_host(
-            self._h, B, lmbd.ctypes.data, lm_stride, lmbd_r.ctypes.data, lr_stride,
-            gamma.ctypes.data, w.ctypes.data, cost.ctypes.data, *ptrs)
+        fn = self._lib.lompc_solve_batch_host if wait else self._lib.lompc_solve_batch_host_async
+        rc = fn(self._h, B, lmbd.ctypes.data, lm_stride, lmbd_r.ctypes.data, lr_stride,
+                gamma.ctypes.data, w.ctypes.data, cost.ctypes.data, *ptrs)
         _native.raise_for(rc)
+        if not wait:
+            self._pending = (lmbd, lmbd_r, gamma, w, cost, ptrs)  # keep the host buffers alive
         if return_info:
             return w, cost, {"status": status, "iters": iters, "kkt_res": kkt}
         return w, cost
@@ -197,6 +201,12 @@ class LoMPC:
         if return_info:
             return w, cost, {"status": status, "iters": iters, "kkt_res": kkt}
         return w, cost
+
+    def wait(self) -> None:
+        """Completes a ``solve_lompc_batch(..., wait=False)``; raises like the blocking call."""
+        rc = self._lib.lompc_host_wait(self._h)
+        self._pending = None
+        _native.raise_for(rc)
 
     # --------------------------------------------------------------- accessors
     def get_sc_modulus(self) -> float:

@@ -61,6 +61,11 @@ struct lompc_handle {
   // grow-only device workspace for the _host entry points
   void* ws;
   size_t ws_bytes;
+  cudaStream_t hstream;       // stream of the host entry points (non-blocking, created on first use)
+  int32_t* hst;               // pinned status buffer used when the caller passes status = NULL
+  size_t hst_cap;
+  int64_t pending_B;          // batch of the enqueued, not yet awaited host call
+  const int32_t* pending_status;
   // grow-only device workspace of the price loop + pinned poll word
   int variant;  // 0 auto, 1 = any-N shared-memory kernel, 2.. = register-kernel variants
   int loop_mode;  // price loop: 0 auto (fused one-CTA-per-group kernel when compiled for N), 1 = phase-split host loop
@@ -225,6 +230,11 @@ int lompc_create(int N, double delta, double theta, double y_max, double w_max, 
   h->delta = delta;
   h->ws = nullptr;
   h->ws_bytes = 0;
+  h->hstream = nullptr;
+  h->hst = nullptr;
+  h->hst_cap = 0;
+  h->pending_B = 0;
+  h->pending_status = nullptr;
   h->variant = 0;
   h->loop_mode = 0;
   h->last_qp_solves = 0;
@@ -241,6 +251,11 @@ int lompc_create(int N, double delta, double theta, double y_max, double w_max, 
 int lompc_destroy(lompc_t* h) {
   if (!h) return LOMPC_OK;
   cudaSetDevice(h->device);
+  if (h->hstream) {
+    cudaStreamSynchronize(h->hstream);
+    cudaStreamDestroy(h->hstream);
+  }
+  if (h->hst) cudaFreeHost(h->hst);
   if (h->ws) cudaFree(h->ws);
   if (h->pws) cudaFree(h->pws);
   if (h->poll) cudaFreeHost(h->poll);
@@ -310,16 +325,20 @@ int lompc_solve_batch_dev(lompc_t* h, int64_t B, const double* lmbd, int64_t lmb
   return h->cs.large ? launch_solve<4>(h, a, s) : launch_solve<1>(h, a, s);
 }
 
-int lompc_solve_batch_host(lompc_t* h, int64_t B, const double* lmbd, int64_t lmbd_stride,
-                           const double* lmbd_r, int64_t lmbd_r_stride, const double* gamma,
-                           double* w_out, double* cost_out, int32_t* status, int32_t* iters,
-                           double* kkt_res) {
+// Host entry point in two halves: enqueue (copies in, kernel, copies out on the handle's own
+// non-blocking stream) and wait (synchronise, map the per-QP status onto the return code).
+int lompc_solve_batch_host_async(lompc_t* h, int64_t B, const double* lmbd, int64_t lmbd_stride,
+                                 const double* lmbd_r, int64_t lmbd_r_stride, const double* gamma,
+                                 double* w_out, double* cost_out, int32_t* status, int32_t* iters,
+                                 double* kkt_res) {
   if (!h || B < 0 || !lmbd || !lmbd_r || !gamma || !w_out || !cost_out) return LOMPC_ERR_ARG;
+  h->pending_B = 0;
   if (B == 0) return LOMPC_OK;
   const int N = h->cs.N;
   if (lmbd_stride != 0 && lmbd_stride != 3 * (int64_t)N) return LOMPC_ERR_ARG;
   if (lmbd_r_stride != 0 && lmbd_r_stride != 1) return LOMPC_ERR_ARG;
   CK(cudaSetDevice(h->device));
+  if (!h->hstream) CK(cudaStreamCreateWithFlags(&h->hstream, cudaStreamNonBlocking));
   const size_t n_lm = (lmbd_stride ? (size_t)B : 1) * 3 * N;
   const size_t n_lr = lmbd_r_stride ? (size_t)B : 1;
   auto al = [](size_t x) { return (x + 255) & ~(size_t)255; };
@@ -334,8 +353,18 @@ int lompc_solve_batch_host(lompc_t* h, int64_t B, const double* lmbd, int64_t lm
   const size_t total = o_it + al((size_t)B * 4);
   int rc = ensure_ws(h, total);
   if (rc) return rc;
+  if (!status) {  // the status is always fetched: it carries the reference's error conventions
+    if (h->hst_cap < (size_t)B) {
+      if (h->hst) CK(cudaFreeHost(h->hst));
+      h->hst = nullptr;
+      h->hst_cap = 0;
+      CK(cudaMallocHost(&h->hst, (size_t)B * 4 + 1024));
+      h->hst_cap = (size_t)B + 256;
+    }
+    status = h->hst;
+  }
   char* ws = static_cast<char*>(h->ws);
-  cudaStream_t s = 0;
+  cudaStream_t s = h->hstream;
   CK(cudaMemcpyAsync(ws + o_lm, lmbd, n_lm * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ws + o_lr, lmbd_r, n_lr * 8, cudaMemcpyHostToDevice, s));
   CK(cudaMemcpyAsync(ws + o_ga, gamma, (size_t)B * 8, cudaMemcpyHostToDevice, s));
@@ -346,32 +375,39 @@ int lompc_solve_batch_host(lompc_t* h, int64_t B, const double* lmbd, int64_t lm
   if (rc) return rc;
   CK(cudaMemcpyAsync(w_out, ws + o_w, (size_t)B * N * 8, cudaMemcpyDeviceToHost, s));
   CK(cudaMemcpyAsync(cost_out, ws + o_c, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
-  // status is always fetched: it carries the reference's error conventions
-  int32_t* st_host = status;
-  int32_t* st_tmp = nullptr;
-  if (!st_host) {
-    st_tmp = new (std::nothrow) int32_t[B];
-    if (!st_tmp) return LOMPC_ERR_ARG;
-    st_host = st_tmp;
-  }
-  cudaError_t e = cudaMemcpyAsync(st_host, ws + o_st, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess && iters)
-    e = cudaMemcpyAsync(iters, ws + o_it, (size_t)B * 4, cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess && kkt_res)
-    e = cudaMemcpyAsync(kkt_res, ws + o_k, (size_t)B * 8, cudaMemcpyDeviceToHost, s);
-  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
-  if (e != cudaSuccess) {
-    delete[] st_tmp;
-    return cuda_fail(e, "copy-out");
-  }
-  rc = LOMPC_OK;
+  CK(cudaMemcpyAsync(status, ws + o_st, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+  if (iters) CK(cudaMemcpyAsync(iters, ws + o_it, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+  if (kkt_res) CK(cudaMemcpyAsync(kkt_res, ws + o_k, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+  h->pending_B = B;
+  h->pending_status = status;
+  return LOMPC_OK;
+}
+
+int lompc_host_wait(lompc_t* h) {
+  if (!h) return LOMPC_ERR_ARG;
+  if (!h->hstream || h->pending_B == 0) return LOMPC_OK;
+  CK(cudaSetDevice(h->device));
+  CK(cudaStreamSynchronize(h->hstream));
+  const int64_t B = h->pending_B;
+  const int32_t* st = h->pending_status;
+  h->pending_B = 0;
+  int rc = LOMPC_OK;
   for (int64_t i = 0; i < B; ++i) {
-    if (st_host[i] == LOMPC_ST_BAD_GAMMA) { rc = LOMPC_ERR_GAMMA; break; }
-    if (st_host[i] == LOMPC_ST_NEGATIVE) { rc = LOMPC_ERR_NEGATIVE; break; }
-    if (st_host[i] == LOMPC_ST_MAXITER) rc = LOMPC_ERR_NOT_CONVERGED;
+    if (st[i] == LOMPC_ST_BAD_GAMMA) { rc = LOMPC_ERR_GAMMA; break; }
+    if (st[i] == LOMPC_ST_NEGATIVE) { rc = LOMPC_ERR_NEGATIVE; break; }
+    if (st[i] == LOMPC_ST_MAXITER) rc = LOMPC_ERR_NOT_CONVERGED;
   }
-  delete[] st_tmp;
   return rc;
+}
+
+int lompc_solve_batch_host(lompc_t* h, int64_t B, const double* lmbd, int64_t lmbd_stride,
+                           const double* lmbd_r, int64_t lmbd_r_stride, const double* gamma,
+                           double* w_out, double* cost_out, int32_t* status, int32_t* iters,
+                           double* kkt_res) {
+  int rc = lompc_solve_batch_host_async(h, B, lmbd, lmbd_stride, lmbd_r, lmbd_r_stride, gamma, w_out, cost_out,
+                                        status, iters, kkt_res);
+  if (rc) return rc;
+  return lompc_host_wait(h);
 }
 
 

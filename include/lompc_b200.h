@@ -88,6 +88,17 @@ int lompc_solve_batch_host(lompc_t* h, int64_t B, const double* lmbd, int64_t lm
                            double* w_out, double* cost_out, int32_t* status, int32_t* iters,
                            double* kkt_res);
 
+/* The host call in two halves, so that independent handles (the two EV types, several batches)
+ * overlap their copies and kernels: _async enqueues copies-in, the solve and copies-out on the
+ * handle's own stream and returns; lompc_host_wait blocks until they are done and returns what
+ * lompc_solve_batch_host would have.  Host buffers must stay alive (and should be pinned) until
+ * the wait; one pending call per handle.                                                       */
+int lompc_solve_batch_host_async(lompc_t* h, int64_t B, const double* lmbd, int64_t lmbd_stride,
+                                 const double* lmbd_r, int64_t lmbd_r_stride, const double* gamma,
+                                 double* w_out, double* cost_out, int32_t* status, int32_t* iters,
+                                 double* kkt_res);
+int lompc_host_wait(lompc_t* h);
+
 /* ------------------------------------------------------------------------
  * Price loop (reference price_solver.py / price_regularizer.py), batched over
  * G independent groups = (station, EV type, partition) triples.  EVs are sorted

@@ -193,3 +193,27 @@ def test_hard_cases():
         assert np.all(info["status"] == 0), (key, info["status"], info["kkt_res"])
         assert np.max(np.abs(w - z[key + "_w"])) <= W_RTOL * o.w_max, key
         assert np.max(np.abs(cost - z[key + "_cost"]) / np.maximum(1, np.abs(z[key + "_cost"]))) <= C_RTOL, key
+
+
+def test_async_host_api_matches_blocking_call():
+    """solve_lompc_batch(wait=False) on two independent handles + wait() == the blocking calls."""
+    from chargingstation.lompc import LoMPC, LoMPCConstants
+    N, B = 24, 300
+    rng = np.random.default_rng(21)
+    solvers, ins, ref = {}, {}, {}
+    for ev in ("small", "large"):
+        c = _consts(ev)
+        solvers[ev] = LoMPC(N, LoMPCConstants(c.delta, c.theta, c.y_max, c.w_max, c.ev_type))
+        ins[ev] = (c.theta * rng.random((B, 3 * N)), 3 * N * c.delta * rng.random(B), c.y_max * rng.random(B))
+        ref[ev] = solvers[ev].solve_lompc_batch(*ins[ev])
+    outs = {ev: (np.empty((B, N)), np.empty(B)) for ev in solvers}
+    for ev in solvers:
+        solvers[ev].solve_lompc_batch(*ins[ev], out=outs[ev], wait=False)
+    for ev in solvers:
+        solvers[ev].wait()
+        assert np.array_equal(outs[ev][0], ref[ev][0]) and np.array_equal(outs[ev][1], ref[ev][1])
+    bad = ins["small"][2].copy()
+    bad[7] = 0.95  # gamma > y_max (lompc.py:87) surfaces at wait()
+    solvers["small"].solve_lompc_batch(ins["small"][0], ins["small"][1], bad, wait=False)
+    with pytest.raises(AssertionError):
+        solvers["small"].wait()
