@@ -197,13 +197,13 @@ def test_hard_cases():
 
 def test_async_host_api_matches_blocking_call():
     """solve_lompc_batch(wait=False) on two independent handles + wait() == the blocking calls."""
-    from chargingstation.lompc import LoMPC, LoMPCConstants
+    from chargingstation.lompc import LoMPC
     N, B = 24, 300
     rng = np.random.default_rng(21)
     solvers, ins, ref = {}, {}, {}
     for ev in ("small", "large"):
-        c = _consts(ev)
-        solvers[ev] = LoMPC(N, LoMPCConstants(c.delta, c.theta, c.y_max, c.w_max, c.ev_type))
+        c, lc = _consts(ev)
+        solvers[ev] = LoMPC(N, lc)
         ins[ev] = (c.theta * rng.random((B, 3 * N)), 3 * N * c.delta * rng.random(B), c.y_max * rng.random(B))
         ref[ev] = solvers[ev].solve_lompc_batch(*ins[ev])
     outs = {ev: (np.empty((B, N)), np.empty(B)) for ev in solvers}
