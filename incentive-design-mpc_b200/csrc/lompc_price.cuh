@@ -148,34 +148,47 @@ __global__ void colsum_kernel(int N, int G, const int32_t* __restrict__ off, con
   }
 }
 
-// x = (diag(d) + c A'A)^{-1} b by the scalar Riccati recursion (A = tril(ones)), by ONE thread
-// on contiguous vectors.  d_k = dvec[k] (+ dadd).  K/KAP are scratch.  Homogeneous form of the
-// recursion (P = pa/pb, r = pr/pb): two dependent FMAs per stage, the reciprocal off the chain.
+// x = (diag(d) + c A'A)^{-1} b by the scalar Riccati recursion (A = tril(ones)), by ONE WARP on
+// contiguous vectors (every lane must call).  d_k = dvec[k] (+ dadd).  K/KAP are scratch.
+// Homogeneous form of the recursion (P = pa/pb, r = pr/pb): lane 0 runs the dependent chain (two
+// FMAs per stage) and only STORES the numerators / denominators; the N reciprocals and gains are
+// then formed by all lanes at once (off the chain), and lane 0 runs the forward substitution.
 __device__ __forceinline__ void ric_solve(int N, const double* dvec, double dadd, double c, const double* bvec,
-                                          double* x, double* K, double* KAP) {
-  double pa = 0.0, pb = 1.0, pr = 0.0;
-  for (int k = N - 1; k >= 0; --k) {
-    const double d = (dvec ? dvec[k] : 0.0) + dadd;
-    const double gk = -bvec[k];
-    const double tq = fma(c, pb, pa);   // Q pb,  Q = c + P
-    const double bn = fma(d, pb, tq);   // (d + Q) pb
-    const double ib = fast_rcp(bn);
-    K[k] = tq * ib;                     // Q / (d + Q)
-    KAP[k] = fma(gk, pb, pr) * ib;      // (r + g_k) / (d + Q)
-    pa = d * tq;                        // P <- Q d / (d + Q)
-    pr = fma(d, pr, -tq * gk);          // r <- (d r - Q g_k) / (d + Q)
-    pb = bn;
-    if ((k & 7) == 0 && pb > 0x1p600) {  // keep the homogeneous triple in range (exact rescale)
-      pa *= 0x1p-600;
-      pb *= 0x1p-600;
-      pr *= 0x1p-600;
+                                          double* x, double* K, double* KAP, int lane) {
+  if (lane == 0) {
+    double pa = 0.0, pb = 1.0, pr = 0.0;
+    for (int k = N - 1; k >= 0; --k) {
+      const double d = (dvec ? dvec[k] : 0.0) + dadd;
+      const double gk = -bvec[k];
+      const double tq = fma(c, pb, pa);   // Q pb,  Q = c + P
+      const double bn = fma(d, pb, tq);   // (d + Q) pb
+      K[k] = tq;                          // numerator of Q / (d + Q)
+      KAP[k] = fma(gk, pb, pr);           // numerator of (r + g_k) / (d + Q)
+      x[k] = bn;                          // common denominator
+      pa = d * tq;                        // P <- Q d / (d + Q)
+      pr = fma(d, pr, -tq * gk);          // r <- (d r - Q g_k) / (d + Q)
+      pb = bn;
+      if ((k & 7) == 0 && pb > 0x1p600) {  // keep the homogeneous triple in range (exact rescale)
+        pa *= 0x1p-600;
+        pb *= 0x1p-600;
+        pr *= 0x1p-600;
+      }
     }
   }
-  double s = 0.0;
-  for (int k = 0; k < N; ++k) {
-    const double xk = -fma(K[k], s, KAP[k]);
-    x[k] = xk;
-    s += xk;
+  __syncwarp();
+  for (int k = lane; k < N; k += 32) {
+    const double ib = fast_rcp(x[k]);
+    K[k] *= ib;
+    KAP[k] *= ib;
+  }
+  __syncwarp();
+  if (lane == 0) {
+    double s = 0.0;
+    for (int k = 0; k < N; ++k) {
+      const double xk = -fma(K[k], s, KAP[k]);
+      x[k] = xk;
+      s += xk;
+    }
   }
 }
 
@@ -228,7 +241,7 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
     U[k] = th * (lk[k] - lk[N + k]) + (nb == 3 ? c3 * lk[2 * N + k] : 0.0);
   }
   __syncwarp();
-  if (lane == 0) ric_solve(N, nullptr, kappa, 1.0, U, V, KS, KAPS);
+  ric_solve(N, nullptr, kappa, 1.0, U, V, KS, KAPS, lane);
   __syncwarp();
   double gs = 1.0;
   for (int k = lane; k < N; k += 32) {
@@ -272,7 +285,7 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
       U[k] = rhs;
     }
     __syncwarp();
-    if (lane == 0) ric_solve(N, TD, 2.0 * m * eps * kappa, 2.0 * m * eps, U, V, KS, KAPS);  // z
+    ric_solve(N, TD, 2.0 * m * eps * kappa, 2.0 * m * eps, U, V, KS, KAPS, lane);  // z
     __syncwarp();
     for (int k = lane; k < N; k += 32) {
       const double coef[3] = {th, -th, C3[k]};
@@ -287,7 +300,7 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
       U[k] = u;
     }
     __syncwarp();
-    if (lane == 0) ric_solve(N, nullptr, kappa, 1.0, U, V, KS, KAPS);  // v = A_bar^{-1} B' l
+    ric_solve(N, nullptr, kappa, 1.0, U, V, KS, KAPS, lane);  // v = A_bar^{-1} B' l
     __syncwarp();
     bool same = true;
     for (int k = lane; k < N; k += 32) {
