@@ -226,6 +226,8 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
   double* TD = V + N;      // [N]
   const int nb = r / N;    // 2 or 3 price blocks
   const double th = cs.theta, qs = cs.q_scale, m = cs.c;
+  // FP64 division is a ~30-instruction sequence: divide once, multiply everywhere
+  const double inv2m = 1.0 / (2.0 * m), inv_eps = 1.0 / eps;
   const unsigned full = 0xffffffffu;
   auto ordered_sum = [&](void) {  // lane 0: sum of TERM in (k, j) order
     double acc = 0.0;
@@ -245,7 +247,7 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
   __syncwarp();
   double gs = 1.0;
   for (int k = lane; k < N; k += 32) {
-    const double v = V[k] / (2.0 * m);
+    const double v = V[k] * inv2m;
     const double dw = wk[k] - wr[k];
     const double dphi[3] = {th * dw, -th * dw, qs * (wk[k] * wk[k] - wr[k] * wr[k])};
     const double coef[3] = {th, -th, C3[k]};
@@ -293,7 +295,7 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
       double u = 0.0;
       for (int j = 0; j < nb; ++j) {
         const int i = j * N + k;
-        const double l = FREE[i] ? (RHO[i] - coef[j] * z) / eps : 0.0;
+        const double l = FREE[i] ? (RHO[i] - coef[j] * z) * inv_eps : 0.0;
         LAM[i] = l;
         u += coef[j] * l;
       }
@@ -305,7 +307,7 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
     bool same = true;
     for (int k = lane; k < N; k += 32) {
       const double coef[3] = {th, -th, C3[k]};
-      const double v = V[k] / (2.0 * m);
+      const double v = V[k] * inv2m;
       for (int j = 0; j < nb; ++j) {
         const int i = j * N + k;
         const double l = LAM[i];
@@ -346,14 +348,15 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
 // Errors of _get_w_err (price_solver.py:211-214) for a mean trajectory w_sum / n.
 __device__ __forceinline__ void price_errors(int N, double kappa, const double* w_sum, double n, const double* w_ref,
                                              double& w_avg_err, double& w0_err) {
+  const double inv_n = 1.0 / n;
   double cum = 0.0, e2 = 0.0;
   for (int k = 0; k < N; ++k) {
-    const double v = w_sum[k] / n - w_ref[k];
+    const double v = w_sum[k] * inv_n - w_ref[k];
     cum += v;
     e2 += cum * cum + kappa * v * v;
   }
   w_avg_err = sqrt(e2);
-  w0_err = fabs(w_sum[0] / n - w_ref[0]);
+  w0_err = fabs(w_sum[0] * inv_n - w_ref[0]);
 }
 
 // One WARP per group: errors, the convergence test (price_solver.py:121-127) and -- for
