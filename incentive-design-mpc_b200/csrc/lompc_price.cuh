@@ -153,10 +153,15 @@ __global__ void colsum_kernel(int N, int G, const int32_t* __restrict__ off, con
 // Homogeneous form of the recursion (P = pa/pb, r = pr/pb): lane 0 runs the dependent chain (two
 // FMAs per stage) and only STORES the numerators / denominators; the N reciprocals and gains are
 // then formed by all lanes at once (off the chain), and lane 0 runs the forward substitution.
-__device__ __forceinline__ void ric_solve(int N, const double* dvec, double dadd, double c, const double* bvec,
+// NT = compile-time horizon (fully unrolled: the loads of a stage are issued ahead of the chain) or
+// 0 for a run-time N.
+template <int NT>
+__device__ __forceinline__ void ric_solve(int Nrt, const double* dvec, double dadd, double c, const double* bvec,
                                           double* x, double* K, double* KAP, int lane) {
+  const int N = NT ? NT : Nrt;
   if (lane == 0) {
     double pa = 0.0, pb = 1.0, pr = 0.0;
+#pragma unroll
     for (int k = N - 1; k >= 0; --k) {
       const double d = (dvec ? dvec[k] : 0.0) + dadd;
       const double gk = -bvec[k];
@@ -184,6 +189,7 @@ __device__ __forceinline__ void ric_solve(int N, const double* dvec, double dadd
   __syncwarp();
   if (lane == 0) {
     double s = 0.0;
+#pragma unroll
     for (int k = 0; k < N; ++k) {
       const double xk = -fma(K[k], s, KAP[k]);
       x[k] = xk;
@@ -209,12 +215,13 @@ __host__ __device__ inline int price_step_scratch_doubles(int N, int r) { return
 // rarely changes between iterations, so a warm start costs one verification pass.  Sums that
 // feed statistics are taken by lane 0 in (k, j) order, so the result does not depend on the
 // number of lanes.
+template <int NT>
 __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double kappa, double eps, double* lk,
                                                 const double* wk, const double* wr, double* ws,
                                                 unsigned char* FREE, int lane, bool first, bool warm,
                                                 bool need_dec, double& lamdiff_out, double& dec_pred_out,
                                                 int& status_out) {
-  const int N = cs.N;
+  const int N = NT ? NT : cs.N;
   double* LAM = ws;        // [r] new prices
   double* RHO = LAM + r;   // [r]
   double* TERM = RHO + r;  // [r] summands of the ordered sums
@@ -243,7 +250,7 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
     U[k] = th * (lk[k] - lk[N + k]) + (nb == 3 ? c3 * lk[2 * N + k] : 0.0);
   }
   __syncwarp();
-  ric_solve(N, nullptr, kappa, 1.0, U, V, KS, KAPS, lane);
+  ric_solve<NT>(N, nullptr, kappa, 1.0, U, V, KS, KAPS, lane);
   __syncwarp();
   double gs = 1.0;
   for (int k = lane; k < N; k += 32) {
@@ -251,7 +258,9 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
     const double dw = wk[k] - wr[k];
     const double dphi[3] = {th * dw, -th * dw, qs * (wk[k] * wk[k] - wr[k] * wr[k])};
     const double coef[3] = {th, -th, C3[k]};
-    for (int j = 0; j < nb; ++j) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (j >= nb) break;
       const double l = lk[j * N + k];
       const double Pl = eps * l + coef[j] * v;
       const double rho = Pl + 0.5 * dphi[j];
@@ -272,14 +281,17 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
       for (int k = lane; k < N; k += 32) {
         const double dw = wk[k] - wr[k];
         const double dphi[3] = {th * dw, -th * dw, qs * (wk[k] * wk[k] - wr[k] * wr[k])};
-        for (int j = 0; j < nb; ++j) FREE[j * N + k] = (lk[j * N + k] > 0.0) || (dphi[j] > 0.0);
+#pragma unroll
+        for (int j = 0; j < 3; ++j)
+          if (j < nb) FREE[j * N + k] = (lk[j * N + k] > 0.0) || (dphi[j] > 0.0);
       }
     }
     for (int k = lane; k < N; k += 32) {
       const double coef[3] = {th, -th, C3[k]};
       double t = 0.0, rhs = 0.0;
-      for (int j = 0; j < nb; ++j)
-        if (FREE[j * N + k]) {
+#pragma unroll
+      for (int j = 0; j < 3; ++j)
+        if (j < nb && FREE[j * N + k]) {
           t += coef[j] * coef[j];
           rhs += coef[j] * RHO[j * N + k];
         }
@@ -287,13 +299,15 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
       U[k] = rhs;
     }
     __syncwarp();
-    ric_solve(N, TD, 2.0 * m * eps * kappa, 2.0 * m * eps, U, V, KS, KAPS, lane);  // z
+    ric_solve<NT>(N, TD, 2.0 * m * eps * kappa, 2.0 * m * eps, U, V, KS, KAPS, lane);  // z
     __syncwarp();
     for (int k = lane; k < N; k += 32) {
       const double coef[3] = {th, -th, C3[k]};
       const double z = V[k];
       double u = 0.0;
-      for (int j = 0; j < nb; ++j) {
+  #pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (j >= nb) break;
         const int i = j * N + k;
         const double l = FREE[i] ? (RHO[i] - coef[j] * z) * inv_eps : 0.0;
         LAM[i] = l;
@@ -302,13 +316,15 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
       U[k] = u;
     }
     __syncwarp();
-    ric_solve(N, nullptr, kappa, 1.0, U, V, KS, KAPS, lane);  // v = A_bar^{-1} B' l
+    ric_solve<NT>(N, nullptr, kappa, 1.0, U, V, KS, KAPS, lane);  // v = A_bar^{-1} B' l
     __syncwarp();
     bool same = true;
     for (int k = lane; k < N; k += 32) {
       const double coef[3] = {th, -th, C3[k]};
       const double v = V[k] * inv2m;
-      for (int j = 0; j < nb; ++j) {
+  #pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (j >= nb) break;
         const int i = j * N + k;
         const double l = LAM[i];
         const double Pl = eps * l + coef[j] * v;
@@ -332,7 +348,9 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
   // ---- write back (price_solver.py:129,135-140)
   for (int k = lane; k < N; k += 32) {
     const double phir[3] = {th * wr[k], th * (cs.w_max - wr[k]), qs * wr[k] * wr[k]};
-    for (int j = 0; j < nb; ++j) {
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+      if (j >= nb) break;
       const double ln = fmax(LAM[j * N + k], 0.0);
       if (first) TERM[j * N + k] = (lk[j * N + k] - ln) * phir[j];
       lk[j * N + k] = ln;
@@ -398,7 +416,7 @@ __global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
   __syncwarp();
   double lamdiff, dec;
   int st;
-  price_step_warp(cs, r, kappa, p.eps_reg, p.lmbd + (size_t)g * 3 * N, p.w_k + (size_t)g * N,
+  price_step_warp<0>(cs, r, kappa, p.eps_reg, p.lmbd + (size_t)g * 3 * N, p.w_k + (size_t)g * N,
                   p.w_ref + (size_t)g * N, ws, FREE, lane, it == 0, warm, p.hist_ac != nullptr || p.want_dec, lamdiff,
                   dec, st);
   for (int i = lane; i < r; i += 32) gfree[i] = FREE[i];

@@ -222,7 +222,7 @@ __device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArg
       flag = __shfl_sync(0xffffffffu, flag, 0);
       if (flag == 0) {
         int st;
-        price_step_warp(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, tid, it == 0, it > 0, a.hist_ac != nullptr,
+        price_step_warp<N>(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, tid, it == 0, it > 0, a.hist_ac != nullptr,
                         lamdiff, dec_pred, st);
         nnqp_bad |= st;
       }
