@@ -112,7 +112,7 @@ struct BiArgs {
 BI_HD size_t scratch_doubles(int N, int P, int T) {
   const int Q2 = 2 * P, QN = Q2 * N, nb = Q2 + 1;
   return (size_t)9 * QN + (size_t)(QN + N) + 2 * (size_t)(nb * (nb + 1) / 2) + 2 * (size_t)nb * nb +
-         (size_t)40 * N + 8 * (size_t)nb + 3 * (size_t)T + 4 * Q2 + 16;
+         (size_t)40 * N + 8 * (size_t)nb + 3 * (size_t)T + 5 * Q2 + 16;
 }
 
 // Deterministic block reduction of (sum, max, min): partials in tid order.
@@ -172,27 +172,28 @@ BI_FN double vec_dot(const double* a, const double* b, int n) {
 
 // One station.  `sm` = scratch_doubles(N, P, T) doubles private to this CTA.
 BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double* sm, double* LI, int tid, int T) {
-  const int N = c.N, P = c.P, Q2 = 2 * P, QN = Q2 * N;
-  const int nb = Q2 + 1, np = nb * (nb + 1) / 2;
+  const int N = c.N, P = c.P;
+  // all 2P partition blocks size the scratch; the loops run over the ACTIVE ones only (see below)
+  const int Q2max = 2 * P, QNmax = Q2max * N, nbmax = Q2max + 1, npmax = nbmax * (nbmax + 1) / 2;
   // matrix-vector products: `nsub` adjacent lanes share one row (T >= 128), else one thread per row
   const int nsub = (T >= 128) ? 4 : 1, row = tid / nsub, part = tid - row * nsub, rows_pp = T / nsub;
   // dense block operations: thread (tx, ty) = (column, row group)
   const int nx = T < 32 ? T : 32, tx = tid % nx, ty = tid / nx, ny = T / nx;
   // ---- carve
   double* W = sm;             // [Q2,N] iterate
-  double* S1 = W + QN;        // slack / multiplier of w >= 0
-  double* Z1 = S1 + QN;
-  double* S2 = Z1 + QN;       // slack / multiplier of w <= wmax
-  double* Z2 = S2 + QN;
-  double* RDW = Z2 + QN;      // dual residual, w block
-  double* DXA = RDW + QN;     // affine direction, w block
-  double* DX = DXA + QN;      // Newton right-hand side, then the current direction, w block
-  double* EW = DX + QN;       // barrier diagonal z1/s1 + z2/s2
-  double* XI = EW + QN;       // [N,nb] block-tridiagonal solve vector (cumulative coordinates)
-  double* LPS = XI + QN + N;  // [2,np] shared-memory copy of the inverse factor of the last two stages
-  double* SW = LPS + 2 * (size_t)np;  // [nb,nb] Schur complement of the current stage
-  double* XW = SW + nb * nb;  // [nb,nb] the identity the elimination turns into the inverse factor
-  double* pk = XW + nb * nb;  // per-k vectors
+  double* S1 = W + QNmax;        // slack / multiplier of w >= 0
+  double* Z1 = S1 + QNmax;
+  double* S2 = Z1 + QNmax;       // slack / multiplier of w <= wmax
+  double* Z2 = S2 + QNmax;
+  double* RDW = Z2 + QNmax;      // dual residual, w block
+  double* DXA = RDW + QNmax;     // affine direction, w block
+  double* DX = DXA + QNmax;      // Newton right-hand side, then the current direction, w block
+  double* EW = DX + QNmax;       // barrier diagonal z1/s1 + z2/s2
+  double* XI = EW + QNmax;       // [N,nb] block-tridiagonal solve vector (cumulative coordinates)
+  double* LPS = XI + QNmax + N;  // [2,np] shared-memory copy of the inverse factor of the last two stages
+  double* SW = LPS + 2 * (size_t)npmax;  // [nb,nb] Schur complement of the current stage
+  double* XW = SW + nbmax * nbmax;  // [nb,nb] the identity the elimination turns into the inverse factor
+  double* pk = XW + nbmax * nbmax;  // per-k vectors
   double* U = pk;             pk += N;
   double* S3 = pk;            pk += N;
   double* Z3 = pk;            pk += N;
@@ -225,18 +226,19 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
   double* DEM = pk;           pk += N;
   double* OM = pk;            pk += N;
   pk += 9 * N;                          // (spare, keeps the 40 N budget)
-  double* AV = pk;            pk += nb;  // a = (-m, 1)
-  double* LA = pk;            pk += nb;  // Linv_{k-1} a
-  double* TL = pk;            pk += nb;  // T' la
-  pk += nb;
-  double* TV1 = pk;           pk += nb;
-  double* TV2 = pk;           pk += nb;
-  pk += 2 * nb;
+  double* AV = pk;            pk += nbmax;  // a = (-m, 1)
+  double* LA = pk;            pk += nbmax;  // Linv_{k-1} a
+  double* TL = pk;            pk += nbmax;  // T' la
+  pk += nbmax;
+  double* TV1 = pk;           pk += nbmax;
+  double* TV2 = pk;           pk += nbmax;
+  pk += 2 * nbmax;
   double* RED = pk;           pk += 3 * T;
-  double* MQ = pk;            pk += Q2;   // m_q
-  double* AQ = pk;            pk += Q2;   // a_q
-  double* GQ = pk;            pk += Q2;   // gamma_q
-  double* WMX = pk;           pk += Q2;   // wmax_q
+  double* MQ = pk;            pk += Q2max;   // m_q
+  double* AQ = pk;            pk += Q2max;   // a_q
+  double* GQ = pk;            pk += Q2max;   // gamma_q
+  double* WMX = pk;           pk += Q2max;   // wmax_q
+  double* QIDX = pk;          pk += Q2max;   // active block -> partition index (small P, then large P)
 
   // ---- station data
   const double x0 = a.x0[st_idx];
@@ -248,18 +250,34 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
     dot_l += a.Mp_l[(size_t)st_idx * P + p] * a.beta_l[(size_t)st_idx * P + p];
   }
   const double derr = c.theta_s * dot_s + c.theta_l * dot_l;
-  for (int q = tid; q < Q2; q += T) {
-    const bool small = q < P;
-    const int p = small ? q : q - P;
-    const double mp = small ? a.Mp_s[(size_t)st_idx * P + p] : a.Mp_l[(size_t)st_idx * P + p];
-    const double th = small ? c.theta_s : c.theta_l;
-    MQ[q] = th * mp;
-    AQ[q] = c.cost_type == 0 ? (th * mp) * (th * mp) : 1.0;
-    GQ[q] = small ? a.gamma_sm[(size_t)st_idx * P + p] : a.gamma_lm[(size_t)st_idx * P + p];
-    WMX[q] = small ? c.w_max_s : c.w_max_l;
-    AV[q] = -th * mp;
+  // A partition with no EVs (m_q = 0) and nothing to track (gamma_q = 0, or zero cost weight) is
+  // decoupled from the rest of the program and its optimum is w_q = 0: it is left out of the
+  // Newton system (the block size 2P+1 shrinks to active+1; early in a simulation only a third
+  // of the partitions is populated).  Thread 0 builds the compact list.
+  if (tid == 0) {
+    int cnt = 0;
+    for (int q = 0; q < Q2max; ++q) {
+      const bool small = q < P;
+      const int p = small ? q : q - P;
+      const double mp = small ? a.Mp_s[(size_t)st_idx * P + p] : a.Mp_l[(size_t)st_idx * P + p];
+      const double th = small ? c.theta_s : c.theta_l;
+      const double gq = small ? a.gamma_sm[(size_t)st_idx * P + p] : a.gamma_lm[(size_t)st_idx * P + p];
+      const double aq = c.cost_type == 0 ? (th * mp) * (th * mp) : 1.0;
+      if (th * mp == 0.0 && (gq == 0.0 || aq == 0.0)) continue;
+      MQ[cnt] = th * mp;
+      AQ[cnt] = aq;
+      GQ[cnt] = gq;
+      WMX[cnt] = small ? c.w_max_s : c.w_max_l;
+      AV[cnt] = -th * mp;
+      QIDX[cnt] = (double)q;
+      ++cnt;
+    }
+    AV[cnt] = 1.0;
+    RED[0] = (double)cnt;
   }
-  if (tid == 0) AV[Q2] = 1.0;
+  BI_SYNC();
+  const int Q2 = (int)RED[0], QN = Q2 * N, nb = Q2 + 1, np = nb * (nb + 1) / 2;
+  BI_SYNC();
   for (int k = tid; k < N; k += T) {
     DEM[k] = a.demand[(size_t)st_idx * N + k];
     OM[k] = a.omega[k];
@@ -724,10 +742,15 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
     BI_TOC(3);
   }
 
-  // ---- outputs (clipped into the box like the oracle)
+  // ---- outputs (clipped into the box like the oracle; inactive partitions: w = 0)
+  for (int i = tid; i < P * N; i += T) {
+    a.w_hat_s[(size_t)st_idx * P * N + i] = 0.0;
+    a.w_hat_l[(size_t)st_idx * P * N + i] = 0.0;
+  }
+  BI_SYNC();
   for (int i = tid; i < QN; i += T) {
-    const int q = i / N, k = i - q * N;
-    const double x = fmin(fmax(W[i], 0.0), WMX[q]);
+    const int cq = i / N, k = i - cq * N, q = (int)QIDX[cq];
+    const double x = fmin(fmax(W[i], 0.0), WMX[cq]);
     if (q < P) a.w_hat_s[((size_t)st_idx * P + q) * N + k] = x;
     else a.w_hat_l[((size_t)st_idx * P + (q - P)) * N + k] = x;
   }

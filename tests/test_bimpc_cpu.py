@@ -59,13 +59,17 @@ def test_kernel_algorithm_matches_oracle(cost_type, N, P):
         # same algorithm -> same iteration count; objective and the generation schedule are
         # pinned (strictly convex); the split of early charging between partitions is only
         # weakly determined under the exponential weights 5^(k-N+1) (curvature 1e-8)
-        assert abs(int(info["iters"][s]) - io["iters"]) <= 1
+        assert abs(int(info["iters"][s]) - io["iters"]) <= 3  # (the kernel leaves decoupled empty partitions out)
         k = bo.kkt_certificate(c, par, ws[s], wl[s], ug[s])
         assert k["max_violation"] <= 1e-8
         assert abs(k["objective"] - io["objective"]) <= 1e-7 * max(1.0, abs(io["objective"]))
         assert np.max(np.abs(ug[s] - ugo)) <= 2e-5
         tol_w = 5e-3 if cost_type == bo.EXP_UNWEIGHTED else 2e-5
-        assert np.max(np.abs(ws[s] - wso)) <= tol_w and np.max(np.abs(wl[s] - wlo)) <= tol_w
+        # (with the WEIGHTED cost an empty partition has zero weight: its w is arbitrary - the oracle
+        #  returns the analytic centre, the kernel leaves the block out and returns 0)
+        ks = par[0] > 0 if cost_type == bo.WEIGHTED else np.ones(P, dtype=bool)
+        kl = par[1] > 0 if cost_type == bo.WEIGHTED else np.ones(P, dtype=bool)
+        assert np.max(np.abs(ws[s] - wso)[ks]) <= tol_w and np.max(np.abs(wl[s] - wlo)[kl]) <= tol_w
 
 
 def test_kernel_algorithm_tight_tolerance_is_stable():

@@ -29,7 +29,7 @@ def test_batch_against_oracle(cost_type, N, P):
     assert (info["status"] == 0).all(), info
     for s, par in enumerate(stations):
         wso, wlo, ugo, io = bo.solve_ipm(c, *par)
-        assert abs(int(info["iters"][s]) - io["iters"]) <= 1
+        assert abs(int(info["iters"][s]) - io["iters"]) <= 3  # (the kernel leaves decoupled empty partitions out)
         k = bo.kkt_certificate(c, par, ws[s], wl[s], ug[s])
         assert k["max_violation"] <= 1e-8
         # north-star bar: objective <= 1e-6 relative
@@ -37,7 +37,11 @@ def test_batch_against_oracle(cost_type, N, P):
         assert abs(info["objective"][s] - k["objective"]) <= 1e-9 * max(1.0, abs(k["objective"]))
         assert np.max(np.abs(ug[s] - ugo)) <= 2e-5
         tol_w = 5e-3 if cost_type == bo.EXP_UNWEIGHTED else 2e-5
-        assert np.max(np.abs(ws[s] - wso)) <= tol_w and np.max(np.abs(wl[s] - wlo)) <= tol_w
+        # (with the WEIGHTED cost an empty partition has zero weight: its w is arbitrary - the oracle
+        #  returns the analytic centre, the kernel leaves the block out and returns 0)
+        ks = par[0] > 0 if cost_type == bo.WEIGHTED else np.ones(P, dtype=bool)
+        kl = par[1] > 0 if cost_type == bo.WEIGHTED else np.ones(P, dtype=bool)
+        assert np.max(np.abs(ws[s] - wso)[ks]) <= tol_w and np.max(np.abs(wl[s] - wlo)[kl]) <= tol_w
 
 
 def test_scalar_api_shapes_and_asserts():
