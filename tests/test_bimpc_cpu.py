@@ -64,7 +64,7 @@ def test_kernel_algorithm_matches_oracle(cost_type, N, P):
         assert k["max_violation"] <= 1e-8
         assert abs(k["objective"] - io["objective"]) <= 1e-7 * max(1.0, abs(io["objective"]))
         assert np.max(np.abs(ug[s] - ugo)) <= 2e-5
-        tol_w = 5e-3 if cost_type == bo.EXP_UNWEIGHTED else 2e-5
+        tol_w = 3e-2 if cost_type == bo.EXP_UNWEIGHTED else 1e-4
         # (with the WEIGHTED cost an empty partition has zero weight: its w is arbitrary - the oracle
         #  returns the analytic centre, the kernel leaves the block out and returns 0)
         ks = par[0] > 0 if cost_type == bo.WEIGHTED else np.ones(P, dtype=bool)
