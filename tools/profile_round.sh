@@ -17,7 +17,7 @@ for ev in small large; do
 done
 # fused price loop + BiMPC inside the closed loop (64 stations, 4 steps; the captured launches are from step 3)
 run python tools/run_fleet.py --stations 64 --steps 4 > $OUT/${TAG}_plain_fleet.log 2>&1 &&
-$NCU -k regex:price_group_loop -s 40 -c 2 -o $OUT/${TAG}_price_loop -f python tools/run_fleet.py --stations 64 --steps 4 > $OUT/${TAG}_ncu_price_loop.log 2>&1
+$NCU -k regex:price_station_chain -s 4 -c 1 -o $OUT/${TAG}_price_loop -f python tools/run_fleet.py --stations 64 --steps 4 > $OUT/${TAG}_ncu_price_loop.log 2>&1
 $NCU -k regex:bimpc_solve -s 2 -c 1 -o $OUT/${TAG}_bimpc -f python tools/run_fleet.py --stations 256 --steps 3 > $OUT/${TAG}_ncu_bimpc.log 2>&1
 # launch list of the bench command
 run python bench.py --steps 2 --warmup 1 --closed-loop-stations 64 --closed-loop-steps 3 --no-cpu-baseline > $OUT/${TAG}_plain_bench.log 2>&1 &&
