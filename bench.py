@@ -439,7 +439,7 @@ def closed_loop_leg(args, rank, world, dev):
             "qp_solves_per_s": float(solves.item() / (ms.sum() * 1e-3)),
             "price_iters_mean": float(niter.mean()), "price_iters_p95": float(np.percentile(niter.cpu().numpy(), 95)),
             "bimpc_not_converged": int((fleet.log["bimpc_status"] != 0).sum()),
-            "aggregate_allreduce_ms_p50": float(np.median(agg_ms)),
+            "aggregate_allreduce_wait_ms_p50": float(np.median(agg_ms)),  # includes waiting for the slowest rank
             "config": "BASELINE.json configs[3] shape (SURVEY.md 8d config 4): stations of 500+500 EVs, P=12, "
                       "N_lo=N_bi=24, demand profile shifted U{0..23} h and scaled U(0.22,0.26)/0.25 per station, "
                       "device RNG; full size = 4096 stations x 96 steps (tools/run_fleet.py, profiles/)"}

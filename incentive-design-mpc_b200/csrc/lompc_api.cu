@@ -909,8 +909,18 @@ int price_solve_chain_dev(lompc_t* h, int32_t S, int32_t P, int64_t B, const int
     // no fused kernel for this horizon: the same chain as P phase-split loops, one per partition slice
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int N = h->cs.N;
-    int32_t* reb = nullptr;
-    CK(cudaMalloc(&reb, (size_t)(S + 1) * sizeof(int32_t)));
+    // rebased offsets of the current slice live in the handle's second grow-only allocation
+    // (price_solve_dev below uses the first one)
+    const size_t need = (size_t)(S + 1) * sizeof(int32_t) + ((size_t)S * (N + 5) + 64) * sizeof(double);
+    if (h->rws_bytes < need) {
+      if (h->rws) CK(cudaFree(h->rws));
+      h->rws = nullptr;
+      h->rws_bytes = 0;
+      CK(cudaMalloc(&h->rws, need + need / 8));
+      h->rws_bytes = need + need / 8;
+    }
+    int32_t* reb = reinterpret_cast<int32_t*>(static_cast<char*>(h->rws) +
+                                              ((h->rws_bytes - (size_t)(S + 1) * sizeof(int32_t)) & ~(size_t)15));
     int rc = LOMPC_OK;
     for (int p = 0; p < P && rc == LOMPC_OK; ++p) {
       const int32_t* off_p = group_off + (size_t)p * S;
@@ -937,7 +947,6 @@ int price_solve_chain_dev(lompc_t* h, int32_t S, int32_t P, int64_t B, const int
       COUNT_LAUNCH();
     }
     cudaStreamSynchronize(s);
-    cudaFree(reb);
     return rc;
   }
   return price_solve_fused_entry(h, S * P, B, group_off, y0, w_ref, lmbd_r, r, max_iter, tol_type_max, eps_reg, eps_tol,
