@@ -6,11 +6,14 @@ from chargingstation.demand_data import MEDIUM_TERM_LOAD_FORECAST_MW, medium_ter
 
 
 def test_demand_forecast_semantics():
-    """demand_data.py:21-37: 24 hourly values repeated; interpolation = midpoints with wrap-around."""
+    """demand_data.py:21-37: the forecast is a mid-hour value; the half-hourly series puts it on the odd
+    half hours and the mean of neighbouring hours (wrapping around midnight) on the full hours; the hourly
+    series (interpolate=False) is every other sample starting at 00:00, i.e. those means."""
     f24 = np.asarray(MEDIUM_TERM_LOAD_FORECAST_MW, dtype=float)
     d = medium_term_demand_forecast(66, 0.25)
     assert d.shape == (66,)
-    assert np.array_equal(d[:24], 0.25 * f24) and np.array_equal(d[24:48], d[:24]) and np.array_equal(d[48:], d[:18])
+    assert np.allclose(d[:24], 0.25 * (f24 + np.roll(f24, 1)) / 2, rtol=1e-15)
+    assert np.array_equal(d[24:48], d[:24]) and np.array_equal(d[48:], d[:18])
     di = medium_term_demand_forecast(30, 1 / 3, interpolate=True)
     assert di.shape == (60,)
     assert np.allclose(di[1::2][:24], f24 / 3) and np.isclose(di[0], (f24[0] + f24[-1]) / 2 / 3)
