@@ -116,9 +116,7 @@ int launch_solve_reg_variant(const lompc_handle* h, const lompc::SolveArgs& a, c
     case 3: return launch_solve_reg<N, NSEG, 64, 6, true>(h, a, stream);
     case 4: return launch_solve_reg<N, NSEG, 128, 3, true>(h, a, stream);
     case 5: return launch_solve_reg<N, NSEG, 64, 5, true>(h, a, stream);
-    case 6: return launch_solve_reg<N, NSEG, 64, 8, false>(h, a, stream);
     default:  // measured on B200 (tools/sweep_variants.sh): small EV best at (64,4,G in smem), large at (128,3,G in regs)
-      if (N == 12) return launch_solve_reg<N, NSEG, 64, 8, false>(h, a, stream);  // half the state: 16 warps per SM
       if (NSEG == 1) return launch_solve_reg<N, NSEG, 64, 4, false>(h, a, stream);
       return launch_solve_reg<N, NSEG, 128, 3, true>(h, a, stream);
   }
@@ -276,7 +274,7 @@ int lompc_set_options(lompc_t* h, int max_iter, double tol) {
 }
 
 int lompc_set_kernel_variant(lompc_t* h, int variant) {
-  if (!h || variant < 0 || variant > 6) return LOMPC_ERR_ARG;
+  if (!h || variant < 0 || variant > 5) return LOMPC_ERR_ARG;
   h->variant = variant;
   return LOMPC_OK;
 }
@@ -796,10 +794,10 @@ int price_solve_fused(lompc_handle* h, const lompc::FusedArgs& a, cudaStream_t s
   const int N = h->cs.N;
   if (h->cs.large) {
     if (N == 24) return launch_fused<24, 4, 64, 4, true>(h, a, s);
-    if (N == 12) return launch_fused<12, 4, 64, 8, true>(h, a, s);  // half the per-QP state: 16 warps per SM
+    if (N == 12) return launch_fused<12, 4, 64, 4, true>(h, a, s);
   } else {
     if (N == 24) return launch_fused<24, 1, 64, 4, false>(h, a, s);
-    if (N == 12) return launch_fused<12, 1, 64, 8, false>(h, a, s);
+    if (N == 12) return launch_fused<12, 1, 64, 4, false>(h, a, s);
   }
   return LOMPC_ERR_ARG;
 }
