@@ -55,7 +55,7 @@ SIGNATURES = {
                                   C.c_void_p, C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_void_p]),
     "price_solve_chain_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p,
                                         C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_double, C.c_double] +
-                              [C.c_void_p] * 5 + [C.POINTER(C.c_int32), C.c_void_p]),
+                              [C.c_void_p] * 6 + [C.POINTER(C.c_int32), C.c_void_p]),
     "price_set_loop_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "price_last_qp_solves": (C.c_int64, [C.c_void_p]),
     "price_last_cycles": (C.c_int64, [C.c_void_p, C.c_int]),

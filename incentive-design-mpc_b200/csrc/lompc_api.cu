@@ -808,7 +808,8 @@ int price_solve_fused_entry(lompc_handle* h, int32_t G, int64_t B, const int32_t
                             const double* w_ref, const double* lmbd_r, int r, int max_iter, int tol_type_max,
                             double eps_reg, double eps_tol, double* prices, int32_t* iters, double* price_pre,
                             double* price_post, double* w_k_out, double* hist_ac, double* hist_pred, int hist_cap,
-                            int32_t* total_iters, int chain_S, int chain_P, double* chain_prev, void* stream) {
+                            int32_t* total_iters, int chain_S, int chain_P, double* chain_prev,
+                            const int32_t* chain_order, void* stream) {
   {
     if ((r != 2 * h->cs.N && r != 3 * h->cs.N) || max_iter < 1) return LOMPC_ERR_ARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
@@ -830,7 +831,7 @@ int price_solve_fused_entry(lompc_handle* h, int32_t G, int64_t B, const int32_t
     a.qp_count = reinterpret_cast<unsigned long long*>(flags + 4);
     a.w_scratch = reinterpret_cast<double*>(static_cast<char*>(h->pws) + 256);
     a.B = B;
-    a.chain_S = chain_S; a.chain_P = chain_P; a.chain_prev = chain_prev;
+    a.chain_S = chain_S; a.chain_P = chain_P; a.chain_prev = chain_prev; a.chain_order = chain_order;
     rc = price_solve_fused(h, a, s);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->poll, flags, 64, cudaMemcpyDeviceToHost, s));
@@ -863,7 +864,7 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
   if ((h->cs.N == 24 || h->cs.N == 12) && h->variant != 1 && h->loop_mode != 1)
     return price_solve_fused_entry(h, G, B, group_off, y0, w_ref, lmbd_r, r, max_iter, tol_type_max, eps_reg, eps_tol,
                                    prices, iters, price_pre, price_post, w_k_out, hist_ac, hist_pred, hist_cap,
-                                   total_iters, 0, 0, nullptr, stream);
+                                   total_iters, 0, 0, nullptr, nullptr, stream);
   // phase-split loop (any horizon; also the path a multi-GPU caller drives, see price_shard_*):
   // the reduction buffers live in a second grow-only allocation of the handle
   const int N = h->cs.N;
@@ -899,7 +900,8 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
 int price_solve_chain_dev(lompc_t* h, int32_t S, int32_t P, int64_t B, const int32_t* group_off, const double* y0,
                           const double* w_ref, const double* lmbd_r, int r, int max_iter, int tol_type_max,
                           double eps_reg, double eps_tol, double* prev_prices, double* prices, int32_t* iters,
-                          double* price_pre, double* price_post, int32_t* max_group_iters, void* stream) {
+                          double* price_pre, double* price_post, const int32_t* station_order,
+                          int32_t* max_group_iters, void* stream) {
   if (!h || S < 1 || P < 1 || B < 0 || !group_off || !y0 || !w_ref || !lmbd_r || !prev_prices || !prices || !iters ||
       !price_pre || !price_post)
     return LOMPC_ERR_ARG;
@@ -951,7 +953,7 @@ int price_solve_chain_dev(lompc_t* h, int32_t S, int32_t P, int64_t B, const int
   }
   return price_solve_fused_entry(h, S * P, B, group_off, y0, w_ref, lmbd_r, r, max_iter, tol_type_max, eps_reg, eps_tol,
                                  prices, iters, price_pre, price_post, nullptr, nullptr, nullptr, 0, max_group_iters, S,
-                                 P, prev_prices, stream);
+                                 P, prev_prices, station_order, stream);
 }
 
 int price_lp_rows_dev(int device, int N, int nb, const double* a, const double* b, const double* c,

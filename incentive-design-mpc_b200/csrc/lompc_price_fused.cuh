@@ -47,6 +47,7 @@ struct FusedArgs {
   int64_t B;
   int chain_S, chain_P;      // price_station_chain_kernel: stations, partitions (G = chain_P * chain_S)
   double* chain_prev;        // [chain_S, 3N] warm start carried along the chain (in/out)
+  const int32_t* chain_order;  // [chain_S] station handled by CTA i (a permutation) or NULL
   unsigned long long* qp_count;  // [0] total LoMPC QP solves, [1] / [2] SM cycles summed over groups spent in
                                  // the LoMPC passes / in thread 0's price step (or NULL)
 };
@@ -275,7 +276,9 @@ __global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts 
 template <int N, int NSEG, int T, int MINB, bool GREG>
 __global__ void __launch_bounds__(T, MINB) price_station_chain_kernel(const Consts cs, const FusedArgs a) {
   extern __shared__ double smem[];
-  const int s = blockIdx.x, S = a.chain_S;
+  // launch order: longest expected chains first (the caller sorts stations by last step's iteration
+  // totals), so that a station stuck at the iteration cap does not start in the last wave
+  const int S = a.chain_S, s = a.chain_order ? a.chain_order[blockIdx.x] : (int)blockIdx.x;
   double* prev = a.chain_prev + (size_t)s * 3 * N;
   for (int p = 0; p < a.chain_P; ++p) {
     const int g = p * S + s;

@@ -166,11 +166,14 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
  * prices[P*S,3N] receives every group's regularised prices (zeros for an empty group,
  * charging_station.py:270; its iters = -1).  One CTA per station runs its P loops back to back, so
  * stations do not wait for each other (N = 12, 24; other horizons run the same chain as P phase-split
- * loops, one per partition slice).  Synchronises; max_group_iters = length of the longest loop.      */
+ * loops, one per partition slice).  station_order[S] (may be NULL) = a permutation of the stations:
+ * the order in which CTAs pick them up (longest expected chains first shortens the tail).
+ * Synchronises; max_group_iters = length of the longest loop.                                       */
 int price_solve_chain_dev(lompc_t* h, int32_t S, int32_t P, int64_t B, const int32_t* group_off, const double* y0,
                           const double* w_ref, const double* lmbd_r, int r, int max_iter, int tol_type_max,
                           double eps_reg, double eps_tol, double* prev_prices, double* prices, int32_t* iters,
-                          double* price_pre, double* price_post, int32_t* max_group_iters, void* stream);
+                          double* price_pre, double* price_post, const int32_t* station_order,
+                          int32_t* max_group_iters, void* stream);
 
 /* price_solve_dev runs, for the compiled horizons (N = 12, 24), ONE fused kernel with one
  * CTA per group that iterates its group to convergence on the device (mode 0, default);
