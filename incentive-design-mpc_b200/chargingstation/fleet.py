@@ -115,6 +115,7 @@ class ChargingStationFleet:
             self.log[f"niter_{k}"] = z(Tf, P, S, dtype=i32)
             self.log[f"Mp_{k}"] = z(Tf, P, S, dtype=i32)
         self.ncharged_logged = {k: z(S, dtype=i32) for k in ("s", "l")}
+        self.sort_stations = True
         self.order = {"s": None, "l": None}  # launch order of the chain kernel (longest chains of the last step first)
         self.price_loop_iters = []  # per step: total device-loop iterations of the price loops
         self.qp_solves = 0   # LoMPC QPs solved inside the price loops so far
@@ -206,8 +207,9 @@ class ChargingStationFleet:
                         w["iters"].data_ptr(), w["pre"].data_ptr(), w["post"].data_ptr(),
                         self.order[k].data_ptr() if self.order[k] is not None else None, C.byref(total), sp))
                     # next step's launch order: stations with the longest chains first
-                    self.order[k] = torch.argsort(w["iters"].view(P, S).clamp(min=0).sum(dim=0), descending=True,
-                                                  stable=True).to(torch.int32)
+                    if self.sort_stations:
+                        self.order[k] = torch.argsort(w["iters"].view(P, S).clamp(min=0).sum(dim=0), descending=True,
+                                                      stable=True).to(torch.int32)
                     iters_sum += total.value
                     self._account(h)
                     self._ck(lib.fleet_keep_prices_dev(

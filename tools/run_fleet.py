@@ -65,6 +65,7 @@ def main():
     fleet = ChargingStationFleet(consts, args.stations, demand=demand, seed=4, rng="device", chain=args.chain,
                                  max_price_iter=args.max_price_iter)
     fleet.profile = args.profile
+    fleet.sort_stations = not os.environ.get("FLEET_NO_ORDER")
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     wall = []
