@@ -26,11 +26,7 @@ namespace lompc {
 template <int N, int NSEG, int T, bool GREG>
 struct RegSmem {
   static constexpr int kArrays = 3 + (GREG ? 0 : 1) + (NSEG > 1 ? 1 : 0);  // KK, KAP, WN [, G] [, INV]
-  // The stand-alone kernel stages the CTA's price rows ([T, 3N] contiguous in HBM) through shared
-  // memory with a padded row stride of 3N+1 doubles (conflict-free column reads): T*(3N+1) doubles =
-  // kPad + KK + KAP + WN exactly, so the staging area is the pad plus the first three arrays.
-  static constexpr int kPad = T;
-  static constexpr size_t bytes = (size_t)(kArrays * N * T + kPad) * sizeof(double);
+  static constexpr size_t bytes = (size_t)kArrays * N * T * sizeof(double);
 };
 
 // The solve itself: one QP per thread, iterate / diagonal / linear term in the caller's
@@ -40,7 +36,6 @@ struct RegSmem {
 template <int N, int NSEG, int T, bool GREG>
 __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, const double lr, const double gam,
                                           const double tol, const int max_iter, const bool warm,
-                                          const bool sync_after_setup,
                                           double* smem_t, double (&W)[N],
                                           double (&D)[N], double (&GR)[GREG ? N : 1], double& l2sum_out,
                                           double& gscale_out, double& viol_out, int& st_out, int& it_out) {
@@ -66,9 +61,6 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
     l2sum += l2;
     LOMPC_STAGE_FENCE();
   }
-  // `lm` is not read after this point: a caller that staged it in the shared-memory arrays below
-  // (all threads of the CTA call, uniformly) lets everyone finish reading before they are reused
-  if (sync_after_setup) __syncthreads();
   if (gam > cs.y_max) st = LOMPC_ST_BAD_GAMMA;
   const double c = cs.c, wmax = cs.w_max;
   const double gscale = fmax(1.0, gmax + c * N * cs.y_max);
@@ -218,30 +210,12 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
 template <int N, int NSEG, int T, int MINB, bool GREG>
 __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts cs, const SolveArgs a) {
   extern __shared__ double smem[];
-  constexpr int kPad = RegSmem<N, NSEG, T, GREG>::kPad;
   const int t = threadIdx.x;
-  const int64_t b0 = (int64_t)blockIdx.x * T;
-  // Independent rows (one price vector per QP, rows contiguous): the CTA's [T, 3N] input block is
-  // copied to shared memory with coalesced loads and the [T, N] result leaves the same way; every
-  // thread of the CTA then takes part in the barriers (threads past the end redo the last QP).
-  const bool staged = a.group_of == nullptr && a.lmbd_stride == 3 * N && a.price0_out == nullptr && a.w_init == nullptr;
-  int64_t b = b0 + t;
-  const bool live = b < a.B;
-  if (!staged && !live) return;
-  if (!live) b = a.B - 1;
+  const int64_t b = (int64_t)blockIdx.x * T + t;
+  if (b >= a.B) return;
   const int64_t row = a.group_of ? (int64_t)a.group_of[b] : b;
-  if (a.skip && a.skip[row]) return;  // group mode only (never staged)
+  if (a.skip && a.skip[row]) return;
   const double* lm = a.lmbd + row * a.lmbd_stride;
-  if (staged) {
-    const int nrows = (int)((a.B - b0) < T ? (a.B - b0) : T);
-    const double* src = a.lmbd + b0 * (3 * N);
-    for (int i = t; i < nrows * 3 * N; i += T) {
-      const int r = i / (3 * N), c = i - r * (3 * N);
-      smem[r * (3 * N + 1) + c] = src[i];
-    }
-    __syncthreads();
-    lm = smem + (live ? t : nrows - 1) * (3 * N + 1);
-  }
   const double lr = a.lmbd_r[row * a.lmbd_r_stride];
   const double gam = a.gamma[b];
   double W[N], D[N], GR[GREG ? N : 1];
@@ -253,9 +227,9 @@ __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts c
 #pragma unroll
     for (int k = 0; k < N; ++k) W[k] = wi[k];
   }
-  solve_reg<N, NSEG, T, GREG>(cs, lm, lr, gam, a.tol, a.max_iter, warm, staged, smem + kPad + t, W, D, GR, l2sum,
-                              gscale, viol, st, it);
-  const double* GS = smem + kPad + t + 3 * N * T;
+  solve_reg<N, NSEG, T, GREG>(cs, lm, lr, gam, a.tol, a.max_iter, warm, smem + t, W, D, GR, l2sum, gscale, viol, st,
+                              it);
+  const double* GS = smem + t + 3 * N * T;
 #define LOMPC_G(k) (GREG ? GR[GREG ? (k) : 0] : GS[(k) * T])
   const double c = cs.c, wmax = cs.w_max;
   double slope[NSEG], brk[NSEG + 1];
@@ -267,7 +241,7 @@ __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts c
   // ---- outputs ----
   double cost = cs.theta * wmax * l2sum;
   double s = 0.0;
-  double* wo = (a.w_out && !staged) ? a.w_out + b * (int64_t)N : nullptr;
+  double* wo = a.w_out ? a.w_out + b * (int64_t)N : nullptr;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     const double x = W[k];
@@ -279,23 +253,6 @@ __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts c
       for (int j = 1; j < NSEG; ++j) cost += (slope[j] - slope[j - 1]) * dmax2(x - brk[j], 0.0);
     }
     LOMPC_STAGE_FENCE();
-  }
-  if (staged) {
-    // [T, N] results through shared memory (row stride N+1: T*(N+1) doubles = pad + KK), coalesced stores
-    __syncthreads();  // every thread is done with its columns of KK / KAP / WN
-    double* OUT = smem;
-#pragma unroll
-    for (int k = 0; k < N; ++k) OUT[t * (N + 1) + k] = W[k];
-    __syncthreads();
-    if (a.w_out) {
-      const int nrows = (int)((a.B - b0) < T ? (a.B - b0) : T);
-      double* dst = a.w_out + b0 * N;
-      for (int i = t; i < nrows * N; i += T) {
-        const int r = i / N, c = i - r * N;
-        dst[i] = OUT[r * (N + 1) + c];
-      }
-    }
-    if (!live) return;
   }
   if (a.cost_out) a.cost_out[b] = cost;
   if (a.err_out) {
