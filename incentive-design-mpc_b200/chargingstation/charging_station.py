@@ -25,17 +25,17 @@ from chargingstation.settings import (ADD_RESIDUAL_CHARGE_TO_BATTERY, MAX_INITIA
 
 @dataclass
 class ChargingStationConstants:
-    """
-    simulation_length:  Length of the simulation [hours].
-    horizon_bimpc:      BiMPC horizon.
-    horizon_lompc:      LoMPC horizon (<= BiMPC horizon).
-    nEVs_per_EV_type:   Number of small (and large) EVs.
-    npartitions:        Number of partitions per EV type.
-    demand:             External demand vector.
-    bimpc_consts:       Normalized constants for the BiMPC.
-    small_EV_consts:    Constants for the small EV LoMPC.
-    large_EV_consts:    Constants for the large EV LoMPC.
-    price_type:         "linear" or "linear-convex".
+    """Scenario of one station (field names and order as in the reference, charging_station.py:16-41).
+
+    simulation_length   closed-loop steps (hours)
+    horizon_bimpc       planning horizon of the upper level, >= horizon_lompc
+    horizon_lompc       horizon of every EV's own problem
+    nEVs_per_EV_type    EVs of each class (small, large) plugged in at any time
+    npartitions         SoC classes per EV type (one price vector each)
+    demand              external demand [kWh per step], at least simulation_length + horizon_bimpc + 1 values
+    bimpc_consts        BiMPCConstants, normalised by the total EV capacity
+    small_EV_consts / large_EV_consts   LoMPCConstants of the two classes
+    price_type          "linear" or "linear-convex"
     """
 
     simulation_length: int
@@ -140,9 +140,7 @@ class ChargingStation:
 
     def _step(self):
         if settings.PRINT_LEVEL >= 1:
-            print("-" * 50)
-            print(f"Iteration {self.t}")
-            print("-" * 50)
+            print(f"===== closed-loop step {self.t} =====")
         lmbd_r = 0  # charging_station.py:162
         w_hat_s, w_hat_l, u_g, stats_bi = self._get_bimpc_solution(lmbd_r)
         prices_s, prices_l, stats_s, stats_l = self._get_optimal_prices(w_hat_s, w_hat_l, lmbd_r)
@@ -175,24 +173,16 @@ class ChargingStation:
         w_hat_s, w_hat_l, u_g = self.bimpc.solve_bimpc(params)
         stats_bi = {"Mp_s": Mp_s, "Mp_l": Mp_l, "beta_s": beta_s, "beta_l": beta_l,
                     "gamma_sm": gamma_sm, "gamma_lm": gamma_lm}
-        if settings.PRINT_LEVEL >= 1:  # charging_station.py:229-263
-            total_w0_hat = self.consts_s.theta * Mp_s_ @ w_hat_s[:, 0] + self.consts_l.theta * Mp_l_ @ w_hat_l[:, 0]
-            u0_b_hat = u_g[0] - demand[0] - total_w0_hat
-            u0_b_err = self.consts_s.theta * Mp_s_ @ beta_s + self.consts_l.theta * Mp_l_ @ beta_l
-            x_hat = self.x + u0_b_hat
-            for name, Mp in (("small", Mp_s), ("large", Mp_l)):
-                print(f"EV distribution ({name}): " + " + ".join("{:4d}".format(n) for n in Mp)
-                      + " = {:4d}".format(np.sum(Mp)))
-            print(f"Electricity generated  : {u_g[0]:13.8f} | Max: {self.consts_bi.u_g_max:13.8f}")
-            print(f"Demand                 : {demand[0]:13.8f}")
-            print(f"Predicted output (EVs) : {total_w0_hat:13.8f}")
-            print(f"Predicted battery input: [{u0_b_hat - u0_b_err:8.5f}, {u0_b_hat + u0_b_err:8.5f}] "
-                  f"| Max (mag): {self.consts_bi.u_b_max:8.5f}")
-            print(f"Current battery state  : {self.x}")
-            print(f"Predicted battery state: Min: 0 | [{x_hat - u0_b_err:8.5f}, {x_hat + u0_b_err:8.5f}] "
-                  f"| Max: {self.consts_bi.x_max:8.5f}")
-            if settings.PRINT_LEVEL >= 2:
-                print("")
+        if settings.PRINT_LEVEL >= 1:  # the report of charging_station.py:229-263, condensed
+            load0 = self.consts_s.theta * Mp_s_ @ w_hat_s[:, 0] + self.consts_l.theta * Mp_l_ @ w_hat_l[:, 0]
+            ub0 = u_g[0] - demand[0] - load0
+            margin = self.consts_s.theta * Mp_s_ @ beta_s + self.consts_l.theta * Mp_l_ @ beta_l
+            print("partition sizes  small", Mp_s.tolist(), " large", Mp_l.tolist())
+            print(f"plan for this step: generation {u_g[0]:.6f} (limit {self.consts_bi.u_g_max:g}), demand "
+                  f"{demand[0]:.6f}, EV load {load0:.6f}")
+            print(f"battery: rate in [{ub0 - margin:.5f}, {ub0 + margin:.5f}] (limit {self.consts_bi.u_b_max:g}), state "
+                  f"{self.x:.5f} -> [{self.x + ub0 - margin:.5f}, {self.x + ub0 + margin:.5f}] "
+                  f"(capacity {self.consts_bi.x_max:g})")
         return w_hat_s, w_hat_l, u_g, stats_bi
 
     # ------------------------------------------------------------------ price loop
@@ -215,14 +205,10 @@ class ChargingStation:
                     continue
                 solver.set_charge_levels(y0p)
                 if settings.PRINT_LEVEL >= 1:
-                    print(f"{name} EVs, partition {p:2d}: ", end="")
-                    if settings.PRINT_LEVEL >= 2:
-                        print("\n" + "-" * 27)
+                    print(f"[{name.lower()} EVs, partition {p}] ", end="")
                 lmbd_, stats_ = solver.compute_optimal_prices(w_ref[key][p, :], lmbd_r)
                 prices[key][p, :] = lmbd_[: self.r]
                 stats[key].append(stats_)
-                if settings.PRINT_LEVEL >= 2:
-                    print("")
         return prices["s"], prices["l"], stats["s"], stats["l"]
 
     def _get_w0_price0(self, prices_s: np.ndarray, prices_l: np.ndarray, lmbd_r: float
@@ -268,9 +254,7 @@ class ChargingStation:
                        + residual_charge - self.demand[self.t]) / self.B
         self.x += u0_b
         if settings.PRINT_LEVEL >= 1:
-            print(f"# small EVs charged    : {self.ncharged_s:5d}")
-            print(f"# large EVs charged    : {self.ncharged_l:5d}")
-            print("")
+            print(f"departed so far: {self.ncharged_s} small, {self.ncharged_l} large EVs\n")
 
     def _update_logs(self, lmbd_r: float, nu: tuple, stats: tuple, price0: tuple) -> None:
         """charging_station.py:371-433 (same keys, same conventions: -1 iterations and NaN

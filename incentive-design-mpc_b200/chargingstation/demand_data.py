@@ -4,7 +4,8 @@ demand profile the example tiles over the simulation (demand_data.py:21-37).
 The reference parses its bundled ``data/Real-Time Total Load.csv`` and uses only data rows
 31-54, column 2: the 24 values of the "MediumTermLoadForecast" table (mid-hour load
 forecast in MW, 18-Aug-2024).  Those 24 numbers are kept here as a constant so that the
-example runs without the CSV; ``csv_path`` reads any file of the same layout instead."""
+example runs without the CSV; ``csv_path`` reads any file of the same layout instead.  (The
+reference's ``main()`` only plots the two series with matplotlib, which this image lacks.)"""
 from __future__ import annotations
 
 import csv
@@ -39,19 +40,3 @@ def medium_term_demand_forecast(hours: int, scale: float, interpolate: bool = Fa
     if not interpolate:
         demand = demand[0::2]
     return scale * np.array(demand)
-
-
-def main() -> None:  # demand_data.py:40-50 (needs matplotlib, which this image lacks)
-    from matplotlib import pyplot as plt
-    hours = 48
-    demand = medium_term_demand_forecast(hours, 1 / 4, interpolate=False)
-    demand_interp = medium_term_demand_forecast(hours, 1 / 4, interpolate=True)
-    _, ax = plt.subplots(1, layout="constrained")
-    ax.plot(np.arange(len(demand)), demand, "-b", label="uninterpolated")
-    ax.plot(np.arange(len(demand_interp)) / 2, demand_interp, "-r", label="interpolated")
-    ax.legend()
-    plt.show()
-
-
-if __name__ == "__main__":
-    main()

@@ -18,41 +18,40 @@ from chargingstation.charging_station import ChargingStation, ChargingStationCon
 from chargingstation.demand_data import medium_term_demand_forecast
 from chargingstation.lompc import LoMPCConstants
 
-## Simulation parameters.
-SIMULATION_LENGTH = 49  # [hours].
+# Scenario of the reference's example (real_time_price_control.py:11-79); the module-level names are kept.
+SIMULATION_LENGTH = 49   # hours simulated
+HORIZON_LOMPC, HORIZON_BIMPC = 12, 16
+NUM_EVS_PER_EV_TYPE, NUM_PARTITIONS = 500, 12
+PRICE_TYPE = "linear-convex"   # or "linear"
+DEMAND_SCALE = 1 / 4           # the reference also lists 1 / 3
 
-HORIZON_LOMPC = 12
-HORIZON_BIMPC = 16
-
-NUM_EVS_PER_EV_TYPE = 500
-NUM_PARTITIONS = 12
-
-PRICE_TYPE = "linear-convex"
-# PRICE_TYPE = "linear"
-
-DEMAND_SCALE = 1 / 4  # {1 / 4, 1 / 3}.
+# EV classes: (delta, theta [kWh], y_max, w_max)
+_EV = {"small": (0.05, 10, 0.9, 0.25), "large": (0.025, 50, 0.9, 0.15)}
+# normalised station: charging-cost weight, generation cost, generation / battery-rate / battery-size limits
+_STATION = dict(delta=1e3, c_g=1, u_g_max=1, u_b_max=0.3, x_max=0.3,
+                charging_cost_type=BiMPCChargingCostType.EXP_UNWEIGHTED, exp_rate=5)
 
 
 def _get_lompc_consts() -> tuple[LoMPCConstants, LoMPCConstants]:
-    consts_s = LoMPCConstants(delta=0.05, theta=10, y_max=0.9, w_max=0.25, ev_type="small")
-    consts_l = LoMPCConstants(delta=0.025, theta=50, y_max=0.9, w_max=0.15, ev_type="large")
-    return consts_s, consts_l
+    return tuple(LoMPCConstants(*_EV[kind], kind) for kind in ("small", "large"))
 
 
 def _get_normalized_bimpc_consts() -> BiMPCConstants:
-    return BiMPCConstants(delta=1e3, c_g=1, u_g_max=1, u_b_max=0.3, x_max=0.3,
-                          charging_cost_type=BiMPCChargingCostType.EXP_UNWEIGHTED, exp_rate=5)
+    return BiMPCConstants(**_STATION)
 
 
 def _get_unnormalized_external_demand(simulation_length: int = SIMULATION_LENGTH) -> np.ndarray:
-    return medium_term_demand_forecast(simulation_length + HORIZON_BIMPC + 1, DEMAND_SCALE, interpolate=False)
+    hours = simulation_length + HORIZON_BIMPC + 1
+    return medium_term_demand_forecast(hours, DEMAND_SCALE, interpolate=False)
 
 
 def get_chargingstation_consts(simulation_length: int = SIMULATION_LENGTH) -> ChargingStationConstants:
-    consts_s, consts_l = _get_lompc_consts()
-    return ChargingStationConstants(simulation_length, HORIZON_BIMPC, HORIZON_LOMPC, NUM_EVS_PER_EV_TYPE,
-                                    NUM_PARTITIONS, _get_unnormalized_external_demand(simulation_length),
-                                    _get_normalized_bimpc_consts(), consts_s, consts_l, PRICE_TYPE)
+    small, large = _get_lompc_consts()
+    return ChargingStationConstants(
+        simulation_length=simulation_length, horizon_bimpc=HORIZON_BIMPC, horizon_lompc=HORIZON_LOMPC,
+        nEVs_per_EV_type=NUM_EVS_PER_EV_TYPE, npartitions=NUM_PARTITIONS,
+        demand=_get_unnormalized_external_demand(simulation_length), bimpc_consts=_get_normalized_bimpc_consts(),
+        small_EV_consts=small, large_EV_consts=large, price_type=PRICE_TYPE)
 
 
 def main() -> None:
