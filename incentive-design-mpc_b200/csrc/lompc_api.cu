@@ -118,6 +118,9 @@ int launch_solve_reg_variant(const lompc_handle* h, const lompc::SolveArgs& a, c
     case 5: return launch_solve_reg<N, NSEG, 64, 5, true>(h, a, stream);
     default:  // measured on B200 (tools/sweep_variants.sh): small EV best at (64,4,G in smem), large at (128,3,G in regs)
       if (NSEG == 1) return launch_solve_reg<N, NSEG, 64, 4, false>(h, a, stream);
+      // large EV: a grid that cannot fill the GPU is latency-bound -> the 255-register variant (no spills,
+      // 73 vs 85 us for 512 QPs); saturating batches -> 168 registers, 3 CTAs of 128 threads per SM
+      if (a.B < 32768) return launch_solve_reg<N, NSEG, 64, 4, false>(h, a, stream);
       return launch_solve_reg<N, NSEG, 128, 3, true>(h, a, stream);
   }
 }
