@@ -166,34 +166,17 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
     // ---------------- forward sweep: stage-optimal rollout ----------------
     double fn = 0.0;
     s = 0.0;
-    // gains of stage k are loaded one stage ahead (their latency hides behind stage k-1's chain)
-    double kk_n = KK[0], kap_n = KAP[0], inv_n = (NSEG > 1) ? INV[0] : 0.0;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      const double kk = kk_n, kap = kap_n, inv = inv_n;
-      if (k + 1 < N) {
-        kk_n = KK[(k + 1) * T];
-        kap_n = KAP[(k + 1) * T];
-        if (NSEG > 1) inv_n = INV[(k + 1) * T];
-      }
-      double x;
+      const double x0 = -fma(KK[k * T], s, KAP[k * T]);
+      double x = x0;
       if (NSEG > 1) {
-        // minimiser of  stage cost + cost-to-go  over [0, w_max]: with c_j = -(kk s + kap + slope_j inv) the
-        // stationary point on piece j, x = max(0, max_j min(c_j, brk[j+1]))  (brk[NSEG] = w_max).  Only one
-        // FMA per candidate depends on s; the mins are independent and the max is a tree.
-        double m[NSEG];
+        const double inv = INV[k * T];
+        x = fma(-slope[NSEG - 1], inv, x0);
 #pragma unroll
-        for (int j = 0; j < NSEG; ++j) m[j] = dmin2(fma(-kk, s, -fma(slope[j], inv, kap)), brk[j + 1]);
-        if (NSEG == 4) x = dmax2(dmax2(m[0], m[1]), dmax2(m[2], m[3]));
-        else {
-          x = m[0];
-#pragma unroll
-          for (int j = 1; j < NSEG; ++j) x = dmax2(x, m[j]);
-        }
-        x = dmax2(x, 0.0);
-      } else {
-        x = dmin2(dmax2(-fma(kk, s, kap), 0.0), wmax);
+        for (int j = NSEG - 2; j >= 0; --j) x = dmin2(fma(-slope[j], inv, x0), dmax2(brk[j + 1], x));
       }
+      x = dmin2(dmax2(x, 0.0), wmax);
       WN[k * T] = x;
       s += x;
       const double e = s - gam;
