@@ -87,7 +87,7 @@ class LoMPC:
         _native.raise_for(self._lib.lompc_set_options(self._h, int(max_iter), float(tol)))
 
     def set_kernel_variant(self, variant: int = 0) -> None:
-        """0 = automatic; 1 = any-N shared-memory kernel; 2-5 = register-kernel variants (tuning)."""
+        """0 = automatic; 1 = any-N shared-memory kernel; 2, 3 = the two register-kernel shapes (tuning)."""
         _native.raise_for(self._lib.lompc_set_kernel_variant(self._h, int(variant)))
 
     def solve_lompc(self, lmbd: np.ndarray, lmbd_r: float, gamma: float) -> tuple[np.ndarray, float]:

@@ -113,9 +113,7 @@ template <int N, int NSEG>
 int launch_solve_reg_variant(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t stream) {
   switch (h->variant) {
     case 2: return launch_solve_reg<N, NSEG, 64, 4, false>(h, a, stream);
-    case 3: return launch_solve_reg<N, NSEG, 64, 6, true>(h, a, stream);
-    case 4: return launch_solve_reg<N, NSEG, 128, 3, true>(h, a, stream);
-    case 5: return launch_solve_reg<N, NSEG, 64, 5, true>(h, a, stream);
+    case 3: return launch_solve_reg<N, NSEG, 128, 3, true>(h, a, stream);
     default:  // measured on B200 (tools/sweep_variants.sh): small EV best at (64,4,G in smem), large at (128,3,G in regs)
       if (NSEG == 1) return launch_solve_reg<N, NSEG, 64, 4, false>(h, a, stream);
       // large EV: a grid that cannot fill the GPU is latency-bound -> the 255-register variant (no spills,
@@ -277,7 +275,7 @@ int lompc_set_options(lompc_t* h, int max_iter, double tol) {
 }
 
 int lompc_set_kernel_variant(lompc_t* h, int variant) {
-  if (!h || variant < 0 || variant > 5) return LOMPC_ERR_ARG;
+  if (!h || variant < 0 || variant > 3) return LOMPC_ERR_ARG;
   h->variant = variant;
   return LOMPC_OK;
 }

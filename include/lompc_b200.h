@@ -64,8 +64,9 @@ double lompc_sc_modulus(const lompc_t* h);
 /* Solver knobs (defaults: max_iter 200, tol 1e-11 relative KKT residual). */
 int lompc_set_options(lompc_t* h, int max_iter, double tol);
 
-/* Kernel choice: 0 = automatic (register-resident kernel for N = 12, 24, the
- * any-N shared-memory kernel otherwise), 1 = always the any-N kernel.        */
+/* Kernel choice: 0 = automatic (register-resident kernel for N = 12, 24, the any-N shared-memory kernel
+ * otherwise), 1 = always the any-N kernel, 2 / 3 = the two register-kernel shapes (64 threads x 4 CTAs per
+ * SM with the linear term in shared memory / 128 x 3 with it in registers) regardless of the batch size. */
 int lompc_set_kernel_variant(lompc_t* h, int variant);
 
 /* Replaces LoMPC.solve_lompc (lompc.py:137-156), batched over B independent
