@@ -217,3 +217,31 @@ def test_async_host_api_matches_blocking_call():
     solvers["small"].solve_lompc_batch(ins["small"][0], ins["small"][1], bad, wait=False)
     with pytest.raises(AssertionError):
         solvers["small"].wait()
+
+
+@pytest.mark.parametrize("ev", ["small", "large"])
+def test_robustness_bound_of_the_reference_script(ev):
+    """test/test_lompc.py:60-86 plots, for 100 SoC spreads, the A_bar-distance between the mean response of
+    10 EVs and the response at the mid-point gamma against the bound sqrt(N) * Gamma_bar (and the first-step
+    bound scaled by min(1, 1/sqrt(kappa))).  Here the same quantities are ASSERTED (one batch per spread)."""
+    from chargingstation.lompc import LoMPC
+    o, c = _consts(ev)
+    N, nEVs = 12, 10
+    solver = LoMPC(N, c)
+    rng = np.random.default_rng(11)
+    A = solver.get_input_mat()
+    lmbd = o.theta * rng.random(3 * N)
+    kappa = 3 * N * rng.random() + 1e-5
+    lmbd_r = o.delta * kappa
+    A_bar = A.T @ A + kappa * np.eye(N)
+    gamma_max_arr = o.y_max * np.arange(1, 0, -0.01)
+    gam = gamma_max_arr[:, None] * rng.random((len(gamma_max_arr), nEVs))
+    gam_ref = (gam.max(axis=1) + gam.min(axis=1)) / 2
+    w, _ = solver.solve_lompc_batch(lmbd, lmbd_r, np.concatenate([gam.ravel(), gam_ref]))
+    w_avg = w[: gam.size].reshape(len(gamma_max_arr), nEVs, N).mean(axis=1)
+    d = w_avg - w[gam.size:]
+    w_err = np.sqrt(np.einsum("ij,jk,ik->i", d, A_bar, d))
+    w0_err = np.abs(d[:, 0])
+    bound = np.sqrt(N) * gamma_max_arr / 2
+    assert np.all(w_err <= bound + 1e-12)
+    assert np.all(w0_err <= bound * min(1.0, 1.0 / np.sqrt(kappa)) + 1e-12)
