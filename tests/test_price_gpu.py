@@ -236,3 +236,35 @@ def test_sharded_phases_two_emulated_ranks(ev):
     assert np.array_equal(outs[0][1]["iter"], stats_ref["iter"])
     # different summation order across ranks: last-bit differences only
     assert np.max(np.abs(outs[0][0] - prices_ref)) <= 1e-8 * max(1.0, np.max(np.abs(prices_ref)))
+
+
+_REF_SCENARIOS = (  # the four families of test/test_price_solver.py:38-108: (name, nEVs, N, price_type, lmbd_r, max_charge)
+    [("single", 1, 12, pt, 0.0, 1 / 3.0) for pt in ("linear", "linear-convex")] +
+    [("multiple", 100, 12, "linear-convex", 0.0, 1 / 36.0)] +
+    [("horizon", 10, N, "linear-convex", 0.0, 1 / 36.0) for N in (12, 24)] +
+    [("robustness", 10, 12, "linear-convex", float(lr), 1 / 36.0) for lr in (0, 12, 24, 36)])
+
+
+@pytest.mark.parametrize("ev", ["small", "large"])
+@pytest.mark.parametrize("scenario", _REF_SCENARIOS, ids=lambda s: f"{s[0]}-{s[1]}ev-N{s[2]}-{s[3]}-lr{s[4]:g}")
+def test_reference_convergence_scenarios(ev, scenario):
+    """test/test_price_solver.py runs these cases and prints `w0-error | w0 error bound`
+    (price_solver.py:150-164); here the printed invariants are asserted: the loop converges before
+    the cap, the mean response tracks w_ref within the tolerance, the first-step error respects its
+    bound, and the regularisation leaves the response unchanged while not raising the price."""
+    from chargingstation.price_solver import PriceSolver
+    _, nEVs, N, price_type, lmbd_r, max_charge = scenario
+    o, c = _consts(ev)
+    rng = np.random.default_rng(1000 + nEVs + N + int(lmbd_r))
+    ps = PriceSolver(N, c, price_type)
+    y0 = max_charge * o.y_max * rng.random(nEVs)
+    w_ref = o.w_max * rng.random(N)
+    ps.set_charge_levels(y0)
+    lam, st = ps.compute_optimal_prices(w_ref, lmbd_r)
+    assert st["iter"] < 999
+    tol, w0_bound = ps.get_robustness_bounds(lmbd_r)
+    w_err_max, w0_err, w_avg_err = ps._get_w_err(lam, lmbd_r, w_ref, None)
+    assert w_avg_err <= tol + 1e-7        # converged iterate; regularisation keeps w*(lmbd) (price_solver.py:249-250)
+    assert w0_err <= w0_bound + 1e-9      # price_solver.py:162-164
+    assert st["price_after_reg"] <= st["price_before_reg"] + 1e-9 * max(1.0, abs(st["price_before_reg"]))
+    assert np.all(lam >= 0) and (price_type == "linear-convex" or np.all(lam[2 * N:] == 0))
