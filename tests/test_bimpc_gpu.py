@@ -78,3 +78,50 @@ def test_infeasible_station_reports_status():
     par[7] = par[7] * 10.0  # demand far above u_g_max + battery: no feasible point
     ws, wl, ug, info = _mirror(c).solve_bimpc_batch(*stack([par]))
     assert info["status"][0] != 0
+
+
+@pytest.mark.parametrize("random_Mp", [False, True])
+@pytest.mark.parametrize("random_gamma", [False, True])
+@pytest.mark.parametrize("early_peak_demand", [False, True])
+def test_reference_scenario(random_Mp, random_gamma, early_peak_demand):
+    """The scenario of test/test_bimpc.py:45-106 (N = 24, P = 12, 500 + 500 EVs, u_g_max = x_max = 1.5,
+    exponential weights, optional random EV distribution / targets / early demand peak).  The reference
+    plots the plan against its limits (dashed lines of _plot_figure); here the limits are asserted and the
+    objective is compared with the dense oracle."""
+    from chargingstation.bimpc import BiMPC, BiMPCChargingCostType, BiMPCConstants, BiMPCParameters
+    from chargingstation.demand_data import medium_term_demand_forecast
+    from chargingstation.lompc import LoMPCConstants
+    N, P, M_s, M_l = 24, 12, 500, 500
+    cs, cl = LoMPCConstants(0.05, 10, 0.9, 0.25, "small"), LoMPCConstants(0.025, 50, 0.9, 0.15, "large")
+    cb = BiMPCConstants(1e3, 1, 1.5, 0.3, 1.5, BiMPCChargingCostType.EXP_UNWEIGHTED, 5)
+    rng = np.random.default_rng(4 * random_Mp + 2 * random_gamma + early_peak_demand)
+    simplex = lambda: (lambda v: v / v.sum())(rng.random(P) + 1e-6)  # noqa: E731
+    B = cs.theta * M_s + cl.theta * M_l
+    Mp_s = M_s * simplex() / B if random_Mp else M_s * np.ones(P) / (P * B)
+    Mp_l = M_l * simplex() / B if random_Mp else M_l * np.ones(P) / (P * B)
+    beta = np.sqrt(N) * 0.3 / P * np.ones(P)
+    gamma_sm = 0.6 * rng.random(P) if random_gamma else 0.6 * np.ones(P)
+    gamma_lm = 0.6 * rng.random(P) if random_gamma else 0.6 * np.ones(P)
+    if early_peak_demand:
+        demand = (medium_term_demand_forecast(24 + N, 1 / 4) / B)[17:17 + N]
+    else:
+        demand = medium_term_demand_forecast(N, 1 / 4) / B
+    par = (Mp_s, Mp_l, beta, beta.copy(), gamma_sm, gamma_lm, 0.0, demand)
+    bimpc = BiMPC(N, P, cb, cs, cl)
+    w_s, w_l, u_g = bimpc.solve_bimpc(BiMPCParameters(*par))
+    assert bimpc.last_info["status"] == 0
+    c = bo.BiConsts(N, P, cb.delta, cb.c_g, cb.u_g_max, cb.u_b_max, cb.x_max, bo.EXP_UNWEIGHTED, 5.0, cs.theta,
+                    cl.theta, cs.w_max, cl.w_max)
+    # the dashed limit lines of the reference's figure
+    assert np.all(w_s >= 0) and np.all(w_s <= cs.w_max) and np.all(w_l >= 0) and np.all(w_l <= cl.w_max)
+    assert np.all(u_g >= 0) and np.all(u_g <= cb.u_g_max)
+    A = bimpc.get_bat_input_mat()
+    x_hat = A @ (u_g - demand - cs.theta * Mp_s @ w_s - cl.theta * Mp_l @ w_l)
+    d_err = cs.theta * Mp_s @ beta + cl.theta * Mp_l @ beta
+    assert np.all(x_hat - d_err >= -1e-8) and np.all(x_hat + d_err <= cb.x_max + 1e-8)
+    k = bo.kkt_certificate(c, par, w_s, w_l, u_g)
+    assert k["max_violation"] <= 1e-8
+    _, _, ugo, io = bo.solve_ipm(c, *par)
+    assert io["status"] == 0
+    assert abs(k["objective"] - io["objective"]) <= 1e-7 * max(1.0, abs(io["objective"]))
+    assert np.max(np.abs(u_g - ugo)) <= 2e-5
