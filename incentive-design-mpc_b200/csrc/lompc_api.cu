@@ -842,6 +842,7 @@ int price_solve_fused_entry(lompc_handle* h, int32_t G, int64_t B, const int32_t
     h->last_cycles[0] = *reinterpret_cast<unsigned long long*>(h->poll + 6);
     h->last_cycles[1] = *reinterpret_cast<unsigned long long*>(h->poll + 8);
     if (h->poll[1]) return LOMPC_ERR_CONSTS;  // y0 outside [0, y_max], price_solver.py:71
+    if (h->poll[3]) return LOMPC_ERR_NOT_CONVERGED;  // some LoMPC solve inside the loop did not converge
     return LOMPC_OK;
   }
 }

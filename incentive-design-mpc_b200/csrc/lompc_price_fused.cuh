@@ -41,7 +41,8 @@ struct FusedArgs {
   double* hist_pred;
   int hist_cap;
   int32_t* flags;            // [0] += groups whose NNQP hit its iteration cap, [1] = some y0 outside [0, y_max],
-                             // [2] = max over groups of the LoMPC passes run (loop length of the slowest group)
+                             // [2] = max over groups of the LoMPC passes run (loop length of the slowest group),
+                             // [3] += LoMPC solves that ended with a status other than OK
   double* w_scratch;         // [B + G, N] LoMPC iterates of groups with more than T - 1 EVs (rows b0 + i; the
                              // virtual EV of group g in row B + g); smaller groups keep them in registers
   int64_t B;
@@ -147,6 +148,7 @@ __device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArg
         }
         solve_reg<N, NSEG, T, GREG>(cs, LM, lr, gam, a.qp_tol, a.qp_max_iter, warm, smem + tid, W, D, GR, l2sum,
                                     gscale, viol, st, qit);
+        if (st != LOMPC_ST_OK) atomicAdd(a.flags + 3, 1);  // a LoMPC solve that did not converge (never observed)
         if (!single) {
 #pragma unroll
           for (int k = 0; k < N; ++k) wrow[k] = W[k];
