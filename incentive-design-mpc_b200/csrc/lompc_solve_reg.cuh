@@ -143,19 +143,18 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
       KK[k * T] = tq_ * ib;                  // Q / (dm + Q)
       KAP[k * T] = fma(gm, pb, tu) * ib;     // (r - c gamma + gm) / (dm + Q)
       if (NSEG > 1) INV[k * T] = pb * ib;    // 1 / (dm + Q)
-      // binding: P <- Q, r <- Q w + r - c gamma (denominator unchanged); free: P <- Q dm/(dm+Q),
-      // r <- (dm (r - c gamma) - Q h)/(dm+Q).  Both candidates are two FP64 ops: computed and
-      // selected instead of branched on (lanes diverge here at almost every stage).
-      const double pa_f = dm * tq_, pr_f = fma(dm, tu, -tq_ * (gm + sl));
-      const double pr_b = fma(tq_, wk, tu);
-      pa = binding ? tq_ : pa_f;
-      pr = binding ? pr_b : pr_f;
-      pb = binding ? pb : bn;
-      if ((k & 7) == 0) {  // keep the homogeneous triple in range (exact rescale by a power of two)
-        const double sc = (pb > 0x1p600) ? 0x1p-600 : 1.0;
-        pa *= sc;
-        pb *= sc;
-        pr *= sc;
+      if (binding) {  // P <- Q, r <- Q w + r - c gamma (denominator unchanged)
+        pa = tq_;
+        pr = fma(tq_, wk, tu);
+      } else {        // P <- Q dm/(dm+Q), r <- (dm (r - c gamma) - Q h)/(dm+Q)
+        pa = dm * tq_;
+        pr = fma(dm, tu, -tq_ * (gm + sl));
+        pb = bn;
+      }
+      if ((k & 7) == 0 && pb > 0x1p600) {  // keep the homogeneous triple in range (exact rescale)
+        pa *= 0x1p-600;
+        pb *= 0x1p-600;
+        pr *= 0x1p-600;
       }
       s -= wk;
       LOMPC_STAGE_FENCE();
