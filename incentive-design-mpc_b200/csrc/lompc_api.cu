@@ -52,25 +52,6 @@ struct PriceSession {  // state of one (possibly sharded) compute_optimal_prices
   lompc::PriceArgs p;
 };
 
-struct HostCallKey {  // identifies a host call for the CUDA-graph cache of lompc_solve_batch_host_async
-  int64_t B = -1;
-  const void* lmbd = nullptr;
-  int64_t lmbd_stride = 0;
-  const void* lmbd_r = nullptr;
-  int64_t lmbd_r_stride = 0;
-  const void *gamma = nullptr, *w_out = nullptr, *cost_out = nullptr, *status = nullptr, *iters = nullptr,
-             *kkt_res = nullptr, *ws = nullptr;
-  int max_iter = 0;
-  double tol = 0.0;
-  int variant = 0;
-  bool operator==(const HostCallKey& o) const {
-    return B == o.B && lmbd == o.lmbd && lmbd_stride == o.lmbd_stride && lmbd_r == o.lmbd_r &&
-           lmbd_r_stride == o.lmbd_r_stride && gamma == o.gamma && w_out == o.w_out && cost_out == o.cost_out &&
-           status == o.status && iters == o.iters && kkt_res == o.kkt_res && ws == o.ws && max_iter == o.max_iter &&
-           tol == o.tol && variant == o.variant;
-  }
-};
-
 struct lompc_handle {
   lompc::Consts cs;
   int device;
@@ -84,9 +65,6 @@ struct lompc_handle {
   int32_t* hst;               // pinned status buffer used when the caller passes status = NULL
   size_t hst_cap;
   int64_t pending_B;          // batch of the enqueued, not yet awaited host call
-  HostCallKey hlast_key, hgraph_key;  // last plain call / the call the cached graph replays
-  cudaGraphExec_t hgraph_exec;
-  bool hgraph_failed;
   const int32_t* pending_status;
   // grow-only device workspace of the price loop + pinned poll word
   int variant;  // 0 auto, 1 = any-N shared-memory kernel, 2.. = register-kernel variants
@@ -258,8 +236,6 @@ int lompc_create(int N, double delta, double theta, double y_max, double w_max, 
   h->hst_cap = 0;
   h->pending_B = 0;
   h->pending_status = nullptr;
-  h->hgraph_exec = nullptr;
-  h->hgraph_failed = false;
   h->variant = 0;
   h->loop_mode = 0;
   h->last_qp_solves = 0;
@@ -280,7 +256,6 @@ int lompc_destroy(lompc_t* h) {
     cudaStreamSynchronize(h->hstream);
     cudaStreamDestroy(h->hstream);
   }
-  if (h->hgraph_exec) cudaGraphExecDestroy(h->hgraph_exec);
   if (h->hst) cudaFreeHost(h->hst);
   if (h->ws) cudaFree(h->ws);
   if (h->pws) cudaFree(h->pws);
@@ -391,62 +366,19 @@ int lompc_solve_batch_host_async(lompc_t* h, int64_t B, const double* lmbd, int6
   }
   char* ws = static_cast<char*>(h->ws);
   cudaStream_t s = h->hstream;
-  // copies in, the solve, copies out: the sequence this call enqueues
-  auto enqueue = [&]() -> int {
-    CK(cudaMemcpyAsync(ws + o_lm, lmbd, n_lm * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ws + o_lr, lmbd_r, n_lr * 8, cudaMemcpyHostToDevice, s));
-    CK(cudaMemcpyAsync(ws + o_ga, gamma, (size_t)B * 8, cudaMemcpyHostToDevice, s));
-    int rc2 = lompc_solve_batch_dev(h, B, (const double*)(ws + o_lm), lmbd_stride,
-                                    (const double*)(ws + o_lr), lmbd_r_stride, (const double*)(ws + o_ga),
-                                    (double*)(ws + o_w), (double*)(ws + o_c), (int32_t*)(ws + o_st),
-                                    (int32_t*)(ws + o_it), (double*)(ws + o_k), s);
-    if (rc2) return rc2;
-    CK(cudaMemcpyAsync(w_out, ws + o_w, (size_t)B * N * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(cost_out, ws + o_c, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
-    CK(cudaMemcpyAsync(status, ws + o_st, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-    if (iters) CK(cudaMemcpyAsync(iters, ws + o_it, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
-    if (kkt_res) CK(cudaMemcpyAsync(kkt_res, ws + o_k, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
-    return LOMPC_OK;
-  };
-  // A caller that repeats the call with the same buffers (a control loop with persistent pinned
-  // arrays) gets the whole sequence as ONE CUDA-graph launch: the second identical call captures it,
-  // later ones replay it.  Anything that does not capture (pageable memory, ...) falls back for good.
-  const HostCallKey key{B, lmbd, lmbd_stride, lmbd_r, lmbd_r_stride, gamma, w_out, cost_out, status, iters, kkt_res,
-                        h->ws, h->max_iter, h->tol, h->variant};
-  if (h->hgraph_exec && key == h->hgraph_key) {
-    CK(cudaGraphLaunch(h->hgraph_exec, s));
-    g_launches.fetch_add(1, std::memory_order_relaxed);
-  } else if (!h->hgraph_failed && key == h->hlast_key) {
-    if (h->hgraph_exec) {
-      cudaGraphExecDestroy(h->hgraph_exec);
-      h->hgraph_exec = nullptr;
-    }
-    cudaGraph_t graph = nullptr;
-    bool ok = cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal) == cudaSuccess;
-    if (ok) {
-      const int64_t before = g_launches.load();
-      const int rc2 = enqueue();
-      ok = (cudaStreamEndCapture(s, &graph) == cudaSuccess) && rc2 == LOMPC_OK && graph != nullptr;
-      g_launches.store(before);  // the captured launch has not run yet
-    }
-    if (ok) ok = cudaGraphInstantiate(&h->hgraph_exec, graph, 0) == cudaSuccess;
-    if (graph) cudaGraphDestroy(graph);
-    if (ok) {
-      h->hgraph_key = key;
-      CK(cudaGraphLaunch(h->hgraph_exec, s));
-      g_launches.fetch_add(1, std::memory_order_relaxed);
-    } else {
-      cudaGetLastError();
-      h->hgraph_exec = nullptr;
-      h->hgraph_failed = true;
-      rc = enqueue();
-      if (rc) return rc;
-    }
-  } else {
-    rc = enqueue();
-    if (rc) return rc;
-    h->hlast_key = key;
-  }
+  CK(cudaMemcpyAsync(ws + o_lm, lmbd, n_lm * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ws + o_lr, lmbd_r, n_lr * 8, cudaMemcpyHostToDevice, s));
+  CK(cudaMemcpyAsync(ws + o_ga, gamma, (size_t)B * 8, cudaMemcpyHostToDevice, s));
+  rc = lompc_solve_batch_dev(h, B, (const double*)(ws + o_lm), lmbd_stride,
+                             (const double*)(ws + o_lr), lmbd_r_stride, (const double*)(ws + o_ga),
+                             (double*)(ws + o_w), (double*)(ws + o_c), (int32_t*)(ws + o_st),
+                             (int32_t*)(ws + o_it), (double*)(ws + o_k), s);
+  if (rc) return rc;
+  CK(cudaMemcpyAsync(w_out, ws + o_w, (size_t)B * N * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(cost_out, ws + o_c, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaMemcpyAsync(status, ws + o_st, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+  if (iters) CK(cudaMemcpyAsync(iters, ws + o_it, (size_t)B * 4, cudaMemcpyDeviceToHost, s));
+  if (kkt_res) CK(cudaMemcpyAsync(kkt_res, ws + o_k, (size_t)B * 8, cudaMemcpyDeviceToHost, s));
   h->pending_B = B;
   h->pending_status = status;
   return LOMPC_OK;
