@@ -441,7 +441,8 @@ __global__ void bookkeep_kernel(const PriceArgs p, int it) {
 // price_solver.py:145-147,248-255 with the LP of price_regularizer.py:68-85 in closed form:
 // row k of Dphi' touches only (x1_k, x2_k, x3_k); b_k = theta(l1-l2) + 2 q w_k l3;
 // b_k < 0: x2 = -b_k/theta;  b_k >= 0: x3 = b_k/(2 q w_k) if r = 3N and w_k > 0 (unit cost
-// w_k/2 beats x1's w_k) else x1 = b_k/theta.
+// w_k/2 beats x1's w_k) else x1 = b_k/theta.  "w_k > 0" means w_k above the LoMPC solver's eps-band
+// (1e-9 w_max): for a w_k of rounding-error size the LP is degenerate and x3 = b_k/(2 q w_k) would be ~1e11.
 __device__ __forceinline__ void regularize_core(const Consts& cs, int r, const double* w, double* l, double& pre_out,
                                                 double& post_out) {
   const int N = cs.N;
@@ -455,7 +456,7 @@ __device__ __forceinline__ void regularize_core(const Consts& cs, int r, const d
     const double bk = th * (l[k] - l[N + k]) + 2.0 * qs * wk * l3;
     double x1 = 0.0, x2 = 0.0, x3 = 0.0;
     if (bk < 0.0) x2 = -bk / th;
-    else if (r == 3 * N && wk > 0.0) x3 = bk / (2.0 * qs * wk);
+    else if (r == 3 * N && wk > 1e-9 * wm) x3 = bk / (2.0 * qs * wk);  // (w_k inside the LoMPC solver's eps-band of 0 counts as 0)
     else x1 = bk / th;
     l[k] = x1;
     l[N + k] = x2;

@@ -78,14 +78,13 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
   const double gam = a.gamma[b];
   int st = LOMPC_ST_OK;
   if (gam < 0.0 || lr < 0.0) st = LOMPC_ST_NEGATIVE;  // nonneg parameters, lompc.py:78-82
-  double l2sum = 0.0, gmax = 0.0, dmax = 0.0;
+  double l2sum = 0.0, gmax = 0.0;
   for (int k = 0; k < N; ++k) {
     const double l1 = lm[k], l2 = lm[N + k], l3 = lm[2 * N + k];
     if (l1 < 0.0 || l2 < 0.0 || l3 < 0.0) st = LOMPC_ST_NEGATIVE;
     const double g = cs.theta * (l1 - l2);
     const double d = 2.0 * (lr * cs.theta2 + cs.q_scale * l3) + cs.d_base;
     D[k * T] = d;
-    dmax = fmax(dmax, d);
     G[k * T] = g;
     WA[k * T] = 0.0;
     gmax = fmax(gmax, fabs(g));
@@ -101,9 +100,9 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
   // epsilon-binding set of projected Newton: without it a coordinate 1 ulp off a
   // bound, pushed towards it, would stay "free" and stall the search).
   const double band = 1e-9 * wmax;
-  // Objective values closer than ftol cannot be ordered in fp64.
-  const double ftol = 1e-15 * (c * N * cs.y_max * cs.y_max +
-                               N * wmax * (gmax + 0.5 * dmax * wmax + cs.slope[NSEG - 1]));
+  // Objective values closer than ~1e-15 of the summed magnitudes cannot be ordered in fp64 (fixed part for
+  // the linear / tracking / pwl terms, 1e-15 (|f| + |fn|) for the quadratic ones; see lompc_solve_reg.cuh).
+  const double fbase = 1e-15 * (c * N * cs.y_max * cs.y_max + N * wmax * (gmax + cs.slope[NSEG - 1]));
 
   double* W = WA;   // current feasible iterate
   double* WN = WB;  // candidate
@@ -210,7 +209,7 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
       fn += x * fma(0.5 * D[k * T], x, G[k * T]) + 0.5 * c * e * e;
       if (NSEG > 1) fn += pwl_value<NSEG>(cs, x);
     }
-    if (fn <= f + ftol) {
+    if (fn <= f + (fbase + 1e-15 * (fabs(f) + fabs(fn)))) {
       double* tmp = W;
       W = WN;
       WN = tmp;

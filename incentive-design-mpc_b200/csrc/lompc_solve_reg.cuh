@@ -47,7 +47,7 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
 #define LOMPC_G(k) (GREG ? GR[GREG ? (k) : 0] : GS[(k) * T])
   int st = LOMPC_ST_OK;
   if (gam < 0.0 || lr < 0.0) st = LOMPC_ST_NEGATIVE;
-  double l2sum = 0.0, gmax = 0.0, dmax = 0.0;
+  double l2sum = 0.0, gmax = 0.0;
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     const double l1 = lm[k], l2 = lm[N + k], l3 = lm[2 * N + k];
@@ -57,7 +57,6 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
     D[k] = 2.0 * (lr * cs.theta2 + cs.q_scale * l3) + cs.d_base;
     if (!warm) W[k] = 0.0;
     gmax = dmax2(gmax, fabs(g));
-    dmax = dmax2(dmax, D[k]);
     l2sum += l2;
     LOMPC_STAGE_FENCE();
   }
@@ -67,7 +66,11 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
   const double tq = tol * gscale;
   const double cg = c * gam;
   const double band = 1e-9 * wmax;
-  const double ftol = 1e-15 * (c * N * cs.y_max * cs.y_max + N * wmax * (gmax + 0.5 * dmax * wmax + cs.slope[NSEG - 1]));
+  // Objective values closer than ~1e-15 of the magnitudes that were summed cannot be ordered in fp64:
+  // a fixed part for the linear / tracking / pwl terms plus 1e-15 (|f| + |fn|) for the quadratic ones (NOT
+  // a worst-case bound with max_k d_k: the closed-form regulariser can return lmbd3_k ~ 1e11 where w_k ~ 0,
+  // and a tolerance scaled by it would accept ascent steps and let the iteration wander).
+  const double fbase = 1e-15 * (c * N * cs.y_max * cs.y_max + N * wmax * (gmax + cs.slope[NSEG - 1]));
   double brk[NSEG + 1], slope[NSEG];
 #pragma unroll
   for (int i = 0; i <= NSEG; ++i) brk[i] = cs.brk[i];
@@ -187,7 +190,7 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
       }
       LOMPC_STAGE_FENCE();
     }
-    if (fn <= f + ftol) {
+    if (fn <= f + (fbase + 1e-15 * (fabs(f) + fabs(fn)))) {
 #pragma unroll
       for (int k = 0; k < N; ++k) W[k] = WN[k * T];
       f = dmin2(f, fn);

@@ -55,7 +55,7 @@ def regularize_closed_form(N: int, consts: orc.OracleConsts, r: int, w: np.ndarr
     for k in range(N):
         if bk[k] < 0:
             x[N + k] = -bk[k] / th
-        elif r == 3 * N and w[k] > 0:
+        elif r == 3 * N and w[k] > 1e-9 * consts.w_max:  # w_k of rounding-error size counts as 0 (degenerate LP)
             x[2 * N + k] = bk[k] / (2 * q * w[k])
         else:
             x[k] = bk[k] / th
