@@ -117,7 +117,7 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
 #pragma unroll
     for (int k = N - 1; k >= 0; --k) {
       const double wk = W[k], dk = D[k], gk = LOMPC_G(k);
-      p = fma(c, s, p) - cg;
+      p = fma(c, s - gam, p);  // costate: c * sum_{j>=k} (s_j - gamma); the subtraction is off the chain
       const double q = fma(dk, wk, gk) + p;
       // Subdifferential [s_lo, s_hi] of the separable term at w_k, a coordinate within `band` of
       // a breakpoint counting as sitting on it (+-1e300 at the box ends).  Interior of a piece:
@@ -135,7 +135,9 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
       const bool right = mq > s_hi + tq, left = mq < s_lo - tq, atbp = s_lo < s_hi;
       const bool binding = atbp && !right && !left;
       const double sl = left ? s_lo : s_hi;  // slope of the working piece (unused when binding)
-      const double v = right ? mq - s_hi : (left ? s_lo - mq : (atbp ? 0.0 : fabs(mq - s_hi)));
+      // distance of -q from [s_lo, s_hi] (<= 0 inside it; branch-free: a ladder of ?: here compiles to a
+      // divergent DSETP -> BRA chain per stage that also splits the sweep into basic blocks)
+      const double v = dmax2(mq - s_hi, s_lo - mq);
       viol = dmax2(viol, v);
       const double dm = dk + mu;  // proximal model of the safeguard: d + mu, g - mu w
       const double gm = fma(-mu, wk, gk);
@@ -180,7 +182,8 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
         for (int j = NSEG - 2; j >= 0; --j) x = dmin2(fma(-slope[j], inv, x0), dmax2(brk[j + 1], x));
       }
       x = dmin2(dmax2(x, 0.0), wmax);
-      WN[k * T] = x;
+      WN[k * T] = W[k];  // the current iterate is parked (restored only if the rollout is rejected)
+      W[k] = x;
       s += x;
       const double e = s - gam;
       fn += x * fma(0.5 * D[k], x, LOMPC_G(k)) + 0.5 * c * e * e;
@@ -191,12 +194,12 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
       LOMPC_STAGE_FENCE();
     }
     if (fn <= f + (fbase + 1e-15 * (fabs(f) + fabs(fn)))) {
-#pragma unroll
-      for (int k = 0; k < N; ++k) W[k] = WN[k * T];
       f = dmin2(f, fn);
       sN = s;
       mu = 0.0;
     } else {
+#pragma unroll
+      for (int k = 0; k < N; ++k) W[k] = WN[k * T];
       mu = fmax(4.0 * c, 4.0 * mu);
       if (mu > 1e30) break;
     }
