@@ -114,12 +114,14 @@ int launch_solve_reg_variant(const lompc_handle* h, const lompc::SolveArgs& a, c
   switch (h->variant) {
     case 2: return launch_solve_reg<N, NSEG, 64, 4, false>(h, a, stream);
     case 3: return launch_solve_reg<N, NSEG, 128, 3, true>(h, a, stream);
-    default:  // measured on B200 (tools/sweep_variants.sh): small EV best at (64,4,G in smem), large at (128,3,G in regs)
-      if (NSEG == 1) return launch_solve_reg<N, NSEG, 64, 4, false>(h, a, stream);
-      // large EV: a grid that cannot fill the GPU is latency-bound -> the 255-register variant (no spills,
-      // 73 vs 85 us for 512 QPs); saturating batches -> 168 registers, 3 CTAs of 128 threads per SM
-      if (a.B < 32768) return launch_solve_reg<N, NSEG, 64, 4, false>(h, a, stream);
-      return launch_solve_reg<N, NSEG, 128, 3, true>(h, a, stream);
+    case 4: return launch_solve_reg<N, NSEG, 64, 4, true>(h, a, stream);
+    case 5: return launch_solve_reg<N, NSEG, 64, 5, true>(h, a, stream);
+    default:
+      // measured on B200 (tools/sweep_variants.sh, r1i): 4 CTAs of 64 threads per SM with W, d AND g in registers
+      // (255 registers, no spills; KK, kappa, parked iterate [, 1/(d+Q)] in shared memory) is the fastest
+      // shape for both EV types, saturating and latency-bound grids alike; (128,3) pays for its 168-register
+      // cap with spills and is limited to 8 warps per SM by shared memory anyway.
+      return launch_solve_reg<N, NSEG, 64, 4, true>(h, a, stream);
   }
 }
 
@@ -275,7 +277,7 @@ int lompc_set_options(lompc_t* h, int max_iter, double tol) {
 }
 
 int lompc_set_kernel_variant(lompc_t* h, int variant) {
-  if (!h || variant < 0 || variant > 3) return LOMPC_ERR_ARG;
+  if (!h || variant < 0 || variant > 5) return LOMPC_ERR_ARG;
   h->variant = variant;
   return LOMPC_OK;
 }

@@ -48,6 +48,14 @@ __device__ __forceinline__ double fast_rcp(double x) {
 // ~8 SASS instructions per call in FP64; a NaN here propagates and ends as LOMPC_ST_MAXITER.)
 __device__ __forceinline__ double dmax2(double a, double b) { return a > b ? a : b; }
 __device__ __forceinline__ double dmin2(double a, double b) { return a < b ? a : b; }
+// max(x, 0) on the integer pipe: clears every bit when the sign bit is set (-0.0 -> +0.0, NaN stays NaN).
+// `x > 0.0 ? x : 0.0` is canonicalised to max.f64 by the compiler, which ptxas expands to DSETP.MAX + selects
+// + a NaN fix-up (8 instructions, one of them on the FP64 pipe); this is a shift and two ANDs.
+__device__ __forceinline__ double dpos(double x) {
+  const int hi = __double2hiint(x), lo = __double2loint(x);
+  const int keep = ~(hi >> 31);
+  return __hiloint2double(hi & keep, lo & keep);
+}
 
 struct SolveArgs {
   int64_t B;

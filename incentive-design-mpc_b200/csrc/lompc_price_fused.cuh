@@ -179,7 +179,7 @@ __device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArg
             cost += x * fma(0.5 * D[k], x, gk) + 0.5 * cs.c * s * (s - 2.0 * gam);
             if (NSEG > 1) {
 #pragma unroll
-              for (int j = 1; j < NSEG; ++j) cost += (cs.slope[j] - cs.slope[j - 1]) * dmax2(x - cs.brk[j], 0.0);
+              for (int j = 1; j < NSEG; ++j) cost += (cs.slope[j] - cs.slope[j - 1]) * dpos(x - cs.brk[j]);
             }
             LOMPC_STAGE_FENCE();
           }

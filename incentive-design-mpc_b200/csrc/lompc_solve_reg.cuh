@@ -90,14 +90,14 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
     double s0 = 0.0, f0 = 0.0;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      const double x = dmin2(dmax2(W[k], 0.0), wmax);
+      const double x = dmin2(dpos(W[k]), wmax);
       W[k] = x;
       s0 += x;
       const double e = s0 - gam;
       f0 += x * fma(0.5 * D[k], x, LOMPC_G(k)) + 0.5 * c * e * e;
       if (NSEG > 1) {
 #pragma unroll
-        for (int j = 1; j < NSEG; ++j) f0 += (slope[j] - slope[j - 1]) * dmax2(x - brk[j], 0.0);
+        for (int j = 1; j < NSEG; ++j) f0 += (slope[j] - slope[j - 1]) * dpos(x - brk[j]);
       }
       LOMPC_STAGE_FENCE();
     }
@@ -173,15 +173,30 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
     s = 0.0;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      const double x0 = -fma(KK[k * T], s, KAP[k * T]);
-      double x = x0;
+      // The state s is the loop-carried dependency of the sweep; everything that does not depend on it is
+      // kept off that chain.
+      const double kk = KK[k * T], kap = KAP[k * T];
+      double x;
       if (NSEG > 1) {
+        // minimiser of  stage cost + cost-to-go  over [0, w_max]: with c_j = -(kk s + kap + slope_j inv) the
+        // stationary point of piece j,  x = max(0, max_j min(c_j, brk[j+1]))  (brk[NSEG] = w_max): one FMA per
+        // candidate on the chain, the mins are independent and the max is a tree.
         const double inv = INV[k * T];
-        x = fma(-slope[NSEG - 1], inv, x0);
+        double m[NSEG];
 #pragma unroll
-        for (int j = NSEG - 2; j >= 0; --j) x = dmin2(fma(-slope[j], inv, x0), dmax2(brk[j + 1], x));
+        for (int j = 0; j < NSEG; ++j) m[j] = dmin2(fma(-kk, s, -fma(slope[j], inv, kap)), brk[j + 1]);
+#pragma unroll
+        for (int h = 1; h < NSEG; h *= 2) {
+#pragma unroll
+          for (int j = 0; j + h < NSEG; j += 2 * h) m[j] = dmax2(m[j], m[j + h]);
+        }
+        x = dpos(m[0]);
+      } else {
+        // clip with both comparisons on x0 (in parallel) instead of a min(max()) chain
+        const double x0 = -fma(kk, s, kap);
+        x = x0 > wmax ? wmax : x0;
+        x = x0 < 0.0 ? 0.0 : x;
       }
-      x = dmin2(dmax2(x, 0.0), wmax);
       WN[k * T] = W[k];  // the current iterate is parked (restored only if the rollout is rejected)
       W[k] = x;
       s += x;
@@ -189,7 +204,7 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
       fn += x * fma(0.5 * D[k], x, LOMPC_G(k)) + 0.5 * c * e * e;
       if (NSEG > 1) {
 #pragma unroll
-        for (int j = 1; j < NSEG; ++j) fn += (slope[j] - slope[j - 1]) * dmax2(x - brk[j], 0.0);
+        for (int j = 1; j < NSEG; ++j) fn += (slope[j] - slope[j - 1]) * dpos(x - brk[j]);
       }
       LOMPC_STAGE_FENCE();
     }
@@ -256,7 +271,7 @@ __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts c
     cost += x * fma(0.5 * D[k], x, LOMPC_G(k)) + 0.5 * c * s * (s - 2.0 * gam);
     if (NSEG > 1) {
 #pragma unroll
-      for (int j = 1; j < NSEG; ++j) cost += (slope[j] - slope[j - 1]) * dmax2(x - brk[j], 0.0);
+      for (int j = 1; j < NSEG; ++j) cost += (slope[j] - slope[j - 1]) * dpos(x - brk[j]);
     }
     LOMPC_STAGE_FENCE();
   }
