@@ -119,7 +119,8 @@ class ChargingStationFleet:
         self.order = {"s": None, "l": None}  # launch order of the chain kernel (longest chains of the last step first)
         self.price_loop_iters = []  # per step: total device-loop iterations of the price loops
         self.qp_solves = 0   # LoMPC QPs solved inside the price loops so far
-        self.cycles = [0, 0]  # SM cycles (summed over groups) in the LoMPC passes / the price steps
+        self.cycles = [0, 0, 0, 0, 0]  # SM cycles (summed over groups) in the LoMPC passes / the price steps; K1
+        # iterations summed over the solves; warp passes without a K1 iteration; warp passes
         from concurrent.futures import ThreadPoolExecutor
         self._pool = ThreadPoolExecutor(max_workers=2)
         self.streams = {k: torch.cuda.Stream(self.dev) for k in ("s", "l")}
@@ -139,6 +140,8 @@ class ChargingStationFleet:
             self.qp_solves += self._lib.price_last_qp_solves(h)
             self.cycles[0] += self._lib.price_last_cycles(h, 0)
             self.cycles[1] += self._lib.price_last_cycles(h, 1)
+            for i in (2, 3, 4):
+                self.cycles[i] += self._lib.price_last_cycles(h, i)
 
     # ------------------------------------------------------------------ one closed-loop step
     def step(self) -> None:

@@ -70,7 +70,8 @@ struct lompc_handle {
   int variant;  // 0 auto, 1 = any-N shared-memory kernel, 2.. = register-kernel variants
   int loop_mode;  // price loop: 0 auto (fused one-CTA-per-group kernel when compiled for N), 1 = phase-split host loop
   unsigned long long last_qp_solves;  // LoMPC QPs solved by the last fused price loop
-  unsigned long long last_cycles[2];  // its SM cycles in the LoMPC passes / the price steps (summed over groups)
+  unsigned long long last_cycles[5];  // its SM cycles in the LoMPC passes / the price steps (summed over groups),
+                                      // K1 iterations summed over its solves, warp passes with no K1 iteration, warp passes
   void* pws;
   size_t pws_bytes;
   int32_t* poll;  // pinned host
@@ -241,7 +242,7 @@ int lompc_create(int N, double delta, double theta, double y_max, double w_max, 
   h->variant = 0;
   h->loop_mode = 0;
   h->last_qp_solves = 0;
-  h->last_cycles[0] = h->last_cycles[1] = 0;
+  for (auto& c : h->last_cycles) c = 0;
   h->pws = nullptr;
   h->pws_bytes = 0;
   h->poll = nullptr;
@@ -291,7 +292,7 @@ int price_set_loop_mode(lompc_t* h, int mode) {
 int64_t price_last_qp_solves(const lompc_t* h) { return h ? (int64_t)h->last_qp_solves : 0; }
 
 int64_t price_last_cycles(const lompc_t* h, int which) {
-  return (h && which >= 0 && which < 2) ? (int64_t)h->last_cycles[which] : 0;
+  return (h && which >= 0 && which < 5) ? (int64_t)h->last_cycles[which] : 0;
 }
 
 int lompc_solve_batch_dev(lompc_t* h, int64_t B, const double* lmbd, int64_t lmbd_stride,
@@ -440,7 +441,7 @@ int ensure_pws(lompc_handle* h, size_t bytes) {
   h->variant = 0;
   h->loop_mode = 0;
   h->last_qp_solves = 0;
-  h->last_cycles[0] = h->last_cycles[1] = 0;
+  for (auto& c : h->last_cycles) c = 0;
   h->pws = nullptr;
   h->pws_bytes = 0;
   const size_t want = bytes + bytes / 8;
@@ -843,6 +844,7 @@ int price_solve_fused_entry(lompc_handle* h, int32_t G, int64_t B, const int32_t
     h->last_qp_solves = *reinterpret_cast<unsigned long long*>(h->poll + 4);
     h->last_cycles[0] = *reinterpret_cast<unsigned long long*>(h->poll + 6);
     h->last_cycles[1] = *reinterpret_cast<unsigned long long*>(h->poll + 8);
+    for (int i = 2; i < 5; ++i) h->last_cycles[i] = *reinterpret_cast<unsigned long long*>(h->poll + 6 + 2 * i);
     if (h->poll[1]) return LOMPC_ERR_CONSTS;  // y0 outside [0, y_max], price_solver.py:71
     if (h->poll[3]) return LOMPC_ERR_NOT_CONVERGED;  // some LoMPC solve inside the loop did not converge
     return LOMPC_OK;

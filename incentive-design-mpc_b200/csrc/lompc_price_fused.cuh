@@ -50,7 +50,8 @@ struct FusedArgs {
   double* chain_prev;        // [chain_S, 3N] warm start carried along the chain (in/out)
   const int32_t* chain_order;  // [chain_S] station handled by CTA i (a permutation) or NULL
   unsigned long long* qp_count;  // [0] total LoMPC QP solves, [1] / [2] SM cycles summed over groups spent in
-                                 // the LoMPC passes / in thread 0's price step (or NULL)
+                                 // the LoMPC passes / in thread 0's price step, [3] K1 iterations summed over
+                                 // the solves, [4] warp passes in which no lane iterated, [5] warp passes (or NULL)
 };
 
 template <int N, int NSEG, int T, bool GREG>
@@ -123,7 +124,7 @@ __device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArg
 
   double dual_cost = 0.0, lamdiff = 0.0, dec_pred = 0.0;  // thread 0 only
   int it = 0, nnqp_bad = 0;
-  unsigned long long solves = 0;
+  unsigned long long solves = 0, k1_iters = 0, warp_pass0 = 0, warp_pass = 0;
   const bool single = n + 1 <= T;  // one LoMPC pass covers the group: iterates stay in registers
   double W[N];
   long long cyc_qp = 0, cyc_step = 0;  // thread 0: cycles in the LoMPC passes / in the price step
@@ -149,6 +150,15 @@ __device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArg
         solve_reg<N, NSEG, T, GREG>(cs, LM, lr, gam, a.qp_tol, a.qp_max_iter, warm, smem + tid, W, D, GR, l2sum,
                                     gscale, viol, st, qit);
         if (st != LOMPC_ST_OK) atomicAdd(a.flags + 3, 1);  // a LoMPC solve that did not converge (never observed)
+        if (a.qp_count) {
+          k1_iters += qit;
+          const unsigned act = __activemask();
+          const bool none = __all_sync(act, qit == 0);
+          if ((tid & 31) == 0) {
+            warp_pass0 += none;
+            ++warp_pass;
+          }
+        }
         if (!single) {
 #pragma unroll
           for (int k = 0; k < N; ++k) wrow[k] = W[k];
@@ -233,6 +243,13 @@ __device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArg
     }
     __syncthreads();
     if (SC[1] != 0.0) break;
+  }
+  if (a.qp_count) {
+    if (k1_iters) atomicAdd(a.qp_count + 3, k1_iters);
+    if (warp_pass) {
+      atomicAdd(a.qp_count + 4, warp_pass0);
+      atomicAdd(a.qp_count + 5, warp_pass);
+    }
   }
   // ---- regularisation (price_solver.py:145-147) and outputs
   if (tid == 0) {

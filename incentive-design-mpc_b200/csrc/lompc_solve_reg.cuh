@@ -64,6 +64,7 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
   const double c = cs.c, wmax = cs.w_max;
   const double gscale = fmax(1.0, gmax + c * N * cs.y_max);
   const double tq = tol * gscale;
+  const int tqh = __double2hiint(tq);
   const double cg = c * gam;
   const double band = 1e-9 * wmax;
   // Objective values closer than ~1e-15 of the magnitudes that were summed cannot be ordered in fp64:
@@ -83,7 +84,8 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
     bhi[i] = brk[i] + band;
   }
 
-  double sN = 0.0, f = 0.5 * c * N * gam * gam, viol = 0.0, mu = 0.0;
+  double sN = 0.0, f = 0.5 * c * N * gam * gam, mu = 0.0;
+  int vh = 0;
   if (warm) {
     // start from the caller's feasible W (the solution at the previous prices of the price
     // loop): the active set is usually already right and one verification sweep remains
@@ -112,12 +114,12 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
     // Riccati recursion in homogeneous form: P = pa/pb, r = pr/pb.  The numerators and
     // the denominator obey a LINEAR recurrence (2 dependent FMAs per stage); the one
     // reciprocal per stage (1/pb_new, needed only for the gains) is off the dependency chain.
-    double pa = 0.0, pb = 1.0, pr = 0.0, p = 0.0, s = sN;
-    viol = 0.0;
+    double pa = 0.0, pb = 1.0, pr = 0.0, p = 0.0, e = sN - gam;  // e = s_k - gamma
+    vh = 0;  // high word of the largest KKT violation (non-negative doubles order like their high words)
 #pragma unroll
     for (int k = N - 1; k >= 0; --k) {
       const double wk = W[k], dk = D[k], gk = LOMPC_G(k);
-      p = fma(c, s - gam, p);  // costate: c * sum_{j>=k} (s_j - gamma); the subtraction is off the chain
+      p = fma(c, e, p);  // costate: c * sum_{j>=k} (s_j - gamma)
       const double q = fma(dk, wk, gk) + p;
       // Subdifferential [s_lo, s_hi] of the separable term at w_k, a coordinate within `band` of
       // a breakpoint counting as sitting on it (+-1e300 at the box ends).  Interior of a piece:
@@ -125,20 +127,26 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
       // the coordinate onto the neighbouring piece, inside it the coordinate stays put (binding).
       const double mq = -q;
       double s_hi = slope[0], s_lo = slope[0];
+      bool atbp = false;  // sitting on a breakpoint or a box end  (<=> s_lo < s_hi)
 #pragma unroll
       for (int j = 1; j < NSEG; ++j) {
-        if (wk >= blo[j]) s_hi = slope[j];
-        if (wk > bhi[j]) s_lo = slope[j];
+        const bool ge = wk >= blo[j], gt = wk > bhi[j];
+        if (ge) s_hi = slope[j];
+        if (gt) s_lo = slope[j];
+        atbp |= (ge != gt);
       }
-      if (wk >= blo[NSEG]) s_hi = 1e300;
-      if (wk <= band) s_lo = -1e300;
-      const bool right = mq > s_hi + tq, left = mq < s_lo - tq, atbp = s_lo < s_hi;
+      const bool top = wk >= blo[NSEG], bot = wk <= band;
+      if (top) s_hi = 1e300;
+      if (bot) s_lo = -1e300;
+      atbp |= top | bot;
+      // distance of -q from [s_lo, s_hi]: at most one of va, vb is positive.  Everything below is branch-free
+      // (a ladder of ?: compiles to a divergent DSETP -> BRA chain per stage that also splits the sweep into
+      // basic blocks), and the running maximum is kept on the integer pipe.
+      const double va = mq - s_hi, vb = s_lo - mq;
+      const bool right = va > tq, left = vb > tq;
       const bool binding = atbp && !right && !left;
       const double sl = left ? s_lo : s_hi;  // slope of the working piece (unused when binding)
-      // distance of -q from [s_lo, s_hi] (<= 0 inside it; branch-free: a ladder of ?: here compiles to a
-      // divergent DSETP -> BRA chain per stage that also splits the sweep into basic blocks)
-      const double v = dmax2(mq - s_hi, s_lo - mq);
-      viol = dmax2(viol, v);
+      vh = max(vh, max(__double2hiint(va), __double2hiint(vb)));
       const double dm = dk + mu;  // proximal model of the safeguard: d + mu, g - mu w
       const double gm = fma(-mu, wk, gk);
       const double tq_ = fma(c, pb, pa);     // Q * pb,  Q = c + P
@@ -161,16 +169,15 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
         pb *= 0x1p-600;
         pr *= 0x1p-600;
       }
-      s -= wk;
+      e -= wk;
       LOMPC_STAGE_FENCE();
     }
-    if (viol <= tq) {
+    if (vh < tqh) {  // => violation < tol * scale (the comparison of the high words is the stricter one)
       converged = true;
       break;
     }
     // ---------------- forward sweep: stage-optimal rollout ----------------
-    double fn = 0.0;
-    s = 0.0;
+    double fn = 0.0, s = 0.0;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       // The state s is the loop-carried dependency of the sweep; everything that does not depend on it is
@@ -222,7 +229,7 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
   if (!converged && st == LOMPC_ST_OK) st = LOMPC_ST_MAXITER;
   l2sum_out = l2sum;
   gscale_out = gscale;
-  viol_out = viol;
+  viol_out = __hiloint2double(vh, vh ? -1 : 0);  // upper bound of the last sweep's violation (2^-20 relative)
   st_out = st;
   it_out = it;
 #undef LOMPC_G

@@ -87,7 +87,8 @@ def main():
            "bimpc_iters_mean": float(log["bimpc_iters"].double().mean()),
            "bimpc_failed": int((log["bimpc_status"] != 0).sum()),
            "price_loop_qp_solves": int(fleet.qp_solves), "qp_solves_per_s": fleet.qp_solves / (ms.sum() * 1e-3),
-           "cycles_lompc_passes": fleet.cycles[0], "cycles_price_steps": fleet.cycles[1]}
+           "cycles_lompc_passes": fleet.cycles[0], "cycles_price_steps": fleet.cycles[1],
+           "k1_iters_per_solve": fleet.cycles[2] / max(1, fleet.qp_solves), "warp_passes_without_k1_iteration": fleet.cycles[3] / max(1, fleet.cycles[4])}
     if args.profile:
         out["phase_ms_median"] = {k: float(np.median([d[k] for d in fleet.phase_ms])) for k in fleet.phase_ms[0]}
     for k in ("s", "l"):
