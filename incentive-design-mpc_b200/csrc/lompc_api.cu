@@ -104,7 +104,10 @@ int launch_solve_reg(const lompc_handle* h, const lompc::SolveArgs& a, cudaStrea
     configured = true;
   }
   const int64_t blocks = (a.B + T - 1) / T;
-  lompc::lompc_solve_reg_kernel<N, NSEG, T, MINB, GREG><<<(unsigned)blocks, T, smem, stream>>>(h->cs, a);
+  lompc::SolveArgs av = a;
+  av.vec16 = (reinterpret_cast<uintptr_t>(a.lmbd) % 16 == 0) && (a.lmbd_stride % 2 == 0) &&
+             (reinterpret_cast<uintptr_t>(a.w_out) % 16 == 0);
+  lompc::lompc_solve_reg_kernel<N, NSEG, T, MINB, GREG><<<(unsigned)blocks, T, smem, stream>>>(h->cs, av);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
   return LOMPC_OK;

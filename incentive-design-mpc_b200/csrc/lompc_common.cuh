@@ -80,6 +80,7 @@ struct SolveArgs {
   double* price0_out;       // [B] LoMPC.get_price0 (lompc.py:164-170)
   const double* w_init;     // [B,N] feasible starting points (the previous solutions of the price loop;
                             // register kernel only) or NULL: start from w = 0
+  int vec16;                // register kernel: lmbd rows and w_out rows are 16-byte aligned (set by the launcher)
 };
 
 }  // namespace lompc

@@ -147,7 +147,7 @@ __device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArg
 #pragma unroll
           for (int k = 0; k < N; ++k) W[k] = wrow[k];
         }
-        solve_reg<N, NSEG, T, GREG>(cs, LM, lr, gam, a.qp_tol, a.qp_max_iter, warm, smem + tid, W, D, GR, l2sum,
+        solve_reg<N, NSEG, T, GREG>(cs, LM, lr, gam, a.qp_tol, a.qp_max_iter, warm, false, smem + tid, W, D, GR, l2sum,
                                     gscale, viol, st, qit);
         if (st != LOMPC_ST_OK) atomicAdd(a.flags + 3, 1);  // a LoMPC solve that did not converge (never observed)
         if (a.qp_count) {

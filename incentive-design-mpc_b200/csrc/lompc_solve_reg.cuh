@@ -35,7 +35,7 @@ struct RegSmem {
 // row in shared memory).  `warm`: W holds a feasible starting point on entry (else W = 0).
 template <int N, int NSEG, int T, bool GREG>
 __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, const double lr, const double gam,
-                                          const double tol, const int max_iter, const bool warm,
+                                          const double tol, const int max_iter, const bool warm, const bool vec,
                                           double* smem_t, double (&W)[N],
                                           double (&D)[N], double (&GR)[GREG ? N : 1], double& l2sum_out,
                                           double& gscale_out, double& viol_out, int& st_out, int& it_out) {
@@ -48,9 +48,7 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
   int st = LOMPC_ST_OK;
   if (gam < 0.0 || lr < 0.0) st = LOMPC_ST_NEGATIVE;
   double l2sum = 0.0, gmax = 0.0;
-#pragma unroll
-  for (int k = 0; k < N; ++k) {
-    const double l1 = lm[k], l2 = lm[N + k], l3 = lm[2 * N + k];
+  auto stage_data = [&](const int k, const double l1, const double l2, const double l3) {
     if (l1 < 0.0 || l2 < 0.0 || l3 < 0.0) st = LOMPC_ST_NEGATIVE;
     const double g = cs.theta * (l1 - l2);
     if (GREG) GR[GREG ? k : 0] = g; else GS[k * T] = g;
@@ -58,7 +56,24 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
     if (!warm) W[k] = 0.0;
     gmax = dmax2(gmax, fabs(g));
     l2sum += l2;
-    LOMPC_STAGE_FENCE();
+  };
+  if (vec && N % 2 == 0) {
+    // 16-byte loads of the thread's own price row (the rows of a warp are 3N doubles apart, so every load
+    // instruction touches 32 lines whatever its width: half as many instructions, half the LSU wavefronts)
+    const double2* lm2 = reinterpret_cast<const double2*>(lm);
+#pragma unroll
+    for (int k = 0; k < N; k += 2) {
+      const double2 a1 = lm2[k / 2], a2 = lm2[(N + k) / 2], a3 = lm2[(2 * N + k) / 2];
+      stage_data(k, a1.x, a2.x, a3.x);
+      stage_data(k + 1, a1.y, a2.y, a3.y);
+      LOMPC_STAGE_FENCE();
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      stage_data(k, lm[k], lm[N + k], lm[2 * N + k]);
+      LOMPC_STAGE_FENCE();
+    }
   }
   if (gam > cs.y_max) st = LOMPC_ST_BAD_GAMMA;
   const double c = cs.c, wmax = cs.w_max;
@@ -255,8 +270,8 @@ __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts c
 #pragma unroll
     for (int k = 0; k < N; ++k) W[k] = wi[k];
   }
-  solve_reg<N, NSEG, T, GREG>(cs, lm, lr, gam, a.tol, a.max_iter, warm, smem + t, W, D, GR, l2sum, gscale, viol, st,
-                              it);
+  solve_reg<N, NSEG, T, GREG>(cs, lm, lr, gam, a.tol, a.max_iter, warm, a.vec16 != 0, smem + t, W, D, GR, l2sum,
+                              gscale, viol, st, it);
   const double* GS = smem + t + 3 * N * T;
 #define LOMPC_G(k) (GREG ? GR[GREG ? (k) : 0] : GS[(k) * T])
   const double c = cs.c, wmax = cs.w_max;
@@ -270,10 +285,19 @@ __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts c
   double cost = cs.theta * wmax * l2sum;
   double s = 0.0;
   double* wo = a.w_out ? a.w_out + b * (int64_t)N : nullptr;
+  if (wo) {
+    if (a.vec16 && N % 2 == 0) {
+      double2* wo2 = reinterpret_cast<double2*>(wo);
+#pragma unroll
+      for (int k = 0; k < N; k += 2) wo2[k / 2] = make_double2(W[k], W[k + 1]);
+    } else {
+#pragma unroll
+      for (int k = 0; k < N; ++k) wo[k] = W[k];
+    }
+  }
 #pragma unroll
   for (int k = 0; k < N; ++k) {
     const double x = W[k];
-    if (wo) wo[k] = x;
     s += x;
     cost += x * fma(0.5 * D[k], x, LOMPC_G(k)) + 0.5 * c * s * (s - 2.0 * gam);
     if (NSEG > 1) {
