@@ -120,11 +120,16 @@ int launch_solve_reg_variant(const lompc_handle* h, const lompc::SolveArgs& a, c
     case 3: return launch_solve_reg<N, NSEG, 128, 3, true>(h, a, stream);
     case 4: return launch_solve_reg<N, NSEG, 64, 4, true>(h, a, stream);
     case 5: return launch_solve_reg<N, NSEG, 64, 5, true>(h, a, stream);
+    case 6: return launch_solve_reg<N, NSEG, 128, 2, true>(h, a, stream);
+    case 7: return launch_solve_reg<N, NSEG, 256, 1, true>(h, a, stream);
     default:
-      // measured on B200 (tools/sweep_variants.sh, r1i): 4 CTAs of 64 threads per SM with W, d AND g in registers
-      // (255 registers, no spills; KK, kappa, parked iterate [, 1/(d+Q)] in shared memory) is the fastest
-      // shape for both EV types, saturating and latency-bound grids alike; (128,3) pays for its 168-register
-      // cap with spills and is limited to 8 warps per SM by shared memory anyway.
+      // measured on B200 (tools/sweep_variants.sh, r1j): W, d AND g in registers (255 registers, no spills; KK,
+      // kappa, parked iterate [, 1/(d+Q)] in shared memory), 8 warps per SM.  Small EV: 4 CTAs of 64 threads (the
+      // 24 KB loop body fits the instruction cache; small CTAs keep the tail short).  Large EV: the unrolled loop
+      // body is 50 KB and the kernel is instruction-fetch bound (ncu: no_instruction = 36 % of the stall samples,
+      // spread evenly over the body) unless the warps of an SM run in step and share the fetched lines: ONE CTA of
+      // 256 threads per SM (+17..21 % over 4 x 64) once the grid fills the GPU; latency-bound grids keep 64.
+      if (NSEG > 1 && a.B >= 65536) return launch_solve_reg<N, NSEG, 256, 1, true>(h, a, stream);
       return launch_solve_reg<N, NSEG, 64, 4, true>(h, a, stream);
   }
 }
@@ -281,7 +286,7 @@ int lompc_set_options(lompc_t* h, int max_iter, double tol) {
 }
 
 int lompc_set_kernel_variant(lompc_t* h, int variant) {
-  if (!h || variant < 0 || variant > 5) return LOMPC_ERR_ARG;
+  if (!h || variant < 0 || variant > 7) return LOMPC_ERR_ARG;
   h->variant = variant;
   return LOMPC_OK;
 }
