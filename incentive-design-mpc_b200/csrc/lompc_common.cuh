@@ -44,6 +44,18 @@ __device__ __forceinline__ double fast_rcp(double x) {
   return fma(y, t, y);
 }
 
+// The two halves of fast_rcp, for callers that want other work between the MUFU and the refinement.
+__device__ __forceinline__ double rcp_seed(double x) {
+  double y;
+  asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  return y;
+}
+__device__ __forceinline__ double rcp_refine(double x, double y) {
+  const double e = fma(-x, y, 1.0);
+  const double t = fma(e, e, e);
+  return fma(y, t, y);
+}
+
 // max / min of two non-NaN doubles: one DSETP + a select.  (fmax / fmin quiet NaNs, which costs
 // ~8 SASS instructions per call in FP64; a NaN here propagates and ends as LOMPC_ST_MAXITER.)
 __device__ __forceinline__ double dmax2(double a, double b) { return a > b ? a : b; }

@@ -190,16 +190,60 @@ __device__ __forceinline__ void ric_solve(int Nrt, const double* dvec, double da
   if (lane == 0) {
     double s = 0.0;
 #pragma unroll
-    for (int k = 0; k < N; ++k) {
-      const double xk = -fma(K[k], s, KAP[k]);
-      x[k] = xk;
-      s += xk;
+    for (int k = 0; k < N; ++k) {  // s_{k+1} = s_k + x_k = (1 - K_k) s_k - kappa_k: ONE dependent FMA per stage
+      const double kk = K[k], kap = KAP[k];
+      x[k] = -fma(kk, s, kap);
+      s = fma(1.0 - kk, s, -kap);
     }
   }
 }
 
-// Scratch of one price step: (3r + 6N) doubles.
-__host__ __device__ inline int price_step_scratch_doubles(int N, int r) { return 3 * r + 6 * N; }
+// A_bar = A'A + kappa I is the same for every solve of a group: its Riccati gains are computed ONCE
+// (fac[0:N] = K_k = Q_k/(kappa + Q_k), fac[N:2N] = 1 - K_k, fac[2N:3N] = 1/(kappa + Q_k), Q_k = 1 + kappa K_{k+1})
+// and a solve is then two chains of one dependent FMA per stage, without reciprocals.
+template <int NT>
+__device__ __forceinline__ void abar_factor(int Nrt, double kappa, double* fac, int lane) {
+  const int N = NT ? NT : Nrt;
+  if (lane == 0) {
+    double P = 0.0;
+    for (int k = N - 1; k >= 0; --k) {
+      const double Q = 1.0 + P;
+      const double ib = 1.0 / (kappa + Q);
+      const double K = Q * ib;
+      fac[k] = K;
+      fac[N + k] = kappa * ib;
+      fac[2 * N + k] = ib;
+      P = kappa * K;
+    }
+  }
+  __syncwarp();
+}
+
+// x = A_bar^{-1} b with the cached gains (every lane must call; lane 0 runs the two chains, KAP is scratch).
+template <int NT>
+__device__ __forceinline__ void abar_solve(int Nrt, const double* fac, const double* bvec, double* x, double* KAP,
+                                           int lane) {
+  const int N = NT ? NT : Nrt;
+  if (lane == 0) {
+    double r = 0.0;
+#pragma unroll
+    for (int k = N - 1; k >= 0; --k) {  // kappa_k = (r_{k+1} - b_k)/(kappa + Q_k);  r_k = (1 - K_k) r_{k+1} + K_k b_k
+      const double bk = bvec[k];
+      KAP[k] = (r - bk) * fac[2 * N + k];
+      r = fma(fac[N + k], r, fac[k] * bk);
+    }
+    double s = 0.0;
+#pragma unroll
+    for (int k = 0; k < N; ++k) {
+      const double kap = KAP[k];
+      x[k] = -fma(fac[k], s, kap);
+      s = fma(fac[N + k], s, -kap);
+    }
+  }
+}
+
+// Scratch of one price step: (3r + 9N) doubles (the last 3N: the cached gains of A_bar).
+__host__ __device__ inline int price_step_scratch_doubles(int N, int r) { return 3 * r + 9 * N; }
 
 // The exact solution of the non-negative QP of the price step
 //     min_{l >= 0} l'P l + q'l,  P = Dphi A_bar^{-1} Dphi'/(2m) + eps I,  q = -2 P l_k - (phi(w_k) - phi(w_ref))
@@ -219,8 +263,8 @@ template <int NT>
 __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double kappa, double eps, double* lk,
                                                 const double* wk, const double* wr, double* ws,
                                                 unsigned char* FREE, int lane, bool first, bool warm,
-                                                bool need_dec, double& lamdiff_out, double& dec_pred_out,
-                                                int& status_out) {
+                                                bool need_dec, bool have_fac, double& lamdiff_out,
+                                                double& dec_pred_out, int& status_out) {
   const int N = NT ? NT : cs.N;
   double* LAM = ws;        // [r] new prices
   double* RHO = LAM + r;   // [r]
@@ -231,6 +275,7 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
   double* U = KAPS + N;    // [N]
   double* V = U + N;       // [N]
   double* TD = V + N;      // [N]
+  double* FAC = TD + N;    // [3N] gains of A_bar (abar_factor): computed here unless the caller keeps them
   const int nb = r / N;    // 2 or 3 price blocks
   const double th = cs.theta, qs = cs.q_scale, m = cs.c;
   // FP64 division is a ~30-instruction sequence: divide once, multiply everywhere
@@ -249,8 +294,9 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
     C3[k] = c3;
     U[k] = th * (lk[k] - lk[N + k]) + (nb == 3 ? c3 * lk[2 * N + k] : 0.0);
   }
+  if (!have_fac) abar_factor<NT>(N, kappa, FAC, lane);
   __syncwarp();
-  ric_solve<NT>(N, nullptr, kappa, 1.0, U, V, KS, KAPS, lane);
+  abar_solve<NT>(N, FAC, U, V, KAPS, lane);
   __syncwarp();
   double gs = 1.0;
   for (int k = lane; k < N; k += 32) {
@@ -316,7 +362,7 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
       U[k] = u;
     }
     __syncwarp();
-    ric_solve<NT>(N, nullptr, kappa, 1.0, U, V, KS, KAPS, lane);  // v = A_bar^{-1} B' l
+    abar_solve<NT>(N, FAC, U, V, KAPS, lane);  // v = A_bar^{-1} B' l
     __syncwarp();
     bool same = true;
     for (int k = lane; k < N; k += 32) {
@@ -417,8 +463,8 @@ __global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
   double lamdiff, dec;
   int st;
   price_step_warp<0>(cs, r, kappa, p.eps_reg, p.lmbd + (size_t)g * 3 * N, p.w_k + (size_t)g * N,
-                  p.w_ref + (size_t)g * N, ws, FREE, lane, it == 0, warm, p.hist_ac != nullptr || p.want_dec, lamdiff,
-                  dec, st);
+                  p.w_ref + (size_t)g * N, ws, FREE, lane, it == 0, warm, p.hist_ac != nullptr || p.want_dec, false,
+                  lamdiff, dec, st);
   for (int i = lane; i < r; i += 32) gfree[i] = FREE[i];
   if (lane == 0) {
     p.nnqp_status[g] = st;

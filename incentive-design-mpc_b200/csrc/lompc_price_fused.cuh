@@ -57,8 +57,8 @@ struct FusedArgs {
 template <int N, int NSEG, int T, bool GREG>
 struct FusedSmem {
   static constexpr int kK1 = RegSmem<N, NSEG, T, GREG>::kArrays * N * T;
-  // LM[3N] WREF[N] WK[N] WSUM[N] + price-step scratch (3*3N + 6N) + ERR[T] + 8 scalars
-  static constexpr int kDoubles = kK1 + 3 * N + 3 * N + 15 * N + T + 8;
+  // LM[3N] WREF[N] WK[N] WSUM[N] + price-step scratch (3*3N + 9N) + ERR[T] + 8 scalars
+  static constexpr int kDoubles = kK1 + 3 * N + 3 * N + 18 * N + T + 8;
   static constexpr size_t bytes = (size_t)kDoubles * sizeof(double) + 3 * N + 16;
 };
 
@@ -80,8 +80,8 @@ __device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArg
   double* WREF = LM + 3 * N;        // [N]
   double* WK = WREF + N;            // [N] LoMPC solution at gamma_sc for LM
   double* WSUM = WK + N;            // [N]
-  double* WS = WSUM + N;            // price-step scratch, 3r + 6N <= 15N doubles
-  double* ERR = WS + 15 * N;        // [T]
+  double* WS = WSUM + N;            // price-step scratch, 3r + 9N <= 18N doubles
+  double* ERR = WS + 18 * N;        // [T]
   double* SC = ERR + T;             // scalars: 0 cost_sc, 1 flag
   unsigned char* WSB = reinterpret_cast<unsigned char*>(SC + 8);  // [r]
   double* WN = smem + 2 * N * T;    // K1's candidate array doubles as the [k][tid] transpose buffer
@@ -121,6 +121,8 @@ __device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArg
   const double lr = a.lmbd_r[g];
   const double kappa = lr / cs.delta;
   const double tolg = sqrt((double)N) * y0_rng + a.eps_tol;  // price_solver.py:184
+  // gains of A_bar = A'A + kappa I, once per group (they sit where price_step_warp expects them)
+  if (tid < 32) abar_factor<N>(N, kappa, WS + 3 * a.r + 6 * N, tid);
 
   double dual_cost = 0.0, lamdiff = 0.0, dec_pred = 0.0;  // thread 0 only
   int it = 0, nnqp_bad = 0;
@@ -236,7 +238,7 @@ __device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArg
       if (flag == 0) {
         int st;
         price_step_warp<N>(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, tid, it == 0, it > 0, a.hist_ac != nullptr,
-                        lamdiff, dec_pred, st);
+                        true, lamdiff, dec_pred, st);
         nnqp_bad |= st;
       }
       if (tid == 0) cyc_step += clock64() - t_b;

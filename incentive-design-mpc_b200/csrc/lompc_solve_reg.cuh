@@ -48,15 +48,16 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
   int st = LOMPC_ST_OK;
   if (gam < 0.0 || lr < 0.0) st = LOMPC_ST_NEGATIVE;
   double l2sum = 0.0, gmax = 0.0;
-  auto stage_data = [&](const int k, const double l1, const double l2, const double l3) {
-    if (l1 < 0.0 || l2 < 0.0 || l3 < 0.0) st = LOMPC_ST_NEGATIVE;
-    const double g = cs.theta * (l1 - l2);
-    if (GREG) GR[GREG ? k : 0] = g; else GS[k * T] = g;
-    D[k] = 2.0 * (lr * cs.theta2 + cs.q_scale * l3) + cs.d_base;
-    if (!warm) W[k] = 0.0;
-    gmax = dmax2(gmax, fabs(g));
-    l2sum += l2;
-  };
+#define LOMPC_STAGE_DATA(k, l1, l2, l3)                                      \
+  {                                                                         \
+    if ((l1) < 0.0 || (l2) < 0.0 || (l3) < 0.0) st = LOMPC_ST_NEGATIVE;     \
+    const double g_ = cs.theta * ((l1) - (l2));                             \
+    if (GREG) GR[GREG ? (k) : 0] = g_; else GS[(k) * T] = g_;               \
+    D[k] = 2.0 * (lr * cs.theta2 + cs.q_scale * (l3)) + cs.d_base;          \
+    if (!warm) W[k] = 0.0;                                                  \
+    gmax = dmax2(gmax, fabs(g_));                                           \
+    l2sum += (l2);                                                          \
+  }
   if (vec && N % 2 == 0) {
     // 16-byte loads of the thread's own price row (the rows of a warp are 3N doubles apart, so every load
     // instruction touches 32 lines whatever its width: half as many instructions, half the LSU wavefronts)
@@ -64,17 +65,19 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
 #pragma unroll
     for (int k = 0; k < N; k += 2) {
       const double2 a1 = lm2[k / 2], a2 = lm2[(N + k) / 2], a3 = lm2[(2 * N + k) / 2];
-      stage_data(k, a1.x, a2.x, a3.x);
-      stage_data(k + 1, a1.y, a2.y, a3.y);
+      LOMPC_STAGE_DATA(k, a1.x, a2.x, a3.x);
+      LOMPC_STAGE_DATA(k + 1, a1.y, a2.y, a3.y);
       LOMPC_STAGE_FENCE();
     }
   } else {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      stage_data(k, lm[k], lm[N + k], lm[2 * N + k]);
+      const double l1 = lm[k], l2 = lm[N + k], l3 = lm[2 * N + k];
+      LOMPC_STAGE_DATA(k, l1, l2, l3);
       LOMPC_STAGE_FENCE();
     }
   }
+#undef LOMPC_STAGE_DATA
   if (gam > cs.y_max) st = LOMPC_ST_BAD_GAMMA;
   const double c = cs.c, wmax = cs.w_max;
   const double gscale = fmax(1.0, gmax + c * N * cs.y_max);
@@ -130,6 +133,7 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
     // the denominator obey a LINEAR recurrence (2 dependent FMAs per stage); the one
     // reciprocal per stage (1/pb_new, needed only for the gains) is off the dependency chain.
     double pa = 0.0, pb = 1.0, pr = 0.0, p = 0.0, e = sN - gam;  // e = s_k - gamma
+    double dl_y = 0.0, dl_bn = 1.0, dl_tq = 0.0, dl_kn = 0.0, dl_pb = 0.0;  // stage k+1's deferred gain data
     vh = 0;  // high word of the largest KKT violation (non-negative doubles order like their high words)
 #pragma unroll
     for (int k = N - 1; k >= 0; --k) {
@@ -167,10 +171,20 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
       const double tq_ = fma(c, pb, pa);     // Q * pb,  Q = c + P
       const double tu = fma(-cg, pb, pr);    // (r - c gamma) * pb
       const double bn = fma(dm, pb, tq_);    // (dm + Q) * pb
-      const double ib = fast_rcp(bn);
-      KK[k * T] = tq_ * ib;                  // Q / (dm + Q)
-      KAP[k * T] = fma(gm, pb, tu) * ib;     // (r - c gamma + gm) / (dm + Q)
-      if (NSEG > 1) INV[k * T] = pb * ib;    // 1 / (dm + Q)
+      // Gains of stage k: Q/(dm+Q), (r - c gamma + gm)/(dm+Q), 1/(dm+Q).  Only the seed of the reciprocal is
+      // issued here; its Newton step, the three products and the stores are written one stage LATER (software
+      // pipelining: the MUFU latency and the 4-deep FMA chain of the refinement hide behind the next stage).
+      if (k < N - 1) {
+        const double ib = rcp_refine(dl_bn, dl_y);
+        KK[(k + 1) * T] = -(dl_tq * ib);   // the gains are stored NEGATED: the rollout is x0 = KK s + KAP
+        KAP[(k + 1) * T] = -(dl_kn * ib);  // (a separate negation would sit on the forward chain)
+        if (NSEG > 1) INV[(k + 1) * T] = dl_pb * ib;
+      }
+      dl_y = rcp_seed(bn);
+      dl_bn = bn;
+      dl_tq = tq_;
+      dl_kn = fma(gm, pb, tu);
+      dl_pb = pb;
       if (binding) {  // P <- Q, r <- Q w + r - c gamma (denominator unchanged)
         pa = tq_;
         pr = fma(tq_, wk, tu);
@@ -191,22 +205,36 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
       converged = true;
       break;
     }
+    {  // gains of stage 0 (deferred)
+      const double ib = rcp_refine(dl_bn, dl_y);
+      KK[0] = -(dl_tq * ib);
+      KAP[0] = -(dl_kn * ib);
+      if (NSEG > 1) INV[0] = dl_pb * ib;
+    }
     // ---------------- forward sweep: stage-optimal rollout ----------------
     double fn = 0.0, s = 0.0;
+    // gains of stage k are loaded one stage ahead: the chain of stage k+1 can start as soon as s is known and
+    // the objective terms of stage k fill its latencies
+    double kk_n = KK[0], kap_n = KAP[0], inv_n = (NSEG > 1) ? INV[0] : 0.0;
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       // The state s is the loop-carried dependency of the sweep; everything that does not depend on it is
       // kept off that chain.
-      const double kk = KK[k * T], kap = KAP[k * T];
+      const double kk = kk_n, kap = kap_n;
+      const double inv = inv_n;
+      if (k + 1 < N) {
+        kk_n = KK[(k + 1) * T];
+        kap_n = KAP[(k + 1) * T];
+        if (NSEG > 1) inv_n = INV[(k + 1) * T];
+      }
       double x;
       if (NSEG > 1) {
-        // minimiser of  stage cost + cost-to-go  over [0, w_max]: with c_j = -(kk s + kap + slope_j inv) the
+        // minimiser of  stage cost + cost-to-go  over [0, w_max]: with c_j = kk s + kap - slope_j inv (kk, kap: negated gains) the
         // stationary point of piece j,  x = max(0, max_j min(c_j, brk[j+1]))  (brk[NSEG] = w_max): one FMA per
         // candidate on the chain, the mins are independent and the max is a tree.
-        const double inv = INV[k * T];
         double m[NSEG];
 #pragma unroll
-        for (int j = 0; j < NSEG; ++j) m[j] = dmin2(fma(-kk, s, -fma(slope[j], inv, kap)), brk[j + 1]);
+        for (int j = 0; j < NSEG; ++j) m[j] = dmin2(fma(kk, s, fma(-slope[j], inv, kap)), brk[j + 1]);
 #pragma unroll
         for (int h = 1; h < NSEG; h *= 2) {
 #pragma unroll
@@ -215,7 +243,7 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
         x = dpos(m[0]);
       } else {
         // clip with both comparisons on x0 (in parallel) instead of a min(max()) chain
-        const double x0 = -fma(kk, s, kap);
+        const double x0 = fma(kk, s, kap);
         x = x0 > wmax ? wmax : x0;
         x = x0 < 0.0 ? 0.0 : x;
       }
