@@ -59,13 +59,15 @@ def draw_workload(batch: int, N: int, seed: int):
     return out
 
 
-def flops_per_qp(ev: str, N: int, iters_mean: float) -> float:
-    """Algorithmic FP64 flops of one solve (FMA = 2):
-    setup+final cost 16N (25N large), backward sweep 19N (20N), forward sweep 14N (31N);
-    a solve that stops after `it` iterations ran it+1 backward and it forward sweeps."""
+def flops_per_qp(ev: str, N: int, iters_mean: float, optimistic: bool = True) -> float:
+    """Algorithmic FP64 flops of one solve (FMA = 2, comparisons / selects not counted):
+    setup + final cost 16N (25N large), backward sweep 19N (20N), forward sweep 14N (31N) with the objective
+    of the rollout, 3N (17N) without it -- the optimistic phase of K1, which is the one that runs on strictly
+    convex stage costs such as this workload's (every price > 0).  A solve that stops after `it` iterations
+    ran it+1 backward and it forward sweeps."""
     if ev == "small":
-        return N * (16 + 19 * (iters_mean + 1) + 14 * iters_mean)
-    return N * (25 + 20 * (iters_mean + 1) + 31 * iters_mean)
+        return N * (16 + 19 * (iters_mean + 1) + (3 if optimistic else 14) * iters_mean)
+    return N * (25 + 20 * (iters_mean + 1) + (17 if optimistic else 31) * iters_mean)
 
 
 def bytes_per_qp(N: int) -> int:

@@ -195,6 +195,29 @@ def test_hard_cases():
         assert np.max(np.abs(cost - z[key + "_cost"]) / np.maximum(1, np.abs(z[key + "_cost"]))) <= C_RTOL, key
 
 
+@pytest.mark.parametrize("ev", ["small", "large"])
+def test_optimistic_phase_hands_over_to_the_safeguarded_loop(ev):
+    """K1 runs its first iterations without evaluating the objective when every stage cost of every QP of the
+    warp is strictly convex.  (a) nearly degenerate but convex stages (lmbd_r = 1e-9, sparse prices): the
+    optimistic phase is chosen, converges slowly and hands over; (b) the same rows with exact zeros interleaved
+    (mixed warps: the warp votes for the safeguarded loop).  Both must reach the oracle's optimum."""
+    from chargingstation.lompc import LoMPC
+    o, c = _consts(ev)
+    N, B = 24, 256
+    rng = np.random.default_rng(77)
+    lm = 0.05 * o.theta * rng.random((B, 3 * N)) * (rng.random((B, 3 * N)) < 0.5)
+    gam = o.y_max - (0.3 + 0.2 * rng.random(B))
+    solver = LoMPC(N, c)
+    for lr in (np.full(B, 1e-9), np.where(np.arange(B) % 3 == 0, 0.0, 1e-9)):
+        w, cost, info = solver.solve_lompc_batch(lm, lr, gam, return_info=True)
+        assert np.all(info["status"] == 0), info["iters"].max()
+        assert info["kkt_res"].max() <= 1e-10
+        for b in range(0, B, 16):
+            wo, co, _ = orc.solve_active_set(N, o, lm[b], lr[b], gam[b])
+            assert np.max(np.abs(w[b] - wo)) <= W_RTOL * o.w_max, (b, info["iters"][b])
+            assert abs(cost[b] - co) <= C_RTOL * max(1, abs(co))
+
+
 def test_async_host_api_matches_blocking_call():
     """solve_lompc_batch(wait=False) on two independent handles + wait() == the blocking calls."""
     from chargingstation.lompc import LoMPC

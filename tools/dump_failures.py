@@ -12,7 +12,7 @@ for ev in ("small", "large"):
     delta, theta, y_max, w_max = EV_CONSTS[ev]
     for N in (24, 96):
         solver = LoMPC(N, LoMPCConstants(delta, theta, y_max, w_max, ev))
-        for mode in (0, 1, 2, 3):
+        for mode in (0, 1, 2, 3, 4):
             B = 1 << 20 if N == 24 else 1 << 17
             rng = np.random.default_rng(mode)
             if mode == 0:
@@ -23,8 +23,11 @@ for ev in ("small", "large"):
             elif mode == 2:
                 lm = np.zeros((B, 3 * N)); lm[:, :2 * N] = 0.05 * theta * rng.random((B, 2 * N))
                 lr, gam = np.zeros(B), y_max * rng.random(B)
-            else:
+            elif mode == 3:
                 lm, lr, gam = np.zeros((B, 3 * N)), np.zeros(B), y_max * rng.random(B)
+            else:  # nearly degenerate but strictly convex stages: the optimistic phase of K1 hands over
+                lm = 0.05 * theta * rng.random((B, 3 * N)) * (rng.random((B, 3 * N)) < 0.5)
+                lr, gam = np.full(B, 1e-9), y_max - (0.3 + 0.2 * rng.random(B))
             t = [torch.from_numpy(x).to(dev) for x in (lm, lr, gam)]
             w, cost, info = solver.solve_lompc_batch(*t, return_info=True)
             st = info["status"].cpu().numpy(); it = info["iters"].cpu().numpy(); kk = info["kkt_res"].cpu().numpy()

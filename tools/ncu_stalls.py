@@ -12,7 +12,8 @@ KEYS = ["gpu__time_duration.sum", "launch__registers_per_thread", "sm__warps_act
         "sm__inst_executed_pipe_alu.sum", "sm__inst_executed_pipe_fma.sum", "sm__inst_executed_pipe_lsu.sum",
         "sm__inst_executed_pipe_xu.sum", "smsp__inst_executed_op_branch.sum"]
 for rep in sys.argv[1:]:
-    out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    out = (open(rep).read() if rep.endswith(".csv") else
+           subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout)
     rows = list(csv.reader(out.splitlines()))
     h, u = rows[0], rows[1]
     for v in rows[2:]:

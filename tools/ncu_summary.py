@@ -16,7 +16,8 @@ want = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum
         'l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_ld.sum',
         'l1tex__t_sectors_pipe_lsu_mem_global_op_st.sum', 'l1tex__t_requests_pipe_lsu_mem_global_op_st.sum',
         'lts__t_sectors_op_read.sum', 'lts__t_sectors_op_write.sum', 'sm__inst_executed.avg.per_cycle_elapsed']
-txt = subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout
+txt = (open(sys.argv[1]).read() if sys.argv[1].endswith('.csv') else
+       subprocess.run(['ncu', '-i', sys.argv[1], '--page', 'raw', '--csv'], capture_output=True, text=True).stdout)
 rows = list(csv.reader(io.StringIO(txt)))
 hdr, units, vals = rows[0], rows[1], rows[2]
 print(f"## {sys.argv[2]}\n\n`{vals[hdr.index('Kernel Name')]}`\n\n| metric | unit | value |\n|---|---|---|")
