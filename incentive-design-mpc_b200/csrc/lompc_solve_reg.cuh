@@ -1,16 +1,18 @@
 // K1, register-resident variant for compile-time horizons (N = 12, 24): same algorithm
 // as lompc_solve.cuh (see the header there), restructured for the B200 SM:
 //   * the iterate w, the diagonal d and the linear term g live in REGISTERS (fully
-//     unrolled sweeps, no address arithmetic); only the Riccati gains (K, kappa[, inv]),
-//     the rollout candidate and the 1-byte working-set codes live in shared memory
-//     (column-per-thread [k][128] layout, bank-conflict free), so two 128-thread CTAs
-//     fit per SM instead of one;
-//   * the reciprocal of the Riccati pivot is MUFU.RCP64H + two Newton steps (4 DFMA)
-//     instead of the IEEE division sequence with its slow-path branch;
-//   * with TMA staging (kStage): every thread issues ONE cp.async.bulk for its own
-//     3N-double price row into a padded shared-memory slot (16-byte aligned, 2-way
-//     conflict at worst) instead of 3N uncoalesced loads, and results leave through a
-//     cp.async.bulk store of the [k][tid]->row transposed tile.
+//     unrolled sweeps, no address arithmetic); only the Riccati gains (K, kappa[, inv], stored
+//     negated) and the parked previous iterate live in shared memory (column-per-thread
+//     [k][T] layout, bank-conflict free): 8 warps per SM;
+//   * the FP64 pipe issues one warp instruction every 2 cycles per scheduler whatever the number of
+//     active lanes (tools/ubench_fp64_halfwarp.cu), and with 2 warps per scheduler it is the binding
+//     resource: everything that is not arithmetic is kept off it (violation maximum as an integer,
+//     max(x, 0) by bit masking, breakpoint flag from predicates) and the sweeps are branch-free, so
+//     that ptxas schedules across the 24 unrolled stages (tools/sass_sched.py shows the result);
+//   * the reciprocal of the Riccati pivot is MUFU.RCP64H + one cubic Newton step instead of the
+//     IEEE division sequence, and the gains of stage k are formed while stage k-1 runs;
+//   * the thread's own 3N-double price row is read with 16-byte loads (the rows of a warp are 576 B
+//     apart, every load touches 32 lines whatever its width) and the result leaves the same way.
 #pragma once
 #include <type_traits>
 
