@@ -143,8 +143,20 @@ int launch_solve(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t 
   }
   // Threads per block: as many as fit the 227 KB of shared memory, capped at 128;
   // small batches use small blocks so that more SMs take part.
-  int T = 128;
-  while (T > 32 && lompc::SmemLayout<NSEG>::bytes(N, T) > 200 * 1024) T >>= 1;
+  // Threads per block: the size that keeps most warps resident per SM (shared memory is the limit: 6-7 vectors of
+  // N doubles per QP), capped at 128; small batches use small blocks so that more SMs take part.
+  int T = 32;
+  {
+    size_t best = 0;
+    for (int cand = 32; cand <= 128; cand <<= 1) {
+      const size_t per_cta = lompc::SmemLayout<NSEG>::bytes(N, cand) + 1024;
+      const size_t warps = (size_t)(227 * 1024 / per_cta) * (cand / 32);
+      if (warps >= best && per_cta <= 227 * 1024) {
+        best = warps;
+        T = cand;
+      }
+    }
+  }
   while (T > 32 && (a.B + T - 1) / T < 148) T >>= 1;
   const size_t smem = lompc::SmemLayout<NSEG>::bytes(N, T);
   if (smem > 227 * 1024) return LOMPC_ERR_ARG;

@@ -95,6 +95,7 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
   const double wmax = cs.w_max;
   const double gscale = fmax(1.0, gmax + c * N * cs.y_max);
   const double tq = a.tol * gscale;
+  const int tqh = __double2hiint(tq);
   const double cg = c * gam;
   // A coordinate within `band` of a breakpoint is treated as sitting on it (the
   // epsilon-binding set of projected Newton: without it a coordinate 1 ulp off a
@@ -103,117 +104,118 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
   // Objective values closer than ~1e-15 of the summed magnitudes cannot be ordered in fp64 (fixed part for
   // the linear / tracking / pwl terms, 1e-15 (|f| + |fn|) for the quadratic ones; see lompc_solve_reg.cuh).
   const double fbase = 1e-15 * (c * N * cs.y_max * cs.y_max + N * wmax * (gmax + cs.slope[NSEG - 1]));
+  double brk[NSEG + 1], slope[NSEG], blo[NSEG + 1], bhi[NSEG + 1];
+#pragma unroll
+  for (int i = 0; i <= NSEG; ++i) {
+    brk[i] = cs.brk[i];
+    blo[i] = brk[i] - band;
+    bhi[i] = brk[i] + band;
+  }
+#pragma unroll
+  for (int j = 0; j < NSEG; ++j) slope[j] = cs.slope[j];
 
   double* W = WA;   // current feasible iterate
   double* WN = WB;  // candidate
   double sN = 0.0;  // s_{N-1} of the current iterate
   double f = 0.5 * c * N * gam * gam;  // objective at w = 0 (without kappa0)
-  double viol = 0.0;
+  int vh = 0;       // high word of the largest KKT violation of the last backward sweep
   double mu = 0.0;  // proximal weight of the safeguard
   int it = 0;
-  bool converged = false;
-  if (st != LOMPC_ST_OK) {
-    converged = true;  // invalid input: report, output zeros
-    viol = 0.0;
-  }
+  bool converged = (st != LOMPC_ST_OK);  // invalid input: report, output zeros
 
+  // The two sweeps are those of lompc_solve_reg.cuh (same formulas, see the comments there: Riccati recursion in
+  // homogeneous form with the reciprocal off the chain, branch-free KKT test, violation maximum on the integer
+  // pipe, tree-shaped pwl minimiser, negated gains) with the per-stage vectors in shared memory and run-time N.
   for (; !converged && it < a.max_iter; ++it) {
     // ---------------- backward sweep ----------------
-    double P = 0.0, r = 0.0, p = 0.0, s = sN;
-    viol = 0.0;
+    double pa = 0.0, pb = 1.0, pr = 0.0, p = 0.0, e = sN - gam;
+    vh = 0;
     for (int k = N - 1; k >= 0; --k) {
       const double wk = W[k * T], dk = D[k * T], gk = G[k * T];
-      p = fma(c, s, p) - cg;
+      p = fma(c, e, p);
       const double q = fma(dk, wk, gk) + p;
-      // KKT test of coordinate k -> binding flag and working segment
-      bool binding = false;
-      int seg = 0;
-      double v;
-      if (NSEG == 1) {
-        if (wk <= band) {
-          binding = (q >= -tq);
-          v = binding ? 0.0 : -q;
-        } else if (wk >= wmax - band) {
-          binding = (q <= tq);
-          v = binding ? 0.0 : q;
-        } else {
-          v = fabs(q);
-        }
-      } else {
-        int at = -1;
+      const double mq = -q;
+      double s_hi = slope[0], s_lo = slope[0];
+      bool atbp = false;
 #pragma unroll
-        for (int i = 0; i <= NSEG; ++i)
-          if (fabs(wk - cs.brk[i]) <= band) at = i;
-        if (at >= 0) {
-          const double mq = -q;
-          if (at < NSEG && mq > cs.slope[at] + tq) {
-            seg = at;
-            v = mq - cs.slope[seg];
-          } else if (at > 0 && mq < cs.slope[at - 1] - tq) {
-            seg = at - 1;
-            v = cs.slope[seg] - mq;
-          } else {
-            binding = true;
-            seg = at < NSEG ? at : NSEG - 1;
-            v = 0.0;
-          }
-        } else {
-#pragma unroll
-          for (int j = 1; j < NSEG; ++j) seg += (wk > cs.brk[j]) ? 1 : 0;
-          v = fabs(q + cs.slope[seg]);
-        }
+      for (int j = 1; j < NSEG; ++j) {
+        const bool ge = wk >= blo[j], gt = wk > bhi[j];
+        if (ge) s_hi = slope[j];
+        if (gt) s_lo = slope[j];
+        atbp |= (ge != gt);
       }
-      viol = fmax(viol, v);
-      // Riccati step
-      const double Q = c + P;
-      const double rp = r - cg;
-      const double dm = dk + mu;            // proximal model: d + mu, g - mu w
+      const bool top = wk >= blo[NSEG], bot = wk <= band;
+      if (top) s_hi = 1e300;
+      if (bot) s_lo = -1e300;
+      atbp |= top | bot;
+      const double va = mq - s_hi, vb = s_lo - mq;
+      const bool right = va > tq, left = vb > tq;
+      const bool binding = atbp && !right && !left;
+      const double sl = left ? s_lo : s_hi;
+      vh = max(vh, max(__double2hiint(va), __double2hiint(vb)));
+      const double dm = dk + mu;  // proximal model: d + mu, g - mu w
       const double gm = fma(-mu, wk, gk);
-      const double inv = 1.0 / (dm + Q);
-      const double h = gm + ((NSEG > 1) ? cs.slope[seg] : 0.0);
+      const double tq_ = fma(c, pb, pa);
+      const double tu = fma(-cg, pb, pr);
+      const double bn = fma(dm, pb, tq_);
+      const double ib = fast_rcp(bn);
+      KK[k * T] = -(tq_ * ib);
+      KAP[k * T] = -(fma(gm, pb, tu) * ib);
+      if (NSEG > 1) INV[k * T] = pb * ib;
       if (binding) {
-        P = Q;
-        r = fma(Q, wk, rp);
+        pa = tq_;
+        pr = fma(tq_, wk, tu);
       } else {
-        P = Q * dm * inv;
-        r = (dm * rp - Q * h) * inv;
+        pa = dm * tq_;
+        pr = fma(dm, tu, -tq_ * (gm + sl));
+        pb = bn;
       }
-      KK[k * T] = Q * inv;
-      KAP[k * T] = (rp + gm) * inv;
-      if (NSEG > 1) INV[k * T] = inv;
-      s -= wk;
+      if (pb > 0x1p600) {  // keep the homogeneous triple in range (exact rescale)
+        pa *= 0x1p-600;
+        pb *= 0x1p-600;
+        pr *= 0x1p-600;
+      }
+      e -= wk;
     }
-    if (viol <= tq) {
+    if (vh < tqh) {
       converged = true;
       break;
     }
     // ---------------- forward sweep: stage-optimal rollout ----------------
-    double fn = 0.0;
-    s = 0.0;
+    double fn = 0.0, s = 0.0;
     for (int k = 0; k < N; ++k) {
-      const double x0 = -fma(KK[k * T], s, KAP[k * T]);
+      const double kk = KK[k * T], kap = KAP[k * T];
       double x;
-      if (NSEG == 1) {
-        x = x0;
-      } else {
+      if (NSEG > 1) {
         const double inv = INV[k * T];
-        x = x0 - cs.slope[NSEG - 1] * inv;
+        double m[NSEG];
 #pragma unroll
-        for (int j = NSEG - 2; j >= 0; --j)
-          x = fmin(x0 - cs.slope[j] * inv, fmax(cs.brk[j + 1], x));
+        for (int j = 0; j < NSEG; ++j) m[j] = dmin2(fma(kk, s, fma(-slope[j], inv, kap)), brk[j + 1]);
+#pragma unroll
+        for (int h = 1; h < NSEG; h *= 2) {
+#pragma unroll
+          for (int j = 0; j + h < NSEG; j += 2 * h) m[j] = dmax2(m[j], m[j + h]);
+        }
+        x = dpos(m[0]);
+      } else {
+        const double x0 = fma(kk, s, kap);
+        x = x0 > wmax ? wmax : x0;
+        x = x0 < 0.0 ? 0.0 : x;
       }
-      x = fmin(fmax(x, 0.0), wmax);
       WN[k * T] = x;
       s += x;
-      const double e = s - gam;
-      fn += x * fma(0.5 * D[k * T], x, G[k * T]) + 0.5 * c * e * e;
-      if (NSEG > 1) fn += pwl_value<NSEG>(cs, x);
+      const double ee = s - gam;
+      fn += x * fma(0.5 * D[k * T], x, G[k * T]) + 0.5 * c * ee * ee;
+      if (NSEG > 1) {
+#pragma unroll
+        for (int j = 1; j < NSEG; ++j) fn += (slope[j] - slope[j - 1]) * dpos(x - brk[j]);
+      }
     }
     if (fn <= f + (fbase + 1e-15 * (fabs(f) + fabs(fn)))) {
       double* tmp = W;
       W = WN;
       WN = tmp;
-      f = fmin(f, fn);
+      f = dmin2(f, fn);
       sN = s;
       mu = 0.0;
     } else {
@@ -253,7 +255,7 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
                       cs.theta2 * w0 * w0 * lr;
   if (a.status) a.status[b] = st;
   if (a.iters) a.iters[b] = it;
-  if (a.kkt_res) a.kkt_res[b] = viol / gscale;
+  if (a.kkt_res) a.kkt_res[b] = __hiloint2double(vh, vh ? -1 : 0) / gscale;  // upper bound (2^-20 relative)
 }
 
 }  // namespace lompc
