@@ -1,8 +1,5 @@
-python -m pytest tests -m gpu -x -q 2>&1 | tail -3
-python tools/run_horizon_sweep.py 2>&1 | tail -4 | tee gpurun_out/r1k_horizon_sweep.jsonl
-python tools/profile_solve.py --ev small --batch 262144 --reps 3 --variant 1 | tail -1
-python tools/profile_solve.py --ev large --batch 262144 --reps 3 --variant 1 | tail -1
-python tools/profile_solve.py --ev small --batch 131072 --N 48 --reps 3 | tail -1
-python tools/profile_solve.py --ev large --batch 131072 --N 48 --reps 3 | tail -1
-python tools/profile_solve.py --ev small --batch 65536 --N 96 --reps 3 | tail -1
-python tools/profile_solve.py --ev large --batch 65536 --N 96 --reps 3 | tail -1
+python -m pytest tests/test_lompc_gpu.py -m gpu -x -q 2>&1 | tail -2
+for ev in small large; do for m in 0 1; do echo -n "ev=$ev mode=$m : "; python tools/profile_solve.py --ev $ev --batch 1048576 --reps 4 --mode $m | tail -1; done; done
+python bench.py --steps 50 --warmup 5 --no-cpu-baseline --closed-loop-stations 64 --closed-loop-steps 3 2>/dev/null | python -c "
+import json,sys
+d=json.loads(sys.stdin.readlines()[-1]); print('value',d['value'],'ms',d['ms_per_step'],'e2e',d['e2e']['value'],'sat',{k:v['qp_per_s']/1e6 for k,v in d['saturated']['per_type'].items()})"
