@@ -56,7 +56,7 @@ struct FusedArgs {
 
 template <int N, int NSEG, int T, bool GREG>
 struct FusedSmem {
-  static constexpr int kK1 = RegSmem<N, NSEG, T, GREG>::kArrays * N * T;
+  static constexpr int kK1 = RegSmem<N, NSEG, T, GREG>::kArrays * N * T + RegSmem<N, NSEG, T, GREG>::kTab;
   // LM[3N] WREF[N] WK[N] WSUM[N] + price-step scratch (3*3N + 9N) + ERR[T] + 8 scalars
   static constexpr int kDoubles = kK1 + 3 * N + 3 * N + 18 * N + T + 8;
   static constexpr size_t bytes = (size_t)kDoubles * sizeof(double) + 3 * N + 16;
@@ -76,6 +76,7 @@ __device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArg
     return false;
   }
   constexpr int kK1 = FusedSmem<N, NSEG, T, GREG>::kK1;
+  double* TAB = smem + kK1 - RegSmem<N, NSEG, T, GREG>::kTab;  // piece table of K1 (filled by the kernels below)
   double* LM = smem + kK1;          // [3N] current prices
   double* WREF = LM + 3 * N;        // [N]
   double* WK = WREF + N;            // [N] LoMPC solution at gamma_sc for LM
@@ -151,7 +152,7 @@ __device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArg
         }
         // (safeguarded loop only: the fused kernel is instruction-fetch bound and a second copy of the sweeps
         // costs more than the optimistic phase saves: 39.6k vs 33.0k cycles per large-EV pass)
-        solve_reg<N, NSEG, T, GREG, false>(cs, LM, lr, gam, a.qp_tol, a.qp_max_iter, warm, false, smem + tid, W, D, GR, l2sum,
+        solve_reg<N, NSEG, T, GREG, false>(cs, LM, lr, gam, a.qp_tol, a.qp_max_iter, warm, false, smem + tid, TAB, W, D, GR, l2sum,
                                     gscale, viol, st, qit);
         if (st != LOMPC_ST_OK) atomicAdd(a.flags + 3, 1);  // a LoMPC solve that did not converge (never observed)
         if (a.qp_count) {
@@ -284,6 +285,8 @@ __device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArg
 template <int N, int NSEG, int T, int MINB, bool GREG>
 __global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts cs, const FusedArgs a) {
   extern __shared__ double smem[];
+  piece_table<NSEG>(cs, smem + FusedSmem<N, NSEG, T, GREG>::kK1 - RegSmem<N, NSEG, T, GREG>::kTab, threadIdx.x);
+  __syncthreads();
   const int g = blockIdx.x;
   double* row = a.prices + (size_t)g * 3 * N;
   group_loop_body<N, NSEG, T, GREG>(cs, a, g, smem, row, row, nullptr);
@@ -299,6 +302,8 @@ __global__ void __launch_bounds__(T, MINB) price_group_loop_kernel(const Consts 
 template <int N, int NSEG, int T, int MINB, bool GREG>
 __global__ void __launch_bounds__(T, MINB) price_station_chain_kernel(const Consts cs, const FusedArgs a) {
   extern __shared__ double smem[];
+  piece_table<NSEG>(cs, smem + FusedSmem<N, NSEG, T, GREG>::kK1 - RegSmem<N, NSEG, T, GREG>::kTab, threadIdx.x);
+  __syncthreads();
   // launch order: longest expected chains first (the caller sorts stations by last step's iteration
   // totals), so that a station stuck at the iteration cap does not start in the last wave
   const int S = a.chain_S, s = a.chain_order ? a.chain_order[blockIdx.x] : (int)blockIdx.x;

@@ -30,8 +30,30 @@ namespace lompc {
 template <int N, int NSEG, int T, bool GREG>
 struct RegSmem {
   static constexpr int kArrays = 3 + (GREG ? 0 : 1) + (NSEG > 1 ? 1 : 0);  // KK, KAP, WN [, G] [, INV]
-  static constexpr size_t bytes = (size_t)kArrays * N * T * sizeof(double);
+  // + the CTA's table of subdifferentials [s_lo, s_hi] per piece code (piece_table), after the arrays
+  static constexpr int kTab = 2 * (2 * NSEG + 1);
+  static constexpr size_t bytes = ((size_t)kArrays * N * T + kTab) * sizeof(double);
 };
+
+// Piece code of a coordinate w_k: 2i = sitting on breakpoint i (0: the lower box end, NSEG: the upper one),
+// 2j + 1 = inside piece j.  The table holds (s_lo, s_hi) = the subdifferential of the separable term there
+// (+-1e300 at the box ends; both = slope_j inside a piece), one double2 per code.  Filled by the first
+// 2 NSEG + 1 threads of the CTA; the caller synchronises.
+template <int NSEG>
+__device__ __forceinline__ void piece_table(const Consts& cs, double* tab, int t) {
+  if (t <= 2 * NSEG) {
+    const int i = t >> 1;
+    double lo, hi;
+    if (t & 1) {
+      lo = hi = cs.slope[i];
+    } else {
+      lo = i > 0 ? cs.slope[i - 1] : -1e300;
+      hi = i < NSEG ? cs.slope[i] : 1e300;
+    }
+    tab[2 * t] = lo;
+    tab[2 * t + 1] = hi;
+  }
+}
 
 // The solve itself: one QP per thread, iterate / diagonal / linear term in the caller's
 // registers.  `smem_t` = this thread's column of the CTA's shared-memory arrays (base + t).
@@ -40,7 +62,7 @@ struct RegSmem {
 template <int N, int NSEG, int T, bool GREG, bool OPT = true>
 __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, const double lr, const double gam,
                                           const double tol, const int max_iter, const bool warm, const bool vec,
-                                          double* smem_t, double (&W)[N],
+                                          double* smem_t, const double* tab, double (&W)[N],
                                           double (&D)[N], double (&GR)[GREG ? N : 1], double& l2sum_out,
                                           double& gscale_out, double& viol_out, int& st_out, int& it_out) {
   double* KK = smem_t;
@@ -110,6 +132,17 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
 
   double sN = 0.0, f = 0.0, mu = 0.0;
   int vh = 0;
+  // Piece codes of the iterate (see piece_table), 4 bits per stage.  They are a by-product of the forward sweep
+  // (which branch of its min/max tree produced x_k says where x_k sits), so that the backward sweep's KKT test
+  // reads the subdifferential from the table instead of comparing w_k with every breakpoint again; only a
+  // caller-provided starting point is classified by comparisons (a coordinate within `band` of a breakpoint
+  // counts as sitting on it).  W = 0: every coordinate sits on the lower box end (code 0).
+  // (Small EV, one piece: two comparisons per stage are cheaper than the bookkeeping, so no codes there.)
+  constexpr bool kCodes = NSEG > 1;
+  constexpr int kCW = kCodes ? (4 * N + 31) / 32 : 1;
+  unsigned codes[kCW], codes_old[kCW];  // of W, of the iterate parked in WN
+#pragma unroll
+  for (int i = 0; i < kCW; ++i) codes[i] = codes_old[i] = 0u;
   if (warm) {
     // start from the caller's feasible W (the solution at the previous prices of the price
     // loop): the active set is usually already right and one verification sweep remains
@@ -119,6 +152,14 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
       const double x = dmin2(dpos(W[k]), wmax);
       W[k] = x;
       s0 += x;
+      if (kCodes) {
+        int cd = 1;  // nge + ngt + 1: 2i on breakpoint i (nge = i, ngt = i - 1), 2j + 1 inside piece j
+#pragma unroll
+        for (int j = 1; j < NSEG; ++j) cd += (x >= blo[j] ? 1 : 0) + (x > bhi[j] ? 1 : 0);
+        if (x >= blo[NSEG]) cd = 2 * NSEG;
+        if (x <= band) cd = 0;
+        codes[(kCodes ? k : 0) / 8] |= (unsigned)cd << (4 * (k % 8));
+      }
       if (!OPT) {  // no optimistic phase: the safeguarded loop starts here and needs the objective of W
         const double e = s0 - gam;
         f0 += x * fma(0.5 * D[k], x, LOMPC_G(k)) + 0.5 * c * e * e;
@@ -156,19 +197,20 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
       // s_lo == s_hi = its slope.  -q outside the interval (by more than the tolerance) moves
       // the coordinate onto the neighbouring piece, inside it the coordinate stays put (binding).
       const double mq = -q;
-      double s_hi = slope[0], s_lo = slope[0];
-      bool atbp = false;  // sitting on a breakpoint or a box end  (<=> s_lo < s_hi)
-#pragma unroll
-      for (int j = 1; j < NSEG; ++j) {
-        const bool ge = wk >= blo[j], gt = wk > bhi[j];
-        if (ge) s_hi = slope[j];
-        if (gt) s_lo = slope[j];
-        atbp |= (ge != gt);
+      double s_lo, s_hi;
+      bool atbp;  // sitting on a breakpoint or a box end  (<=> s_lo < s_hi)
+      if (kCodes) {
+        const unsigned cd = (codes[(kCodes ? k : 0) / 8] >> (4 * (k % 8))) & 15u;
+        const double2 sub = reinterpret_cast<const double2*>(tab)[cd];
+        s_lo = sub.x;
+        s_hi = sub.y;
+        atbp = (cd & 1u) == 0u;
+      } else {
+        const bool top = wk >= blo[NSEG], bot = wk <= band;
+        s_hi = top ? 1e300 : slope[0];
+        s_lo = bot ? -1e300 : slope[0];
+        atbp = top | bot;
       }
-      const bool top = wk >= blo[NSEG], bot = wk <= band;
-      if (top) s_hi = 1e300;
-      if (bot) s_lo = -1e300;
-      atbp |= top | bot;
       // distance of -q from [s_lo, s_hi]: at most one of va, vb is positive.  Everything below is branch-free
       // (a ladder of ?: compiles to a divergent DSETP -> BRA chain per stage that also splits the sweep into
       // basic blocks), and the running maximum is kept on the integer pipe.
@@ -227,6 +269,12 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
   auto forward = [&](auto obj_tag, double& s_end) -> double {
     constexpr bool OBJ = decltype(obj_tag)::value;
     double fn = 0.0, s = 0.0;
+    unsigned ncodes[kCW];
+#pragma unroll
+    for (int i = 0; i < kCW; ++i) {
+      ncodes[i] = 0u;
+      codes_old[i] = codes[i];
+    }
     // gains of stage k are loaded one stage ahead: the chain of stage k+1 can start as soon as s is known and
     // the objective terms of stage k fill its latencies
     double kk_n = KK[0], kap_n = KAP[0], inv_n = (NSEG > 1) ? INV[0] : 0.0;
@@ -242,25 +290,43 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
         if (NSEG > 1) inv_n = INV[(k + 1) * T];
       }
       double x;
+      int cd_new;
       if (NSEG > 1) {
         // minimiser of  stage cost + cost-to-go  over [0, w_max]: with c_j = kk s + kap - slope_j inv (kk, kap: negated gains) the
         // stationary point of piece j,  x = max(0, max_j min(c_j, brk[j+1]))  (brk[NSEG] = w_max): one FMA per
         // candidate on the chain, the mins are independent and the max is a tree.
+        // The winner of the tree tells where x sits: candidate c_j itself -> inside piece j (code 2j + 1), its
+        // cap brk[j+1] -> on that breakpoint (code 2j + 2), a negative maximum -> clipped to the lower end (0).
         double m[NSEG];
+        int mc[NSEG];
 #pragma unroll
-        for (int j = 0; j < NSEG; ++j) m[j] = dmin2(fma(kk, s, fma(-slope[j], inv, kap)), brk[j + 1]);
+        for (int j = 0; j < NSEG; ++j) {
+          const double cj = fma(kk, s, fma(-slope[j], inv, kap));
+          const bool below = cj < brk[j + 1];
+          m[j] = below ? cj : brk[j + 1];
+          mc[j] = below ? 2 * j + 1 : 2 * j + 2;
+        }
 #pragma unroll
         for (int h = 1; h < NSEG; h *= 2) {
 #pragma unroll
-          for (int j = 0; j + h < NSEG; j += 2 * h) m[j] = dmax2(m[j], m[j + h]);
+          for (int j = 0; j + h < NSEG; j += 2 * h) {
+            const bool first = m[j] > m[j + h];
+            m[j] = first ? m[j] : m[j + h];
+            mc[j] = first ? mc[j] : mc[j + h];
+          }
         }
+        const bool neg = __double2hiint(m[0]) < 0;
         x = dpos(m[0]);
+        cd_new = neg ? 0 : mc[0];
       } else {
         // clip with both comparisons on x0 (in parallel) instead of a min(max()) chain
         const double x0 = fma(kk, s, kap);
-        x = x0 > wmax ? wmax : x0;
-        x = x0 < 0.0 ? 0.0 : x;
+        const bool over = x0 > wmax, under = x0 < 0.0;
+        x = over ? wmax : x0;
+        x = under ? 0.0 : x;
+        cd_new = under ? 0 : (over ? 2 : 1);
       }
+      if (kCodes) ncodes[(kCodes ? k : 0) / 8] |= (unsigned)cd_new << (4 * (k % 8));
       WN[k * T] = W[k];  // the current iterate is parked (restored only if the rollout is rejected)
       W[k] = x;
       s += x;
@@ -274,6 +340,8 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
       }
       LOMPC_STAGE_FENCE();
     }
+#pragma unroll
+    for (int i = 0; i < kCW; ++i) codes[i] = ncodes[i];
     s_end = s;
     return fn;
   };
@@ -331,6 +399,8 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
       } else {
 #pragma unroll
         for (int k = 0; k < N; ++k) W[k] = WN[k * T];
+#pragma unroll
+        for (int i = 0; i < kCW; ++i) codes[i] = codes_old[i];
         mu = fmax(4.0 * c, 4.0 * mu);
         if (mu > 1e30) break;
       }
@@ -349,6 +419,9 @@ template <int N, int NSEG, int T, int MINB, bool GREG>
 __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts cs, const SolveArgs a) {
   extern __shared__ double smem[];
   const int t = threadIdx.x;
+  double* tab = smem + (size_t)RegSmem<N, NSEG, T, GREG>::kArrays * N * T;
+  piece_table<NSEG>(cs, tab, t);
+  __syncthreads();
   const int64_t b = (int64_t)blockIdx.x * T + t;
   if (b >= a.B) return;
   const int64_t row = a.group_of ? (int64_t)a.group_of[b] : b;
@@ -365,7 +438,7 @@ __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts c
 #pragma unroll
     for (int k = 0; k < N; ++k) W[k] = wi[k];
   }
-  solve_reg<N, NSEG, T, GREG>(cs, lm, lr, gam, a.tol, a.max_iter, warm, a.vec16 != 0, smem + t, W, D, GR, l2sum,
+  solve_reg<N, NSEG, T, GREG>(cs, lm, lr, gam, a.tol, a.max_iter, warm, a.vec16 != 0, smem + t, tab, W, D, GR, l2sum,
                               gscale, viol, st, it);
   const double* GS = smem + t + 3 * N * T;
 #define LOMPC_G(k) (GREG ? GR[GREG ? (k) : 0] : GS[(k) * T])
