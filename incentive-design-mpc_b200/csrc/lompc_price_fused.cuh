@@ -150,9 +150,10 @@ __device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArg
 #pragma unroll
           for (int k = 0; k < N; ++k) W[k] = wrow[k];
         }
-        // (safeguarded loop only: the fused kernel is instruction-fetch bound and a second copy of the sweeps
-        // costs more than the optimistic phase saves: 39.6k vs 33.0k cycles per large-EV pass)
-        solve_reg<N, NSEG, T, GREG, false>(cs, LM, lr, gam, a.qp_tol, a.qp_max_iter, warm, false, smem + tid, TAB, W, D, GR, l2sum,
+        // (large EV: safeguarded loop only - closed-loop prices have d_k = 0 stages anyway, the fused kernel is
+        // instruction-fetch bound and a second copy of the sweeps costs more than it saves: 39.6k vs 33.0k cycles
+        // per pass.  Small EV: every stage is strictly convex, the optimistic phase always applies: -11 % per pass)
+        solve_reg<N, NSEG, T, GREG, (NSEG == 1)>(cs, LM, lr, gam, a.qp_tol, a.qp_max_iter, warm, false, smem + tid, TAB, W, D, GR, l2sum,
                                     gscale, viol, st, qit);
         if (st != LOMPC_ST_OK) atomicAdd(a.flags + 3, 1);  // a LoMPC solve that did not converge (never observed)
         if (a.qp_count) {
