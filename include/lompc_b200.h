@@ -64,9 +64,11 @@ double lompc_sc_modulus(const lompc_t* h);
 /* Solver knobs (defaults: max_iter 200, tol 1e-11 relative KKT residual). */
 int lompc_set_options(lompc_t* h, int max_iter, double tol);
 
-/* Kernel choice: 0 = automatic (register-resident kernel for N = 12, 24, the any-N shared-memory kernel
- * otherwise), 1 = always the any-N kernel, 2 / 3 = the two register-kernel shapes (64 threads x 4 CTAs per
- * SM with the linear term in shared memory / 128 x 3 with it in registers) regardless of the batch size. */
+/* Kernel choice: 0 = automatic (register-resident kernel for N = 12, 24 - 64 threads x 4 CTAs per SM; large EV
+ * on grids that fill the GPU: one 256-thread CTA per SM - and the any-N shared-memory kernel otherwise),
+ * 1 = always the any-N kernel, 2..7 = one register-kernel shape regardless of the batch size (threads x CTAs
+ * per SM, linear term g in shared memory / registers): 2 = 64x4 smem, 3 = 128x3 regs, 4 = 64x4 regs,
+ * 5 = 64x5 regs, 6 = 128x2 regs, 7 = 256x1 regs (tools/sweep_variants.sh). */
 int lompc_set_kernel_variant(lompc_t* h, int variant);
 
 /* Replaces LoMPC.solve_lompc (lompc.py:137-156), batched over B independent
