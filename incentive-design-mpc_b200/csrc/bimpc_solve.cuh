@@ -779,7 +779,7 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
 }
 
 #ifndef BIMPC_HOSTSIM
-__global__ void __launch_bounds__(kThreads) bimpc_solve_kernel(const BiConsts c, const BiArgs a) {
+__global__ void __launch_bounds__(kThreads, 3) bimpc_solve_kernel(const BiConsts c, const BiArgs a) {
   extern __shared__ double bimpc_smem[];
   for (int s = blockIdx.x; s < a.S; s += gridDim.x) {
     solve_station(c, a, s, bimpc_smem, a.li_scratch + (size_t)blockIdx.x * c.N * ((2 * c.P + 1) * (2 * c.P + 2) / 2),
