@@ -856,6 +856,7 @@ int price_solve_fused_entry(lompc_handle* h, int32_t G, int64_t B, const int32_t
     a.w_scratch = reinterpret_cast<double*>(static_cast<char*>(h->pws) + 256);
     a.B = B;
     a.chain_S = chain_S; a.chain_P = chain_P; a.chain_prev = chain_prev; a.chain_order = chain_order;
+    a.compact_step = (chain_P > 0 ? chain_S : G) >= 2 * 148 * 4;  // CTAs of the launch vs. 2 resident waves
     rc = price_solve_fused(h, a, s);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->poll, flags, 64, cudaMemcpyDeviceToHost, s));

@@ -154,14 +154,14 @@ __global__ void colsum_kernel(int N, int G, const int32_t* __restrict__ off, con
 // FMAs per stage) and only STORES the numerators / denominators; the N reciprocals and gains are
 // then formed by all lanes at once (off the chain), and lane 0 runs the forward substitution.
 // NT = compile-time horizon (fully unrolled: the loads of a stage are issued ahead of the chain) or
-// 0 for a run-time N.
+// 0 for a run-time N (rolled, compact code: the fused price loop is instruction-fetch bound at fleet scale).
 template <int NT>
 __device__ __forceinline__ void ric_solve(int Nrt, const double* dvec, double dadd, double c, const double* bvec,
                                           double* x, double* K, double* KAP, int lane) {
   const int N = NT ? NT : Nrt;
   if (lane == 0) {
     double pa = 0.0, pb = 1.0, pr = 0.0;
-#pragma unroll
+#pragma unroll(NT ? NT : 1)
     for (int k = N - 1; k >= 0; --k) {
       const double d = (dvec ? dvec[k] : 0.0) + dadd;
       const double gk = -bvec[k];
@@ -189,7 +189,7 @@ __device__ __forceinline__ void ric_solve(int Nrt, const double* dvec, double da
   __syncwarp();
   if (lane == 0) {
     double s = 0.0;
-#pragma unroll
+#pragma unroll(NT ? NT : 1)
     for (int k = 0; k < N; ++k) {  // s_{k+1} = s_k + x_k = (1 - K_k) s_k - kappa_k: ONE dependent FMA per stage
       const double kk = K[k], kap = KAP[k];
       x[k] = -fma(kk, s, kap);
@@ -226,14 +226,14 @@ __device__ __forceinline__ void abar_solve(int Nrt, const double* fac, const dou
   const int N = NT ? NT : Nrt;
   if (lane == 0) {
     double r = 0.0;
-#pragma unroll
+#pragma unroll(NT ? NT : 1)
     for (int k = N - 1; k >= 0; --k) {  // kappa_k = (r_{k+1} - b_k)/(kappa + Q_k);  r_k = (1 - K_k) r_{k+1} + K_k b_k
       const double bk = bvec[k];
       KAP[k] = (r - bk) * fac[2 * N + k];
       r = fma(fac[N + k], r, fac[k] * bk);
     }
     double s = 0.0;
-#pragma unroll
+#pragma unroll(NT ? NT : 1)
     for (int k = 0; k < N; ++k) {
       const double kap = KAP[k];
       x[k] = -fma(fac[k], s, kap);

@@ -49,6 +49,7 @@ struct FusedArgs {
   int chain_S, chain_P;      // price_station_chain_kernel: stations, partitions (G = chain_P * chain_S)
   double* chain_prev;        // [chain_S, 3N] warm start carried along the chain (in/out)
   const int32_t* chain_order;  // [chain_S] station handled by CTA i (a permutation) or NULL
+  int compact_step;            // price step with rolled loops (set by the launcher for grids of several waves)
   unsigned long long* qp_count;  // [0] total LoMPC QP solves, [1] / [2] SM cycles summed over groups spent in
                                  // the LoMPC passes / in thread 0's price step, [3] K1 iterations summed over
                                  // the solves, [4] warp passes in which no lane iterated, [5] warp passes (or NULL)
@@ -241,8 +242,14 @@ __device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArg
       flag = __shfl_sync(0xffffffffu, flag, 0);
       if (flag == 0) {
         int st;
-        price_step_warp<N>(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, tid, it == 0, it > 0, a.hist_ac != nullptr,
-                        true, lamdiff, dec_pred, st);
+        // compact (rolled) price step when the grid is several waves deep: there the kernel is instruction-fetch
+        // bound and the step's unrolled code is a third of what an MM iteration streams through the cache
+        if (a.compact_step)
+          price_step_warp<0>(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, tid, it == 0, it > 0,
+                             a.hist_ac != nullptr, true, lamdiff, dec_pred, st);
+        else
+          price_step_warp<N>(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, tid, it == 0, it > 0,
+                             a.hist_ac != nullptr, true, lamdiff, dec_pred, st);
         nnqp_bad |= st;
       }
       if (tid == 0) cyc_step += clock64() - t_b;
