@@ -44,6 +44,16 @@ SIGNATURES = {
                                                C.c_void_p, C.c_void_p]),
     "lompc_host_wait": (C.c_int, [C.c_void_p]),
     "lompc_launch_count": (C.c_int64, []),
+    "lompc_set_create": (C.c_int, [C.POINTER(C.c_void_p), C.c_int, C.POINTER(C.c_int64), C.POINTER(C.c_void_p)]),
+    "lompc_set_destroy": (C.c_int, [C.c_void_p]),
+    "lompc_set_buffers": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [C.POINTER(C.c_void_p)] * 5),
+    "lompc_set_info_buffers": (C.c_int, [C.c_void_p, C.c_int] + [C.POINTER(C.c_void_p)] * 3),
+    "lompc_set_solve_host_async": (C.c_int, [C.c_void_p, C.c_int]),
+    "lompc_set_wait": (C.c_int, [C.c_void_p]),
+    "lompc_set_solve_host": (C.c_int, [C.c_void_p, C.c_int]),
+    "lompc_set_solve_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "lompc_set_copy": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "lompc_set_bytes": (C.c_int64, [C.c_void_p, C.c_int]),
     "price_group_stats_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 7),
     "price_w_err_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 11),
     "price_step_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int] + [C.c_void_p] * 7),

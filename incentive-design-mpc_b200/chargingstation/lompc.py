@@ -87,7 +87,8 @@ class LoMPC:
         _native.raise_for(self._lib.lompc_set_options(self._h, int(max_iter), float(tol)))
 
     def set_kernel_variant(self, variant: int = 0) -> None:
-        """0 = automatic; 1 = any-N shared-memory kernel; 2, 3 = the two register-kernel shapes (tuning)."""
+        """0 = automatic; 1 = any-N shared-memory kernel; 2..7 = register-kernel shapes (tuning);
+        8 / 9 = the warp-cooperative latency kernel with 3 / 6 stages per lane (include/lompc_b200.h)."""
         _native.raise_for(self._lib.lompc_set_kernel_variant(self._h, int(variant)))
 
     def solve_lompc(self, lmbd: np.ndarray, lmbd_r: float, gamma: float) -> tuple[np.ndarray, float]:
@@ -238,3 +239,89 @@ class LoMPC:
             (self.theta * np.eye(self.N), -self.theta * np.eye(self.N),
              2 * self.q_scale * np.diag(w))
         )
+
+
+class LoMPCSet:
+    """The QPs of several ``LoMPC`` objects (e.g. a station's small-EV and large-EV solver,
+    charging_station.py:59-60) solved by ONE kernel launch with ONE copy each way
+    (``lompc_set_*`` in include/lompc_b200.h).  Not in the reference: it replaces the
+    caller-side loops over ``LoMPC.solve_lompc`` (test/test_lompc.py:30-40,
+    price_solver.py:203-204) for callers that hold their inputs in host memory.
+
+    The set owns packed pinned-host and device blocks; ``lmbd[i]``, ``lmbd_r[i]``,
+    ``gamma[i]`` are numpy views of segment ``i`` of the pinned input block (write the
+    inputs IN PLACE), ``w[i]`` / ``cost[i]`` views of the pinned output block (valid
+    after ``solve()``), so neither side makes a staging copy."""
+
+    def __init__(self, solvers, batch_sizes) -> None:
+        solvers = list(solvers)
+        batch_sizes = [int(b) for b in batch_sizes]
+        assert len(solvers) == len(batch_sizes) and 1 <= len(solvers) <= 4
+        assert all(s.N == solvers[0].N and s.device == solvers[0].device for s in solvers)
+        self.solvers, self.batch_sizes = solvers, batch_sizes
+        self.N, self.device = solvers[0].N, solvers[0].device
+        self._lib = _native.load()
+        self._h = C.c_void_p()
+        hs = (C.c_void_p * len(solvers))(*[s._h for s in solvers])
+        Bs = (C.c_int64 * len(solvers))(*batch_sizes)
+        _native.raise_for(self._lib.lompc_set_create(hs, len(solvers), Bs, C.byref(self._h)))
+        N = self.N
+        self.lmbd, self.lmbd_r, self.gamma, self.w, self.cost = [], [], [], [], []
+        self.status, self.iters, self.kkt_res = [], [], []
+        self._dev_ptrs = []
+
+        def view(ptr, shape, ctype, dtype):
+            n = int(np.prod(shape))
+            if n == 0:
+                return np.empty(shape, dtype=dtype)
+            return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(ctype)), shape=(n,)).reshape(shape)
+
+        for i, B in enumerate(batch_sizes):
+            p = [C.c_void_p() for _ in range(5)]
+            _native.raise_for(self._lib.lompc_set_buffers(self._h, 0, i, *[C.byref(x) for x in p]))
+            self.lmbd.append(view(p[0], (B, 3 * N), C.c_double, np.float64))
+            self.lmbd_r.append(view(p[1], (B,), C.c_double, np.float64))
+            self.gamma.append(view(p[2], (B,), C.c_double, np.float64))
+            self.w.append(view(p[3], (B, N), C.c_double, np.float64))
+            self.cost.append(view(p[4], (B,), C.c_double, np.float64))
+            q = [C.c_void_p() for _ in range(3)]
+            _native.raise_for(self._lib.lompc_set_info_buffers(self._h, i, *[C.byref(x) for x in q]))
+            self.status.append(view(q[0], (B,), C.c_int32, np.int32))
+            self.iters.append(view(q[1], (B,), C.c_int32, np.int32))
+            self.kkt_res.append(view(q[2], (B,), C.c_double, np.float64))
+            d = [C.c_void_p() for _ in range(5)]
+            _native.raise_for(self._lib.lompc_set_buffers(self._h, 1, i, *[C.byref(x) for x in d]))
+            self._dev_ptrs.append(tuple(x.value for x in d))
+        self.h2d_bytes = int(self._lib.lompc_set_bytes(self._h, 0))
+        self.d2h_bytes = int(self._lib.lompc_set_bytes(self._h, 1))
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h is not None and h.value:
+            self._lib.lompc_set_destroy(h)
+            self._h = C.c_void_p()
+
+    def solve(self, info: bool = False) -> None:
+        """Host round trip (one H2D copy, one launch, one D2H copy, synchronised); raises like ``solve_lompc``."""
+        _native.raise_for(self._lib.lompc_set_solve_host(self._h, 1 if info else 0))
+
+    def solve_async(self, info: bool = False) -> None:
+        _native.raise_for(self._lib.lompc_set_solve_host_async(self._h, 1 if info else 0))
+
+    def wait(self) -> None:
+        _native.raise_for(self._lib.lompc_set_wait(self._h))
+
+    def upload(self, stream: int = 0) -> None:
+        """Copies the pinned input block to the device block (asynchronous on ``stream``)."""
+        _native.raise_for(self._lib.lompc_set_copy(self._h, 0, stream))
+
+    def download(self, stream: int = 0) -> None:
+        _native.raise_for(self._lib.lompc_set_copy(self._h, 1, stream))
+
+    def solve_dev(self, stream: int = 0, info: bool = False) -> None:
+        """Launch only, device block to device block, asynchronous on ``stream`` (a raw cudaStream_t)."""
+        _native.raise_for(self._lib.lompc_set_solve_dev(self._h, 1 if info else 0, stream))
+
+    def device_pointers(self, i: int):
+        """(lmbd, lmbd_r, gamma, w, cost) device addresses of segment ``i``."""
+        return self._dev_ptrs[i]

@@ -56,26 +56,46 @@ int bimpc_create(int N, int P, double delta, double c_g, double u_g_max, double 
   h->li = nullptr;
   h->omega = nullptr;
   cudaDeviceProp prop;
-  CK(cudaGetDeviceProperties(&prop, device));
+  if (cudaError_t e = cudaGetDeviceProperties(&prop, device); e != cudaSuccess) {
+    delete h;
+    return lompc_detail::cuda_fail(e, "cudaGetDeviceProperties");
+  }
   h->sms = prop.multiProcessorCount;
   if (h->smem > (size_t)prop.sharedMemPerBlockOptin) {
     delete h;
     return LOMPC_ERR_ARG;
   }
-  CK(cudaFuncSetAttribute(bimpc::bimpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)h->smem));
+  // The opt-in is a per-device attribute of the FUNCTION, shared by every handle: always ask for the device's
+  // maximum, so that a later, smaller handle cannot lower the limit under an earlier, larger one.
+  if (cudaError_t e = cudaFuncSetAttribute(bimpc::bimpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           (int)prop.sharedMemPerBlockOptin);
+      e != cudaSuccess) {
+    delete h;
+    return lompc_detail::cuda_fail(e, "cudaFuncSetAttribute(bimpc_solve_kernel)");
+  }
+  // from here on a failing CUDA call releases the handle and whatever it already owns
+#define CKH(call)                                        \
+  do {                                                   \
+    cudaError_t e__ = (call);                            \
+    if (e__ != cudaSuccess) {                            \
+      bimpc_destroy(h);                                  \
+      return lompc_detail::cuda_fail(e__, #call);        \
+    }                                                    \
+  } while (0)
   int occ = 1;
-  CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bimpc::bimpc_solve_kernel, h->threads, h->smem));
+  CKH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bimpc::bimpc_solve_kernel, h->threads, h->smem));
   h->ctas_per_sm = occ < 1 ? 1 : occ;
   {
     const size_t nb = 2 * (size_t)P + 1, np = nb * (nb + 1) / 2;
-    CK(cudaMalloc(&h->li, (size_t)h->sms * h->ctas_per_sm * N * np * sizeof(double)));
+    CKH(cudaMalloc(&h->li, (size_t)h->sms * h->ctas_per_sm * N * np * sizeof(double)));
   }
   // stage weights of the charging cost: exp_rate^(k-N+1) (bimpc.py:255-257), ones otherwise
   std::vector<double> om(N, 1.0);
   if (cost_type == BIMPC_COST_EXP_UNWEIGHTED)
     for (int k = 0; k < N; ++k) om[k] = std::pow(exp_rate, (double)(k - N + 1));
-  CK(cudaMalloc(&h->omega, N * sizeof(double)));
-  CK(cudaMemcpy(h->omega, om.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+  CKH(cudaMalloc(&h->omega, N * sizeof(double)));
+  CKH(cudaMemcpy(h->omega, om.data(), N * sizeof(double), cudaMemcpyHostToDevice));
+#undef CKH
   *out = h;
   return LOMPC_OK;
 }

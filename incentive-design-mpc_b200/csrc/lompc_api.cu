@@ -82,6 +82,15 @@ struct lompc_handle {
 
 namespace {
 
+// One bit per device ordinal (< 64): "this kernel's shared-memory opt-in has been set on that device".
+// Devices beyond 63 simply set the attribute on every launch.
+inline bool device_flag_test(const std::atomic<uint64_t>& m, int dev) {
+  return dev < 64 && ((m.load(std::memory_order_acquire) >> dev) & 1u);
+}
+inline void device_flag_set(std::atomic<uint64_t>& m, int dev) {
+  if (dev < 64) m.fetch_or(uint64_t(1) << dev, std::memory_order_release);
+}
+
 int ensure_ws(lompc_handle* h, size_t bytes) {
   if (h->ws_bytes >= bytes) return LOMPC_OK;
   if (h->ws) CK(cudaFree(h->ws));
@@ -97,11 +106,12 @@ int ensure_ws(lompc_handle* h, size_t bytes) {
 template <int N, int NSEG, int T, int MINB, bool GREG>
 int launch_solve_reg(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t stream) {
   constexpr size_t smem = lompc::RegSmem<N, NSEG, T, GREG>::bytes;
-  static bool configured = false;
-  if (!configured) {
+  // the opt-in is a per-device (per-context) attribute of the function: one flag per device ordinal
+  static std::atomic<uint64_t> configured{0};
+  if (!device_flag_test(configured, h->device)) {
     CK(cudaFuncSetAttribute(lompc::lompc_solve_reg_kernel<N, NSEG, T, MINB, GREG>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    device_flag_set(configured, h->device);
   }
   const int64_t blocks = (a.B + T - 1) / T;
   lompc::SolveArgs av = a;
@@ -134,9 +144,29 @@ int launch_solve_reg_variant(const lompc_handle* h, const lompc::SolveArgs& a, c
   }
 }
 
+// Batches below this many QPs go to the warp-cooperative kernel (lompc_solve_warp.cuh) in automatic mode: one QP
+// per thread needs ~150 k QPs to fill the GPU (148 SMs x 8 warps x 32 lanes x a few waves), below that
+// its warps sit alone on their schedulers and the time-parallel sweeps win (measured crossover: DESIGN.md 4).
+constexpr int64_t kWarpKernelMaxBatch = 1 << 16;
+
 template <int NSEG>
 int launch_solve(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t stream) {
   const int N = h->cs.N;
+  {
+    // plain batched solves only: the group mode of the price loop (shared prices, skip mask, fused epilogues,
+    // warm starts) stays on the thread kernels
+    const bool plain = !a.group_of && !a.skip && !a.w_ref && !a.err_out && !a.w0_out && !a.price0_out && !a.w_init;
+    const int spl = h->variant == 9 ? 6 : 3;
+    const bool want = h->variant == 8 || h->variant == 9 || (h->variant == 0 && a.B <= kWarpKernelMaxBatch);
+    if (plain && want && lompc_detail::warp_kernel_supports(N, spl)) {
+      lompc::WarpArgs wa;
+      memset(&wa, 0, sizeof(wa));
+      wa.nsegs = 1;
+      wa.seg[0].cs = h->cs;
+      wa.seg[0].a = a;
+      return lompc_detail::launch_k1_warp(h->device, N, spl, wa, stream);
+    }
+  }
   if (h->variant != 1) {
     if (N == 24) return launch_solve_reg_variant<24, NSEG>(h, a, stream);
     if (N == 12) return launch_solve_reg_variant<12, NSEG>(h, a, stream);
@@ -160,12 +190,11 @@ int launch_solve(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t 
   while (T > 32 && (a.B + T - 1) / T < 148) T >>= 1;
   const size_t smem = lompc::SmemLayout<NSEG>::bytes(N, T);
   if (smem > 227 * 1024) return LOMPC_ERR_ARG;
-  static thread_local size_t configured[2] = {0, 0};
-  const int slot = NSEG > 1 ? 1 : 0;
-  if (smem > configured[slot]) {
+  static std::atomic<uint64_t> configured{0};  // per device ordinal (the attribute is per context)
+  if (!device_flag_test(configured, h->device)) {
     CK(cudaFuncSetAttribute(lompc::lompc_solve_kernel<NSEG>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    configured[slot] = 227 * 1024;
+    device_flag_set(configured, h->device);
   }
   const int64_t blocks = (a.B + T - 1) / T;
   lompc::lompc_solve_kernel<NSEG><<<(unsigned)blocks, T, smem, stream>>>(h->cs, a);
@@ -176,9 +205,16 @@ int launch_solve(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t 
 
 }  // namespace
 
+namespace lompc_detail {
+HandleView handle_view(const lompc_t* h) { return HandleView{&h->cs, h->device, h->max_iter, h->tol, h->variant}; }
+int launch_k1(const lompc_t* h, const lompc::SolveArgs& a, cudaStream_t s) {
+  return h->cs.large ? launch_solve<4>(h, a, s) : launch_solve<1>(h, a, s);
+}
+}  // namespace lompc_detail
+
 extern "C" {
 
-const char* lompc_version(void) { return "lompc_b200 0.1 (sm_100a)"; }
+const char* lompc_version(void) { return "lompc_b200 0.2 (sm_100a)"; }
 
 const char* lompc_strerror(int code) {
   switch (code) {
@@ -298,7 +334,7 @@ int lompc_set_options(lompc_t* h, int max_iter, double tol) {
 }
 
 int lompc_set_kernel_variant(lompc_t* h, int variant) {
-  if (!h || variant < 0 || variant > 7) return LOMPC_ERR_ARG;
+  if (!h || variant < 0 || variant > 9) return LOMPC_ERR_ARG;
   h->variant = variant;
   return LOMPC_OK;
 }
@@ -458,10 +494,6 @@ int ensure_pws(lompc_handle* h, size_t bytes) {
   if (!h->poll) CK(cudaMallocHost(&h->poll, 64));
   if (h->pws_bytes >= bytes) return LOMPC_OK;
   if (h->pws) CK(cudaFree(h->pws));
-  h->variant = 0;
-  h->loop_mode = 0;
-  h->last_qp_solves = 0;
-  for (auto& c : h->last_cycles) c = 0;
   h->pws = nullptr;
   h->pws_bytes = 0;
   const size_t want = bytes + bytes / 8;
@@ -796,13 +828,13 @@ namespace {
 template <int N, int NSEG, int T, int MINB, bool GREG>
 int launch_fused(lompc_handle* h, const lompc::FusedArgs& a, cudaStream_t s) {
   constexpr size_t smem = lompc::FusedSmem<N, NSEG, T, GREG>::bytes;
-  static bool configured = false;
-  if (!configured) {
+  static std::atomic<uint64_t> configured{0};  // per device ordinal
+  if (!device_flag_test(configured, h->device)) {
     CK(cudaFuncSetAttribute(lompc::price_group_loop_kernel<N, NSEG, T, MINB, GREG>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(lompc::price_station_chain_kernel<N, NSEG, T, MINB, GREG>,
                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    configured = true;
+    device_flag_set(configured, h->device);
   }
   if (a.chain_P > 0)
     lompc::price_station_chain_kernel<N, NSEG, T, MINB, GREG><<<(unsigned)a.chain_S, T, smem, s>>>(h->cs, a);

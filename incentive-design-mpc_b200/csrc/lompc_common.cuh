@@ -12,6 +12,29 @@ int cuda_fail(cudaError_t e, const char* what);   // records the message, return
 }  // namespace lompc_detail
 
 namespace lompc {
+struct Consts;
+struct SolveArgs;
+struct WarpArgs;
+}  // namespace lompc
+
+namespace lompc_detail {
+// What the other translation units need to know of a handle (defined in lompc_api.cu).
+struct HandleView {
+  const lompc::Consts* cs;
+  int device;
+  int max_iter;
+  double tol;
+  int variant;
+};
+HandleView handle_view(const lompc_t* h);
+// K1 with the handle's automatic kernel choice (lompc_api.cu).
+int launch_k1(const lompc_t* h, const lompc::SolveArgs& a, cudaStream_t s);
+// Warp-cooperative K1 (lompc_warp_api.cu).  spl = stages per lane (3 or 6); fills warp_begin / total_warps.
+bool warp_kernel_supports(int N, int spl);
+int launch_k1_warp(int device, int N, int spl, lompc::WarpArgs& wa, cudaStream_t s);
+}  // namespace lompc_detail
+
+namespace lompc {
 
 constexpr int kMaxSeg = 4;  // pieces of the large-EV pwl (lompc.py:111-115)
 
@@ -93,6 +116,23 @@ struct SolveArgs {
   const double* w_init;     // [B,N] feasible starting points (the previous solutions of the price loop;
                             // register kernel only) or NULL: start from w = 0
   int vec16;                // register kernel: lmbd rows and w_out rows are 16-byte aligned (set by the launcher)
+};
+
+// ---- warp-cooperative K1 (lompc_solve_warp.cuh): one launch serves up to kMaxWarpSegs segments (EV types) ----
+constexpr int kMaxWarpSegs = 4;  // == LOMPC_SET_MAX_SEGMENTS
+
+struct WarpSeg {
+  Consts cs;
+  SolveArgs a;
+  int warp_begin;  // first warp of the launch that belongs to this segment
+};
+
+struct WarpArgs {
+  int nsegs;
+  int total_warps;
+  const unsigned long long* epoch_src;  // device word holding the call's epoch (NULL: epoch 0)
+  unsigned long long* summary;          // atomicMax(epoch * 4 + worst status of the launch); NULL: no summary
+  WarpSeg seg[kMaxWarpSegs];
 };
 
 }  // namespace lompc

@@ -1,0 +1,540 @@
+// K1, latency variant: one QP per LANE GROUP of a warp (time-parallel sweeps), for small and
+// medium batches where one-QP-per-thread (lompc_solve_reg.cuh) cannot fill the GPU.
+//
+// Same algorithm as lompc_solve.cuh / lompc_solve_reg.cuh (active-set Newton: backward KKT test +
+// Riccati recursion, forward stage-optimal rollout, optimistic phase, then the safeguarded phase
+// with the proximal retry) and the same decisions (epsilon-band, tolerances, piece codes), so the
+// iteration counts agree with the thread kernels; but the horizon is cut into LPQ = N / SPL blocks
+// of SPL consecutive stages, one block per lane, and every sweep over the horizon becomes
+//   a serial pass over the SPL stages a lane owns  +  a log2(LPQ)-step scan across the group:
+//   * states s_k (prefix sum of w) and costates p_k = c sum_{j>=k}(s_j - gamma), written as
+//     c [(N-k)(s_k - gamma) + sum_{i>k}(N-i) w_i] so that BOTH scans start at once;
+//   * the Riccati recursion in its homogeneous form (pa, pb, pr), which is LINEAR: stage k is a
+//     3x3 matrix [[A, 0], [v', m]] (7 entries, power-of-two normalised), a lane composes the SPL
+//     matrices of its block, the group runs a suffix scan of block operators, and each lane then
+//     rolls the triple through its own stages to form the gains (reciprocals off every chain);
+//   * the forward rollout s_k = s_{k-1} + x_k(s_{k-1}) is piecewise affine in the state: with a
+//     GUESS of the piece every stage lands on (the piece codes of the iterate, moved one piece by
+//     the KKT test) a block is an affine map, the group scans the maps, every lane replays its SPL
+//     stages EXACTLY from the scanned entry state and reports the pieces it really landed on; the
+//     guess is replaced by them until nothing changes (lane l is final after l + 1 passes at the
+//     latest; one or two passes in practice, one at convergence).
+// N = 24, SPL = 3: 8 lanes per QP, 4 QPs per warp, no shared memory, ~60 registers.  The groups of
+// a warp iterate in lock step until all of them are done (finished groups are predicated off).
+// One launch serves up to kMaxWarpSegs segments (EV types) -- a warp belongs to one segment.
+#pragma once
+#include "lompc_common.cuh"
+
+namespace lompc {
+
+constexpr unsigned kFullMask = 0xffffffffu;
+
+// Per-phase cycle counters of tools/prof_warp.cu (compiled out of the library).
+#ifdef LOMPC_WARP_PROF
+__device__ unsigned long long g_warp_prof[8];  // setup, A, B, C, epilogue cycles; warps; loop trips; C passes
+#define LOMPC_PROF_T(var) const long long var = clock64()
+#define LOMPC_PROF_ADD(i, v) prof[i] += (unsigned long long)(v)
+#else
+#define LOMPC_PROF_T(var)
+#define LOMPC_PROF_ADD(i, v)
+#endif
+
+template <int LPQ>
+__device__ __forceinline__ double grp_sum(double v) {
+#pragma unroll
+  for (int d = LPQ / 2; d >= 1; d >>= 1) v += __shfl_xor_sync(kFullMask, v, d, LPQ);
+  return v;
+}
+template <int LPQ>
+__device__ __forceinline__ int grp_max_int(int v) {
+#pragma unroll
+  for (int d = LPQ / 2; d >= 1; d >>= 1) v = max(v, __shfl_xor_sync(kFullMask, v, d, LPQ));
+  return v;
+}
+template <int LPQ>
+__device__ __forceinline__ int grp_min_int(int v) {
+#pragma unroll
+  for (int d = LPQ / 2; d >= 1; d >>= 1) v = min(v, __shfl_xor_sync(kFullMask, v, d, LPQ));
+  return v;
+}
+template <int LPQ>
+__device__ __forceinline__ double grp_max_nonneg(double v) {  // v >= 0
+#pragma unroll
+  for (int d = LPQ / 2; d >= 1; d >>= 1) v = dmax2(v, __shfl_xor_sync(kFullMask, v, d, LPQ));
+  return v;
+}
+template <int LPQ>
+__device__ __forceinline__ bool grp_any(bool p, int lane) {
+  const unsigned bal = __ballot_sync(kFullMask, p);
+  const unsigned gmask = (LPQ == 32 ? kFullMask : ((1u << LPQ) - 1u)) << (lane & ~(LPQ - 1));
+  return (bal & gmask) != 0u;
+}
+
+// Stage operator of the homogeneous Riccati recursion, x_k = M_k x_{k+1}, x = (pa, pb, pr)':
+//   [ a11 a12 0 ]
+//   [ a21 a22 0 ]
+//   [ v1  v2  m ]
+struct RicMat {
+  double a11, a12, a21, a22, v1, v2, m;
+};
+// L * R (L = the earlier stage, applied after R)
+__device__ __forceinline__ RicMat ric_mul(const RicMat& L, const RicMat& R) {
+  RicMat o;
+  o.a11 = fma(L.a11, R.a11, L.a12 * R.a21);
+  o.a12 = fma(L.a11, R.a12, L.a12 * R.a22);
+  o.a21 = fma(L.a21, R.a11, L.a22 * R.a21);
+  o.a22 = fma(L.a21, R.a12, L.a22 * R.a22);
+  o.v1 = fma(L.m, R.v1, fma(L.v1, R.a11, L.v2 * R.a21));
+  o.v2 = fma(L.m, R.v2, fma(L.v1, R.a12, L.v2 * R.a22));
+  o.m = L.m * R.m;
+  return o;
+}
+__device__ __forceinline__ RicMat ric_shfl_down(const RicMat& x, int d, int width) {
+  RicMat o;
+  o.a11 = __shfl_down_sync(kFullMask, x.a11, d, width);
+  o.a12 = __shfl_down_sync(kFullMask, x.a12, d, width);
+  o.a21 = __shfl_down_sync(kFullMask, x.a21, d, width);
+  o.a22 = __shfl_down_sync(kFullMask, x.a22, d, width);
+  o.v1 = __shfl_down_sync(kFullMask, x.v1, d, width);
+  o.v2 = __shfl_down_sync(kFullMask, x.v2, d, width);
+  o.m = __shfl_down_sync(kFullMask, x.m, d, width);
+  return o;
+}
+
+// 2^-e for x = f 2^e (x positive, finite, normal): an exact scale that brings x into [1, 2).
+__device__ __forceinline__ double pow2_inv_scale(double x) {
+  const int be = (__double2hiint(x) >> 20) & 0x7ff;
+  return __hiloint2double((2046 - be) << 20, 0);
+}
+
+// The solve of one lane group.  `li` = lane index inside the group (owns stages li*SPL .. li*SPL+SPL-1),
+// `live` = the group has a QP (a partial last warp keeps its idle groups in the shuffles).
+template <int N, int NSEG, int SPL>
+__device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a, const int64_t b, const bool live,
+                                           const int lane, int& st_out) {
+  constexpr int LPQ = N / SPL;
+  static_assert(N % SPL == 0 && (LPQ & (LPQ - 1)) == 0 && LPQ <= 32 && LPQ >= 1, "N = SPL * 2^m, at most 32 lanes");
+  const int li = lane & (LPQ - 1);
+  const int k0 = li * SPL;
+  const double c = cs.c, wmax = cs.w_max;
+#ifdef LOMPC_WARP_PROF
+  unsigned long long prof[8] = {0, 0, 0, 0, 0, 1, 0, 0};
+#endif
+  LOMPC_PROF_T(t_begin);
+
+  // ---- problem data: this lane's SPL stages of the three price segments (lompc.py:101-135) ----
+  const int64_t row = live ? b : 0;
+  const double* lm = a.lmbd + row * a.lmbd_stride;
+  const double lr = live ? a.lmbd_r[row * a.lmbd_r_stride] : 0.0;
+  const double gam = live ? a.gamma[row] : 0.0;
+  double W[SPL], D[SPL], G[SPL], WN[SPL];
+  int CD[SPL], CDO[SPL];  // piece codes of W / of the parked iterate (see lompc_solve_reg.cuh: piece_table)
+  bool neg = (gam < 0.0) || (lr < 0.0);
+  double l2loc = 0.0, gmaxloc = 0.0;
+  int dmin_hi = 0x7ff00000;
+#pragma unroll
+  for (int j = 0; j < SPL; ++j) {
+    double l1 = 0.0, l2 = 0.0, l3 = 0.0;
+    if (live) {
+      l1 = lm[k0 + j];
+      l2 = lm[N + k0 + j];
+      l3 = lm[2 * N + k0 + j];
+    }
+    neg |= (l1 < 0.0) || (l2 < 0.0) || (l3 < 0.0);
+    G[j] = cs.theta * (l1 - l2);
+    D[j] = 2.0 * (lr * cs.theta2 + cs.q_scale * l3) + cs.d_base;
+    dmin_hi = min(dmin_hi, __double2hiint(D[j]));
+    W[j] = 0.0;
+    WN[j] = 0.0;
+    CD[j] = 0;
+    CDO[j] = 0;
+    gmaxloc = dmax2(gmaxloc, fabs(G[j]));
+    l2loc += l2;
+  }
+  const double l2sum = grp_sum<LPQ>(l2loc);
+  const double gmax = grp_max_nonneg<LPQ>(gmaxloc);
+  dmin_hi = grp_min_int<LPQ>(dmin_hi);
+  int st = LOMPC_ST_OK;
+  if (grp_any<LPQ>(neg, lane)) st = LOMPC_ST_NEGATIVE;
+  if (gam > cs.y_max) st = LOMPC_ST_BAD_GAMMA;
+  const double gscale = fmax(1.0, gmax + c * N * cs.y_max);
+  const double tq = a.tol * gscale;
+  const int tqh = __double2hiint(tq);
+  const double cg = c * gam;
+  const double band = 1e-9 * wmax;
+  const double fbase = 1e-15 * (c * N * cs.y_max * cs.y_max + N * wmax * (gmax + cs.slope[NSEG - 1]));
+  const double top_lo = cs.brk[NSEG] - band;
+
+  constexpr int kOptimistic = 10;  // as in lompc_solve_reg.cuh
+  const int n_opt = dmin_hi > 0 ? kOptimistic : 0;
+  int it = 0;
+  bool done = !live || st != LOMPC_ST_OK;  // group-uniform
+  bool converged = false;
+  bool have_f = false;      // f holds the objective of an accepted iterate (safeguarded phase)
+  bool pending = false;     // W is a rollout that has not been accepted yet
+  double f = 0.0, mu = 0.0;
+  double sl[SPL];           // local inclusive prefix sums of W
+  double off = 0.0;         // state entering this lane's block
+  int vh_last = 0;
+
+  // states of the iterate: s_k = off + sl[j]
+  auto scan_states = [&](double& texc) {
+    double run = 0.0, utot = 0.0;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+      run += W[j];
+      sl[j] = run;
+      utot = fma((double)(N - (k0 + j)), W[j], utot);
+    }
+    double incl = run, tincl = utot;
+#pragma unroll
+    for (int d = 1; d < LPQ; d <<= 1) {
+      const double t1 = __shfl_up_sync(kFullMask, incl, d, LPQ);
+      const double t2 = __shfl_down_sync(kFullMask, tincl, d, LPQ);
+      if (li >= d) incl += t1;
+      if (li + d < LPQ) tincl += t2;
+    }
+    off = incl - run;
+    texc = tincl - utot;
+  };
+  // objective of W (without kappa0), from the states scan_states left behind
+  auto objective = [&]() -> double {
+    double floc = 0.0;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+      const double x = W[j];
+      const double e = (off + sl[j]) - gam;
+      floc += x * fma(0.5 * D[j], x, G[j]) + 0.5 * c * e * e;
+      if (NSEG > 1) {
+#pragma unroll
+        for (int i = 1; i < NSEG; ++i) floc += (cs.slope[i] - cs.slope[i - 1]) * dpos(x - cs.brk[i]);
+      }
+    }
+    return grp_sum<LPQ>(floc);
+  };
+
+  LOMPC_PROF_T(t_setup);
+  LOMPC_PROF_ADD(0, t_setup - t_begin);
+  while (true) {
+    // ================= A: states, acceptance of the pending rollout, KKT test =================
+    LOMPC_PROF_T(t_a);
+    LOMPC_PROF_ADD(6, 1);
+    double texc;
+    scan_states(texc);
+    const bool safeg = it >= n_opt;  // group-uniform
+    if (__any_sync(kFullMask, safeg && !done)) {
+      const double fn = objective();
+      if (safeg && !done) {
+        if (pending && have_f && !(fn <= f + (fbase + 1e-15 * (fabs(f) + fabs(fn))))) {
+          // rejected: back to the parked iterate, retry with a larger proximal weight
+#pragma unroll
+          for (int j = 0; j < SPL; ++j) {
+            W[j] = WN[j];
+            CD[j] = CDO[j];
+          }
+          mu = fmax(4.0 * c, 4.0 * mu);
+          if (mu > 1e30) done = true;  // gives up (LOMPC_ST_MAXITER)
+        } else {
+          f = have_f ? dmin2(f, fn) : fn;
+          have_f = true;
+          mu = 0.0;
+        }
+      }
+      // a rejection changed W in some group: its states are recomputed (the other groups recompute the same values)
+      if (__any_sync(kFullMask, safeg && !done && mu > 0.0)) scan_states(texc);
+    }
+    pending = false;
+    if (it >= a.max_iter) done = true;
+
+    // costate, gradient, KKT test; decides binding / the working piece of every stage
+    bool binding[SPL];
+    double slw[SPL];
+    int vh = 0;
+    {
+      double tloc = texc;
+#pragma unroll
+      for (int j = SPL - 1; j >= 0; --j) {
+        const int k = k0 + j;
+        const double wk = W[j];
+        const double e = (off + sl[j]) - gam;
+        const double p = c * fma((double)(N - k), e, tloc);
+        tloc = fma((double)(N - k), wk, tloc);
+        const double q = fma(D[j], wk, G[j]) + p;
+        const double mq = -q;
+        double s_lo, s_hi;
+        bool atbp;
+        if (NSEG > 1) {
+          const int cd = CD[j];
+          const int i = cd >> 1;
+          atbp = (cd & 1) == 0;
+          if (atbp) {
+            s_lo = i > 0 ? cs.slope[i - 1] : -1e300;
+            s_hi = i < NSEG ? cs.slope[i < NSEG ? i : 0] : 1e300;
+          } else {
+            s_lo = s_hi = cs.slope[i < NSEG ? i : 0];
+          }
+        } else {
+          const bool top = wk >= top_lo, bot = wk <= band;
+          s_hi = top ? 1e300 : cs.slope[0];
+          s_lo = bot ? -1e300 : cs.slope[0];
+          atbp = top | bot;
+        }
+        const double va = mq - s_hi, vb = s_lo - mq;
+        const bool right = va > tq, left = vb > tq;
+        binding[j] = atbp && !right && !left;
+        slw[j] = left ? s_lo : s_hi;
+        vh = max(vh, max(__double2hiint(va), __double2hiint(vb)));
+        // guess of the piece the rollout will land on: a coordinate pushed off a breakpoint moves into the
+        // neighbouring piece, everything else stays where it is
+        if (NSEG > 1) {
+          CDO[j] = CD[j] + ((atbp && right) ? 1 : 0) - ((atbp && left) ? 1 : 0);
+        } else {
+          const bool top = wk >= top_lo, bot = wk <= band;
+          CDO[j] = (atbp && (right || left)) ? 1 : (top ? 2 : (bot ? 0 : 1));
+        }
+      }
+    }
+    vh = grp_max_int<LPQ>(vh);
+    if (!done) {
+      vh_last = vh;
+      if (vh < tqh) {
+        converged = true;
+        done = true;
+      }
+    }
+    LOMPC_PROF_T(t_b);
+    LOMPC_PROF_ADD(1, t_b - t_a);
+    if (__all_sync(kFullMask, done)) break;
+
+    // ================= B: Riccati recursion (block operators + suffix scan) -> gains =================
+    double KK[SPL], KAP[SPL], INV[SPL];
+    {
+      RicMat blk;
+#pragma unroll
+      for (int j = SPL - 1; j >= 0; --j) {
+        const double wk = W[j];
+        const double dm = D[j] + mu;
+        const double gm = fma(-mu, wk, G[j]);
+        RicMat M;
+        if (binding[j]) {
+          M.a11 = 1.0; M.a12 = c; M.a21 = 0.0; M.a22 = 1.0;
+          M.v1 = wk; M.v2 = fma(c, wk, -cg); M.m = 1.0;
+        } else {
+          const double h = gm + slw[j];
+          const double sg = pow2_inv_scale(dm + c);
+          const double dms = dm * sg;
+          M.a11 = dms; M.a12 = dms * c; M.a21 = sg; M.a22 = (dm + c) * sg;
+          M.v1 = -(h * sg); M.v2 = -(fma(dm, cg, c * h) * sg); M.m = dms;
+        }
+        if (j == SPL - 1)
+          blk = M;
+        else
+          blk = ric_mul(M, blk);
+      }
+      // inclusive suffix scan over the lanes of the group: S_l = B_l B_{l+1} ... B_{LPQ-1}
+#pragma unroll
+      for (int d = 1; d < LPQ; d <<= 1) {
+        const RicMat o = ric_shfl_down(blk, d, LPQ);
+        if (li + d < LPQ) blk = ric_mul(blk, o);
+      }
+      // triple entering this block from above: second column of S_{l+1} ((0, 1, 0)' for the last block)
+      double pa = __shfl_down_sync(kFullMask, blk.a12, 1, LPQ);
+      double pb = __shfl_down_sync(kFullMask, blk.a22, 1, LPQ);
+      double pr = __shfl_down_sync(kFullMask, blk.v2, 1, LPQ);
+      if (li == LPQ - 1) {
+        pa = 0.0;
+        pb = 1.0;
+        pr = 0.0;
+      }
+#pragma unroll
+      for (int j = SPL - 1; j >= 0; --j) {
+        const double wk = W[j];
+        const double dm = D[j] + mu;
+        const double gm = fma(-mu, wk, G[j]);
+        const double tq_ = fma(c, pb, pa);
+        const double tu = fma(-cg, pb, pr);
+        const double bn = fma(dm, pb, tq_);
+        const double ib = fast_rcp(bn);
+        KK[j] = -(tq_ * ib);
+        KAP[j] = -(fma(gm, pb, tu) * ib);
+        INV[j] = pb * ib;
+        if (binding[j]) {
+          pa = tq_;
+          pr = fma(tq_, wk, tu);
+        } else {
+          pa = dm * tq_;
+          pr = fma(dm, tu, -tq_ * (gm + slw[j]));
+          pb = bn;
+        }
+      }
+    }
+
+    // ================= C: forward rollout (guess the pieces, scan, replay, repeat) =================
+    LOMPC_PROF_T(t_c);
+    LOMPC_PROF_ADD(2, t_c - t_b);
+    {
+      double X[SPL];
+      int CN[SPL];
+#pragma unroll
+      for (int j = 0; j < SPL; ++j) CN[j] = CDO[j];  // the guess (CDO is rewritten with the parked codes below)
+      for (int pass = 0; pass <= LPQ; ++pass) {
+        LOMPC_PROF_ADD(7, 1);
+        // block map s_out = am * s_in + bm under the guess
+        double am = 1.0, bm = 0.0;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+          const int cd = CN[j];
+          double al, be;  // x = al * s + be
+          if (NSEG > 1) {
+            const int i = cd >> 1;
+            if (cd & 1) {
+              al = KK[j];
+              be = fma(-cs.slope[i < NSEG ? i : 0], INV[j], KAP[j]);
+            } else {
+              al = 0.0;
+              be = cs.brk[i];
+            }
+          } else {
+            al = cd == 1 ? KK[j] : 0.0;
+            be = cd == 1 ? KAP[j] : (cd == 2 ? wmax : 0.0);
+          }
+          const double a1 = 1.0 + al;
+          am *= a1;
+          bm = fma(a1, bm, be);
+        }
+        // inclusive prefix scan of the maps; the entry state of block l is the offset of the composite of blocks < l
+#pragma unroll
+        for (int d = 1; d < LPQ; d <<= 1) {
+          const double oa = __shfl_up_sync(kFullMask, am, d, LPQ);
+          const double ob = __shfl_up_sync(kFullMask, bm, d, LPQ);
+          if (li >= d) {
+            bm = fma(am, ob, bm);
+            am *= oa;
+          }
+        }
+        double s = __shfl_up_sync(kFullMask, bm, 1, LPQ);
+        if (li == 0) s = 0.0;
+        // exact replay of this lane's stages from s
+        bool mis = false;
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+          double x;
+          int cdn;
+          if (NSEG > 1) {
+            double m[NSEG];
+            int mc[NSEG];
+#pragma unroll
+            for (int i = 0; i < NSEG; ++i) {
+              const double cj = fma(KK[j], s, fma(-cs.slope[i], INV[j], KAP[j]));
+              const bool below = cj < cs.brk[i + 1];
+              m[i] = below ? cj : cs.brk[i + 1];
+              mc[i] = below ? 2 * i + 1 : 2 * i + 2;
+            }
+#pragma unroll
+            for (int h = 1; h < NSEG; h *= 2) {
+#pragma unroll
+              for (int i = 0; i + h < NSEG; i += 2 * h) {
+                const bool first = m[i] > m[i + h];
+                m[i] = first ? m[i] : m[i + h];
+                mc[i] = first ? mc[i] : mc[i + h];
+              }
+            }
+            const bool ng = __double2hiint(m[0]) < 0;
+            x = dpos(m[0]);
+            cdn = ng ? 0 : mc[0];
+          } else {
+            const double x0 = fma(KK[j], s, KAP[j]);
+            const bool over = x0 > wmax, under = x0 < 0.0;
+            x = over ? wmax : x0;
+            x = under ? 0.0 : x;
+            cdn = under ? 0 : (over ? 2 : 1);
+          }
+          mis |= cdn != CN[j];
+          CN[j] = cdn;
+          X[j] = x;
+          s += x;
+        }
+        if (!__any_sync(kFullMask, mis && !done)) break;
+      }
+      if (!done) {
+#pragma unroll
+        for (int j = 0; j < SPL; ++j) {
+          WN[j] = W[j];
+          CDO[j] = CD[j];
+          W[j] = X[j];
+          CD[j] = CN[j];
+        }
+        pending = true;
+        ++it;
+      }
+    }
+    LOMPC_PROF_T(t_e);
+    LOMPC_PROF_ADD(3, t_e - t_c);
+  }
+  LOMPC_PROF_T(t_out);
+  if (!converged && st == LOMPC_ST_OK) st = LOMPC_ST_MAXITER;
+  st_out = live ? st : LOMPC_ST_OK;
+
+  // ================= outputs (the states of the final iterate are in off / sl) =================
+  if (live) {
+    double closs = 0.0;
+    double* wo = a.w_out + b * (int64_t)N + k0;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+      const double x = W[j];
+      const double s = off + sl[j];
+      wo[j] = x;
+      closs += x * fma(0.5 * D[j], x, G[j]) + 0.5 * c * s * (s - 2.0 * gam);
+      if (NSEG > 1) {
+#pragma unroll
+        for (int i = 1; i < NSEG; ++i) closs += (cs.slope[i] - cs.slope[i - 1]) * dpos(x - cs.brk[i]);
+      }
+    }
+    const double cost = cs.theta * wmax * l2sum + grp_sum<LPQ>(closs);
+    if (li == 0) {
+      if (a.cost_out) a.cost_out[b] = cost;
+      if (a.status) a.status[b] = st;
+      if (a.iters) a.iters[b] = it;
+      if (a.kkt_res) a.kkt_res[b] = __hiloint2double(vh_last, vh_last ? -1 : 0) / gscale;
+    }
+  } else {
+    (void)grp_sum<LPQ>(0.0);
+  }
+#ifdef LOMPC_WARP_PROF
+  prof[4] = (unsigned long long)(clock64() - t_out);
+  if (lane == 0)
+    for (int i = 0; i < 8; ++i) atomicAdd(&g_warp_prof[i], prof[i]);
+#endif
+}
+
+// One warp = 32 / LPQ QPs of one segment.  WPC warps per CTA (small CTAs spread a small batch over all SMs).
+template <int N, int SPL, int WPC>
+__global__ void __launch_bounds__(32 * WPC) lompc_solve_warp_kernel(const __grid_constant__ WarpArgs wa) {
+  constexpr int LPQ = N / SPL, QPW = 32 / LPQ;
+  const int lane = threadIdx.x & 31;
+  const int warp = blockIdx.x * WPC + (threadIdx.x >> 5);
+  if (warp >= wa.total_warps) return;
+  int sg = 0;
+#pragma unroll
+  for (int i = 1; i < kMaxWarpSegs; ++i)
+    if (i < wa.nsegs && warp >= wa.seg[i].warp_begin) sg = i;
+  const WarpSeg& S = wa.seg[sg];
+  const int64_t b = (int64_t)(warp - S.warp_begin) * QPW + lane / LPQ;
+  const bool live = b < S.a.B;
+  int st;
+  if (S.cs.large)
+    solve_warp<N, 4, SPL>(S.cs, S.a, b, live, lane, st);
+  else
+    solve_warp<N, 1, SPL>(S.cs, S.a, b, live, lane, st);
+  if (wa.summary) {
+    // worst status of the launch, tagged with the call's epoch (no memset between calls): every warp with a
+    // failure reports it, warp 0 always reports
+    const int worst = __reduce_max_sync(kFullMask, st);
+    if (lane == 0 && (worst != LOMPC_ST_OK || warp == 0)) {
+      const unsigned long long ep = wa.epoch_src ? *wa.epoch_src : 0ull;
+      atomicMax(wa.summary, ep * 4ull + (unsigned long long)worst);
+    }
+  }
+}
+
+}  // namespace lompc

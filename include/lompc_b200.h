@@ -68,7 +68,10 @@ int lompc_set_options(lompc_t* h, int max_iter, double tol);
  * on grids that fill the GPU: one 256-thread CTA per SM - and the any-N shared-memory kernel otherwise),
  * 1 = always the any-N kernel, 2..7 = one register-kernel shape regardless of the batch size (threads x CTAs
  * per SM, linear term g in shared memory / registers): 2 = 64x4 smem, 3 = 128x3 regs, 4 = 64x4 regs,
- * 5 = 64x5 regs, 6 = 128x2 regs, 7 = 256x1 regs (tools/sweep_variants.sh). */
+ * 5 = 64x5 regs, 6 = 128x2 regs, 7 = 256x1 regs (tools/sweep_variants.sh);
+ * 8 = the warp-cooperative latency kernel (one QP per group of N/3 lanes, time-parallel sweeps; N = 12, 24,
+ * 48, 96), which automatic mode picks for batches too small to fill the GPU with one QP per thread,
+ * 9 = the same kernel with 6 stages per lane (N = 24, 48, 96). */
 int lompc_set_kernel_variant(lompc_t* h, int variant);
 
 /* Replaces LoMPC.solve_lompc (lompc.py:137-156), batched over B independent
@@ -101,6 +104,53 @@ int lompc_solve_batch_host_async(lompc_t* h, int64_t B, const double* lmbd, int6
                                  double* w_out, double* cost_out, int32_t* status, int32_t* iters,
                                  double* kkt_res);
 int lompc_host_wait(lompc_t* h);
+
+/* ------------------------------------------------------------------------
+ * Solve set: the QPs of SEVERAL LoMPC objects (the small-EV and the large-EV
+ * solver of a station, charging_station.py:59-60) solved by ONE kernel launch,
+ * with ONE host->device and ONE device->host copy per call.  Replaces the
+ * caller-side loops over LoMPC.solve_lompc (lompc.py:137-156; the timing loop
+ * of test/test_lompc.py:30-40, the EV loops of price_solver.py:203-204,
+ * 280-281) when the caller holds the inputs in host memory.
+ *
+ * The set owns four packed blocks - pinned host in / out, device in / out - and
+ * hands out typed views of them: the caller writes lmbd / lmbd_r / gamma of
+ * segment i IN PLACE into the host (or device) views and reads w / cost from
+ * the output views, so no staging copy is made on either side.
+ *   in  block: [epoch u64 | pad] then per segment lmbd[B_i,3N] lmbd_r[B_i] gamma[B_i]
+ *   out block: [summary u64 | pad] then per segment w[B_i,N] cost[B_i]
+ *   info block (optional third copy): per segment status[B_i] iters[B_i] kkt_res[B_i]
+ * Every segment starts 256-byte aligned.  The worst per-QP status of a call is
+ * reduced on the device into the summary word (tagged with the call's epoch,
+ * so nothing is cleared between calls) and mapped onto the return code exactly
+ * like lompc_solve_batch_host.  All handles must share N and the device.
+ * ------------------------------------------------------------------------ */
+typedef struct lompc_set lompc_set_t;
+#define LOMPC_SET_MAX_SEGMENTS 4
+
+int lompc_set_create(lompc_t* const* handles, int n_handles, const int64_t* batch_sizes, lompc_set_t** out);
+int lompc_set_destroy(lompc_set_t* s);
+/* Views of segment i (any out-pointer may be NULL).  which: 0 = pinned host blocks, 1 = device blocks. */
+int lompc_set_buffers(lompc_set_t* s, int which, int i, double** lmbd, double** lmbd_r, double** gamma,
+                      double** w, double** cost);
+/* Per-QP diagnostics of segment i (pinned host views; filled by a solve with want_info != 0). */
+int lompc_set_info_buffers(lompc_set_t* s, int i, int32_t** status, int32_t** iters, double** kkt_res);
+/* Host round trip: copy the in block to the device, solve every segment in one launch, copy the out block
+ * (and, with want_info, the info block) back, on the set's own stream.  _async enqueues and returns;
+ * lompc_set_wait synchronises and returns LOMPC_ERR_GAMMA / _NEGATIVE / _NOT_CONVERGED like
+ * lompc_solve_batch_host.  lompc_set_solve_host = both.  The sequence is captured once as a CUDA graph
+ * (environment LOMPC_SET_NO_GRAPH=1: three plain stream calls).                                      */
+int lompc_set_solve_host_async(lompc_set_t* s, int want_info);
+int lompc_set_wait(lompc_set_t* s);
+int lompc_set_solve_host(lompc_set_t* s, int want_info);
+/* Launch only: inputs / outputs are the set's DEVICE blocks, asynchronous on `stream`.  summary_out (DEVICE
+ * u64, may be NULL) receives epoch*4 + worst status; the epoch is read from the device in block.     */
+int lompc_set_solve_dev(lompc_set_t* s, int want_info, void* stream);
+/* Copies between the host and device blocks (which: 0 = in block host->device, 1 = out block device->host),
+ * asynchronous on `stream`: for callers that mix the host views with lompc_set_solve_dev.            */
+int lompc_set_copy(lompc_set_t* s, int which, void* stream);
+/* Bytes of one call's host->device / device->host copies (without the info block). */
+int64_t lompc_set_bytes(const lompc_set_t* s, int which);
 
 /* ------------------------------------------------------------------------
  * Price loop (reference price_solver.py / price_regularizer.py), batched over
