@@ -156,8 +156,8 @@ int launch_solve(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t 
     // plain batched solves only: the group mode of the price loop (shared prices, skip mask, fused epilogues,
     // warm starts) stays on the thread kernels
     const bool plain = !a.group_of && !a.skip && !a.w_ref && !a.err_out && !a.w0_out && !a.price0_out && !a.w_init;
-    const int spl = h->variant == 9 ? 6 : 3;
-    const bool want = h->variant == 8 || h->variant == 9 || (h->variant == 0 && a.B <= kWarpKernelMaxBatch);
+    const int spl = 3;
+    const bool want = h->variant == 8 || (h->variant == 0 && a.B <= kWarpKernelMaxBatch);
     if (plain && want && lompc_detail::warp_kernel_supports(N, spl)) {
       lompc::WarpArgs wa;
       memset(&wa, 0, sizeof(wa));
@@ -334,7 +334,7 @@ int lompc_set_options(lompc_t* h, int max_iter, double tol) {
 }
 
 int lompc_set_kernel_variant(lompc_t* h, int variant) {
-  if (!h || variant < 0 || variant > 9) return LOMPC_ERR_ARG;
+  if (!h || variant < 0 || variant > 8) return LOMPC_ERR_ARG;
   h->variant = variant;
   return LOMPC_OK;
 }

@@ -107,6 +107,42 @@ __device__ __forceinline__ double pow2_inv_scale(double x) {
   return __hiloint2double((2046 - be) << 20, 0);
 }
 
+// p ? a : b as ONE select: a C++ ternary whose arms are cheap still compiles to a divergent branch around the
+// unselected arm in several places of the sweeps (BSSY / BRA / BSYNC per stage); a selp cannot.
+__device__ __forceinline__ double dsel(bool p, double a, double b) {
+  double r;
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.s32 q, %3, 0;\n\tselp.f64 %0, %1, %2, q;\n\t}" : "=d"(r) : "d"(a), "d"(b), "r"((int)p));
+  return r;
+}
+
+// v[i] for a run-time i in 0..3 by a select tree (a run-time index into a register array would go through local
+// memory, one into the kernel parameters through the constant cache: ~40 cycles on the critical path either way).
+__device__ __forceinline__ double sel4(int i, double v0, double v1, double v2, double v3) {
+  const bool b0 = (i & 1) != 0;
+  return dsel((i & 2) != 0, dsel(b0, v3, v2), dsel(b0, v1, v0));
+}
+
+// Slopes / breakpoints of the separable term in registers (NSEG = 1: small EV, NSEG = 4: the large-EV pwl).
+template <int NSEG>
+struct Pwl {
+  double slope[NSEG];
+  double brk[NSEG + 1];
+  __device__ __forceinline__ explicit Pwl(const Consts& cs) {
+#pragma unroll
+    for (int i = 0; i < NSEG; ++i) slope[i] = cs.slope[i];
+#pragma unroll
+    for (int i = 0; i <= NSEG; ++i) brk[i] = cs.brk[i];
+  }
+  __device__ __forceinline__ double slope_at(int j) const {  // 0 <= j < NSEG
+    if (NSEG == 4) return sel4(j, slope[0], slope[1], slope[2], slope[3]);
+    return slope[0];
+  }
+  __device__ __forceinline__ double brk_at(int i) const {  // 0 <= i <= NSEG
+    if (NSEG == 4) return dsel(i == 4, brk[NSEG], sel4(i, brk[0], brk[1], brk[2], brk[3]));
+    return dsel(i != 0, brk[NSEG], brk[0]);
+  }
+};
+
 // The solve of one lane group.  `li` = lane index inside the group (owns stages li*SPL .. li*SPL+SPL-1),
 // `live` = the group has a QP (a partial last warp keeps its idle groups in the shuffles).
 template <int N, int NSEG, int SPL>
@@ -114,9 +150,11 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
                                            const int lane, int& st_out) {
   constexpr int LPQ = N / SPL;
   static_assert(N % SPL == 0 && (LPQ & (LPQ - 1)) == 0 && LPQ <= 32 && LPQ >= 1, "N = SPL * 2^m, at most 32 lanes");
+  static_assert(NSEG == 1 || NSEG == 4, "small EV (one piece) or the large-EV pwl (four)");
   const int li = lane & (LPQ - 1);
   const int k0 = li * SPL;
   const double c = cs.c, wmax = cs.w_max;
+  const Pwl<NSEG> pw(cs);
 #ifdef LOMPC_WARP_PROF
   unsigned long long prof[8] = {0, 0, 0, 0, 0, 1, 0, 0};
 #endif
@@ -151,9 +189,17 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
     gmaxloc = dmax2(gmaxloc, fabs(G[j]));
     l2loc += l2;
   }
-  const double l2sum = grp_sum<LPQ>(l2loc);
-  const double gmax = grp_max_nonneg<LPQ>(gmaxloc);
-  dmin_hi = grp_min_int<LPQ>(dmin_hi);
+  // one butterfly for the three group reductions (independent chains share the shuffle latencies)
+#pragma unroll
+  for (int d = LPQ / 2; d >= 1; d >>= 1) {
+    const double t1 = __shfl_xor_sync(kFullMask, l2loc, d, LPQ);
+    const double t2 = __shfl_xor_sync(kFullMask, gmaxloc, d, LPQ);
+    const int t3 = __shfl_xor_sync(kFullMask, dmin_hi, d, LPQ);
+    l2loc += t1;
+    gmaxloc = dmax2(gmaxloc, t2);
+    dmin_hi = min(dmin_hi, t3);
+  }
+  const double l2sum = l2loc, gmax = gmaxloc;
   int st = LOMPC_ST_OK;
   if (grp_any<LPQ>(neg, lane)) st = LOMPC_ST_NEGATIVE;
   if (gam > cs.y_max) st = LOMPC_ST_BAD_GAMMA;
@@ -162,8 +208,8 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
   const int tqh = __double2hiint(tq);
   const double cg = c * gam;
   const double band = 1e-9 * wmax;
-  const double fbase = 1e-15 * (c * N * cs.y_max * cs.y_max + N * wmax * (gmax + cs.slope[NSEG - 1]));
-  const double top_lo = cs.brk[NSEG] - band;
+  const double fbase = 1e-15 * (c * N * cs.y_max * cs.y_max + N * wmax * (gmax + pw.slope[NSEG - 1]));
+  const double top_lo = pw.brk[NSEG] - band;
 
   constexpr int kOptimistic = 10;  // as in lompc_solve_reg.cuh
   const int n_opt = dmin_hi > 0 ? kOptimistic : 0;
@@ -175,7 +221,7 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
   double f = 0.0, mu = 0.0;
   double sl[SPL];           // local inclusive prefix sums of W
   double off = 0.0;         // state entering this lane's block
-  int vh_last = 0;
+  int vh_lane = 0;          // this lane's largest KKT violation (high word) in the last test of a live group
 
   // states of the iterate: s_k = off + sl[j]
   auto scan_states = [&](double& texc) {
@@ -207,7 +253,7 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
       floc += x * fma(0.5 * D[j], x, G[j]) + 0.5 * c * e * e;
       if (NSEG > 1) {
 #pragma unroll
-        for (int i = 1; i < NSEG; ++i) floc += (cs.slope[i] - cs.slope[i - 1]) * dpos(x - cs.brk[i]);
+        for (int i = 1; i < NSEG; ++i) floc += (pw.slope[i] - pw.slope[i - 1]) * dpos(x - pw.brk[i]);
       }
     }
     return grp_sum<LPQ>(floc);
@@ -263,41 +309,42 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
         const double mq = -q;
         double s_lo, s_hi;
         bool atbp;
+        bool top = false, bot = false;
         if (NSEG > 1) {
           const int cd = CD[j];
-          const int i = cd >> 1;
+          const int i = cd >> 1;  // breakpoint i (even code) or piece i (odd code)
           atbp = (cd & 1) == 0;
-          if (atbp) {
-            s_lo = i > 0 ? cs.slope[i - 1] : -1e300;
-            s_hi = i < NSEG ? cs.slope[i < NSEG ? i : 0] : 1e300;
-          } else {
-            s_lo = s_hi = cs.slope[i < NSEG ? i : 0];
-          }
+          const double s_here = pw.slope_at(i & 3);                      // slope[i]     (i < NSEG)
+          const double s_left = pw.slope_at((i - 1) & 3);                // slope[i - 1] (i > 0)
+          s_hi = dsel(atbp && i == NSEG, 1e300, s_here);
+          s_lo = dsel(atbp, dsel(i == 0, -1e300, s_left), s_here);
         } else {
-          const bool top = wk >= top_lo, bot = wk <= band;
-          s_hi = top ? 1e300 : cs.slope[0];
-          s_lo = bot ? -1e300 : cs.slope[0];
+          top = wk >= top_lo;
+          bot = wk <= band;
+          s_hi = top ? 1e300 : pw.slope[0];
+          s_lo = bot ? -1e300 : pw.slope[0];
           atbp = top | bot;
         }
         const double va = mq - s_hi, vb = s_lo - mq;
         const bool right = va > tq, left = vb > tq;
         binding[j] = atbp && !right && !left;
-        slw[j] = left ? s_lo : s_hi;
+        slw[j] = dsel(left, s_lo, s_hi);
         vh = max(vh, max(__double2hiint(va), __double2hiint(vb)));
         // guess of the piece the rollout will land on: a coordinate pushed off a breakpoint moves into the
         // neighbouring piece, everything else stays where it is
         if (NSEG > 1) {
           CDO[j] = CD[j] + ((atbp && right) ? 1 : 0) - ((atbp && left) ? 1 : 0);
         } else {
-          const bool top = wk >= top_lo, bot = wk <= band;
           CDO[j] = (atbp && (right || left)) ? 1 : (top ? 2 : (bot ? 0 : 1));
         }
       }
     }
-    vh = grp_max_int<LPQ>(vh);
+    // converged <=> every lane's violation is below the tolerance: one vote instead of a max-reduction
+    // (the maximum itself is only reported, see the epilogue)
+    const bool viol_any = grp_any<LPQ>(vh >= tqh, lane);
     if (!done) {
-      vh_last = vh;
-      if (vh < tqh) {
+      vh_lane = vh;
+      if (!viol_any) {
         converged = true;
         done = true;
       }
@@ -307,7 +354,8 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
     if (__all_sync(kFullMask, done)) break;
 
     // ================= B: Riccati recursion (block operators + suffix scan) -> gains =================
-    double KK[SPL], KAP[SPL], INV[SPL];
+    double KK[SPL];          // x = KK s + KP[piece] inside a piece
+    double KP[SPL][NSEG];    // kappa - slope_i / (dm + Q): the stationary point of piece i at s = 0
     {
       RicMat blk;
 #pragma unroll
@@ -316,36 +364,57 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
         const double dm = D[j] + mu;
         const double gm = fma(-mu, wk, G[j]);
         RicMat M;
-        if (binding[j]) {
-          M.a11 = 1.0; M.a12 = c; M.a21 = 0.0; M.a22 = 1.0;
-          M.v1 = wk; M.v2 = fma(c, wk, -cg); M.m = 1.0;
-        } else {
-          const double h = gm + slw[j];
+        {  // both forms are a handful of flops: computed side by side and selected (no divergent branch)
+          const bool bd = binding[j];
+          const double h = gm + dsel(bd, 0.0, slw[j]);
           const double sg = pow2_inv_scale(dm + c);
           const double dms = dm * sg;
-          M.a11 = dms; M.a12 = dms * c; M.a21 = sg; M.a22 = (dm + c) * sg;
-          M.v1 = -(h * sg); M.v2 = -(fma(dm, cg, c * h) * sg); M.m = dms;
+          M.a11 = dsel(bd, 1.0, dms);
+          M.a12 = dsel(bd, c, dms * c);
+          M.a21 = dsel(bd, 0.0, sg);
+          M.a22 = dsel(bd, 1.0, (dm + c) * sg);
+          M.v1 = dsel(bd, wk, -(h * sg));
+          M.v2 = dsel(bd, fma(c, wk, -cg), -(fma(dm, cg, c * h) * sg));
+          M.m = dsel(bd, 1.0, dms);
         }
         if (j == SPL - 1)
           blk = M;
         else
           blk = ric_mul(M, blk);
       }
-      // inclusive suffix scan over the lanes of the group: S_l = B_l B_{l+1} ... B_{LPQ-1}
+      // inclusive suffix scan over the lanes of the group: S_l = B_l B_{l+1} ... B_{LPQ-1}.  Only the second
+      // column of S is used (the triple leaving the horizon's end is (0, 1, 0)'), so the last step forms only that.
 #pragma unroll
-      for (int d = 1; d < LPQ; d <<= 1) {
+      for (int d = 1; d < LPQ / 2; d <<= 1) {
         const RicMat o = ric_shfl_down(blk, d, LPQ);
-        if (li + d < LPQ) blk = ric_mul(blk, o);
+        const RicMat pr_ = ric_mul(blk, o);
+        const bool act = li + d < LPQ;
+        blk.a11 = dsel(act, pr_.a11, blk.a11);
+        blk.a12 = dsel(act, pr_.a12, blk.a12);
+        blk.a21 = dsel(act, pr_.a21, blk.a21);
+        blk.a22 = dsel(act, pr_.a22, blk.a22);
+        blk.v1 = dsel(act, pr_.v1, blk.v1);
+        blk.v2 = dsel(act, pr_.v2, blk.v2);
+        blk.m = dsel(act, pr_.m, blk.m);
+      }
+      double ca = blk.a12, cb = blk.a22, cr = blk.v2;
+      if (LPQ > 1) {
+        constexpr int d = LPQ / 2;
+        const double oa = __shfl_down_sync(kFullMask, ca, d, LPQ);
+        const double ob = __shfl_down_sync(kFullMask, cb, d, LPQ);
+        const double orr = __shfl_down_sync(kFullMask, cr, d, LPQ);
+        const bool act = li + d < LPQ;
+        ca = dsel(act, fma(blk.a11, oa, blk.a12 * ob), ca);
+        cb = dsel(act, fma(blk.a21, oa, blk.a22 * ob), cb);
+        cr = dsel(act, fma(blk.m, orr, fma(blk.v1, oa, blk.v2 * ob)), cr);
       }
       // triple entering this block from above: second column of S_{l+1} ((0, 1, 0)' for the last block)
-      double pa = __shfl_down_sync(kFullMask, blk.a12, 1, LPQ);
-      double pb = __shfl_down_sync(kFullMask, blk.a22, 1, LPQ);
-      double pr = __shfl_down_sync(kFullMask, blk.v2, 1, LPQ);
-      if (li == LPQ - 1) {
-        pa = 0.0;
-        pb = 1.0;
-        pr = 0.0;
-      }
+      double pa = __shfl_down_sync(kFullMask, ca, 1, LPQ);
+      double pb = __shfl_down_sync(kFullMask, cb, 1, LPQ);
+      double pr = __shfl_down_sync(kFullMask, cr, 1, LPQ);
+      pa = dsel(li == LPQ - 1, 0.0, pa);
+      pb = dsel(li == LPQ - 1, 1.0, pb);
+      pr = dsel(li == LPQ - 1, 0.0, pr);
 #pragma unroll
       for (int j = SPL - 1; j >= 0; --j) {
         const double wk = W[j];
@@ -355,16 +424,23 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
         const double tu = fma(-cg, pb, pr);
         const double bn = fma(dm, pb, tq_);
         const double ib = fast_rcp(bn);
+        const double kap = -(fma(gm, pb, tu) * ib);
+        const double inv = pb * ib;
         KK[j] = -(tq_ * ib);
-        KAP[j] = -(fma(gm, pb, tu) * ib);
-        INV[j] = pb * ib;
-        if (binding[j]) {
-          pa = tq_;
-          pr = fma(tq_, wk, tu);
-        } else {
-          pa = dm * tq_;
-          pr = fma(dm, tu, -tq_ * (gm + slw[j]));
-          pb = bn;
+#pragma unroll
+        for (int i = 0; i < NSEG; ++i) KP[j][i] = NSEG > 1 ? fma(-pw.slope[i], inv, kap) : kap;
+        {
+          const bool bd = binding[j];
+          const double hs = gm + dsel(bd, 0.0, slw[j]);
+          pa = dsel(bd, tq_, dm * tq_);
+          pr = dsel(bd, fma(tq_, wk, tu), fma(dm, tu, -tq_ * hs));
+          pb = dsel(bd, pb, bn);
+          if (SPL > 4) {  // long blocks: keep the triple in range (exact power-of-two rescale)
+            const double sg = pow2_inv_scale(pb);
+            pa *= sg;
+            pb *= sg;
+            pr *= sg;
+          }
         }
       }
     }
@@ -377,9 +453,11 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
       int CN[SPL];
 #pragma unroll
       for (int j = 0; j < SPL; ++j) CN[j] = CDO[j];  // the guess (CDO is rewritten with the parked codes below)
-      for (int pass = 0; pass <= LPQ; ++pass) {
+      for (int pass = 0; pass <= N; ++pass) {
         LOMPC_PROF_ADD(7, 1);
-        // block map s_out = am * s_in + bm under the guess
+        // Under the guess every stage is an affine map of the state; ps / pt = the state BEFORE stage j as a
+        // function of the state entering the block (s_j = ps[j] s_in + pt[j]), am / bm = the whole block.
+        double ps[SPL], pt[SPL];
         double am = 1.0, bm = 0.0;
 #pragma unroll
         for (int j = 0; j < SPL; ++j) {
@@ -387,37 +465,39 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
           double al, be;  // x = al * s + be
           if (NSEG > 1) {
             const int i = cd >> 1;
-            if (cd & 1) {
-              al = KK[j];
-              be = fma(-cs.slope[i < NSEG ? i : 0], INV[j], KAP[j]);
-            } else {
-              al = 0.0;
-              be = cs.brk[i];
-            }
+            const bool inside = (cd & 1) != 0;
+            al = dsel(inside, KK[j], 0.0);
+            be = dsel(inside, sel4(i & 3, KP[j][0], KP[j][NSEG > 1 ? 1 : 0], KP[j][NSEG > 1 ? 2 : 0], KP[j][NSEG > 1 ? 3 : 0]),
+                      pw.brk_at(i));
           } else {
-            al = cd == 1 ? KK[j] : 0.0;
-            be = cd == 1 ? KAP[j] : (cd == 2 ? wmax : 0.0);
+            al = dsel(cd == 1, KK[j], 0.0);
+            be = dsel(cd == 1, KP[j][0], dsel(cd == 2, wmax, 0.0));
           }
+          ps[j] = am;
+          pt[j] = bm;
           const double a1 = 1.0 + al;
           am *= a1;
           bm = fma(a1, bm, be);
         }
-        // inclusive prefix scan of the maps; the entry state of block l is the offset of the composite of blocks < l
+        // inclusive prefix scan of the block maps; the state entering block l is the offset of the composite of blocks < l
 #pragma unroll
         for (int d = 1; d < LPQ; d <<= 1) {
           const double oa = __shfl_up_sync(kFullMask, am, d, LPQ);
           const double ob = __shfl_up_sync(kFullMask, bm, d, LPQ);
-          if (li >= d) {
-            bm = fma(am, ob, bm);
-            am *= oa;
-          }
+          const bool act = li >= d;
+          bm = dsel(act, fma(am, ob, bm), bm);
+          am = dsel(act, am * oa, am);
         }
-        double s = __shfl_up_sync(kFullMask, bm, 1, LPQ);
-        if (li == 0) s = 0.0;
-        // exact replay of this lane's stages from s
+        double s_in = __shfl_up_sync(kFullMask, bm, 1, LPQ);
+        s_in = dsel(li == 0, 0.0, s_in);
+        // Replay: the stages of the block are evaluated side by side, each from its state under the guess.  A stage's
+        // answer is exact when every stage before it (in this block and the blocks before) landed where it was
+        // guessed; the first stage of the horizon that did not is exact too and corrects its guess, so every
+        // pass fixes at least one stage and a pass without a miss is the exact rollout.
         bool mis = false;
 #pragma unroll
         for (int j = 0; j < SPL; ++j) {
+          const double s = fma(ps[j], s_in, pt[j]);
           double x;
           int cdn;
           if (NSEG > 1) {
@@ -425,9 +505,9 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
             int mc[NSEG];
 #pragma unroll
             for (int i = 0; i < NSEG; ++i) {
-              const double cj = fma(KK[j], s, fma(-cs.slope[i], INV[j], KAP[j]));
-              const bool below = cj < cs.brk[i + 1];
-              m[i] = below ? cj : cs.brk[i + 1];
+              const double cj = fma(KK[j], s, KP[j][i]);
+              const bool below = cj < pw.brk[i + 1];
+              m[i] = below ? cj : pw.brk[i + 1];
               mc[i] = below ? 2 * i + 1 : 2 * i + 2;
             }
 #pragma unroll
@@ -443,7 +523,7 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
             x = dpos(m[0]);
             cdn = ng ? 0 : mc[0];
           } else {
-            const double x0 = fma(KK[j], s, KAP[j]);
+            const double x0 = fma(KK[j], s, KP[j][0]);
             const bool over = x0 > wmax, under = x0 < 0.0;
             x = over ? wmax : x0;
             x = under ? 0.0 : x;
@@ -452,7 +532,6 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
           mis |= cdn != CN[j];
           CN[j] = cdn;
           X[j] = x;
-          s += x;
         }
         if (!__any_sync(kFullMask, mis && !done)) break;
       }
@@ -476,8 +555,8 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
   st_out = live ? st : LOMPC_ST_OK;
 
   // ================= outputs (the states of the final iterate are in off / sl) =================
+  double closs = 0.0;
   if (live) {
-    double closs = 0.0;
     double* wo = a.w_out + b * (int64_t)N + k0;
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
@@ -487,18 +566,22 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
       closs += x * fma(0.5 * D[j], x, G[j]) + 0.5 * c * s * (s - 2.0 * gam);
       if (NSEG > 1) {
 #pragma unroll
-        for (int i = 1; i < NSEG; ++i) closs += (cs.slope[i] - cs.slope[i - 1]) * dpos(x - cs.brk[i]);
+        for (int i = 1; i < NSEG; ++i) closs += (pw.slope[i] - pw.slope[i - 1]) * dpos(x - pw.brk[i]);
       }
     }
-    const double cost = cs.theta * wmax * l2sum + grp_sum<LPQ>(closs);
-    if (li == 0) {
-      if (a.cost_out) a.cost_out[b] = cost;
-      if (a.status) a.status[b] = st;
-      if (a.iters) a.iters[b] = it;
-      if (a.kkt_res) a.kkt_res[b] = __hiloint2double(vh_last, vh_last ? -1 : 0) / gscale;
-    }
-  } else {
-    (void)grp_sum<LPQ>(0.0);
+  }
+#pragma unroll
+  for (int d = LPQ / 2; d >= 1; d >>= 1) {
+    const double t1 = __shfl_xor_sync(kFullMask, closs, d, LPQ);
+    const int t2 = __shfl_xor_sync(kFullMask, vh_lane, d, LPQ);
+    closs += t1;
+    vh_lane = max(vh_lane, t2);
+  }
+  if (live && li == 0) {
+    if (a.cost_out) a.cost_out[b] = cs.theta * wmax * l2sum + closs;
+    if (a.status) a.status[b] = st;
+    if (a.iters) a.iters[b] = it;
+    if (a.kkt_res) a.kkt_res[b] = __hiloint2double(vh_lane, vh_lane ? -1 : 0) / gscale;
   }
 #ifdef LOMPC_WARP_PROF
   prof[4] = (unsigned long long)(clock64() - t_out);
@@ -507,13 +590,15 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
 #endif
 }
 
-// One warp = 32 / LPQ QPs of one segment.  WPC warps per CTA (small CTAs spread a small batch over all SMs).
-template <int N, int SPL, int WPC>
-__global__ void __launch_bounds__(32 * WPC) lompc_solve_warp_kernel(const __grid_constant__ WarpArgs wa) {
+// One warp = 32 / LPQ QPs of one segment, ONE warp per CTA: the warp index is blockIdx.x, so the segment, its EV
+// type and every loop exit are provably warp-uniform and ptxas emits the shuffles without convergence barriers
+// (with several warps per CTA every SHFL of the sweeps was wrapped in WARPSYNC / ENDCOLLECTIVE); 32-thread CTAs
+// also let the block scheduler spread a small batch over all SMs.
+template <int N, int SPL>
+__global__ void __launch_bounds__(32, 1) lompc_solve_warp_kernel(const __grid_constant__ WarpArgs wa) {
   constexpr int LPQ = N / SPL, QPW = 32 / LPQ;
-  const int lane = threadIdx.x & 31;
-  const int warp = blockIdx.x * WPC + (threadIdx.x >> 5);
-  if (warp >= wa.total_warps) return;
+  const int lane = threadIdx.x;
+  const int warp = blockIdx.x;
   int sg = 0;
 #pragma unroll
   for (int i = 1; i < kMaxWarpSegs; ++i)

@@ -26,13 +26,7 @@ int launch_warp_geom(lompc::WarpArgs& wa, cudaStream_t s) {
   }
   wa.total_warps = warps;
   if (warps == 0) return LOMPC_OK;
-  // Small launches: one warp per CTA, so that the block scheduler spreads them over all SMs and every warp
-  // has a scheduler to itself; larger ones: 4 warps per CTA.
-  if (warps <= 148 * 8) {
-    lompc::lompc_solve_warp_kernel<N, SPL, 1><<<warps, 32, 0, s>>>(wa);
-  } else {
-    lompc::lompc_solve_warp_kernel<N, SPL, 4><<<(warps + 3) / 4, 128, 0, s>>>(wa);
-  }
+  lompc::lompc_solve_warp_kernel<N, SPL><<<warps, 32, 0, s>>>(wa);  // one warp per CTA (see the kernel)
   lompc_detail::count_launch();
   CK(cudaGetLastError());
   return LOMPC_OK;
@@ -56,11 +50,9 @@ inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
 
 namespace lompc_detail {
 
-bool warp_kernel_supports(int N, int spl) {
-  if (spl == 3) return N == 12 || N == 24 || N == 48 || N == 96;
-  if (spl == 6) return N == 24 || N == 48 || N == 96;
-  return false;
-}
+// 3 stages per lane: N / 3 = 4, 8, 16, 32 lanes per QP.  (6 stages per lane were measured slower at every
+// horizon - the serial part of a lane grows faster than the scans shrink - and are not compiled.)
+bool warp_kernel_supports(int N, int spl) { return spl == 3 && (N == 12 || N == 24 || N == 48 || N == 96); }
 
 int launch_k1_warp(int device, int N, int spl, lompc::WarpArgs& wa, cudaStream_t s) {
   (void)device;
@@ -70,12 +62,6 @@ int launch_k1_warp(int device, int N, int spl, lompc::WarpArgs& wa, cudaStream_t
       case 24: return launch_warp_geom<24, 3>(wa, s);
       case 48: return launch_warp_geom<48, 3>(wa, s);
       case 96: return launch_warp_geom<96, 3>(wa, s);
-    }
-  } else if (spl == 6) {
-    switch (N) {
-      case 24: return launch_warp_geom<24, 6>(wa, s);
-      case 48: return launch_warp_geom<48, 6>(wa, s);
-      case 96: return launch_warp_geom<96, 6>(wa, s);
     }
   }
   return LOMPC_ERR_ARG;
@@ -139,11 +125,10 @@ int set_launch(lompc_set* S, int want_info, cudaStream_t s) {
   // The warp-cooperative kernel serves every segment in ONE launch; batches large enough to fill the GPU with
   // one QP per thread (or a horizon it is not compiled for) take one thread-kernel launch per segment.
   bool forced_thread = false;
-  int spl = 3;
+  const int spl = 3;
   for (int i = 0; i < S->n; ++i) {
     const int var = lompc_detail::handle_view(S->hs[i]).variant;
     if (var >= 1 && var <= 7) forced_thread = true;
-    if (var == 9) spl = 6;
   }
   const bool warp_ok = lompc_detail::warp_kernel_supports(N, spl) && !forced_thread && S->total <= (int64_t)1 << 17;
   if (warp_ok) {

@@ -70,8 +70,7 @@ int lompc_set_options(lompc_t* h, int max_iter, double tol);
  * per SM, linear term g in shared memory / registers): 2 = 64x4 smem, 3 = 128x3 regs, 4 = 64x4 regs,
  * 5 = 64x5 regs, 6 = 128x2 regs, 7 = 256x1 regs (tools/sweep_variants.sh);
  * 8 = the warp-cooperative latency kernel (one QP per group of N/3 lanes, time-parallel sweeps; N = 12, 24,
- * 48, 96), which automatic mode picks for batches too small to fill the GPU with one QP per thread,
- * 9 = the same kernel with 6 stages per lane (N = 24, 48, 96). */
+ * 48, 96), which automatic mode picks for batches too small to fill the GPU with one QP per thread. */
 int lompc_set_kernel_variant(lompc_t* h, int variant);
 
 /* Replaces LoMPC.solve_lompc (lompc.py:137-156), batched over B independent

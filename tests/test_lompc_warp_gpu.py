@@ -36,7 +36,7 @@ def _regimes(o, N, B, seed):
 
 
 @pytest.mark.parametrize("ev", ["small", "large"])
-@pytest.mark.parametrize("N,variant", [(12, 8), (24, 8), (24, 9), (48, 8), (48, 9), (96, 8), (96, 9)])
+@pytest.mark.parametrize("N,variant", [(12, 8), (24, 8), (48, 8), (96, 8)])
 def test_warp_kernel_against_oracle_and_thread_kernel(ev, N, variant):
     from chargingstation.lompc import LoMPC
     o, c = _consts(ev)

@@ -24,7 +24,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--N", type=int, default=24)
     ap.add_argument("--batches", default="512,2048,8192,32768,131072")
-    ap.add_argument("--variants", default="8,9,4,1")
+    ap.add_argument("--variants", default="8,4,1")
     ap.add_argument("--reps", type=int, default=20)
     ap.add_argument("--set-batch", type=int, default=512, help="QPs per EV type of the solve-set case")
     args = ap.parse_args()
@@ -56,8 +56,6 @@ def main():
             out = (torch.empty((B, N), dtype=torch.float64, device=dev), torch.empty(B, dtype=torch.float64, device=dev))
             for var in [int(v) for v in args.variants.split(",")]:
                 if var == 4 and N not in (12, 24):
-                    continue
-                if var == 9 and N == 12:
                     continue
                 s = LoMPC(N, LoMPCConstants(delta, theta, y_max, w_max, ev))
                 s.set_kernel_variant(var)
