@@ -25,6 +25,11 @@ def load():
             C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int64,
             C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_double, C.c_int,
             C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+        lib.oracle_solve_lompc_exact_batch.restype = C.c_int
+        lib.oracle_solve_lompc_exact_batch.argtypes = [
+            C.c_int, C.c_double, C.c_double, C.c_double, C.c_double, C.c_int, C.c_int64,
+            C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int,
+            C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
         lib.oracle_lompc_cost.restype = C.c_double
         lib.oracle_max_threads.restype = C.c_int
         _lib = lib
@@ -56,3 +61,28 @@ def solve_lompc_batch(N, consts, lmbd, lmbd_r, gamma, tol=1e-8, max_iter=200, nt
     if used < 0:
         raise ValueError("oracle_solve_lompc_batch: bad arguments")
     return w, cost, iters, used
+
+
+def solve_lompc_exact_batch(N, consts, lmbd, lmbd_r, gamma, max_iter=10000, nthreads=0):
+    """The exact active-set oracle (C twin of ``lompc_oracle.solve_active_set``) for B QPs.
+    Returns (w[B,N], cost[B], iters[B])."""
+    lib = load()
+    gamma = np.ascontiguousarray(np.atleast_1d(gamma), dtype=np.float64)
+    B = gamma.shape[0]
+    lmbd = np.ascontiguousarray(lmbd, dtype=np.float64)
+    lm_stride = 0 if lmbd.ndim == 1 else 3 * N
+    lmbd_r = np.ascontiguousarray(np.atleast_1d(lmbd_r), dtype=np.float64)
+    lr_stride = 0 if lmbd_r.shape[0] == 1 else 1
+    w = np.empty((B, N))
+    cost = np.empty(B)
+    iters = np.empty(B, dtype=np.int32)
+    used = lib.oracle_solve_lompc_exact_batch(
+        N, consts.delta, consts.theta, consts.y_max, consts.w_max,
+        1 if consts.ev_type == "large" else 0, B, lmbd.ctypes.data, lm_stride,
+        lmbd_r.ctypes.data, lr_stride, gamma.ctypes.data, max_iter, nthreads,
+        w.ctypes.data, cost.ctypes.data, iters.ctypes.data)
+    if used < 0:
+        raise ValueError("oracle_solve_lompc_exact_batch: bad arguments")
+    if np.any(iters < 0):
+        raise RuntimeError("oracle_solve_lompc_exact_batch: Cholesky breakdown")
+    return w, cost, iters

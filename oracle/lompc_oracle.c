@@ -13,6 +13,9 @@
  * lompc.py:111-115), stopped at Clarabel's default 1e-8 tolerances.  The dense
  * normal equations exploit that every row of G has at most two non-zeros.
  *
+ * It also holds the C twin of the EXACT active-set oracle (oracle/lompc_oracle.py::solve_active_set),
+ * which the price-loop / closed-loop oracles use at the reference's full sizes.
+ *
  * Used by: tests/ (checked against oracle/lompc_oracle.py) and bench.py's
  * cpu_baseline / --impl reference legs (timed on all host threads, OpenMP).
  * Build: make -C oracle   ->  oracle/liblompc_oracle.so
@@ -282,6 +285,126 @@ int oracle_solve_lompc_batch(int N, double delta, double theta, double y_max, do
     double cost;
     int it = solve_one(&c, lmbd + b * lmbd_stride, lmbd_r[b * lmbd_r_stride], gamma[b], tol,
                        max_iter, w_out + b * N, &cost);
+    cost_out[b] = cost;
+    if (iters) iters[b] = it;
+  }
+  return used;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Exact solve: the C twin of oracle/lompc_oracle.py::solve_active_set (same steps, same tie rules),
+ * so that the price-loop and closed-loop oracles can afford the reference's full sizes (500 + 500
+ * EVs, 49 steps).  Each coordinate is FREE inside a piece of the pwl (linear term = that piece's
+ * slope) or FIXED on a breakpoint; a feasible-descent primal active-set iteration with one change
+ * per step and dense Cholesky solves on the free block of H = diag(d) + c A'A, (A'A)_ij = N - max(i,j).
+ * ------------------------------------------------------------------------------------------------ */
+static int solve_exact_one(const oracle_consts* c, const double* lmbd, double lmbd_r, double gamma,
+                           int max_iter, double* w_out, double* cost_out) {
+  const int N = c->N;
+  const double th = c->theta, wm = c->w_max;
+  const double qs = 3.0 * th / (4.0 * wm), cc = 2.0 * c->delta * th * th;
+  double d[MAXN], g[MAXN], w[MAXN], wt[MAXN], rhs[MAXN], grad[MAXN];
+  static _Thread_local double Kf[MAXN * MAXN];
+  int seg[MAXN], at[MAXN], fixed[MAXN], idx[MAXN];
+  double brk[5], slope[4];
+  int nseg;
+  if (!c->large) {
+    nseg = 1; brk[0] = 0.0; brk[1] = wm; slope[0] = 0.0;
+  } else {
+    nseg = 4;
+    const double scale = (th * wm) * (th * wm) / wm;
+    brk[0] = 0.0; brk[1] = 0.125 * wm; brk[2] = 0.5 * wm; brk[3] = 0.75 * wm; brk[4] = wm;
+    for (int j = 0; j < 4; ++j) slope[j] = scale * PWL_A[j];
+  }
+  double gmax = 0.0;
+  for (int k = 0; k < N; ++k) {
+    d[k] = 2.0 * (lmbd_r * th * th + qs * lmbd[2 * N + k]) + (c->large ? 0.0 : 2.0 * th * th / 0.81);
+    g[k] = th * (lmbd[k] - lmbd[N + k]) - cc * gamma * (double)(N - k);
+    gmax = fmax(gmax, fabs(g[k]));
+    w[k] = 0.0; seg[k] = 0; at[k] = 0; fixed[k] = 1;
+  }
+  int it = 0;
+  for (it = 0; it < max_iter; ++it) {
+    int nf = 0;
+    for (int k = 0; k < N; ++k) if (!fixed[k]) idx[nf++] = k;
+    memcpy(wt, w, sizeof(double) * N);
+    if (nf > 0) {
+      for (int a = 0; a < nf; ++a) {
+        const int i = idx[a];
+        double r = -(g[i] + slope[seg[i]]);
+        for (int k = 0; k < N; ++k)
+          if (fixed[k]) r -= cc * (double)(N - (i > k ? i : k)) * w[k];
+        rhs[a] = r;
+        for (int b2 = 0; b2 < nf; ++b2) {
+          const int j = idx[b2];
+          Kf[a * nf + b2] = cc * (double)(N - (i > j ? i : j)) + (i == j ? d[i] : 0.0);
+        }
+      }
+      if (chol(Kf, nf)) return -(it + 1);
+      chol_solve(Kf, nf, rhs);
+      for (int a = 0; a < nf; ++a) wt[idx[a]] = rhs[a];
+    }
+    /* ratio test against the ends of the pieces the free coordinates live in */
+    double alpha = 1.0;
+    int blk = -1, blk_at = -1;
+    for (int a = 0; a < nf; ++a) {
+      const int k = idx[a];
+      const double lo = brk[seg[k]], hi = brk[seg[k] + 1], dk = wt[k] - w[k];
+      if (dk < 0 && wt[k] < lo) {
+        const double al = (lo - w[k]) / dk;
+        if (al < alpha) { alpha = al; blk = k; blk_at = seg[k]; }
+      } else if (dk > 0 && wt[k] > hi) {
+        const double al = (hi - w[k]) / dk;
+        if (al < alpha) { alpha = al; blk = k; blk_at = seg[k] + 1; }
+      }
+    }
+    if (blk >= 0) {
+      for (int k = 0; k < N; ++k) w[k] += alpha * (wt[k] - w[k]);
+      fixed[blk] = 1; at[blk] = blk_at; w[blk] = brk[blk_at];
+      continue;
+    }
+    memcpy(w, wt, sizeof(double) * N);
+    /* multipliers of the fixed coordinates: need -grad_k in [slope_left, slope_right] */
+    for (int i = 0; i < N; ++i) {
+      double r = d[i] * w[i] + g[i];
+      for (int k = 0; k < N; ++k) r += cc * (double)(N - (i > k ? i : k)) * w[k];
+      grad[i] = r;
+    }
+    double worst = 0.0;
+    int wk = -1, wseg = -1;
+    for (int k = 0; k < N; ++k) {
+      if (!fixed[k]) continue;
+      const int i = at[k];
+      const double s_lo = i > 0 ? slope[i - 1] : -INFINITY, s_hi = i < nseg ? slope[i] : INFINITY;
+      if (-grad[k] < s_lo && s_lo + grad[k] > worst) { worst = s_lo + grad[k]; wk = k; wseg = i - 1; }
+      else if (-grad[k] > s_hi && -grad[k] - s_hi > worst) { worst = -grad[k] - s_hi; wk = k; wseg = i; }
+    }
+    if (wk < 0 || worst <= 1e-13 * fmax(1.0, gmax)) break;
+    fixed[wk] = 0; seg[wk] = wseg;
+  }
+  memcpy(w_out, w, sizeof(double) * N);
+  *cost_out = lompc_cost(c, w, lmbd, lmbd_r, gamma);
+  return it;
+}
+
+/* Batched exact solve (OpenMP over QPs); same conventions as oracle_solve_lompc_batch. */
+int oracle_solve_lompc_exact_batch(int N, double delta, double theta, double y_max, double w_max,
+                                   int large, int64_t B, const double* lmbd, int64_t lmbd_stride,
+                                   const double* lmbd_r, int64_t lmbd_r_stride, const double* gamma,
+                                   int max_iter, int nthreads, double* w_out, double* cost_out,
+                                   int32_t* iters) {
+  if (N < 1 || N > MAXN) return -1;
+  oracle_consts c = {N, large, delta, theta, y_max, w_max};
+  int used = 1;
+#ifdef _OPENMP
+  omp_set_num_threads(nthreads > 0 ? nthreads : omp_get_num_procs());
+  used = omp_get_max_threads();
+#endif
+#pragma omp parallel for schedule(dynamic, 8)
+  for (int64_t b = 0; b < B; ++b) {
+    double cost;
+    int it = solve_exact_one(&c, lmbd + b * lmbd_stride, lmbd_r[b * lmbd_r_stride], gamma[b], max_iter,
+                             w_out + b * N, &cost);
     cost_out[b] = cost;
     if (iters) iters[b] = it;
   }

@@ -83,8 +83,12 @@ def nnqp_kkt(P: np.ndarray, q: np.ndarray, x: np.ndarray) -> float:
 class PriceOracle:
     """Mirror of ``PriceSolver`` (price_solver.py:16-285) on the oracle solvers."""
 
-    def __init__(self, N: int, consts: orc.OracleConsts, price_type: str) -> None:
+    def __init__(self, N: int, consts: orc.OracleConsts, price_type: str, fast: bool = False) -> None:
+        """``fast``: solve the LoMPC QPs with the C twin of the exact active-set oracle
+        (``c_oracle.solve_lompc_exact_batch``, bit-compatible with ``lompc_oracle.solve_active_set`` to 1e-15,
+        ~40x faster) so that the reference's full sizes (500 + 500 EVs, N = 24) are affordable."""
         assert price_type in ("linear", "linear-convex")  # price_solver.py:24
+        self.fast = fast
         orc.check_consts(consts)
         self.N = N
         self.r = 2 * N if price_type == "linear" else 3 * N  # :44-47
@@ -100,7 +104,19 @@ class PriceOracle:
     # -- lompc plumbing
     def _solve(self, lmbd, lmbd_r, gamma):
         self.lompc_solves += 1
+        if self.fast:
+            from oracle import c_oracle
+            w, cost, _ = c_oracle.solve_lompc_exact_batch(self.N, self.consts, lmbd, lmbd_r, np.array([gamma]), nthreads=1)
+            return w[0], float(cost[0])
         return orc.solve_lompc(self.N, self.consts, lmbd, lmbd_r, gamma)
+
+    def _solve_evs(self, lmbd, lmbd_r, gamma):
+        """w_i for every EV of the group (rows), in EV order."""
+        self.lompc_solves += len(gamma)
+        if self.fast:
+            from oracle import c_oracle
+            return c_oracle.solve_lompc_exact_batch(self.N, self.consts, lmbd, lmbd_r, gamma)[0]
+        return np.array([orc.solve_lompc(self.N, self.consts, lmbd, lmbd_r, g)[0] for g in gamma]).reshape(-1, self.N)
 
     def phi(self, w):
         return orc.phi(self.N, self.consts, w)
@@ -135,8 +151,9 @@ class PriceOracle:
         w_avg = np.zeros(self.N)
         w_err_max = 0.0
         gamma = self.consts.y_max - self.y0
+        w_all = self._solve_evs(lmbd, lmbd_r, gamma)
         for i in range(self.nEVs):
-            w_i, _ = self._solve(lmbd, lmbd_r, gamma[i])
+            w_i = w_all[i]
             w_avg += w_i
             w_err_i = np.sqrt((w_i - w_ref) @ A_bar @ (w_i - w_ref))
             w_err_max = max(w_err_max, w_err_i)
@@ -211,8 +228,9 @@ class PriceOracle:
         w0 = np.zeros(self.nEVs)
         price0 = 0.0
         gamma = self.consts.y_max - self.y0
+        w_all = self._solve_evs(lmbd_, lmbd_r, gamma)
         for i in range(self.nEVs):
-            w_i, _ = self._solve(lmbd_, lmbd_r, gamma[i])
+            w_i = w_all[i]
             w0[i] = w_i[0]
             price0 += orc.get_price0(self.N, self.consts, w_i, lmbd_, lmbd_r)
         return w0, price0 / self.nEVs

@@ -22,12 +22,13 @@ MIN_FULL_CHARGE_FRACTION = 0.95
 
 class StationOracle:
     def __init__(self, Tf, N_bi, N_lo, M_2, P, demand, bi: bo.BiConsts, cs: orc.OracleConsts,
-                 cl: orc.OracleConsts, price_type: str):
+                 cl: orc.OracleConsts, price_type: str, fast: bool = False):
+        """``fast``: the price loops solve their QPs with the C twin of the exact oracle (see PriceOracle)."""
         assert N_bi >= N_lo >= 1 and demand.shape[0] >= Tf + N_bi + 1  # charging_station.py:44-53
         self.Tf, self.N_bi, self.N_lo, self.M_2, self.P = Tf, N_bi, N_lo, M_2, P
         self.demand, self.bi, self.cs, self.cl = demand, bi, cs, cl
         self.r = 2 * N_lo if price_type == "linear" else 3 * N_lo
-        self.ps = {"s": PriceOracle(N_lo, cs, price_type), "l": PriceOracle(N_lo, cl, price_type)}
+        self.ps = {"s": PriceOracle(N_lo, cs, price_type, fast=fast), "l": PriceOracle(N_lo, cl, price_type, fast=fast)}
         self.edges = {"s": np.linspace(MIN_INITIAL_SOC, cs.y_max, P + 1),
                       "l": np.linspace(MIN_INITIAL_SOC, cl.y_max, P + 1)}
         self.B = (cs.theta + cl.theta) * M_2

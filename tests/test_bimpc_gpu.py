@@ -30,13 +30,22 @@ def test_batch_against_oracle(cost_type, N, P):
     for s, par in enumerate(stations):
         wso, wlo, ugo, io = bo.solve_ipm(c, *par)
         assert abs(int(info["iters"][s]) - io["iters"]) <= 3  # (the kernel leaves decoupled empty partitions out)
-        k = bo.kkt_certificate(c, par, ws[s], wl[s], ug[s])
+        k = bo.kkt_certificate(c, par, ws[s], wl[s], ug[s], multipliers=(s == 0 or N * P <= 100))
         assert k["max_violation"] <= 1e-8
         # north-star bar: objective <= 1e-6 relative
         assert abs(k["objective"] - io["objective"]) <= 1e-7 * max(1.0, abs(io["objective"]))
         assert abs(info["objective"][s] - k["objective"]) <= 1e-9 * max(1.0, abs(k["objective"]))
+        # solver-independent certificate (multipliers reconstructed by NNLS): the kernel's point is stationary
+        # and complementary to 1e-6 / 1e-7 whatever the oracle says
+        assert k["stationarity"] <= 1e-6 and k["complementarity"] <= 1e-7, k  # (0.0 where not computed)
         assert np.max(np.abs(ug[s] - ugo)) <= 2e-5
-        tol_w = 3e-2 if cost_type == bo.EXP_UNWEIGHTED else 1e-4
+        # Trajectories.  UNWEIGHTED: every cumulative charge has unit curvature -> 1e-5 (north-star bar).
+        # WEIGHTED: partition p enters with weight (theta Mp_p)^2 ~ 1e-5..1e-4 of the generation cost's curvature,
+        # so two solves that agree to 1e-9 in the objective differ by ~2e-5 in w (the dense oracle, not the
+        # kernel, is the less accurate one there: at tol 1e-11 its normal equations stall while the kernel's
+        # certificate reaches 1e-10).  EXP_UNWEIGHTED: stage weights 5^(k-N+1) leave the split of early
+        # charging between partitions with curvature ~1e-8 (any 1e-9-accurate solver, CLARABEL included).
+        tol_w = {bo.UNWEIGHTED: 1e-5, bo.WEIGHTED: 1e-4, bo.EXP_UNWEIGHTED: 3e-2}[cost_type]
         # (with the WEIGHTED cost an empty partition has zero weight: its w is arbitrary - the oracle
         #  returns the analytic centre, the kernel leaves the block out and returns 0)
         ks = par[0] > 0 if cost_type == bo.WEIGHTED else np.ones(P, dtype=bool)

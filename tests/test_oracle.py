@@ -145,3 +145,50 @@ def test_c_oracle_matches_numpy_oracle(ev):
         for b in range(0, B, 4):
             wo, co, _ = orc.solve_active_set(N, consts, lm[b], lr[b], gam[b])
             assert np.max(np.abs(wt[b] - wo)) <= 1e-6 * consts.w_max
+
+
+@pytest.mark.parametrize("ev", ["small", "large"])
+@pytest.mark.parametrize("N", [12, 24, 48])
+def test_c_exact_oracle_is_the_python_exact_oracle(ev, N):
+    """oracle/lompc_oracle.c::solve_exact_one is the C twin of solve_active_set (same steps, same tie rules): the
+    full-size price-loop / closed-loop fixtures are generated with it (tests/golden/gen_fullsize_golden.py)."""
+    from oracle import c_oracle
+    consts = orc.small_ev_consts() if ev == "small" else orc.large_ev_consts()
+    rng = np.random.default_rng(N)
+    B = 45
+    lm = np.zeros((B, 3 * N))
+    lr = np.zeros(B)
+    gam = consts.y_max * rng.random(B)
+    lm[:15] = consts.theta * rng.random((15, 3 * N))
+    lr[:15] = 3 * N * consts.delta * rng.random(15)
+    lm[15:30] = 0.05 * consts.theta * rng.random((15, 3 * N)) * (rng.random((15, 3 * N)) < 0.5)
+    lm[30:, :2 * N] = 0.05 * consts.theta * rng.random((15, 2 * N))
+    w, cost, iters = c_oracle.solve_lompc_exact_batch(N, consts, lm, lr, gam)
+    for b in range(B):
+        wo, co, ito = orc.solve_active_set(N, consts, lm[b], lr[b], gam[b])
+        assert np.max(np.abs(w[b] - wo)) <= 1e-14 * consts.w_max
+        assert abs(cost[b] - co) <= 1e-12 * max(1.0, abs(co))
+        assert iters[b] == ito
+    # broadcast prices (the _get_w_err case, price_solver.py:203-204)
+    w1, c1, _ = c_oracle.solve_lompc_exact_batch(N, consts, lm[3], lr[3], gam)
+    w2, c2, _ = c_oracle.solve_lompc_exact_batch(N, consts, np.tile(lm[3], (B, 1)), np.full(B, lr[3]), gam)
+    assert np.array_equal(w1, w2) and np.array_equal(c1, c2)
+
+
+def test_fast_price_oracle_equals_python_price_oracle():
+    """PriceOracle(fast=True) (QPs on the C exact oracle) walks the same loop as the pure-Python one."""
+    from oracle.price_oracle import PriceOracle
+    consts = orc.large_ev_consts()
+    N = 12
+    rng = np.random.default_rng(3)
+    y0 = 0.3 + 0.05 * rng.random(9)
+    w_ref = consts.w_max * rng.random(N) * 0.6
+    a, b = PriceOracle(N, consts, "linear-convex"), PriceOracle(N, consts, "linear-convex", fast=True)
+    for po in (a, b):
+        po.set_charge_levels(y0)
+    la, sa = a.compute_optimal_prices(w_ref, 0.0)
+    lb, sb = b.compute_optimal_prices(w_ref, 0.0)
+    assert sa["iter"] == sb["iter"] and np.max(np.abs(la - lb)) <= 1e-10 * max(1.0, np.max(np.abs(la)))
+    wa, pa = a.get_w0_price0(la[: a.r], 0.0)
+    wb, pb = b.get_w0_price0(lb[: b.r], 0.0)
+    assert np.max(np.abs(wa - wb)) <= 1e-12 and abs(pa - pb) <= 1e-10 * max(1.0, abs(pa))
