@@ -303,6 +303,9 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
     closed = None
     if args.closed_loop_stations > 0:
         closed = closed_loop_leg(args, rank, world, dev)
+    sharded = None
+    if args.sharded_iters > 0:
+        sharded = sharded_leg(args, rank, world, dev)
 
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
     if world > 1:
@@ -368,6 +371,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             "clocks": clocks,
             "saturated": sat,
             "closed_loop": closed,
+            "sharded": sharded,
         }
         if graph is None:
             line["config"]["launch"] = "direct launch (one kernel per step)"
@@ -477,6 +481,84 @@ def closed_loop_leg(args, rank, world, dev):
                       "device RNG; full size = 4096 stations x 96 steps (tools/run_fleet.py, profiles/)"}
 
 
+def sharded_leg(args, rank, world, dev):
+    """BASELINE.json configs[2]: the 65,536-EV batch (2,048 groups x 32 EVs, half small-EV and half large-EV groups,
+    N = 24, "linear-convex" prices, inputs as SURVEY.md 8d config 3, seed 3) sharded by EV index over the ranks, with
+    the aggregate-load all-reduce (the [G, N] fp64 partial sums of price_solver.py:199-210) inside the price loop.
+    STRONG scaling: the batch is fixed, every rank solves B / world EVs per iteration and all ranks run the
+    replicated group phase.  The loop is pipelined (chargingstation/sharded.py): no host synchronisation inside."""
+    import torch
+    import torch.distributed as dist
+    from chargingstation.lompc import LoMPCConstants
+    from chargingstation.price_solver import PriceSolver
+    from chargingstation.sharded import compute_optimal_prices_sharded, shard_groups
+    N, G, EVS, MAX_IT = 24, 1024, 32, args.sharded_iters
+    rng = np.random.default_rng(3)
+    out = {"metric": "sharded_price_loop_ms", "n_gpus": world, "groups": 2 * G, "evs": 2 * G * EVS, "max_iter": MAX_IT,
+           "allreduce_bytes_per_iter": G * N * 8, "per_type": {}}
+    tot_ms, tot_qp, tot_ar_ms = 0.0, 0, 0.0
+    for ev in ("small", "large"):
+        delta, theta, y_max, w_max = EV_CONSTS[ev]
+        off = (np.arange(G + 1) * EVS).astype(np.int64)
+        y0 = 0.3 + 0.2 * rng.random(off[-1])               # charging_station.py:95-100, settings.py:27-28
+        w_ref = w_max * rng.random((G, N))                  # test_price_solver.py:34
+        ps = PriceSolver(N, LoMPCConstants(delta, theta, y_max, w_max, ev), "linear-convex", device=dev.index)
+        loc_off, loc_y0, (lo, hi) = shard_groups(off, y0, rank, world)
+        call = lambda it: compute_optimal_prices_sharded(ps, loc_off, loc_y0, w_ref, np.zeros(G),  # noqa: E731
+                                                         np.zeros((G, 3 * N)), max_iter=it)
+        call(3)  # warm-up: allocations, NCCL channels
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        t0 = time.perf_counter()
+        e0.record()
+        prices, stats = call(MAX_IT)
+        e1.record()
+        torch.cuda.synchronize()
+        wall_ms = (time.perf_counter() - t0) * 1e3
+        ms = e0.elapsed_time(e1)
+        # the collective alone: the same [G, N] buffer all-reduced back to back
+        ar_ms = 0.0
+        if world > 1:
+            buf = torch.zeros((G, N), dtype=torch.float64, device=dev)
+            for _ in range(5):
+                dist.all_reduce(buf)
+            torch.cuda.synchronize()
+            a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a0.record()
+            for _ in range(50):
+                dist.all_reduce(buf)
+            a1.record()
+            torch.cuda.synchronize()
+            ar_ms = a0.elapsed_time(a1) / 50
+        t = torch.tensor([ms, wall_ms, ar_ms], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, wall_ms, ar_ms = (float(v) for v in t)
+        it = np.asarray(stats["iter"])
+        ran = int(stats["total_iters"])
+        loops = min(ran + 1, MAX_IT)  # ev-phases executed
+        qps = int(np.sum((np.minimum(it, MAX_IT - 1) + 1) * (EVS + 2)))
+        out["per_type"][ev] = {"ms": ms, "wall_ms": wall_ms, "iterations": loops, "us_per_iteration": ms * 1e3 / loops,
+                               "allreduce_us": ar_ms * 1e3, "allreduce_share": ar_ms * loops / ms if ms > 0 else 0.0,
+                               "converged_groups": int(np.sum(it < MAX_IT - 1)), "iters_mean": float(it.mean()),
+                               "qp_solves": qps, "price_checksum": float(np.sum(prices)),
+                               "local_evs": int(hi - lo)}
+        tot_ms += ms
+        tot_qp += qps
+        tot_ar_ms += ar_ms * loops
+    out["ms"] = tot_ms
+    out["qp_solves"] = tot_qp
+    out["qp_per_s"] = tot_qp / (tot_ms * 1e-3)
+    out["allreduce_share"] = tot_ar_ms / tot_ms if tot_ms > 0 else 0.0
+    out["scaling"] = "strong (fixed 65,536-EV batch)"
+    out["config"] = ("BASELINE.json configs[2] (SURVEY.md 8d config 3): 1,024 small-EV + 1,024 large-EV groups x 32 EVs, "
+                     "N=24, w_ref = w_max U(0,1), y0 = U(0.3,0.5), seed 3, EVs block-sharded by index (groups straddle "
+                     "ranks), one all-reduce of [G,N] fp64 per price iteration, loop capped at max_iter")
+    return out
+
+
 def cpu_baseline_leg(args):
     work = draw_workload(args.batch, N_HORIZON, 2)
     used = cpu_pass(work, N_HORIZON)  # warm-up
@@ -507,6 +589,8 @@ def main():
                     help="stations per GPU of the closed-loop latency leg (0 = skip; configs[3] is 4096)")
     ap.add_argument("--closed-loop-steps", type=int, default=24, help="closed-loop steps (configs[3]: 96)")
     ap.add_argument("--closed-loop-chain", default="reference", choices=["reference", "partition"])
+    ap.add_argument("--sharded-iters", type=int, default=200,
+                    help="price iterations of the configs[2] leg (65,536 EVs sharded over the ranks; 0 = skip)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

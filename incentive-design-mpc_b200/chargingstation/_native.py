@@ -75,6 +75,8 @@ SIGNATURES = {
     "price_shard_start": (C.c_int, [C.c_void_p, C.c_void_p]),
     "price_shard_ev_phase": (C.c_int, [C.c_void_p, C.c_void_p]),
     "price_shard_group_phase": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_void_p]),
+    "price_shard_group_phase_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "price_shard_poll": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
     "price_shard_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "price_w0_price0_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 7),
     "lompc_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, _dp, _dp]),

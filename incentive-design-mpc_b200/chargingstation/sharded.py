@@ -11,6 +11,14 @@ issued on the same stream as the kernels.  The convergence test, the price step
 and the gamma_sc solve then run replicated on every rank (identical inputs ->
 identical prices, no broadcast).  ``torch.distributed`` is the plumbing (NCCL on
 GPUs); the compute is the C ABI's ``price_shard_*`` phases.
+
+The loop is PIPELINED: the host never synchronises inside it.  An iteration is enqueued as
+kernels + the all-reduce on the stream; the number of still-active groups comes back through a
+pinned ring the device writes (``price_shard_group_phase_async`` / ``price_shard_poll``), and the
+host only makes sure it is never more than ``PIPELINE_DEPTH`` iterations ahead of the GPU.
+Converged groups are skipped on the device, so the few iterations enqueued beyond convergence
+are no-ops; every rank sees the same counts (the group phase is replicated), so every rank
+leaves the loop at the same iteration and the all-reduces stay matched.
 """
 from __future__ import annotations
 
@@ -21,6 +29,9 @@ import numpy as np
 from chargingstation import _native
 from chargingstation.settings import (MAX_PRICE_SOLVER_ITERATIONS,
                                       PRICE_SOLVER_TOL_TYPE)
+
+
+PIPELINE_DEPTH = 4  # iterations the host may run ahead of the device (< the 64-slot ring of the C ABI)
 
 
 def shard_bounds(B: int, rank: int, world: int) -> tuple[int, int]:
@@ -97,6 +108,17 @@ class CudaShardBackend:
         _native.raise_for(self.lib.price_shard_group_phase(self.ps._h, int(it), C.byref(n), self._stream()))
         return int(n.value)
 
+    def group_phase_async(self, it: int) -> None:
+        _native.raise_for(self.lib.price_shard_group_phase_async(self.ps._h, int(it), self._stream()))
+
+    def poll(self, it: int, wait: bool = True):
+        """Active groups after iteration ``it`` (None if not published yet and ``wait`` is False)."""
+        n = C.c_int32(0)
+        rc = self.lib.price_shard_poll(self.ps._h, int(it), 1 if wait else 0, C.byref(n))
+        if rc < 0:
+            _native.raise_for(rc)
+        return int(n.value) if rc == 1 else None
+
     def finish(self, history):
         torch = self.torch
         pre = torch.zeros((self.G,), dtype=torch.float64, device=self.dev)
@@ -113,7 +135,7 @@ class CudaShardBackend:
 
 def compute_optimal_prices_sharded(price_solver, group_off_local, y0_local, w_ref, lmbd_r, prev_prices,
                                    process_group=None, backend=None, history: bool = False,
-                                   max_iter: int = MAX_PRICE_SOLVER_ITERATIONS):
+                                   max_iter: int = MAX_PRICE_SOLVER_ITERATIONS, pipelined: bool = True):
     """``PriceSolver.compute_optimal_prices`` for G groups whose EVs are sharded over the ranks
     of ``process_group`` (None: single process, no collective).  Every rank passes the SAME
     w_ref / lmbd_r / prev_prices and its LOCAL (group_off, y0) from ``shard_groups``; every rank
@@ -130,18 +152,40 @@ def compute_optimal_prices_sharded(price_solver, group_off_local, y0_local, w_re
         dist.all_reduce(smax, op=dist.ReduceOp.MAX, group=process_group)
         dist.all_reduce(ssum, op=dist.ReduceOp.SUM, group=process_group)
         dist.all_reduce(scnt, op=dist.ReduceOp.SUM, group=process_group)
-    be.start()
-    total = 0
-    for it in range(max_iter):
-        w_sum, err_max = be.ev_phase()
-        if distributed:  # w_avg += w_i over all ranks (price_solver.py:205)
+    be.start()  # validates the REDUCED statistics: every rank raises together (price_solver.py:71)
+
+    def reduce_sums(w_sum, err_max):  # w_avg += w_i over all ranks (price_solver.py:205)
+        if distributed:
             dist.all_reduce(w_sum, op=dist.ReduceOp.SUM, group=process_group)
             if PRICE_SOLVER_TOL_TYPE == "max":
                 dist.all_reduce(err_max, op=dist.ReduceOp.MAX, group=process_group)
-        total = it
-        if be.group_phase(it) == 0:
-            break
-        total = it + 1
+
+    total = 0
+    if pipelined and hasattr(be, "group_phase_async"):
+        # no host synchronisation inside the loop: iteration `it` is enqueued while the device may still be
+        # PIPELINE_DEPTH iterations behind; the loop ends at the first iteration whose published count is 0
+        done_at = None
+        for it in range(max_iter):
+            reduce_sums(*be.ev_phase())
+            be.group_phase_async(it)
+            j = it - PIPELINE_DEPTH
+            if j >= 0 and be.poll(j, wait=True) == 0:
+                done_at = j
+                break
+        if done_at is None:  # drain the iterations still in flight
+            last = min(max_iter, it + 1)
+            for j in range(max(0, last - PIPELINE_DEPTH), last):
+                if be.poll(j, wait=True) == 0:
+                    done_at = j
+                    break
+        total = done_at if done_at is not None else max_iter
+    else:
+        for it in range(max_iter):
+            reduce_sums(*be.ev_phase())
+            total = it
+            if be.group_phase(it) == 0:
+                break
+            total = it + 1
     prices, stats = be.finish(history)
     stats["total_iters"] = total
     return prices, stats

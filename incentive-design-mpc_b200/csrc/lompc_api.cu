@@ -13,6 +13,8 @@
 
 namespace {
 
+constexpr int kRingSlots = 64;  // iterations the pinned n_active ring of the sharded price loop can hold
+
 thread_local char g_cuda_err[256] = "";
 std::atomic<int64_t> g_launches{0};
 
@@ -75,6 +77,7 @@ struct lompc_handle {
   void* pws;
   size_t pws_bytes;
   int32_t* poll;  // pinned host
+  int32_t* ring;  // pinned host ring of (tag, n_active) pairs, written by publish_active_kernel
   void* rws;      // reduction buffers of the single-GPU price loop
   size_t rws_bytes;
   PriceSession ses;
@@ -302,6 +305,7 @@ int lompc_create(int N, double delta, double theta, double y_max, double w_max, 
   h->pws = nullptr;
   h->pws_bytes = 0;
   h->poll = nullptr;
+  h->ring = nullptr;
   h->rws = nullptr;
   h->rws_bytes = 0;
   *out = h;
@@ -319,6 +323,7 @@ int lompc_destroy(lompc_t* h) {
   if (h->ws) cudaFree(h->ws);
   if (h->pws) cudaFree(h->pws);
   if (h->poll) cudaFreeHost(h->poll);
+  if (h->ring) cudaFreeHost(h->ring);
   if (h->rws) cudaFree(h->rws);
   delete h;
   return LOMPC_OK;
@@ -745,8 +750,15 @@ int price_shard_start(lompc_t* h, void* stream) {
   cudaStream_t s = static_cast<cudaStream_t>(stream);
   lompc::stats_finalize_kernel<<<nblk(S.G, 128), 128, 0, s>>>(h->cs, S.G, S.max_iter, S.stat_min, S.stat_max,
                                                              S.stat_sum, S.stat_cnt, S.y0_rng, S.gamma_sc,
-                                                             S.gamma_sm, S.skip, S.p.iters, S.nst, S.empty);
+                                                             S.gamma_sm, S.skip, S.p.iters, S.nst, S.empty, S.nact + 1);
   COUNT_LAUNCH();
+  // the one synchronising check of a solve: y0 outside [0, y_max] anywhere in the (all-reduced) statistics
+  CK(cudaMemcpyAsync(h->poll, S.nact, 8, cudaMemcpyDeviceToHost, s));
+  CK(cudaStreamSynchronize(s));
+  if (h->poll[1]) {
+    S.active = false;
+    return LOMPC_ERR_CONSTS;  // price_solver.py:71, raised by every rank
+  }
   // w_k, dual_cost = solve_lompc(lmbd_k, lmbd_r, gamma_sc)   (price_solver.py:106)
   return launch_group_solve(h, S.G, S.p.lmbd, S.p.lmbd_r, S.gamma_sc, nullptr, S.skip, nullptr, S.w_k,
                             S.dual_cost, nullptr, nullptr, nullptr, s);
@@ -800,6 +812,56 @@ int price_shard_group_phase(lompc_t* h, int it, int32_t* n_active, void* stream)
   COUNT_LAUNCH();
   CK(cudaGetLastError());
   return LOMPC_OK;
+}
+
+// price_shard_group_phase without the host round trip: enqueues the convergence test, the price step, the
+// gamma_sc solve and the bookkeeping of iteration `it` and PUBLISHES the number of still-active groups into a
+// pinned ring that price_shard_poll reads.  Converged groups are skipped on the device (every kernel tests the
+// group's flag), so iterations enqueued beyond convergence are no-ops.
+int price_shard_group_phase_async(lompc_t* h, int it, void* stream) {
+  if (!h || !h->ses.active || it < 0) return LOMPC_ERR_ARG;
+  PriceSession& S = h->ses;
+  if (S.G == 0) return LOMPC_OK;
+  CK(cudaSetDevice(h->device));
+  cudaStream_t s = static_cast<cudaStream_t>(stream);
+  if (!h->ring) {
+    CK(cudaMallocHost(&h->ring, kRingSlots * 2 * sizeof(int32_t)));
+    memset(h->ring, 0, kRingSlots * 2 * sizeof(int32_t));
+  }
+  CK(cudaMemsetAsync(S.nact, 0, 4, s));
+  {
+    int rc0 = launch_group_step(h, S.p, it, s);
+    if (rc0) return rc0;
+  }
+  lompc::publish_active_kernel<<<1, 1, 0, s>>>(S.nact, it, h->ring + 2 * (it % kRingSlots));
+  COUNT_LAUNCH();
+  int rc = launch_group_solve(h, S.G, S.p.lmbd, S.p.lmbd_r, S.gamma_sc, nullptr, S.skip, nullptr, S.w_k,
+                              S.cost_new, nullptr, nullptr, nullptr, s, S.w_k);
+  if (rc) return rc;
+  lompc::bookkeep_kernel<<<nblk(S.G, 128), 128, 0, s>>>(S.p, it);
+  COUNT_LAUNCH();
+  CK(cudaGetLastError());
+  return LOMPC_OK;
+}
+
+// Number of active groups after iteration `it` if the device has published it (returns 1), else 0 (wait == 0)
+// or spins on the pinned slot until it has (wait != 0; no synchronising CUDA call is made).  The ring holds kRingSlots
+// iterations: poll iteration `it` before enqueuing iteration it + kRingSlots.
+int price_shard_poll(lompc_t* h, int it, int wait, int32_t* n_active) {
+  if (!h || !n_active || it < 0) return LOMPC_ERR_ARG;
+  *n_active = 0;
+  if (h->ses.G == 0) return 1;
+  if (!h->ring) return 0;
+  volatile int32_t* slot = h->ring + 2 * (it % kRingSlots);
+  for (unsigned spins = 1; slot[0] != it + 1; ++spins) {
+    if (!wait) return 0;
+    if ((spins & 0xfffffu) == 0) {  // now and then: do not spin for ever on a dead context
+      const cudaError_t e = cudaPeekAtLastError();
+      if (e != cudaSuccess) return cuda_fail(e, "price_shard_poll");
+    }
+  }
+  *n_active = slot[1];
+  return 1;
 }
 
 int price_shard_finish(lompc_t* h, double* price_pre, double* price_post, double* w_k_out, void* stream) {

@@ -101,7 +101,12 @@ __global__ void group_stats_local_kernel(const Consts cs, int G, const int32_t* 
   double mn = 1e300, mx = -1e300, sum = 0.0;
   for (int b = b0; b < b1; ++b) {
     const double y = y0[b];
-    if (!(y >= 0.0 && y <= cs.y_max)) atomicExch(bad, 1);
+    // y0 outside [0, y_max] (price_solver.py:71; NaN included) is reported THROUGH the statistics: the minimum
+    // is forced below zero, so that after the caller's MIN all-reduce every rank sees it (stats_finalize_kernel)
+    if (!(y >= 0.0 && y <= cs.y_max)) {
+      atomicExch(bad, 1);
+      mn = -1e300;
+    }
     mn = fmin(mn, y);
     mx = fmax(mx, y);
     sum += y;
@@ -115,10 +120,13 @@ __global__ void stats_finalize_kernel(const Consts cs, int G, int max_iter, cons
                                       const double* __restrict__ scnt, double* __restrict__ y0_rng,
                                       double* __restrict__ gamma_sc, double* __restrict__ gamma_sm,
                                       int32_t* __restrict__ skip, int32_t* __restrict__ iters,
-                                      int32_t* __restrict__ nnqp_status, int32_t* __restrict__ empty_out) {
+                                      int32_t* __restrict__ nnqp_status, int32_t* __restrict__ empty_out,
+                                      int32_t* __restrict__ bad) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= G) return;
   const bool empty = !(scnt[g] > 0.0);
+  // the assert of price_solver.py:71 on the REDUCED statistics: every rank raises, not only the owner of the EV
+  if (!empty && !(smin[g] >= 0.0 && smax[g] <= cs.y_max)) atomicExch(bad, 1);
   empty_out[g] = empty;
   y0_rng[g] = empty ? 0.0 : (smax[g] - smin[g]) / 2;
   gamma_sc[g] = empty ? 0.0 : cs.y_max - (smax[g] + smin[g]) / 2;
@@ -136,7 +144,12 @@ __global__ void colsum_kernel(int N, int G, const int32_t* __restrict__ off, con
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)G * N) return;
   const int g = (int)(idx / N), k = (int)(idx % N);
-  if (skip && skip[g]) return;
+  if (skip && skip[g]) {
+    // a converged group's row is not read again, but a multi-GPU caller keeps all-reducing the whole buffer:
+    // a stale partial sum would be re-summed over the ranks every iteration and grow without bound
+    if (sum_only) w_avg[idx] = 0.0;
+    return;
+  }
   const int b0 = off[g], b1 = off[g + 1];
   double sum = 0.0;
   for (int b = b0; b < b1; ++b) sum += w_ev[(int64_t)b * N + k];
@@ -471,6 +484,14 @@ __global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
     p.lamdiff_phi[g] = lamdiff;
     p.dec_pred[g] = dec;
   }
+}
+
+// Publishes the number of still-active groups of iteration `it` into a slot of a pinned HOST ring (a mapped
+// store: the host polls the slot without any CUDA call); tag = it + 1 marks the slot as written.
+__global__ void publish_active_kernel(const int32_t* __restrict__ n_active, int it, volatile int32_t* slot) {
+  slot[1] = *n_active;
+  __threadfence_system();
+  slot[0] = it + 1;
 }
 
 __global__ void bookkeep_kernel(const PriceArgs p, int it) {

@@ -244,6 +244,9 @@ int64_t price_last_cycles(const lompc_t* h, int which);
  *   w_sum[G,N]               after price_shard_ev_phase : all-reduce SUM
  *   err_max[G]               after price_shard_ev_phase : all-reduce MAX ("max" tolerance type only)
  * (price_solver.py:66-77 and :199-210 are the reductions being distributed).
+ * price_shard_start validates the REDUCED statistics (the assert of price_solver.py:71), so a y0 outside
+ * [0, y_max] makes every rank return LOMPC_ERR_CONSTS together (a rank-local check would leave the others
+ * waiting in the next all-reduce).
  * price_shard_group_phase runs the convergence test, the price step and the
  * gamma_sc solve on every rank identically (replicated, deterministic) and
  * returns the number of still-active groups; stop when it is 0.              */
@@ -255,6 +258,14 @@ int price_shard_begin(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off
 int price_shard_start(lompc_t* h, void* stream);
 int price_shard_ev_phase(lompc_t* h, void* stream);
 int price_shard_group_phase(lompc_t* h, int it, int32_t* n_active, void* stream);
+/* The same phase WITHOUT the host round trip, for a loop that keeps the GPU fed: _async only enqueues (the
+ * number of still-active groups is published into a pinned ring by the device); price_shard_poll returns 1 and
+ * that number once iteration `it` has been published, 0 if not yet (wait = 0), or spins on the pinned word
+ * until it has (wait != 0) - it never makes a synchronising CUDA call.  Groups that have converged are skipped
+ * on the device, so iterations enqueued beyond convergence cost launches only.  The ring holds 64 iterations:
+ * poll iteration `it` before enqueuing iteration it + 64.                                              */
+int price_shard_group_phase_async(lompc_t* h, int it, void* stream);
+int price_shard_poll(lompc_t* h, int it, int wait, int32_t* n_active);
 int price_shard_finish(lompc_t* h, double* price_pre, double* price_post, double* w_k_out, void* stream);
 
 /* PriceSolver.get_w0_price0 (price_solver.py:272-285) for every group:

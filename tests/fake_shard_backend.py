@@ -36,6 +36,8 @@ class OracleShardBackend:
     def start(self):
         smin, smax, ssum, scnt = (t.numpy() for t in self.stats)
         G, N, c = self.G, self.N, self.consts
+        # the assert of price_solver.py:71 on the REDUCED statistics: every rank raises together
+        assert np.all((scnt <= 0) | ((smin >= 0) & (smax <= c.y_max)))
         self.cnt = scnt.copy()
         self.skip = scnt <= 0
         self.y0_rng = np.where(self.skip, 0, (smax - smin) / 2)
@@ -80,6 +82,16 @@ class OracleShardBackend:
             self.w_k[g], self.dual[g] = orc.solve_lompc(N, self.consts, self.prices[g], self.lmbd_r[g],
                                                          self.gamma_sc[g])
         return active
+
+    # the pipelined interface of CudaShardBackend: "enqueue" = run now, the count is published per iteration
+    def group_phase_async(self, it):
+        if not hasattr(self, "_published"):
+            self._published = {}
+        self._published[it] = self.group_phase(it)
+        self.async_calls = getattr(self, "async_calls", 0) + 1
+
+    def poll(self, it, wait=True):
+        return self._published.get(it)
 
     def finish(self, history):
         ora = self.ora

@@ -65,7 +65,7 @@ def _problem():
     return o, N, off, y0, w_ref
 
 
-def _worker(rank, world, port, out):
+def _worker(rank, world, port, out, pipelined=True, bad_y0=False):
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     for p in (root, os.path.join(root, "incentive-design-mpc_b200"), os.path.join(root, "tests")):
         if p not in sys.path:
@@ -73,24 +73,37 @@ def _worker(rank, world, port, out):
     from fake_shard_backend import OracleShardBackend
     dist.init_process_group("gloo", init_method=f"tcp://127.0.0.1:{port}", rank=rank, world_size=world)
     o, N, off, y0, w_ref = _problem()
+    if bad_y0:
+        y0 = y0.copy()
+        y0[-1] = o.y_max + 0.05  # owned by the LAST rank only
     loc_off, loc_y0, _ = shard_groups(off, y0, rank, world)
     G = len(off) - 1
     be = OracleShardBackend(N, o, "linear-convex")
-    prices, stats = compute_optimal_prices_sharded(None, loc_off, loc_y0, w_ref, np.zeros(G), np.zeros((G, 3 * N)),
-                                                   backend=be, max_iter=60)
-    if rank == 0:
-        out["prices"], out["iter"], out["total"] = prices, np.asarray(stats["iter"]), stats["total_iters"]
+    try:
+        prices, stats = compute_optimal_prices_sharded(None, loc_off, loc_y0, w_ref, np.zeros(G), np.zeros((G, 3 * N)),
+                                                       backend=be, max_iter=60, pipelined=pipelined)
+        if rank == 0:
+            out["prices"], out["iter"], out["total"] = prices, np.asarray(stats["iter"]), stats["total_iters"]
+            out["async_calls"] = getattr(be, "async_calls", 0)
+    except AssertionError:
+        out[f"assert_{rank}"] = True
     dist.destroy_process_group()
 
 
 @pytest.mark.timeout(300)
-def test_two_rank_gloo_price_loop_matches_single_process():
+@pytest.mark.parametrize("pipelined", [True, False])
+def test_two_rank_gloo_price_loop_matches_single_process(pipelined):
+    """Both host loops: pipelined (group_phase_async + poll, the host PIPELINE_DEPTH iterations ahead) and the
+    synchronous one; same prices, same iteration counts, and the ranks leave the loop together (the run would
+    hang in gloo otherwise)."""
     world = 2
     port = _free_port()
     with mp.Manager() as m:
         out = m.dict()
-        mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+        mp.spawn(_worker, args=(world, port, out, pipelined), nprocs=world, join=True)
         prices, iters = np.array(out["prices"]), np.array(out["iter"])
+        assert (out["async_calls"] > 0) == pipelined
+        assert out["total"] == max(iters[[0, 2, 3]])  # the loop ends when the last NON-EMPTY group has converged
     # reference: every group on its own, single process, the oracle's own loop
     o, N, off, y0, w_ref = _problem()
     for g in range(len(off) - 1):
@@ -102,3 +115,15 @@ def test_two_rank_gloo_price_loop_matches_single_process():
         lam, st = ora.compute_optimal_prices(w_ref[g], 0.0, max_iter=60)
         assert st["iter"] == iters[g]
         assert np.max(np.abs(lam - prices[g])) <= 1e-9 * max(1.0, np.max(np.abs(lam)))
+
+
+@pytest.mark.timeout(300)
+def test_bad_charge_level_on_one_rank_raises_on_every_rank():
+    """y0 > y_max (the assert of price_solver.py:71) on an EV only the last rank owns: the statistics are
+    validated AFTER their all-reduce, so both ranks raise instead of one of them hanging in the next collective."""
+    world = 2
+    port = _free_port()
+    with mp.Manager() as m:
+        out = m.dict()
+        mp.spawn(_worker, args=(world, port, out, True, True), nprocs=world, join=True)
+        assert out.get("assert_0") and out.get("assert_1")
