@@ -501,6 +501,10 @@ def sharded_leg(args, rank, world, dev):
         delta, theta, y_max, w_max = EV_CONSTS[ev]
         off = (np.arange(G + 1) * EVS).astype(np.int64)
         y0 = 0.3 + 0.2 * rng.random(off[-1])               # charging_station.py:95-100, settings.py:27-28
+        # groups = SoC partitions (charging_station.py:111-116 puts EVs of similar SoC together): sorted, so that
+        # the tolerance sqrt(N) y0_rng + eps_tol (price_solver.py:184) is tight and the groups stay active -
+        # with unsorted SoCs every group converges within 6 iterations and the leg would time its set-up
+        y0.sort()
         w_ref = w_max * rng.random((G, N))                  # test_price_solver.py:34
         ps = PriceSolver(N, LoMPCConstants(delta, theta, y_max, w_max, ev), "linear-convex", device=dev.index)
         loc_off, loc_y0, (lo, hi) = shard_groups(off, y0, rank, world)
@@ -553,9 +557,10 @@ def sharded_leg(args, rank, world, dev):
     out["qp_per_s"] = tot_qp / (tot_ms * 1e-3)
     out["allreduce_share"] = tot_ar_ms / tot_ms if tot_ms > 0 else 0.0
     out["scaling"] = "strong (fixed 65,536-EV batch)"
-    out["config"] = ("BASELINE.json configs[2] (SURVEY.md 8d config 3): 1,024 small-EV + 1,024 large-EV groups x 32 EVs, "
-                     "N=24, w_ref = w_max U(0,1), y0 = U(0.3,0.5), seed 3, EVs block-sharded by index (groups straddle "
-                     "ranks), one all-reduce of [G,N] fp64 per price iteration, loop capped at max_iter")
+    out["config"] = ("BASELINE.json configs[2] (SURVEY.md 8d config 3) as a price loop: 1,024 small-EV + 1,024 large-EV "
+                     "groups x 32 EVs, N=24, w_ref = w_max U(0,1), y0 = U(0.3,0.5) sorted into SoC partitions, seed 3, EVs "
+                     "block-sharded by index (groups straddle ranks), one all-reduce of [G,N] fp64 per price iteration, "
+                     "loop capped at max_iter")
     return out
 
 

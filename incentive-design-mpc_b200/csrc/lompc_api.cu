@@ -150,15 +150,15 @@ int launch_solve_reg_variant(const lompc_handle* h, const lompc::SolveArgs& a, c
 // Batches below this many QPs go to the warp-cooperative kernel (lompc_solve_warp.cuh) in automatic mode: one QP
 // per thread needs ~150 k QPs to fill the GPU (148 SMs x 8 warps x 32 lanes x a few waves), below that
 // its warps sit alone on their schedulers and the time-parallel sweeps win (measured crossover: DESIGN.md 4).
-constexpr int64_t kWarpKernelMaxBatch = 1 << 16;
+constexpr int64_t kWarpKernelMaxBatch = 1 << 14;
 
 template <int NSEG>
 int launch_solve(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t stream) {
   const int N = h->cs.N;
   {
-    // plain batched solves only: the group mode of the price loop (shared prices, skip mask, fused epilogues,
-    // warm starts) stays on the thread kernels
-    const bool plain = !a.group_of && !a.skip && !a.w_ref && !a.err_out && !a.w0_out && !a.price0_out && !a.w_init;
+    // plain batched solves and the group mode of the phase-split price loop (shared prices, skip mask, warm
+    // starts); the fused epilogues (error norm, first-step price) stay on the thread kernels
+    const bool plain = !a.w_ref && !a.err_out && !a.w0_out && !a.price0_out && a.w_out;
     const int spl = 3;
     const bool want = h->variant == 8 || (h->variant == 0 && a.B <= kWarpKernelMaxBatch);
     if (plain && want && lompc_detail::warp_kernel_supports(N, spl)) {

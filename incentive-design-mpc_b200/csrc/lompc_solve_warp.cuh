@@ -146,7 +146,7 @@ struct Pwl {
 // The solve of one lane group.  `li` = lane index inside the group (owns stages li*SPL .. li*SPL+SPL-1),
 // `live` = the group has a QP (a partial last warp keeps its idle groups in the shuffles).
 template <int N, int NSEG, int SPL>
-__device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a, const int64_t b, const bool live,
+__device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a, const int64_t b, const bool live_in,
                                            const int lane, int& st_out) {
   constexpr int LPQ = N / SPL;
   static_assert(N % SPL == 0 && (LPQ & (LPQ - 1)) == 0 && LPQ <= 32 && LPQ >= 1, "N = SPL * 2^m, at most 32 lanes");
@@ -161,10 +161,15 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
   LOMPC_PROF_T(t_begin);
 
   // ---- problem data: this lane's SPL stages of the three price segments (lompc.py:101-135) ----
-  const int64_t row = live ? b : 0;
+  // group mode of the price loop (price_solver.py:196-214): QP b uses the prices of row group_of[b]; rows whose
+  // group has converged are skipped; w_init = the QP's solution at the previous prices (warm start)
+  const int64_t qp = live_in ? b : 0;
+  const int64_t row = (live_in && a.group_of) ? (int64_t)a.group_of[qp] : qp;
+  const bool live = live_in && !(a.skip && a.skip[row]);
   const double* lm = a.lmbd + row * a.lmbd_stride;
   const double lr = live ? a.lmbd_r[row * a.lmbd_r_stride] : 0.0;
-  const double gam = live ? a.gamma[row] : 0.0;
+  const double gam = live ? a.gamma[qp] : 0.0;
+  const bool warm = a.w_init != nullptr;
   double W[SPL], D[SPL], G[SPL], WN[SPL];
   int CD[SPL], CDO[SPL];  // piece codes of W / of the parked iterate (see lompc_solve_reg.cuh: piece_table)
   bool neg = (gam < 0.0) || (lr < 0.0);
@@ -188,6 +193,25 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
     CDO[j] = 0;
     gmaxloc = dmax2(gmaxloc, fabs(G[j]));
     l2loc += l2;
+  }
+  if (warm && live) {
+    // feasible starting point + its piece codes by comparison (a coordinate within `band` of a breakpoint counts
+    // as sitting on it), as in lompc_solve_reg.cuh
+    const double bandw = 1e-9 * wmax;
+    const double* wi = a.w_init + qp * (int64_t)N + k0;
+#pragma unroll
+    for (int j = 0; j < SPL; ++j) {
+      const double x = dmin2(dpos(wi[j]), wmax);
+      W[j] = x;
+      int cd = 1;
+      if (NSEG > 1) {
+#pragma unroll
+        for (int i = 1; i < NSEG; ++i) cd += (x >= pw.brk[i] - bandw ? 1 : 0) + (x > pw.brk[i] + bandw ? 1 : 0);
+      }
+      if (x >= pw.brk[NSEG] - bandw) cd = 2 * NSEG;
+      if (x <= bandw) cd = 0;
+      CD[j] = cd;
+    }
   }
   // one butterfly for the three group reductions (independent chains share the shuffle latencies)
 #pragma unroll
@@ -557,7 +581,7 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
   // ================= outputs (the states of the final iterate are in off / sl) =================
   double closs = 0.0;
   if (live) {
-    double* wo = a.w_out + b * (int64_t)N + k0;
+    double* wo = a.w_out + qp * (int64_t)N + k0;
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
       const double x = W[j];
@@ -578,10 +602,10 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
     vh_lane = max(vh_lane, t2);
   }
   if (live && li == 0) {
-    if (a.cost_out) a.cost_out[b] = cs.theta * wmax * l2sum + closs;
-    if (a.status) a.status[b] = st;
-    if (a.iters) a.iters[b] = it;
-    if (a.kkt_res) a.kkt_res[b] = __hiloint2double(vh_lane, vh_lane ? -1 : 0) / gscale;
+    if (a.cost_out) a.cost_out[qp] = cs.theta * wmax * l2sum + closs;
+    if (a.status) a.status[qp] = st;
+    if (a.iters) a.iters[qp] = it;
+    if (a.kkt_res) a.kkt_res[qp] = __hiloint2double(vh_lane, vh_lane ? -1 : 0) / gscale;
   }
 #ifdef LOMPC_WARP_PROF
   prof[4] = (unsigned long long)(clock64() - t_out);
