@@ -149,8 +149,10 @@ int launch_solve_reg_variant(const lompc_handle* h, const lompc::SolveArgs& a, c
 
 // Batches below this many QPs go to the warp-cooperative kernel (lompc_solve_warp.cuh) in automatic mode: one QP
 // per thread needs ~150 k QPs to fill the GPU (148 SMs x 8 warps x 32 lanes x a few waves), below that
-// its warps sit alone on their schedulers and the time-parallel sweeps win (measured crossover: DESIGN.md 4).
-constexpr int64_t kWarpKernelMaxBatch = 1 << 14;
+// its warps sit alone on their schedulers and the time-parallel sweeps win.  Measured (tools/time_k1.py, N = 24,
+// us per launch, warp / thread kernel): 512 QPs 12.3 / 16.4 small, 16.4 / 22.5 large; 4,096: 14.3 / 16.4,
+// 18.4 / 24.6; 8,192: 20.5 / 18.4, 28.6 / 28.7; 16,384: 30.7 / 18.4, 43.0 / 30.7.
+constexpr int64_t kWarpKernelMaxBatch = 6144;
 
 template <int NSEG>
 int launch_solve(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t stream) {

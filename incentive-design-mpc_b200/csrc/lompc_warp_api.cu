@@ -89,6 +89,7 @@ struct lompc_set {
   cudaStream_t stream = nullptr;
   cudaGraphExec_t graph[2] = {nullptr, nullptr};  // [want_info]
   bool no_graph = false;
+  bool mapped = true;  // the kernel reads / writes the pinned host blocks directly (no copy engine); LOMPC_SET_MAPPED=0: staged
   unsigned long long epoch = 0;
   bool pending = false;
   // solver options / kernel choice of the handles when graph[] was captured (they are kernel arguments)
@@ -98,26 +99,31 @@ struct lompc_set {
 
 namespace {
 
-// Enqueues the kernels of one call (device blocks -> device blocks) on `s`.
-int set_launch(lompc_set* S, int want_info, cudaStream_t s) {
+// Enqueues the kernels of one call on `s`: device blocks -> device blocks, or (host_blocks) the pinned host blocks
+// themselves - they are mapped into the device's address space, so the kernel's loads ARE the host->device transfer
+// and its stores the transfer back (per-QP status into the pinned info block, reduced by the host).
+int set_launch(lompc_set* S, int want_info, cudaStream_t s, bool host_blocks = false) {
   const int N = S->N;
+  char* const in = host_blocks ? S->h_in : S->d_in;
+  char* const outb = host_blocks ? S->h_out : S->d_out;
+  char* const info_b = host_blocks ? S->h_info : S->d_info;
   const unsigned long long* epoch_src = reinterpret_cast<const unsigned long long*>(S->d_in);
-  unsigned long long* summary = reinterpret_cast<unsigned long long*>(S->d_out);
+  unsigned long long* summary = host_blocks ? nullptr : reinterpret_cast<unsigned long long*>(S->d_out);
   auto fill = [&](int i, lompc::SolveArgs& a, bool info) {
     const lompc_detail::HandleView v = lompc_detail::handle_view(S->hs[i]);
     memset(&a, 0, sizeof(a));
     a.B = S->B[i];
-    a.lmbd = reinterpret_cast<const double*>(S->d_in + S->o_lm[i]);
+    a.lmbd = reinterpret_cast<const double*>(in + S->o_lm[i]);
     a.lmbd_stride = 3 * (int64_t)N;
-    a.lmbd_r = reinterpret_cast<const double*>(S->d_in + S->o_lr[i]);
+    a.lmbd_r = reinterpret_cast<const double*>(in + S->o_lr[i]);
     a.lmbd_r_stride = 1;
-    a.gamma = reinterpret_cast<const double*>(S->d_in + S->o_ga[i]);
-    a.w_out = reinterpret_cast<double*>(S->d_out + S->o_w[i]);
-    a.cost_out = reinterpret_cast<double*>(S->d_out + S->o_c[i]);
+    a.gamma = reinterpret_cast<const double*>(in + S->o_ga[i]);
+    a.w_out = reinterpret_cast<double*>(outb + S->o_w[i]);
+    a.cost_out = reinterpret_cast<double*>(outb + S->o_c[i]);
+    if (info || host_blocks) a.status = reinterpret_cast<int32_t*>(info_b + S->o_st[i]);
     if (info) {
-      a.status = reinterpret_cast<int32_t*>(S->d_info + S->o_st[i]);
-      a.iters = reinterpret_cast<int32_t*>(S->d_info + S->o_it[i]);
-      a.kkt_res = reinterpret_cast<double*>(S->d_info + S->o_kk[i]);
+      a.iters = reinterpret_cast<int32_t*>(info_b + S->o_it[i]);
+      a.kkt_res = reinterpret_cast<double*>(info_b + S->o_kk[i]);
     }
     a.max_iter = v.max_iter;
     a.tol = v.tol;
@@ -131,6 +137,7 @@ int set_launch(lompc_set* S, int want_info, cudaStream_t s) {
     if (var >= 1 && var <= 7) forced_thread = true;
   }
   const bool warp_ok = lompc_detail::warp_kernel_supports(N, spl) && !forced_thread && S->total <= (int64_t)1 << 17;
+  if (host_blocks && !warp_ok) return LOMPC_ERR_ARG;  // (the caller falls back to the staged round trip)
   if (warp_ok) {
     lompc::WarpArgs wa;
     memset(&wa, 0, sizeof(wa));
@@ -163,7 +170,17 @@ int set_launch(lompc_set* S, int want_info, cudaStream_t s) {
   return LOMPC_OK;
 }
 
+bool set_uses_host_blocks(const lompc_set* S) {
+  if (!S->mapped || S->total > 8192 || !lompc_detail::warp_kernel_supports(S->N, 3)) return false;
+  for (int i = 0; i < S->n; ++i) {
+    const int var = lompc_detail::handle_view(S->hs[i]).variant;
+    if (var >= 1 && var <= 7) return false;
+  }
+  return true;
+}
+
 int set_enqueue_round_trip(lompc_set* S, int want_info, cudaStream_t s) {
+  if (set_uses_host_blocks(S)) return set_launch(S, want_info, s, true);
   CK(cudaMemcpyAsync(S->d_in, S->h_in, S->in_bytes, cudaMemcpyHostToDevice, s));
   int rc = set_launch(S, want_info, s);
   if (rc) return rc;
@@ -212,6 +229,8 @@ int lompc_set_create(lompc_t* const* handles, int n_handles, const int64_t* batc
   S->info_bytes = info > 0 ? info : 256;
   const char* ng = getenv("LOMPC_SET_NO_GRAPH");
   S->no_graph = ng && ng[0] == '1';
+  const char* mp = getenv("LOMPC_SET_MAPPED");
+  S->mapped = !(mp && mp[0] == '0');
 #define CKS(call)                                       \
   do {                                                  \
     cudaError_t e__ = (call);                           \
@@ -335,6 +354,19 @@ int lompc_set_wait(lompc_set_t* S) {
   S->pending = false;
   CK(cudaSetDevice(S->device));
   CK(cudaStreamSynchronize(S->stream));
+  if (set_uses_host_blocks(S)) {  // the kernel wrote the per-QP status straight into the pinned info block
+    int worst = 0;
+    for (int i = 0; i < S->n; ++i) {
+      const int32_t* st = reinterpret_cast<const int32_t*>(S->h_info + S->o_st[i]);
+      for (int64_t b = 0; b < S->B[i]; ++b) worst = st[b] > worst ? st[b] : worst;
+    }
+    switch (worst) {
+      case LOMPC_ST_OK: return LOMPC_OK;
+      case LOMPC_ST_MAXITER: return LOMPC_ERR_NOT_CONVERGED;
+      case LOMPC_ST_BAD_GAMMA: return LOMPC_ERR_GAMMA;
+      default: return LOMPC_ERR_NEGATIVE;
+    }
+  }
   const unsigned long long sum = *reinterpret_cast<const unsigned long long*>(S->h_out);
   if ((sum >> 2) != S->epoch) return LOMPC_ERR_NOT_CONVERGED;  // the launch did not report: treat as a failure
   switch ((int)(sum & 3ull)) {

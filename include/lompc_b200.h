@@ -138,7 +138,11 @@ int lompc_set_info_buffers(lompc_set_t* s, int i, int32_t** status, int32_t** it
  * (and, with want_info, the info block) back, on the set's own stream.  _async enqueues and returns;
  * lompc_set_wait synchronises and returns LOMPC_ERR_GAMMA / _NEGATIVE / _NOT_CONVERGED like
  * lompc_solve_batch_host.  lompc_set_solve_host = both.  The sequence is captured once as a CUDA graph
- * (environment LOMPC_SET_NO_GRAPH=1: three plain stream calls).                                      */
+ * (environment LOMPC_SET_NO_GRAPH=1: plain stream calls).  Sets of up to 8,192 QPs skip the copy engine
+ * altogether: the pinned host blocks are mapped into the device's address space, the kernel loads its inputs
+ * from them and stores w / cost / status into them over PCIe ("zero copy": the same bytes cross the bus, but
+ * the transfer overlaps the solves and two copy launches disappear; measured 34 us against 44 us per 1,024-QP
+ * call).  LOMPC_SET_MAPPED=0 forces the staged H2D copy -> launch -> D2H copy.                        */
 int lompc_set_solve_host_async(lompc_set_t* s, int want_info);
 int lompc_set_wait(lompc_set_t* s);
 int lompc_set_solve_host(lompc_set_t* s, int want_info);

@@ -139,8 +139,12 @@ def _make_set(N, Bs, Bl):
     return (os_, ol), (small, large), LoMPCSet([small, large], [Bs, Bl])
 
 
+@pytest.mark.parametrize("mapped", ["1", "0"])
 @pytest.mark.parametrize("N", [12, 24])
-def test_solve_set_matches_per_object_solves(N):
+def test_solve_set_matches_per_object_solves(N, mapped, monkeypatch):
+    """Both transfer modes of the host round trip: zero-copy (the kernel reads / writes the pinned host blocks) and
+    staged (H2D copy, launch, D2H copy)."""
+    monkeypatch.setenv("LOMPC_SET_MAPPED", mapped)
     (os_, ol), (small, large), sset = _make_set(N, 301, 217)
     data = []
     for i, o in enumerate((os_, ol)):
@@ -169,7 +173,9 @@ def test_solve_set_matches_per_object_solves(N):
     assert sset.h2d_bytes >= 8 * (3 * N + 2) * (301 + 217) and sset.d2h_bytes >= 8 * (N + 1) * (301 + 217)
 
 
-def test_solve_set_error_conventions_and_async():
+@pytest.mark.parametrize("mapped", ["1", "0"])
+def test_solve_set_error_conventions_and_async(mapped, monkeypatch):
+    monkeypatch.setenv("LOMPC_SET_MAPPED", mapped)
     N = 24
     (os_, ol), (small, large), sset = _make_set(N, 64, 64)
     for i, o in enumerate((os_, ol)):

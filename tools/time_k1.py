@@ -88,9 +88,10 @@ def main():
     med, mn = timed(g.replay, args.reps)
     print(json.dumps({"case": "set_dev", "N": N, "B": 2 * Bs, "us_median": med * 1e3, "us_min": mn * 1e3,
                       "MQPs": 2 * Bs / med / 1e3, "iters_max": [int(x.max()) for x in sset.iters]}), flush=True)
-    for label, env in (("graph", None), ("no_graph", "1")):
+    for label, env in (("graph", None), ("no_graph", "LOMPC_SET_NO_GRAPH"), ("mapped", "LOMPC_SET_MAPPED")):
         if env:
-            os.environ["LOMPC_SET_NO_GRAPH"] = env
+            os.environ.pop("LOMPC_SET_NO_GRAPH", None)
+            os.environ[env] = "1"
             sset2 = LoMPCSet(solvers, [Bs, Bs])
             for i in range(2):
                 sset2.lmbd[i][:], sset2.lmbd_r[i][:], sset2.gamma[i][:] = sset.lmbd[i], sset.lmbd_r[i], sset.gamma[i]
@@ -98,6 +99,7 @@ def main():
             sset2 = sset
         for _ in range(10):
             sset2.solve()
+        assert all(np.array_equal(sset2.w[i], sset.w[i]) for i in range(2)), label
         ts = []
         for _ in range(200):
             t0 = time.perf_counter()
