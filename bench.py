@@ -327,11 +327,11 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         hbm_peak = peaks.get("hbm_gbs", 6650.0)
         traffic, traffic_src = None, None
         try:  # DRAM bytes of the dominant kernel from the committed ncu --set full capture, per launch
-            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))
-            per_qp = 0.5 * (tj["small"]["bytes_per_qp"] + tj["large"]["bytes_per_qp"])
-            traffic = per_qp * (args.batch // 2)
-            traffic_src = (f"{per_qp:.0f} B/QP (dram__bytes_read+write of {tj['source']}) x {args.batch // 2} QPs per "
-                           f"launch; algorithmic {bytes_per_qp(N)} B/QP")
+            tj = json.load(open(os.path.join(ROOT, "profiles", "ncu_traffic.json")))["set_1024"]
+            if args.batch == tj["qps"]:
+                traffic = tj["bytes_per_launch"]
+                traffic_src = (f"dram__bytes_read + dram__bytes_write of one launch, {tj['source']}; algorithmic "
+                               f"{bytes_per_qp(N) * args.batch} B per launch ({tj['note']})")
         except Exception:
             pass
         h2d, d2h = sset.h2d_bytes, sset.d2h_bytes  # the packed blocks actually copied (segments 256-byte aligned)
