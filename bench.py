@@ -548,6 +548,9 @@ def sharded_leg(args, rank, world, dev):
         ran = int(stats["total_iters"])
         loops = min(ran + 1, MAX_IT)  # ev-phases executed
         qps = int(np.sum((np.minimum(it, MAX_IT - 1) + 1) * (EVS + 2)))
+        out["exchange"] = ("NVLink peer memory (CUDA IPC regions, flags, rank-ordered sums inside the group phase)"
+                           if getattr(ps, "_peer_state", None) is not None and world > 1 else
+                           ("dist.all_reduce (NCCL)" if world > 1 else "none (one rank)"))
         out["per_type"][ev] = {"ms": ms, "wall_ms": wall_ms, "iterations": loops, "us_per_iteration": ms * 1e3 / loops,
                                "allreduce_us": ar_ms * 1e3, "allreduce_share": ar_ms * loops / ms if ms > 0 else 0.0,
                                "converged_groups": int(np.sum(it < MAX_IT - 1)), "iters_mean": float(it.mean()),

@@ -77,6 +77,12 @@ SIGNATURES = {
     "price_shard_group_phase": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int32), C.c_void_p]),
     "price_shard_group_phase_async": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "price_shard_poll": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_int32)]),
+    "lompc_ipc_alloc": (C.c_int, [C.c_int, C.c_size_t, C.POINTER(C.c_void_p), C.c_void_p]),
+    "lompc_ipc_open": (C.c_int, [C.c_int, C.c_void_p, C.POINTER(C.c_void_p)]),
+    "lompc_ipc_close": (C.c_int, [C.c_int, C.c_void_p]),
+    "lompc_ipc_free": (C.c_int, [C.c_int, C.c_void_p]),
+    "price_shard_attach_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_size_t]),
+    "price_shard_uses_peers": (C.c_int, [C.c_void_p]),
     "price_shard_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "price_w0_price0_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 7),
     "lompc_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, _dp, _dp]),

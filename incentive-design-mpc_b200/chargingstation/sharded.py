@@ -51,14 +51,68 @@ def shard_groups(group_off: np.ndarray, y0: np.ndarray, rank: int, world: int):
 
 
 class CudaShardBackend:
-    """The five phases on one GPU through the C ABI (``price_shard_*``)."""
+    """The five phases on one GPU through the C ABI (``price_shard_*``).
 
-    def __init__(self, price_solver):
+    With more than one rank (one GPU per rank, NVLink peer access) the per-iteration aggregate does not go
+    through an all-reduce call at all: every rank's partial sums live in a CUDA-IPC region all ranks have mapped,
+    and the group phase adds them up in rank order straight out of the peers' memory
+    (``price_shard_attach_peers``; set ``LOMPC_SHARD_PEER=0`` to keep the ``dist.all_reduce``).  The regions are
+    set up once per PriceSolver (one ``all_gather`` of the 64-byte IPC handles) and reused."""
+
+    def __init__(self, price_solver, process_group=None):
         import torch
         self.torch = torch
         self.ps = price_solver
         self.lib = _native.load()
         self.dev = torch.device("cuda", price_solver.device)
+        self.group = process_group
+
+    def _ensure_peers(self, G: int) -> None:
+        """Collective: every rank calls it with the same G."""
+        import os
+        import torch.distributed as dist
+        torch, lib, ps = self.torch, self.lib, self.ps
+        if not (dist.is_available() and dist.is_initialized()) or os.environ.get("LOMPC_SHARD_PEER", "1") == "0":
+            return
+        world, rank = dist.get_world_size(self.group), dist.get_rank(self.group)
+        if world <= 1 or world > 8:
+            return
+        need = 1024 + 2 * G * ps.N * 8
+        st = getattr(ps, "_peer_state", None)
+        if st is not None and st["bytes"] >= need and st["world"] == world:
+            return
+        if st is not None:  # grow: detach, unmap the peers' regions, free the own one
+            _native.raise_for(lib.price_shard_attach_peers(ps._h, 0, 0, None, 0))
+            torch.cuda.synchronize(self.dev)
+            dist.barrier(self.group)
+            for r, p in enumerate(st["ptrs"]):
+                if r != rank:
+                    lib.lompc_ipc_close(ps.device, p)
+            dist.barrier(self.group)
+            lib.lompc_ipc_free(ps.device, st["ptrs"][rank])
+        nbytes = max(need, 4 << 20)
+        own = C.c_void_p()
+        handle = (C.c_ubyte * 64)()
+        _native.raise_for(lib.lompc_ipc_alloc(ps.device, nbytes, C.byref(own), handle))
+        mine = torch.tensor(list(handle), dtype=torch.uint8, device=self.dev)
+        gathered = [torch.empty_like(mine) for _ in range(world)]
+        dist.all_gather(gathered, mine, group=self.group)
+        ptrs = []
+        for r in range(world):
+            if r == rank:
+                ptrs.append(own.value)
+                continue
+            raw = (C.c_ubyte * 64)(*gathered[r].cpu().tolist())
+            p = C.c_void_p()
+            _native.raise_for(lib.lompc_ipc_open(ps.device, raw, C.byref(p)))
+            ptrs.append(p.value)
+        arr = (C.c_void_p * world)(*ptrs)
+        _native.raise_for(lib.price_shard_attach_peers(ps._h, rank, world, arr, nbytes))
+        ps._peer_state = {"bytes": nbytes, "world": world, "ptrs": ptrs}
+        dist.barrier(self.group)  # nobody raises a flag in a region that is not mapped everywhere yet
+
+    def uses_peers(self) -> bool:
+        return bool(self.lib.price_shard_uses_peers(self.ps._h))
 
     def _t(self, x, dtype=None):
         t = self.torch.from_numpy(np.ascontiguousarray(x))
@@ -72,6 +126,7 @@ class CudaShardBackend:
         N = ps.N
         G = len(group_off) - 1
         self.G, self.B = G, int(group_off[-1])
+        self._ensure_peers(G)
         f64 = dict(dtype=torch.float64, device=self.dev)
         self.off = self._t(np.asarray(group_off, dtype=np.int32))
         self.y0 = self._t(np.asarray(y0, dtype=np.float64)) if self.B > 0 else torch.zeros((1,), **f64)
@@ -143,7 +198,7 @@ def compute_optimal_prices_sharded(price_solver, group_off_local, y0_local, w_re
     import torch
     import torch.distributed as dist
 
-    be = backend if backend is not None else CudaShardBackend(price_solver)
+    be = backend if backend is not None else CudaShardBackend(price_solver, process_group)
     distributed = process_group is not None or (dist.is_available() and dist.is_initialized()
                                                 and dist.get_world_size() > 1)
     smin, smax, ssum, scnt = be.begin(group_off_local, y0_local, w_ref, lmbd_r, prev_prices, max_iter, history)
@@ -154,8 +209,10 @@ def compute_optimal_prices_sharded(price_solver, group_off_local, y0_local, w_re
         dist.all_reduce(scnt, op=dist.ReduceOp.SUM, group=process_group)
     be.start()  # validates the REDUCED statistics: every rank raises together (price_solver.py:71)
 
+    peer_exchange = bool(getattr(be, "uses_peers", lambda: False)())  # the sums travel over NVLink peer memory
+
     def reduce_sums(w_sum, err_max):  # w_avg += w_i over all ranks (price_solver.py:205)
-        if distributed:
+        if distributed and not peer_exchange:
             dist.all_reduce(w_sum, op=dist.ReduceOp.SUM, group=process_group)
             if PRICE_SOLVER_TOL_TYPE == "max":
                 dist.all_reduce(err_max, op=dist.ReduceOp.MAX, group=process_group)

@@ -52,6 +52,8 @@ struct PriceSession {  // state of one (possibly sharded) compute_optimal_prices
   unsigned char* wsb = nullptr;
   double *stat_min = nullptr, *stat_max = nullptr, *stat_sum = nullptr, *stat_cnt = nullptr;
   lompc::PriceArgs p;
+  bool peer = false;            // the aggregate is exchanged through peer memory (price_shard_attach_peers)
+  unsigned long long tag0 = 0;  // flag value of iteration 0 of this session, minus one
 };
 
 struct lompc_handle {
@@ -78,6 +80,9 @@ struct lompc_handle {
   size_t pws_bytes;
   int32_t* poll;  // pinned host
   int32_t* ring;  // pinned host ring of (tag, n_active) pairs, written by publish_active_kernel
+  lompc::PeerView peers;        // world == 0: not attached
+  size_t peer_region_bytes;
+  unsigned long long peer_sessions;
   void* rws;      // reduction buffers of the single-GPU price loop
   size_t rws_bytes;
   PriceSession ses;
@@ -160,7 +165,7 @@ int launch_solve(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t 
   {
     // plain batched solves and the group mode of the phase-split price loop (shared prices, skip mask, warm
     // starts); the fused epilogues (error norm, first-step price) stay on the thread kernels
-    const bool plain = !a.w_ref && !a.err_out && !a.w0_out && !a.price0_out && a.w_out;
+    const bool plain = !a.err_out && !a.w0_out && !a.price0_out && a.w_out;
     const int spl = 3;
     const bool want = h->variant == 8 || (h->variant == 0 && a.B <= kWarpKernelMaxBatch);
     if (plain && want && lompc_detail::warp_kernel_supports(N, spl)) {
@@ -308,6 +313,9 @@ int lompc_create(int N, double delta, double theta, double y_max, double w_max, 
   h->pws_bytes = 0;
   h->poll = nullptr;
   h->ring = nullptr;
+  memset(&h->peers, 0, sizeof(h->peers));
+  h->peer_region_bytes = 0;
+  h->peer_sessions = 0;
   h->rws = nullptr;
   h->rws_bytes = 0;
   *out = h;
@@ -740,6 +748,9 @@ int price_shard_begin(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off
     CK(cudaMemsetAsync(hist_pred, 0, (size_t)G * hist_cap * 8, s));
   }
   CK(cudaGetLastError());
+  S.peer = h->peers.world > 1 && !tol_type_max &&
+           lompc::kPeerFlagBytes + 2 * (size_t)G * N * sizeof(double) <= h->peer_region_bytes;
+  if (S.peer) S.tag0 = (++h->peer_sessions) << 20;  // every rank opens its sessions in the same order
   S.active = true;
   return LOMPC_OK;
 }
@@ -780,11 +791,21 @@ int price_shard_ev_phase(lompc_t* h, void* stream) {
                               nullptr, need_err ? S.err_ev : nullptr, nullptr, nullptr, s,
                               S.ev_passes > 0 ? S.w_ev : nullptr);
   if (rc) return rc;
-  ++S.ev_passes;
+  const int it = S.ev_passes++;
+  // the per-group column sums: into the caller's w_sum buffer (which it all-reduces), or - peer exchange - into
+  // buffer it & 1 of this rank's peer region, followed by the flag on every rank
+  double* sums = S.p.w_avg;
+  if (S.peer)
+    sums = reinterpret_cast<double*>(h->peers.region[h->peers.rank] + lompc::kPeerFlagBytes) +
+           (size_t)(it & 1) * S.G * N;
   lompc::colsum_kernel<<<nblk((int64_t)S.G * N, 128), 128, 0, s>>>(N, S.G, S.group_off, S.skip, S.w_ev,
-                                                                  need_err ? S.err_ev : nullptr, S.p.w_avg,
+                                                                  need_err ? S.err_ev : nullptr, sums,
                                                                   S.p.w_err_max, 1);
   COUNT_LAUNCH();
+  if (S.peer) {
+    lompc::peer_signal_kernel<<<1, 32, 0, s>>>(h->peers, S.tag0 + (unsigned long long)it + 1);
+    COUNT_LAUNCH();
+  }
   CK(cudaGetLastError());
   return LOMPC_OK;
 }
@@ -831,6 +852,12 @@ int price_shard_group_phase_async(lompc_t* h, int it, void* stream) {
     memset(h->ring, 0, kRingSlots * 2 * sizeof(int32_t));
   }
   CK(cudaMemsetAsync(S.nact, 0, 4, s));
+  if (S.peer) {  // the exchange: wait for every rank's partial sums of this iteration and add them in rank order
+    const int64_t cnt = (int64_t)S.G * h->cs.N;
+    lompc::peer_reduce_kernel<<<nblk(cnt, 256), 256, 0, s>>>(h->peers, S.tag0 + (unsigned long long)it + 1, it & 1, cnt,
+                                                             S.p.w_avg, S.nact + 2);
+    COUNT_LAUNCH();
+  }
   {
     int rc0 = launch_group_step(h, S.p, it, s);
     if (rc0) return rc0;
@@ -881,7 +908,72 @@ int price_shard_finish(lompc_t* h, double* price_pre, double* price_post, double
   COUNT_LAUNCH();
   if (w_k_out) CK(cudaMemcpyAsync(w_k_out, S.w_k, (size_t)S.G * N * 8, cudaMemcpyDeviceToDevice, s));
   CK(cudaGetLastError());
+  if (S.peer) {
+    CK(cudaMemcpyAsync(h->poll, S.nact, 16, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
+    if (h->poll[2]) {
+      snprintf(g_cuda_err, sizeof(g_cuda_err), "peer exchange: a rank did not deliver its partial sums within 2 s");
+      return LOMPC_ERR_CUDA;
+    }
+    return LOMPC_OK;
+  }
   CK(cudaStreamSynchronize(s));
+  return LOMPC_OK;
+}
+
+// ---- peer-memory plumbing (CUDA IPC) of the sharded price loop ----
+int lompc_ipc_alloc(int device, size_t bytes, void** dev_ptr, unsigned char* handle_out) {
+  if (!dev_ptr || !handle_out || bytes == 0) return LOMPC_ERR_ARG;
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "the ABI carries the handle as 64 bytes");
+  CK(cudaSetDevice(device));
+  CK(cudaMalloc(dev_ptr, bytes));
+  CK(cudaMemset(*dev_ptr, 0, bytes));
+  cudaIpcMemHandle_t hd;
+  CK(cudaIpcGetMemHandle(&hd, *dev_ptr));
+  memcpy(handle_out, &hd, 64);
+  return LOMPC_OK;
+}
+
+int lompc_ipc_open(int device, const unsigned char* handle, void** dev_ptr) {
+  if (!dev_ptr || !handle) return LOMPC_ERR_ARG;
+  CK(cudaSetDevice(device));
+  cudaIpcMemHandle_t hd;
+  memcpy(&hd, handle, 64);
+  CK(cudaIpcOpenMemHandle(dev_ptr, hd, cudaIpcMemLazyEnablePeerAccess));
+  return LOMPC_OK;
+}
+
+int lompc_ipc_close(int device, void* dev_ptr) {
+  if (!dev_ptr) return LOMPC_OK;
+  CK(cudaSetDevice(device));
+  CK(cudaIpcCloseMemHandle(dev_ptr));
+  return LOMPC_OK;
+}
+
+int lompc_ipc_free(int device, void* dev_ptr) {
+  if (!dev_ptr) return LOMPC_OK;
+  CK(cudaSetDevice(device));
+  CK(cudaFree(dev_ptr));
+  return LOMPC_OK;
+}
+
+int price_shard_uses_peers(const lompc_t* h) { return (h && h->ses.peer) ? 1 : 0; }
+
+int price_shard_attach_peers(lompc_t* h, int rank, int world, void* const* regions, size_t region_bytes) {
+  if (!h || world < 0 || world > lompc::kMaxPeers || (world > 0 && (!regions || rank < 0 || rank >= world)))
+    return LOMPC_ERR_ARG;
+  if (h->ses.active) return LOMPC_ERR_ARG;  // not in the middle of a session
+  memset(&h->peers, 0, sizeof(h->peers));
+  h->peer_region_bytes = 0;
+  if (world <= 1) return LOMPC_OK;
+  if (region_bytes <= lompc::kPeerFlagBytes) return LOMPC_ERR_ARG;
+  h->peers.rank = rank;
+  h->peers.world = world;
+  for (int r = 0; r < world; ++r) {
+    if (!regions[r]) return LOMPC_ERR_ARG;
+    h->peers.region[r] = static_cast<char*>(regions[r]);
+  }
+  h->peer_region_bytes = region_bytes;
   return LOMPC_OK;
 }
 

@@ -494,6 +494,74 @@ __global__ void publish_active_kernel(const int32_t* __restrict__ n_active, int 
   slot[0] = it + 1;
 }
 
+// ---- the aggregate exchange of the sharded price loop over NVLink PEER MEMORY (instead of an NCCL all-reduce) ----
+// Every rank owns a region [flags (kPeerFlagBytes) | partial sums, buffer 0 | buffer 1] that all ranks have mapped
+// (CUDA IPC).  Iteration `it`: colsum_kernel writes this rank's [G, N] partial sums into buffer it & 1 of its OWN
+// region, peer_signal_kernel then raises flag[rank] = tag in EVERY rank's region, and peer_reduce_kernel (first
+// kernel of the group phase) waits until all `world` flags of its own region carry the tag and sums the partials of
+// ranks 0, 1, ... in that fixed order straight out of the peers' memory - every rank gets the same bits, no
+// collective library call, one exchange = two tiny launches.  Double buffering + stream order make the flags enough:
+// a rank rewrites buffer b two iterations later, after the peers' flags of the iteration in between, which they
+// raise only after they have finished reading b.
+constexpr int kMaxPeers = 8;
+constexpr size_t kPeerFlagBytes = 1024;
+
+struct PeerView {
+  int rank, world;
+  char* region[kMaxPeers];
+};
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
+
+__global__ void peer_signal_kernel(const PeerView pv, unsigned long long tag) {
+  const int r = threadIdx.x;
+  if (r >= pv.world) return;
+  __threadfence_system();  // the partial sums of the preceding kernel are visible before the flag is
+  unsigned long long* flag = reinterpret_cast<unsigned long long*>(pv.region[r]) + pv.rank;
+  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(tag) : "memory");
+}
+
+__global__ void peer_reduce_kernel(const PeerView pv, unsigned long long tag, int buf, int64_t count,
+                                   double* __restrict__ out, int32_t* __restrict__ timeout_flag) {
+  __shared__ int ok;
+  if (threadIdx.x == 0) {
+    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(pv.region[pv.rank]);
+    const long long t0 = clock64();
+    int good = 1;
+    for (int r = 0; r < pv.world; ++r) {
+      while (ld_acquire_sys_u64(flags + r) < tag) {
+        if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer is gone - report instead of hanging the GPU
+          good = 0;
+          break;
+        }
+      }
+      if (!good) break;
+    }
+    if (!good) atomicExch(timeout_flag, 1);
+    ok = good;
+  }
+  __syncthreads();
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= count) return;
+  double sum = 0.0;
+  if (ok) {
+    for (int r = 0; r < pv.world; ++r) {
+      const double* part = reinterpret_cast<const double*>(pv.region[r] + kPeerFlagBytes) + (int64_t)buf * count;
+      sum += ld_relaxed_sys_f64(part + idx);
+    }
+  }
+  out[idx] = sum;
+}
+
 __global__ void bookkeep_kernel(const PriceArgs p, int it) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
   if (g >= p.G || p.skip[g]) return;

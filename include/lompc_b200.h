@@ -272,6 +272,24 @@ int price_shard_group_phase_async(lompc_t* h, int it, void* stream);
 int price_shard_poll(lompc_t* h, int it, int wait, int32_t* n_active);
 int price_shard_finish(lompc_t* h, double* price_pre, double* price_post, double* w_k_out, void* stream);
 
+/* The aggregate exchange WITHOUT a collective library call: the per-group partial sums travel over NVLink peer
+ * memory.  Every rank allocates one region with lompc_ipc_alloc (>= 1024 + 2*G*N*8 bytes; the 64-byte CUDA IPC
+ * handle is what the ranks exchange, e.g. with one all_gather at set-up), opens the other ranks' regions with
+ * lompc_ipc_open and hands the `world` device pointers (its own at index `rank`) to price_shard_attach_peers.
+ * From then on price_shard_ev_phase writes the partial sums into the rank's own region and raises a flag on every
+ * rank, and price_shard_group_phase_async starts by waiting for the flags of all ranks and adding the partials in
+ * rank order straight out of the peers' memory (bit-identical on every rank): the caller does NOT all-reduce w_sum
+ * any more ("avg" tolerance type; with "max" the session falls back to the caller's all-reduces).  A rank that
+ * does not deliver within 2 s makes price_shard_finish return LOMPC_ERR_CUDA instead of hanging the GPU.
+ * world <= 1 detaches.  One GPU per rank (kernels of different ranks wait on each other).                    */
+int lompc_ipc_alloc(int device, size_t bytes, void** dev_ptr, unsigned char* handle_out /*[64]*/);
+int lompc_ipc_open(int device, const unsigned char* handle /*[64]*/, void** dev_ptr);
+int lompc_ipc_close(int device, void* dev_ptr);
+int lompc_ipc_free(int device, void* dev_ptr);
+int price_shard_attach_peers(lompc_t* h, int rank, int world, void* const* regions, size_t region_bytes);
+/* 1 if the current / last session exchanges through peer memory (the caller then skips its all-reduce). */
+int price_shard_uses_peers(const lompc_t* h);
+
 /* PriceSolver.get_w0_price0 (price_solver.py:272-285) for every group:
  * w0[B] = first-step charge of each EV, price0[G] = mean first-step price.    */
 int price_w0_price0_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off,
