@@ -282,7 +282,8 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         e1.record()
     barrier()
     launches = lib.lompc_launch_count() - launches0 + per_replay * (args.steps if graph is not None else 0)
-    dev_ms = sum(e0.elapsed_time(e1) for e0, e1 in evs)
+    step_ms = [e0.elapsed_time(e1) for e0, e1 in evs]
+    dev_ms = sum(step_ms)
 
     # end-to-end through the public API with pinned host buffers (wall clock, copies inside)
     for _ in range(max(args.warmup, 3)):
@@ -308,7 +309,13 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
         sharded = sharded_leg(args, rank, world, dev)
 
     t = torch.tensor([dev_ms, e2e_s], dtype=torch.float64, device=dev)
+    per_rank = None
     if world > 1:
+        allt = [torch.empty_like(t) for _ in range(world)]
+        dist.all_gather(allt, t)
+        per_rank = {"ms_per_step": [float(x[0]) / args.steps for x in allt],
+                    "e2e_ms_per_step": [float(x[1]) / args.steps * 1e3 for x in allt],
+                    "step_ms_min_median_max_rank0": [float(np.min(step_ms)), float(np.median(step_ms)), float(np.max(step_ms))]}
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     dev_ms, e2e_s = float(t[0]), float(t[1])
 
@@ -376,6 +383,7 @@ def run_ours(args, rank: int, local_rank: int, world: int) -> None:
             "saturated": sat,
             "closed_loop": closed,
             "sharded": sharded,
+            "per_rank": per_rank,
         }
         if graph is None:
             line["config"]["launch"] = "direct launch (one kernel per step)"

@@ -134,11 +134,10 @@ int launch_solve_reg(const lompc_handle* h, const lompc::SolveArgs& a, cudaStrea
 template <int N, int NSEG>
 int launch_solve_reg_variant(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t stream) {
   switch (h->variant) {
-    case 2: return launch_solve_reg<N, NSEG, 64, 4, false>(h, a, stream);
-    case 3: return launch_solve_reg<N, NSEG, 128, 3, true>(h, a, stream);
+    // (the other shapes of round 1's sweep - 64x4 with g in shared memory, 128x3, 64x5, 128x2 - lost everywhere and
+    // are no longer compiled; their numbers are kept)
+    case 2: case 3: case 5: case 6: return LOMPC_ERR_ARG;
     case 4: return launch_solve_reg<N, NSEG, 64, 4, true>(h, a, stream);
-    case 5: return launch_solve_reg<N, NSEG, 64, 5, true>(h, a, stream);
-    case 6: return launch_solve_reg<N, NSEG, 128, 2, true>(h, a, stream);
     case 7: return launch_solve_reg<N, NSEG, 256, 1, true>(h, a, stream);
     default:
       // measured on B200 (tools/sweep_variants.sh, r1j): W, d AND g in registers (255 registers, no spills; KK,
@@ -157,7 +156,12 @@ int launch_solve_reg_variant(const lompc_handle* h, const lompc::SolveArgs& a, c
 // its warps sit alone on their schedulers and the time-parallel sweeps win.  Measured (tools/time_k1.py, N = 24,
 // us per launch, warp / thread kernel): 512 QPs 12.3 / 16.4 small, 16.4 / 22.5 large; 4,096: 14.3 / 16.4,
 // 18.4 / 24.6; 8,192: 20.5 / 18.4, 28.6 / 28.7; 16,384: 30.7 / 18.4, 43.0 / 30.7.
-constexpr int64_t kWarpKernelMaxBatch = 6144;
+// N = 12: 4,096 QPs 10.2 / 10.2 (small), 16,384: 16.4 / 12.3.  N = 48 and 96 have no register kernel: the warp kernel
+// beats the any-N shared-memory kernel at every batch size measured (16,384 QPs, small EV: 57 vs 92 us at N = 48,
+// 119 vs 457 us at N = 96; 65,536: 197 vs 231, 430 vs 1,584), so it takes all of them.
+inline int64_t warp_kernel_max_batch(int N) {
+  return N == 12 ? 4096 : (N == 24 ? 6144 : INT64_MAX);
+}
 
 template <int NSEG>
 int launch_solve(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t stream) {
@@ -167,7 +171,7 @@ int launch_solve(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t 
     // starts); the fused epilogues (error norm, first-step price) stay on the thread kernels
     const bool plain = !a.err_out && !a.w0_out && !a.price0_out && a.w_out;
     const int spl = 3;
-    const bool want = h->variant == 8 || (h->variant == 0 && a.B <= kWarpKernelMaxBatch);
+    const bool want = h->variant == 8 || (h->variant == 0 && a.B <= warp_kernel_max_batch(N));
     if (plain && want && lompc_detail::warp_kernel_supports(N, spl)) {
       lompc::WarpArgs wa;
       memset(&wa, 0, sizeof(wa));
@@ -349,7 +353,7 @@ int lompc_set_options(lompc_t* h, int max_iter, double tol) {
 }
 
 int lompc_set_kernel_variant(lompc_t* h, int variant) {
-  if (!h || variant < 0 || variant > 8) return LOMPC_ERR_ARG;
+  if (!h || variant < 0 || variant > 8 || variant == 2 || variant == 3 || variant == 5 || variant == 6) return LOMPC_ERR_ARG;
   h->variant = variant;
   return LOMPC_OK;
 }

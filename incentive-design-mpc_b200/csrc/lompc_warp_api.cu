@@ -136,7 +136,9 @@ int set_launch(lompc_set* S, int want_info, cudaStream_t s, bool host_blocks = f
     const int var = lompc_detail::handle_view(S->hs[i]).variant;
     if (var >= 1 && var <= 7) forced_thread = true;
   }
-  const bool warp_ok = lompc_detail::warp_kernel_supports(N, spl) && !forced_thread && S->total <= (int64_t)1 << 17;
+  // one warp-kernel launch for all segments while that beats one thread-kernel launch per segment
+  const int64_t warp_limit = (N == 12 || N == 24) ? 16384 : INT64_MAX;
+  const bool warp_ok = lompc_detail::warp_kernel_supports(N, spl) && !forced_thread && S->total <= warp_limit;
   if (host_blocks && !warp_ok) return LOMPC_ERR_ARG;  // (the caller falls back to the staged round trip)
   if (warp_ok) {
     lompc::WarpArgs wa;

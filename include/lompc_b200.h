@@ -66,9 +66,8 @@ int lompc_set_options(lompc_t* h, int max_iter, double tol);
 
 /* Kernel choice: 0 = automatic (register-resident kernel for N = 12, 24 - 64 threads x 4 CTAs per SM; large EV
  * on grids that fill the GPU: one 256-thread CTA per SM - and the any-N shared-memory kernel otherwise),
- * 1 = always the any-N kernel, 2..7 = one register-kernel shape regardless of the batch size (threads x CTAs
- * per SM, linear term g in shared memory / registers): 2 = 64x4 smem, 3 = 128x3 regs, 4 = 64x4 regs,
- * 5 = 64x5 regs, 6 = 128x2 regs, 7 = 256x1 regs (tools/sweep_variants.sh);
+ * 1 = always the any-N kernel, 4 / 7 = one register-kernel shape regardless of the batch size (4 = 64 threads x
+ * 4 CTAs per SM, 7 = 256 x 1; the other shapes of round 1's sweep are no longer compiled: LOMPC_ERR_ARG);
  * 8 = the warp-cooperative latency kernel (one QP per group of N/3 lanes, time-parallel sweeps; N = 12, 24,
  * 48, 96), which automatic mode picks for batches too small to fill the GPU with one QP per thread. */
 int lompc_set_kernel_variant(lompc_t* h, int variant);

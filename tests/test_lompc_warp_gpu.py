@@ -200,7 +200,7 @@ def test_solve_set_error_conventions_and_async(mapped, monkeypatch):
 
 
 def test_solve_set_large_batches_take_the_thread_kernels():
-    """Beyond 2^17 QPs the set launches one one-QP-per-thread kernel per segment and reduces the status
+    """Beyond 16,384 QPs (N = 12, 24) the set launches one one-QP-per-thread kernel per segment and reduces the status
     on the device; results equal the per-object path."""
     N = 24
     (os_, ol), (small, large), sset = _make_set(N, 70000, 70000)
