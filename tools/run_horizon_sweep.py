@@ -21,8 +21,8 @@ dev = torch.device("cuda:0")
 B = 8192
 for N in (12, 24, 48, 96):
     rng = np.random.default_rng(5)
-    out = {"N": N, "batch": 2 * B, "kernel": "register-resident (lompc_solve_reg_kernel)" if N in (12, 24)
-           else "any-N shared-memory (lompc_solve_kernel)"}
+    out = {"N": N, "batch": 2 * B, "kernel": "register-resident, one QP per thread (lompc_solve_reg_kernel)" if N in (12, 24)
+           else "warp-cooperative, one QP per N/3 lanes (lompc_solve_warp_kernel)"}
     tot_ms = 0.0
     for ev in ("small", "large"):
         delta, theta, y_max, w_max = EV_CONSTS[ev]
