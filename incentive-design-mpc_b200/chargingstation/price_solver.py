@@ -136,6 +136,15 @@ class PriceSolver:
         }
         return lmbd_k, solver_stats
 
+    def set_loop_mode(self, mode: int = 0) -> None:
+        """Kernel behind ``compute_optimal_prices`` (include/lompc_b200.h: price_set_loop_mode): 0 automatic,
+        1 phase-split loop, 2 parametric one-warp-per-group loop (EVs between two pivots with the same active
+        set are interpolated), 3 thread-per-EV loop."""
+        _native.raise_for(self._lib.price_set_loop_mode(self._h, int(mode)))
+
+    def last_pivot_overflows(self) -> int:
+        return int(self._lib.price_last_cycles(self._h, 5))
+
     def get_gamma_sc(self) -> float:
         return self.gamma_sc
 

@@ -10,9 +10,11 @@
 #include "lompc_solve_reg.cuh"
 #include "lompc_price.cuh"
 #include "lompc_price_fused.cuh"
+#include "lompc_price_warp.cuh"
 
 namespace {
 
+constexpr bool kParametricLoopByDefault = true;  // parity: tests/test_fullsize_gpu.py, tools/compare_loop_modes.py; timing: DESIGN.md 4
 constexpr int kRingSlots = 64;  // iterations the pinned n_active ring of the sharded price loop can hold
 
 thread_local char g_cuda_err[256] = "";
@@ -73,6 +75,7 @@ struct lompc_handle {
   // grow-only device workspace of the price loop + pinned poll word
   int variant;  // 0 auto, 1 = any-N shared-memory kernel, 2.. = register-kernel variants
   int loop_mode;  // price loop: 0 auto (fused one-CTA-per-group kernel when compiled for N), 1 = phase-split host loop
+  int last_pivot_overflows;           // groups of the last parametric loop whose pivot pool overflowed (expected 0)
   unsigned long long last_qp_solves;  // LoMPC QPs solved by the last fused price loop
   unsigned long long last_cycles[5];  // its SM cycles in the LoMPC passes / the price steps (summed over groups),
                                       // K1 iterations summed over its solves, warp passes with no K1 iteration, warp passes
@@ -312,6 +315,7 @@ int lompc_create(int N, double delta, double theta, double y_max, double w_max, 
   h->variant = 0;
   h->loop_mode = 0;
   h->last_qp_solves = 0;
+  h->last_pivot_overflows = 0;
   for (auto& c : h->last_cycles) c = 0;
   h->pws = nullptr;
   h->pws_bytes = 0;
@@ -359,7 +363,7 @@ int lompc_set_kernel_variant(lompc_t* h, int variant) {
 }
 
 int price_set_loop_mode(lompc_t* h, int mode) {
-  if (!h || mode < 0 || mode > 1) return LOMPC_ERR_ARG;
+  if (!h || mode < 0 || mode > 3) return LOMPC_ERR_ARG;
   h->loop_mode = mode;
   return LOMPC_OK;
 }
@@ -367,6 +371,7 @@ int price_set_loop_mode(lompc_t* h, int mode) {
 int64_t price_last_qp_solves(const lompc_t* h) { return h ? (int64_t)h->last_qp_solves : 0; }
 
 int64_t price_last_cycles(const lompc_t* h, int which) {
+  if (h && which == 5) return h->last_pivot_overflows;
   return (h && which >= 0 && which < 5) ? (int64_t)h->last_cycles[which] : 0;
 }
 
@@ -510,7 +515,7 @@ struct Carver {  // carves aligned sub-buffers out of one allocation
 };
 
 int ensure_pws(lompc_handle* h, size_t bytes) {
-  if (!h->poll) CK(cudaMallocHost(&h->poll, 64));
+  if (!h->poll) CK(cudaMallocHost(&h->poll, 128));
   if (h->pws_bytes >= bytes) return LOMPC_OK;
   if (h->pws) CK(cudaFree(h->pws));
   h->pws = nullptr;
@@ -1005,9 +1010,30 @@ int launch_fused(lompc_handle* h, const lompc::FusedArgs& a, cudaStream_t s) {
   return LOMPC_OK;
 }
 
+// The parametric loop (lompc_price_warp.cuh): one warp per group / per station.
+template <int N>
+int launch_fused_warp(lompc_handle* h, const lompc::FusedArgs& a, cudaStream_t s) {
+  constexpr size_t smem = lompc::WarpLoopSmem<N>::bytes;
+  static_assert(smem <= 48 * 1024, "no shared-memory opt-in needed");
+  if (a.chain_P > 0)
+    lompc::price_station_chain_warp_kernel<N><<<(unsigned)a.chain_S, 32, smem, s>>>(h->cs, a);
+  else
+    lompc::price_group_warp_kernel<N><<<(unsigned)a.G, 32, smem, s>>>(h->cs, a);
+  COUNT_LAUNCH();
+  CK(cudaGetLastError());
+  return LOMPC_OK;
+}
+
 // compute_optimal_prices for whole groups resident on this GPU: one CTA per group, no host loop.
 int price_solve_fused(lompc_handle* h, const lompc::FusedArgs& a, cudaStream_t s) {
   const int N = h->cs.N;
+  // loop mode 2 = the parametric one-warp-per-group loop ("avg" tolerance type), 3 = the thread-per-EV loop;
+  // 0 = automatic
+  const bool parametric = !a.tol_type_max && (h->loop_mode == 2 || (h->loop_mode == 0 && kParametricLoopByDefault));
+  if (parametric) {
+    if (N == 24) return launch_fused_warp<24>(h, a, s);
+    if (N == 12) return launch_fused_warp<12>(h, a, s);
+  }
   if (h->cs.large) {
     if (N == 24) return launch_fused<24, 4, 64, 4, true>(h, a, s);
     if (N == 12) return launch_fused<12, 4, 64, 4, true>(h, a, s);
@@ -1029,10 +1055,10 @@ int price_solve_fused_entry(lompc_handle* h, int32_t G, int64_t B, const int32_t
   {
     if ((r != 2 * h->cs.N && r != 3 * h->cs.N) || max_iter < 1) return LOMPC_ERR_ARG;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    int rc = ensure_pws(h, 256 + (size_t)(B + G) * h->cs.N * sizeof(double));
+    int rc = ensure_pws(h, 256 + ((size_t)(B + G) * h->cs.N + 2 * (size_t)G + 8) * sizeof(double));
     if (rc) return rc;
     int32_t* flags = static_cast<int32_t*>(h->pws);
-    CK(cudaMemsetAsync(flags, 0, 64, s));
+    CK(cudaMemsetAsync(flags, 0, 128, s));
     const bool hist = hist_ac && hist_pred && hist_cap > 0;
     if (hist) {
       CK(cudaMemsetAsync(hist_ac, 0, (size_t)G * hist_cap * 8, s));
@@ -1051,8 +1077,9 @@ int price_solve_fused_entry(lompc_handle* h, int32_t G, int64_t B, const int32_t
     a.compact_step = (chain_P > 0 ? chain_S : G) >= 2 * 148 * 4;  // CTAs of the launch vs. 2 resident waves
     rc = price_solve_fused(h, a, s);
     if (rc) return rc;
-    CK(cudaMemcpyAsync(h->poll, flags, 64, cudaMemcpyDeviceToHost, s));
+    CK(cudaMemcpyAsync(h->poll, flags, 128, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
+    h->last_pivot_overflows = h->poll[16];
     if (total_iters) *total_iters = h->poll[2];
     h->last_qp_solves = *reinterpret_cast<unsigned long long*>(h->poll + 4);
     h->last_cycles[0] = *reinterpret_cast<unsigned long long*>(h->poll + 6);

@@ -42,7 +42,8 @@ struct FusedArgs {
   int hist_cap;
   int32_t* flags;            // [0] += groups whose NNQP hit its iteration cap, [1] = some y0 outside [0, y_max],
                              // [2] = max over groups of the LoMPC passes run (loop length of the slowest group),
-                             // [3] += LoMPC solves that ended with a status other than OK
+                             // [3] += LoMPC solves that ended with a status other than OK,
+                             // [16] += groups whose pivot pool overflowed (parametric loop, lompc_price_warp.cuh)
   double* w_scratch;         // [B + G, N] LoMPC iterates of groups with more than T - 1 EVs (rows b0 + i; the
                              // virtual EV of group g in row B + g); smaller groups keep them in registers
   int64_t B;

@@ -143,11 +143,27 @@ struct Pwl {
   }
 };
 
+// What one lane group solves: pointers may be global or shared memory (the fused price loop keeps prices, warm
+// starts and solutions in shared memory).
+struct WarpProblem {
+  const double* lm;      // [3N] prices
+  double lr, gam;        // lmbd_r, gamma
+  const double* w_init;  // [N] feasible starting point (the solution at the previous prices) or NULL: start at 0
+  double* w_out;         // [N]
+  double* cost_out;      // scalars of this QP, each may be NULL
+  int32_t* status;
+  int32_t* iters;
+  double* kkt_res;
+  unsigned char* codes_out;  // [N] piece codes of the solution (see lompc_solve_reg.cuh: piece_table) or NULL
+  double tol;
+  int max_iter;
+};
+
 // The solve of one lane group.  `li` = lane index inside the group (owns stages li*SPL .. li*SPL+SPL-1),
-// `live` = the group has a QP (a partial last warp keeps its idle groups in the shuffles).
+// `live` = the group has a QP (idle groups stay in the shuffles of their warp).
 template <int N, int NSEG, int SPL>
-__device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a, const int64_t b, const bool live_in,
-                                           const int lane, int& st_out) {
+__device__ __forceinline__ void solve_warp_core(const Consts& cs, const WarpProblem& P, const bool live, const int lane,
+                                                int& st_out) {
   constexpr int LPQ = N / SPL;
   static_assert(N % SPL == 0 && (LPQ & (LPQ - 1)) == 0 && LPQ <= 32 && LPQ >= 1, "N = SPL * 2^m, at most 32 lanes");
   static_assert(NSEG == 1 || NSEG == 4, "small EV (one piece) or the large-EV pwl (four)");
@@ -161,15 +177,10 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
   LOMPC_PROF_T(t_begin);
 
   // ---- problem data: this lane's SPL stages of the three price segments (lompc.py:101-135) ----
-  // group mode of the price loop (price_solver.py:196-214): QP b uses the prices of row group_of[b]; rows whose
-  // group has converged are skipped; w_init = the QP's solution at the previous prices (warm start)
-  const int64_t qp = live_in ? b : 0;
-  const int64_t row = (live_in && a.group_of) ? (int64_t)a.group_of[qp] : qp;
-  const bool live = live_in && !(a.skip && a.skip[row]);
-  const double* lm = a.lmbd + row * a.lmbd_stride;
-  const double lr = live ? a.lmbd_r[row * a.lmbd_r_stride] : 0.0;
-  const double gam = live ? a.gamma[qp] : 0.0;
-  const bool warm = a.w_init != nullptr;
+  const double* lm = P.lm;
+  const double lr = live ? P.lr : 0.0;
+  const double gam = live ? P.gam : 0.0;
+  const bool warm = P.w_init != nullptr;
   double W[SPL], D[SPL], G[SPL], WN[SPL];
   int CD[SPL], CDO[SPL];  // piece codes of W / of the parked iterate (see lompc_solve_reg.cuh: piece_table)
   bool neg = (gam < 0.0) || (lr < 0.0);
@@ -198,7 +209,7 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
     // feasible starting point + its piece codes by comparison (a coordinate within `band` of a breakpoint counts
     // as sitting on it), as in lompc_solve_reg.cuh
     const double bandw = 1e-9 * wmax;
-    const double* wi = a.w_init + qp * (int64_t)N + k0;
+    const double* wi = P.w_init + k0;
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
       const double x = dmin2(dpos(wi[j]), wmax);
@@ -228,7 +239,7 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
   if (grp_any<LPQ>(neg, lane)) st = LOMPC_ST_NEGATIVE;
   if (gam > cs.y_max) st = LOMPC_ST_BAD_GAMMA;
   const double gscale = fmax(1.0, gmax + c * N * cs.y_max);
-  const double tq = a.tol * gscale;
+  const double tq = P.tol * gscale;
   const int tqh = __double2hiint(tq);
   const double cg = c * gam;
   const double band = 1e-9 * wmax;
@@ -314,7 +325,7 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
       if (__any_sync(kFullMask, safeg && !done && mu > 0.0)) scan_states(texc);
     }
     pending = false;
-    if (it >= a.max_iter) done = true;
+    if (it >= P.max_iter) done = true;
 
     // costate, gradient, KKT test; decides binding / the working piece of every stage
     bool binding[SPL];
@@ -581,12 +592,13 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
   // ================= outputs (the states of the final iterate are in off / sl) =================
   double closs = 0.0;
   if (live) {
-    double* wo = a.w_out + qp * (int64_t)N + k0;
+    double* wo = P.w_out + k0;
 #pragma unroll
     for (int j = 0; j < SPL; ++j) {
       const double x = W[j];
       const double s = off + sl[j];
       wo[j] = x;
+      if (P.codes_out) P.codes_out[k0 + j] = (unsigned char)CD[j];
       closs += x * fma(0.5 * D[j], x, G[j]) + 0.5 * c * s * (s - 2.0 * gam);
       if (NSEG > 1) {
 #pragma unroll
@@ -602,16 +614,41 @@ __device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a,
     vh_lane = max(vh_lane, t2);
   }
   if (live && li == 0) {
-    if (a.cost_out) a.cost_out[qp] = cs.theta * wmax * l2sum + closs;
-    if (a.status) a.status[qp] = st;
-    if (a.iters) a.iters[qp] = it;
-    if (a.kkt_res) a.kkt_res[qp] = __hiloint2double(vh_lane, vh_lane ? -1 : 0) / gscale;
+    if (P.cost_out) *P.cost_out = cs.theta * wmax * l2sum + closs;
+    if (P.status) *P.status = st;
+    if (P.iters) *P.iters = it;
+    if (P.kkt_res) *P.kkt_res = __hiloint2double(vh_lane, vh_lane ? -1 : 0) / gscale;
   }
 #ifdef LOMPC_WARP_PROF
   prof[4] = (unsigned long long)(clock64() - t_out);
   if (lane == 0)
     for (int i = 0; i < 8; ++i) atomicAdd(&g_warp_prof[i], prof[i]);
 #endif
+}
+
+// The batched entry: QP b of a SolveArgs batch.  Group mode of the price loop (price_solver.py:196-214): QP b uses
+// the prices of row group_of[b]; rows whose group has converged are skipped; w_init = the QP's solution at the
+// previous prices (warm start).
+template <int N, int NSEG, int SPL>
+__device__ __forceinline__ void solve_warp(const Consts& cs, const SolveArgs& a, const int64_t b, const bool live_in,
+                                           const int lane, int& st_out) {
+  const int64_t qp = live_in ? b : 0;
+  const int64_t row = (live_in && a.group_of) ? (int64_t)a.group_of[qp] : qp;
+  const bool live = live_in && !(a.skip && a.skip[row]);
+  WarpProblem P;
+  P.lm = a.lmbd + row * a.lmbd_stride;
+  P.lr = live ? a.lmbd_r[row * a.lmbd_r_stride] : 0.0;
+  P.gam = live ? a.gamma[qp] : 0.0;
+  P.w_init = a.w_init ? a.w_init + qp * (int64_t)N : nullptr;
+  P.w_out = a.w_out + qp * (int64_t)N;
+  P.cost_out = a.cost_out ? a.cost_out + qp : nullptr;
+  P.status = a.status ? a.status + qp : nullptr;
+  P.iters = a.iters ? a.iters + qp : nullptr;
+  P.kkt_res = a.kkt_res ? a.kkt_res + qp : nullptr;
+  P.codes_out = nullptr;
+  P.tol = a.tol;
+  P.max_iter = a.max_iter;
+  solve_warp_core<N, NSEG, SPL>(cs, P, live, lane, st_out);
 }
 
 // One warp = 32 / LPQ QPs of one segment, ONE warp per CTA: the warp index is blockIdx.x, so the segment, its EV

@@ -230,10 +230,14 @@ int price_solve_chain_dev(lompc_t* h, int32_t S, int32_t P, int64_t B, const int
                           double* price_pre, double* price_post, const int32_t* station_order,
                           int32_t* max_group_iters, void* stream);
 
-/* price_solve_dev runs, for the compiled horizons (N = 12, 24), ONE fused kernel with one
- * CTA per group that iterates its group to convergence on the device (mode 0, default);
- * mode 1 forces the phase-split loop below (any N; one host poll per iteration).  Both give
- * bit-identical prices.  price_last_qp_solves = LoMPC QPs solved by the last fused call.  */
+/* price_solve_dev / price_solve_chain_dev run, for the compiled horizons (N = 12, 24), ONE kernel that iterates
+ * every group to convergence on the device.  Loop modes: 0 = automatic; 1 = the phase-split loop below (any N; the
+ * path a multi-GPU caller drives); 2 = the PARAMETRIC loop, one warp per group: the EVs of a group differ only in
+ * gamma and the QP's solution is piecewise affine in it, so only the extreme EVs, the virtual EV (gamma_sc) and the
+ * EVs that bracket a change of active set are solved and the rest is interpolated ("avg"
+ * tolerance type, price_solver.py:196-214); 3 = the thread-per-EV loop, one CTA per group.  All give the same
+ * iteration counts and prices up to rounding.  price_last_qp_solves = LoMPC QPs solved by the last fused call;
+ * price_last_cycles(h, 5) = groups of the last parametric call whose pivot pool overflowed (0 in every run so far). */
 int price_set_loop_mode(lompc_t* h, int mode);
 int64_t price_last_qp_solves(const lompc_t* h);
 /* SM cycles of the last fused call summed over groups: which = 0 LoMPC passes, 1 price steps. */

@@ -31,9 +31,10 @@ def _lompc_consts(ev):
     return o, LoMPCConstants(o.delta, o.theta, o.y_max, o.w_max, o.ev_type)
 
 
+@pytest.mark.parametrize("loop_mode", [3, 2], ids=["thread-per-EV", "parametric"])
 @pytest.mark.parametrize("ev", ["small", "large"])
 @pytest.mark.parametrize("price_type,lmbd_r", [("linear-convex", 0), ("linear", 0), ("linear-convex", 24)])
-def test_price_loop_n24_against_golden(ev, price_type, lmbd_r):
+def test_price_loop_n24_against_golden(ev, price_type, lmbd_r, loop_mode):
     """compute_optimal_prices (price_solver.py:79-174) at N = 24, three groups of 70 EVs chained through
     one PriceSolver (prev_prices warm start, :103-104,166): iteration counts equal to the oracle's, prices to 1e-7."""
     from chargingstation import settings
@@ -44,6 +45,7 @@ def test_price_loop_n24_against_golden(ev, price_type, lmbd_r):
     o, c = _lompc_consts(ev)
     N = 24
     ps = PriceSolver(N, c, price_type)
+    ps.set_loop_mode(loop_mode)
     for g in range(3):
         ps.set_charge_levels(z[key + "_y0"][g])
         lam, st = ps.compute_optimal_prices(z[key + "_w_ref"][g], float(lmbd_r))
@@ -55,6 +57,7 @@ def test_price_loop_n24_against_golden(ev, price_type, lmbd_r):
         n = st["iter"]
         assert np.allclose(st["dual_cost_decrease_actual"], z[key + "_dec_actual"][g][:n], rtol=1e-5, atol=1e-7)
         assert np.allclose(st["dual_cost_decrease_predicted"], z[key + "_dec_predicted"][g][:n], rtol=1e-5, atol=1e-7)
+        assert ps.last_pivot_overflows() == 0
         w0, p0 = ps.get_w0_price0(lam[: ps.r], float(lmbd_r))
         assert np.max(np.abs(w0 - z[key + "_w0"][g])) <= 1e-8 * o.w_max
         assert abs(p0 - z[key + "_price0"][g]) <= 1e-7 * max(1.0, abs(z[key + "_price0"][g]))
@@ -88,8 +91,9 @@ def _chain_inputs(z, name, k):
     return steps, S, P, N_lo, off, np.concatenate(y_sorted), w_ref, prev
 
 
+@pytest.mark.parametrize("loop_mode", [3, 2], ids=["thread-per-EV", "parametric"])
 @pytest.mark.parametrize("name", ["n24_unw", "cfg0_unw", "cfg0_exp"])
-def test_chain_kernel_fullsize_teacher_forced(name):
+def test_chain_kernel_fullsize_teacher_forced(name, loop_mode):
     """price_solve_chain_dev (the fleet's price loop; charging_station.py:265-305 for every station) on the
     oracle's recorded steps: per (step, EV type, partition) the iteration count equals the oracle's -
     including the group that runs into the cap of 1000 iterations (cfg0_exp, step 18) - and the prices agree."""
@@ -104,6 +108,7 @@ def test_chain_kernel_fullsize_teacher_forced(name):
         steps, S, P, N, off, y0, w_ref, prev = _chain_inputs(z, name, k)
         o, c = _lompc_consts(k)
         ps = PriceSolver(N, c, "linear-convex")
+        ps.set_loop_mode(loop_mode)
         G = P * S
         t = lambda a, dt=None: torch.from_numpy(np.ascontiguousarray(a)).to(dev)  # noqa: E731
         d_off, d_y0, d_wref, d_prev = t(off), t(y0), t(w_ref), t(prev)
@@ -117,6 +122,7 @@ def test_chain_kernel_fullsize_teacher_forced(name):
                                        d_prices.data_ptr(), d_iters.data_ptr(), d_pre.data_ptr(), d_post.data_ptr(), None,
                                        C.byref(mx), torch.cuda.current_stream().cuda_stream)
         _native.raise_for(rc)
+        assert ps.last_pivot_overflows() == 0
         iters = d_iters.cpu().numpy().reshape(P, S)
         prices = d_prices.cpu().numpy().reshape(P, S, 3 * N)
         capped = 0

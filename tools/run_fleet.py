@@ -57,6 +57,7 @@ def main():
     ap.add_argument("--chain", default="reference")
     ap.add_argument("--max-price-iter", type=int, default=1000)
     ap.add_argument("--profile", action="store_true", help="CUDA-event timing of the phases of every step")
+    ap.add_argument("--loop-mode", type=int, default=0, help="price_set_loop_mode: 0 auto, 2 parametric, 3 thread-per-EV")
     args = ap.parse_args()
     import torch
     from chargingstation.fleet import ChargingStationFleet
@@ -65,6 +66,8 @@ def main():
     fleet = ChargingStationFleet(consts, args.stations, demand=demand, seed=4, rng="device", chain=args.chain,
                                  max_price_iter=args.max_price_iter)
     fleet.profile = args.profile
+    for k in ("s", "l"):
+        fleet.solver[k].set_loop_mode(args.loop_mode)
     fleet.sort_stations = not os.environ.get("FLEET_NO_ORDER")
     ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
@@ -79,7 +82,8 @@ def main():
         wall.append((time.perf_counter() - t0) * 1e3)
     ms = np.array([a.elapsed_time(b) for a, b in zip(ev0, ev1)])
     log = fleet.log
-    out = {"config": f"{args.stations} stations x ({args.evs}+{args.evs}) EVs, P={args.partitions}, N_lo={args.n_lo}, "
+    out = {"loop_mode": args.loop_mode, "pivot_overflows": [fleet.solver[k].last_pivot_overflows() for k in ("s", "l")],
+           "config": f"{args.stations} stations x ({args.evs}+{args.evs}) EVs, P={args.partitions}, N_lo={args.n_lo}, "
                      f"N_bi={args.n_bi}, {args.steps} closed-loop steps, chain={args.chain}",
            "step_ms_p50": float(np.median(ms)), "step_ms_p95": float(np.percentile(ms, 95)),
            "step_ms_first": float(ms[0]), "step_ms_mean": float(ms.mean()), "wall_ms_p50": float(np.median(wall)),
