@@ -44,7 +44,7 @@ struct WarpLoopSmem {
   static constexpr int kDoubles = oSC + 8;
   // then ints PFA / PLB [kMaxPivots]; bytes: PC[kMaxPivots][N], queues 2 x 2 x kQueueCap, WSB[3N]
   static constexpr size_t bytes =
-      (size_t)kDoubles * 8 + 2 * kMaxPivots * 4 + kMaxPivots * N + 4 * kQueueCap + 3 * N + 32;
+      (size_t)kDoubles * 8 + 3 * kMaxPivots * 4 + kMaxPivots * N + 4 * kQueueCap + 3 * N + 32;
 };
 
 // The loop of ONE group by one warp.  Same contract as group_loop_body (lompc_price_fused.cuh).
@@ -72,7 +72,8 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
   double* SC = smem + L::oSC;
   int* PFA = reinterpret_cast<int*>(smem + L::kDoubles);  // first EV index after the pivot
   int* PLB = PFA + kMaxPivots;                             // last EV index before the pivot
-  unsigned char* PC = reinterpret_cast<unsigned char*>(PLB + kMaxPivots);  // [slot][N] piece codes
+  int* PIT = PLB + kMaxPivots;                             // K1 iterations of the slot's last solve (statistics)
+  unsigned char* PC = reinterpret_cast<unsigned char*>(PIT + kMaxPivots);  // [slot][N] piece codes
   unsigned char* Q0 = PC + kMaxPivots * N;                 // interval queues (ping-pong): endpoints a, b
   unsigned char* Q1 = Q0 + 2 * kQueueCap;
   unsigned char* WSB = Q1 + 2 * kQueueCap;                 // [r] free set of the price step
@@ -147,9 +148,11 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
 
   double dual_cost = 0.0, lamdiff = 0.0, dec_pred = 0.0;  // lane 0
   int it = 0, nnqp_bad = 0, flag = 0;
-  unsigned long long solves = 0;
+  unsigned long long solves = 0, rounds = 0, k1_iters = 0;
+  long long cyc_qp = 0, cyc_step = 0, cyc_solve = 0;
   int overflowed = 0;
   for (;; ++it) {
+    const long long t_a = clock64();
     // ================= LoMPC pass: pivots, splitting, interpolated sum =================
     // warp-uniform registers: slot masks, 2-bit reference counts (intervals that use a slot), queue length
     unsigned used = (1u << nperm) - 1u, solved = 0u;
@@ -175,6 +178,7 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
           batch |= 1u << s;
         }
         solves += (unsigned long long)q;
+        ++rounds;
         WarpProblem P;
         const int s = my_slot < 0 ? 0 : my_slot;
         P.lm = LM;
@@ -184,13 +188,15 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
         P.w_out = PW + s * N;
         P.cost_out = (s == 1) ? SC + 0 : nullptr;
         P.status = nullptr;
-        P.iters = nullptr;
+        P.iters = a.qp_count ? PIT + s : nullptr;
         P.kkt_res = nullptr;
         P.codes_out = PC + s * N;
         P.tol = a.qp_tol;
         P.max_iter = a.qp_max_iter;
         int st;
+        const long long t_s = clock64();
         solve_warp_core<N, NSEG, SPL>(cs, P, my_slot >= 0, lane, st);
+        cyc_solve += clock64() - t_s;
         if (__any_sync(full, my_slot >= 0 && st != LOMPC_ST_OK)) {
           if (lane == 0) atomicAdd(a.flags + 3, 1);
         }
@@ -200,6 +206,8 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
           const int sv = __ffs(m) - 1;
           if (lane < N) wsum += PW[sv * N + lane];
         }
+        if (a.qp_count)
+          for (unsigned m = batch; m; m &= m - 1) k1_iters += (unsigned long long)PIT[__ffs(m) - 1];
         solved |= batch;
         continue;
       }
@@ -294,6 +302,8 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
     __syncwarp();
     // ================= lane 0: bookkeeping of the previous step, convergence test; all lanes: price step =================
     flag = 0;
+    const long long t_b = clock64();
+    cyc_qp += t_b - t_a;
     if (lane == 0) {
       const double cost_sc = SC[0];
       if (it > 0 && a.hist_ac && it - 1 < a.hist_cap) {  // price_solver.py:135-139
@@ -313,11 +323,12 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
     if (flag != 0) break;
     {
       int st;
-      price_step_warp<0>(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, lane, it == 0, it > 0, a.hist_ac != nullptr,
+      price_step_warp<N>(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, lane, it == 0, it > 0, a.hist_ac != nullptr,
                          true, lamdiff, dec_pred, st);
       nnqp_bad |= st;
     }
     __syncwarp();
+    cyc_step += clock64() - t_b;
   }
   // ---- regularisation (price_solver.py:145-147) and outputs
   if (lane == 0) {
@@ -329,7 +340,14 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
     if (nnqp_bad) atomicAdd(a.flags, 1);
     if (overflowed) atomicAdd(a.flags + 16, 1);  // (flags[4..15] hold the 64-bit counters)
     atomicMax(a.flags + 2, it);
-    if (a.qp_count) atomicAdd(a.qp_count, solves);
+    if (a.qp_count) {
+      atomicAdd(a.qp_count, solves);
+      atomicAdd(a.qp_count + 1, (unsigned long long)cyc_solve);  // cycles inside the K1 rounds (summed over groups)
+      atomicAdd(a.qp_count + 2, (unsigned long long)cyc_step);  // cycles in the price steps
+      atomicAdd(a.qp_count + 3, k1_iters);                      // K1 iterations summed over the solves
+      atomicAdd(a.qp_count + 4, rounds);                        // solver rounds ...
+      atomicAdd(a.qp_count + 5, (unsigned long long)(it + 1));  // ... over this many LoMPC passes
+    }
   }
   __syncwarp();
   for (int k = lane; k < 3 * N; k += 32) {

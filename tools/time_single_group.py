@@ -19,6 +19,7 @@ N, nev, cap = 24, int(os.environ.get("NEV", "40")), 400
 for ev in ("small", "large"):
     delta, theta, y_max, w_max = EV_CONSTS[ev]
     ps = PriceSolver(N, LoMPCConstants(delta, theta, y_max, w_max, ev), "linear-convex")
+    ps.set_loop_mode(int(os.environ.get("LOOP_MODE", "0")))
     rng = np.random.default_rng(0)
     y0 = 0.3 + 0.05 * rng.random(nev)
     w_ref = np.zeros(N)
@@ -32,5 +33,8 @@ for ev in ("small", "large"):
     it = int(st["iter"][0]) + 1
     cq = ps._lib.price_last_cycles(ps._h, 0)
     cs = ps._lib.price_last_cycles(ps._h, 1)
+    k1 = ps._lib.price_last_cycles(ps._h, 2)
+    rounds = ps._lib.price_last_cycles(ps._h, 3)
     print(f"{ev}: {nev} EVs, {it} iterations, {dt * 1e6 / it:.1f} us/iteration (wall, incl. launch), "
-          f"cycles/iteration: LoMPC pass {cq / it:.0f}, price step {cs / it:.0f}")
+          f"cycles/iteration: LoMPC pass {cq / it:.0f}, price step {cs / it:.0f}; QP solves {ps._lib.price_last_qp_solves(ps._h) / it:.1f} "
+          f"per iteration, K1 iterations {k1 / it:.1f}, solver rounds {rounds / it:.2f} (parametric loop)")
