@@ -134,7 +134,10 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
       const int mid = (lo + hi) >> 1;
       if (GS[mid] <= gamma_sc) lo = mid + 1; else hi = mid;
     }
-    vpos = lo;
+    // the list order is EV 0 <= virtual <= EV n - 1: gamma_sc is the midpoint of the range, but with (nearly) equal
+    // SoCs it rounds onto the largest gamma and the search lands behind the last EV - which would then be counted
+    // twice (inside the first interval and as the pivot of the last one)
+    vpos = n > 1 ? max(1, min(lo, n - 1)) : 1;
   }
   // permanent pivots: slot 0 = EV 0 (lowest gamma), slot 1 = virtual EV, slot 2 = EV n - 1 (n > 1)
   const int nperm = n > 1 ? 3 : 2;
@@ -317,6 +320,7 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
         double w_avg_err, w0_err;
         price_errors(N, kappa, WSUM, (double)n, WREF, w_avg_err, w0_err);
         if (w_avg_err <= tolg) flag = 1;  // price_solver.py:125 ("avg" tolerance type)
+
       }
     }
     flag = __shfl_sync(full, flag, 0);

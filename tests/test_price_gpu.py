@@ -268,3 +268,40 @@ def test_reference_convergence_scenarios(ev, scenario):
     assert w0_err <= w0_bound + 1e-9      # price_solver.py:162-164
     assert st["price_after_reg"] <= st["price_before_reg"] + 1e-9 * max(1.0, abs(st["price_before_reg"]))
     assert np.all(lam >= 0) and (price_type == "linear-convex" or np.all(lam[2 * N:] == 0))
+
+
+@pytest.mark.parametrize("ev", ["small", "large"])
+def test_parametric_loop_degenerate_groups(ev):
+    """The parametric loop (one warp per group, EVs between two pivots with the same active set interpolated,
+    price_set_loop_mode 2) on the groups where its pivot bookkeeping is most fragile: all SoCs equal to the last
+    bit (gamma_sc rounds onto the largest gamma), two distinct SoCs, one and two EVs, a wide group.  Same iteration
+    counts and prices as the thread-per-EV loop and as the oracle loop."""
+    from chargingstation.price_solver import PriceSolver
+    o, c = _consts(ev)
+    N = 12
+    rng = np.random.default_rng(77)
+    base = 0.7627601805992867
+    cases = {
+        "equal_to_the_last_bit": np.array([base, np.nextafter(base, 1.0), np.nextafter(np.nextafter(base, 1.0), 1.0)] * 4),
+        "identical": np.full(9, 0.41),
+        "two_values": np.array([0.35] * 5 + [0.39] * 4),
+        "one_ev": np.array([0.52]),
+        "two_evs": np.array([0.31, 0.33]),
+        "wide": 0.3 + 0.3 * rng.random(37),
+    }
+    for name, y0 in cases.items():
+        w_ref = o.w_max * rng.random(N) * 0.6
+        ora = po.PriceOracle(N, o, "linear-convex", fast=True)
+        ora.set_charge_levels(y0)
+        lam_o, st_o = ora.compute_optimal_prices(w_ref, 0.0, max_iter=300)
+        out = {}
+        for mode in (3, 2):
+            ps = PriceSolver(N, c, "linear-convex")
+            ps.set_loop_mode(mode)
+            off = np.array([0, len(y0)], dtype=np.int32)
+            prices, st = ps.compute_optimal_prices_batch(off, y0, w_ref[None], np.zeros(1), np.zeros((1, 3 * N)), max_iter=300)
+            out[mode] = (prices[0], int(st["iter"][0]))
+            assert ps.last_pivot_overflows() == 0
+        assert out[2][1] == out[3][1] == st_o["iter"], (name, out[2][1], out[3][1], st_o["iter"])
+        small = np.abs(lam_o) <= 1e3
+        assert np.max(np.abs(out[2][0] - lam_o)[small]) <= 1e-6 * max(1.0, np.max(np.abs(lam_o[small]))), name

@@ -8,7 +8,8 @@ for p in (ROOT, os.path.join(ROOT, 'incentive-design-mpc_b200'), os.path.join(RO
 import numpy as np, torch
 from run_fleet import fleet_consts, fleet_demand
 from chargingstation.fleet import ChargingStationFleet
-S, T = 256, 6
+S, T = int(os.environ.get('CMP_S', '256')), int(os.environ.get('CMP_T', '6'))
+dump = None
 consts = fleet_consts(T, 24, 24, 500, 12)
 demand = fleet_demand(consts, S, T, 24)
 fl = {}
@@ -29,4 +30,15 @@ for t in range(T):
         nd = int((ia != ib).sum())
         small = np.abs(pa) <= 1e3
         rel = np.max(np.abs(pa-pb)[small]) if small.any() else 0
+        if nd and dump is None:
+            g = int(np.nonzero(ia != ib)[0][0])
+            off = a.w[k]["off"].cpu().numpy()
+            dump = dict(ev=k, g=g, step=t, y0=a.w[k]["ysort"].cpu().numpy()[off[g]:off[g + 1]], w_ref=a.w[k]["w_ref"].cpu().numpy()[g],
+                        iters_thread=ia[g], iters_param=ib[g], prices_thread=pa[g], prices_param=pb[g],
+                        all_off=off, S=S, P=12)
         print(f"step {t} {k}: groups {ia.size} iter mismatches {nd} (capped a {int((ia>=999).sum())} b {int((ib>=999).sum())}) max |dprice| (entries<=1e3) {rel:.2e}", [ (int(x),int(y)) for x,y in zip(ia[ia!=ib][:6], ib[ia!=ib][:6])])
+
+if dump is not None:
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    np.savez(os.path.join(ROOT, "gpurun_out", "loop_mode_mismatch.npz"), **dump)
+    print("first mismatch dumped:", dump["ev"], dump["g"], dump["step"], dump["iters_thread"], dump["iters_param"], len(dump["y0"]))
