@@ -490,7 +490,7 @@ def closed_loop_leg(args, rank, world, dev):
             "aggregate_allreduce_wait_ms_p50": float(np.median(agg_ms)),  # includes waiting for the slowest rank
             "config": "BASELINE.json configs[3] shape (SURVEY.md 8d config 4): stations of 500+500 EVs, P=12, "
                       "N_lo=N_bi=24, demand profile shifted U{0..23} h and scaled U(0.22,0.26)/0.25 per station, "
-                      "device RNG; full size = 4096 stations x 96 steps (tools/run_fleet.py, profiles/)"}
+                      "device RNG; the full size of configs[3] is 4096 stations x 96 steps (the default of this leg)"}
 
 
 def sharded_leg(args, rank, world, dev):
@@ -605,9 +605,9 @@ def main():
     ap.add_argument("--no-saturated", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="time direct launches instead of the captured step")
-    ap.add_argument("--closed-loop-stations", type=int, default=1024,
-                    help="stations per GPU of the closed-loop latency leg (0 = skip; configs[3] is 4096)")
-    ap.add_argument("--closed-loop-steps", type=int, default=24, help="closed-loop steps (configs[3]: 96)")
+    ap.add_argument("--closed-loop-stations", type=int, default=4096,
+                    help="stations per GPU of the closed-loop latency leg (0 = skip; configs[3]: 4096)")
+    ap.add_argument("--closed-loop-steps", type=int, default=96, help="closed-loop steps (configs[3]: 96)")
     ap.add_argument("--closed-loop-chain", default="reference", choices=["reference", "partition"])
     ap.add_argument("--sharded-iters", type=int, default=200,
                     help="price iterations of the configs[2] leg (65,536 EVs sharded over the ranks; 0 = skip)")
