@@ -759,7 +759,15 @@ int price_shard_begin(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off
   CK(cudaGetLastError());
   S.peer = h->peers.world > 1 && !tol_type_max &&
            lompc::kPeerFlagBytes + 2 * (size_t)G * N * sizeof(double) <= h->peer_region_bytes;
-  if (S.peer) S.tag0 = (++h->peer_sessions) << 20;  // every rank opens its sessions in the same order
+  if (S.peer) {
+    S.tag0 = (++h->peer_sessions) << 20;  // every rank opens its sessions in the same order
+    p.peer_world = h->peers.world;
+    p.peer_rank = h->peers.rank;
+    for (int r = 0; r < h->peers.world; ++r) p.peer_region[r] = h->peers.region[r];
+    p.blocks_done = reinterpret_cast<unsigned int*>(S.nact + 3);
+    p.peer_tag0 = S.tag0;
+    p.peer_timeout = S.nact + 2;
+  }
   S.active = true;
   return LOMPC_OK;
 }
@@ -803,18 +811,17 @@ int price_shard_ev_phase(lompc_t* h, void* stream) {
   const int it = S.ev_passes++;
   // the per-group column sums: into the caller's w_sum buffer (which it all-reduces), or - peer exchange - into
   // buffer it & 1 of this rank's peer region, followed by the flag on every rank
-  double* sums = S.p.w_avg;
-  if (S.peer)
-    sums = reinterpret_cast<double*>(h->peers.region[h->peers.rank] + lompc::kPeerFlagBytes) +
-           (size_t)(it & 1) * S.G * N;
-  lompc::colsum_kernel<<<nblk((int64_t)S.G * N, 128), 128, 0, s>>>(N, S.G, S.group_off, S.skip, S.w_ev,
-                                                                  need_err ? S.err_ev : nullptr, sums,
-                                                                  S.p.w_err_max, 1);
-  COUNT_LAUNCH();
   if (S.peer) {
-    lompc::peer_signal_kernel<<<1, 32, 0, s>>>(h->peers, S.tag0 + (unsigned long long)it + 1);
-    COUNT_LAUNCH();
+    double* sums = reinterpret_cast<double*>(h->peers.region[h->peers.rank] + lompc::kPeerFlagBytes) +
+                   (size_t)(it & 1) * S.G * N;
+    lompc::colsum_signal_kernel<<<nblk((int64_t)S.G * N, 128), 128, 0, s>>>(N, S.G, S.group_off, S.skip, S.w_ev, sums,
+                                                                           S.p, S.tag0 + (unsigned long long)it + 1);
+  } else {
+    lompc::colsum_kernel<<<nblk((int64_t)S.G * N, 128), 128, 0, s>>>(N, S.G, S.group_off, S.skip, S.w_ev,
+                                                                    need_err ? S.err_ev : nullptr, S.p.w_avg,
+                                                                    S.p.w_err_max, 1);
   }
+  COUNT_LAUNCH();
   CK(cudaGetLastError());
   return LOMPC_OK;
 }
@@ -860,23 +867,19 @@ int price_shard_group_phase_async(lompc_t* h, int it, void* stream) {
     CK(cudaMallocHost(&h->ring, kRingSlots * 2 * sizeof(int32_t)));
     memset(h->ring, 0, kRingSlots * 2 * sizeof(int32_t));
   }
-  CK(cudaMemsetAsync(S.nact, 0, 4, s));
-  if (S.peer) {  // the exchange: wait for every rank's partial sums of this iteration and add them in rank order
-    const int64_t cnt = (int64_t)S.G * h->cs.N;
-    lompc::peer_reduce_kernel<<<nblk(cnt, 256), 256, 0, s>>>(h->peers, S.tag0 + (unsigned long long)it + 1, it & 1, cnt,
-                                                             S.p.w_avg, S.nact + 2);
-    COUNT_LAUNCH();
-  }
+  // three launches per group phase: the step (which, with peers attached, first gathers the ranks' partial sums),
+  // the gamma_sc solve, and the bookkeeping (which publishes the active count to the host ring and resets it)
+  lompc::PriceArgs pa = S.p;
+  pa.publish_ring = h->ring;
+  pa.publish_slots = kRingSlots;
   {
-    int rc0 = launch_group_step(h, S.p, it, s);
+    int rc0 = launch_group_step(h, pa, it, s);
     if (rc0) return rc0;
   }
-  lompc::publish_active_kernel<<<1, 1, 0, s>>>(S.nact, it, h->ring + 2 * (it % kRingSlots));
-  COUNT_LAUNCH();
   int rc = launch_group_solve(h, S.G, S.p.lmbd, S.p.lmbd_r, S.gamma_sc, nullptr, S.skip, nullptr, S.w_k,
                               S.cost_new, nullptr, nullptr, nullptr, s, S.w_k);
   if (rc) return rc;
-  lompc::bookkeep_kernel<<<nblk(S.G, 128), 128, 0, s>>>(S.p, it);
+  lompc::bookkeep_kernel<<<nblk(S.G, 128), 128, 0, s>>>(pa, it);
   COUNT_LAUNCH();
   CK(cudaGetLastError());
   return LOMPC_OK;

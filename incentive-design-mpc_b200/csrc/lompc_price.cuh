@@ -49,7 +49,33 @@ struct PriceArgs {
   unsigned char* wsb;        // scratch, r * G bytes (keeps the free set between iterations)
   int cold;                  // 1: never warm-start the free set (stand-alone price_step_dev)
   int want_dec;              // 1: compute dec_pred even without a history buffer
+  // ---- sharded loop without host round trips / with the aggregate exchanged through peer memory (all optional)
+  volatile int32_t* publish_ring;  // pinned host ring of (tag, n_active) pairs, slot it % publish_slots; NULL: none
+  int publish_slots;
+  int peer_world;            // > 1: w_avg is gathered from the ranks' peer regions inside group_step_kernel
+  int peer_rank;
+  char* peer_region[8];
+  unsigned long long peer_tag0;  // flag value of iteration 0, minus one
+  int32_t* peer_timeout;     // set to 1 when a rank did not deliver in time
+  unsigned int* blocks_done; // colsum_kernel's "last block signals" counter
 };
+
+constexpr size_t kPeerFlagBytes = 1024;  // head of a peer region: one 64-bit flag per rank
+constexpr int kMaxPeers = 8;             // == the size of PriceArgs::peer_region
+struct PeerView {                        // the peer regions attached to a handle (price_shard_attach_peers)
+  int rank, world;
+  char* region[kMaxPeers];
+};
+__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
+  unsigned long long v;
+  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
+  double v;
+  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+  return v;
+}
 
 __global__ void group_of_kernel(int64_t B, int G, const int32_t* __restrict__ off, int32_t* __restrict__ group_of) {
   const int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -138,9 +164,58 @@ __global__ void stats_finalize_kernel(const Consts cs, int G, int max_iter, cons
 
 // One thread per (group, time step): w_avg[g,k] = mean_i w_i[k] in EV order; thread k = 0
 // also takes max_i err_i (price_solver.py:199-210).
+// ---- the aggregate exchange of the sharded price loop over NVLink PEER MEMORY (instead of an NCCL all-reduce) ----
+// Every rank owns a region [flags (kPeerFlagBytes) | partial sums, buffer 0 | buffer 1] that all ranks have mapped
+// (CUDA IPC).  Iteration `it`: colsum_signal_kernel writes this rank's [G, N] partial sums into buffer it & 1 of its
+// OWN region and its last block raises flag[rank] = tag in EVERY rank's region; group_step_kernel (first kernel of the
+// group phase) waits, per group, until all `world` flags of its own region carry the tag and adds the partial sums of
+// ranks 0, 1, ... in that fixed order straight out of the peers' memory - every rank gets the same bits, no
+// collective library call and no extra launch.  Double buffering + stream order make the flags enough: a rank
+// rewrites buffer b two iterations later, after the peers' flags of the iteration in between, which they raise only
+// after they have finished reading b.
+//
+// Raises this rank's flag in every rank's peer region: called by ONE thread block after the partial sums are complete.
+__device__ __forceinline__ void peer_raise_flags(int world, int rank, char* const* region, unsigned long long tag) {
+  const int r = threadIdx.x;
+  if (r < world) {
+    unsigned long long* flag = reinterpret_cast<unsigned long long*>(region[r]) + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(tag) : "memory");
+  }
+}
+
+template <bool SIGNAL>
+__device__ __forceinline__ void colsum_body(int N, int G, const int32_t* __restrict__ off, const int32_t* __restrict__ skip,
+                                            const double* __restrict__ w_ev, const double* __restrict__ err_ev,
+                                            double* __restrict__ w_avg, double* __restrict__ w_err_max, int sum_only);
+
 __global__ void colsum_kernel(int N, int G, const int32_t* __restrict__ off, const int32_t* __restrict__ skip,
                               const double* __restrict__ w_ev, const double* __restrict__ err_ev,
                               double* __restrict__ w_avg, double* __restrict__ w_err_max, int sum_only) {
+  colsum_body<false>(N, G, off, skip, w_ev, err_ev, w_avg, w_err_max, sum_only);
+}
+
+// colsum_kernel + the flag of the peer exchange: the block that finishes LAST (a counter in global memory) raises
+// this rank's flag on every rank - one launch less per iteration than a separate signalling kernel.
+__global__ void colsum_signal_kernel(int N, int G, const int32_t* __restrict__ off, const int32_t* __restrict__ skip,
+                                     const double* __restrict__ w_ev, double* __restrict__ sums, const PriceArgs p,
+                                     unsigned long long tag) {
+  colsum_body<false>(N, G, off, skip, w_ev, nullptr, sums, nullptr, 1);
+  __shared__ unsigned int last;
+  __threadfence();  // this block's sums before its tick of the counter
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(p.blocks_done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last) {
+    if (threadIdx.x == 0) *p.blocks_done = 0u;
+    __threadfence_system();
+    peer_raise_flags(p.peer_world, p.peer_rank, p.peer_region, tag);
+  }
+}
+
+template <bool SIGNAL>
+__device__ __forceinline__ void colsum_body(int N, int G, const int32_t* __restrict__ off, const int32_t* __restrict__ skip,
+                                            const double* __restrict__ w_ev, const double* __restrict__ err_ev,
+                                            double* __restrict__ w_avg, double* __restrict__ w_err_max, int sum_only) {
   const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= (int64_t)G * N) return;
   const int g = (int)(idx / N), k = (int)(idx % N);
@@ -450,6 +525,35 @@ __global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
   unsigned char* FREE = reinterpret_cast<unsigned char*>(ws + price_step_scratch_doubles(N, r));
   const double kappa = p.lmbd_r[g] / cs.delta;
   int done = 0;
+  if (p.peer_world > 1) {
+    // the aggregate exchange, fused: wait for every rank's flag of this iteration, then add the ranks' partial sums
+    // of this group in rank order straight out of their memory (same bits on every rank)
+    const unsigned long long tag = p.peer_tag0 + (unsigned long long)it + 1;
+    int good = 1;
+    if (lane == 0) {
+      const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(p.peer_region[p.peer_rank]);
+      const long long t0 = clock64();
+      for (int r = 0; r < p.peer_world && good; ++r)
+        while (ld_acquire_sys_u64(flags + r) < tag)
+          if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer is gone - report instead of hanging the GPU
+            good = 0;
+            break;
+          }
+      if (!good) atomicExch(p.peer_timeout, 1);
+    }
+    good = __shfl_sync(0xffffffffu, good, 0);
+    for (int k = lane; k < N; k += 32) {
+      double sum = 0.0;
+      if (good)
+        for (int r = 0; r < p.peer_world; ++r) {
+          const double* part = reinterpret_cast<const double*>(p.peer_region[r] + kPeerFlagBytes) +
+                               (size_t)(it & 1) * G * N + (size_t)g * N;
+          sum += ld_relaxed_sys_f64(part + k);
+        }
+      p.w_avg[(size_t)g * N + k] = sum;
+    }
+    __syncwarp();
+  }
   if (lane == 0) {
     double w_avg_err, w0_err;
     price_errors(N, kappa, p.w_avg + (size_t)g * N, p.cnt ? p.cnt[g] : 1.0, p.w_ref + (size_t)g * N, w_avg_err,
@@ -486,84 +590,17 @@ __global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
   }
 }
 
-// Publishes the number of still-active groups of iteration `it` into a slot of a pinned HOST ring (a mapped
-// store: the host polls the slot without any CUDA call); tag = it + 1 marks the slot as written.
-__global__ void publish_active_kernel(const int32_t* __restrict__ n_active, int it, volatile int32_t* slot) {
-  slot[1] = *n_active;
-  __threadfence_system();
-  slot[0] = it + 1;
-}
-
-// ---- the aggregate exchange of the sharded price loop over NVLink PEER MEMORY (instead of an NCCL all-reduce) ----
-// Every rank owns a region [flags (kPeerFlagBytes) | partial sums, buffer 0 | buffer 1] that all ranks have mapped
-// (CUDA IPC).  Iteration `it`: colsum_kernel writes this rank's [G, N] partial sums into buffer it & 1 of its OWN
-// region, peer_signal_kernel then raises flag[rank] = tag in EVERY rank's region, and peer_reduce_kernel (first
-// kernel of the group phase) waits until all `world` flags of its own region carry the tag and sums the partials of
-// ranks 0, 1, ... in that fixed order straight out of the peers' memory - every rank gets the same bits, no
-// collective library call, one exchange = two tiny launches.  Double buffering + stream order make the flags enough:
-// a rank rewrites buffer b two iterations later, after the peers' flags of the iteration in between, which they
-// raise only after they have finished reading b.
-constexpr int kMaxPeers = 8;
-constexpr size_t kPeerFlagBytes = 1024;
-
-struct PeerView {
-  int rank, world;
-  char* region[kMaxPeers];
-};
-
-__device__ __forceinline__ unsigned long long ld_acquire_sys_u64(const unsigned long long* p) {
-  unsigned long long v;
-  asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
-  return v;
-}
-__device__ __forceinline__ double ld_relaxed_sys_f64(const double* p) {
-  double v;
-  asm volatile("ld.relaxed.sys.global.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
-  return v;
-}
-
-__global__ void peer_signal_kernel(const PeerView pv, unsigned long long tag) {
-  const int r = threadIdx.x;
-  if (r >= pv.world) return;
-  __threadfence_system();  // the partial sums of the preceding kernel are visible before the flag is
-  unsigned long long* flag = reinterpret_cast<unsigned long long*>(pv.region[r]) + pv.rank;
-  asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(tag) : "memory");
-}
-
-__global__ void peer_reduce_kernel(const PeerView pv, unsigned long long tag, int buf, int64_t count,
-                                   double* __restrict__ out, int32_t* __restrict__ timeout_flag) {
-  __shared__ int ok;
-  if (threadIdx.x == 0) {
-    const unsigned long long* flags = reinterpret_cast<const unsigned long long*>(pv.region[pv.rank]);
-    const long long t0 = clock64();
-    int good = 1;
-    for (int r = 0; r < pv.world; ++r) {
-      while (ld_acquire_sys_u64(flags + r) < tag) {
-        if (clock64() - t0 > 4000000000LL) {  // ~2 s: a peer is gone - report instead of hanging the GPU
-          good = 0;
-          break;
-        }
-      }
-      if (!good) break;
-    }
-    if (!good) atomicExch(timeout_flag, 1);
-    ok = good;
-  }
-  __syncthreads();
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= count) return;
-  double sum = 0.0;
-  if (ok) {
-    for (int r = 0; r < pv.world; ++r) {
-      const double* part = reinterpret_cast<const double*>(pv.region[r] + kPeerFlagBytes) + (int64_t)buf * count;
-      sum += ld_relaxed_sys_f64(part + idx);
-    }
-  }
-  out[idx] = sum;
-}
-
 __global__ void bookkeep_kernel(const PriceArgs p, int it) {
   const int g = blockIdx.x * blockDim.x + threadIdx.x;
+  if (g == 0 && p.publish_ring) {
+    // last kernel of the iteration: publish the number of still-active groups to the host's pinned ring (a mapped
+    // store the host polls without a CUDA call; tag = it + 1 marks the slot as written) and reset the counter
+    volatile int32_t* slot = p.publish_ring + 2 * (it % p.publish_slots);
+    slot[1] = *p.n_active;
+    __threadfence_system();
+    slot[0] = it + 1;
+    *p.n_active = 0;
+  }
   if (g >= p.G || p.skip[g]) return;
   const double ac = p.cost_new[g] - p.dual_cost[g] + p.lamdiff_phi[g];  // price_solver.py:135-137
   p.dual_cost[g] = p.cost_new[g];
