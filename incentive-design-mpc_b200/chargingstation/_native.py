@@ -52,6 +52,8 @@ SIGNATURES = {
     "lompc_set_wait": (C.c_int, [C.c_void_p]),
     "lompc_set_solve_host": (C.c_int, [C.c_void_p, C.c_int]),
     "lompc_set_solve_dev": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
+    "lompc_set_solve_dev_at": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
+    "lompc_set_offsets": (C.c_int, [C.c_void_p, C.c_int, C.POINTER(C.c_int64)]),
     "lompc_set_copy": (C.c_int, [C.c_void_p, C.c_int, C.c_void_p]),
     "lompc_set_bytes": (C.c_int64, [C.c_void_p, C.c_int]),
     "price_group_stats_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 7),

@@ -322,6 +322,17 @@ class LoMPCSet:
         """Launch only, device block to device block, asynchronous on ``stream`` (a raw cudaStream_t)."""
         _native.raise_for(self._lib.lompc_set_solve_dev(self._h, 1 if info else 0, stream))
 
+    def solve_dev_at(self, in_block: int, out_block: int, stream: int = 0) -> None:
+        """The set's launch on caller-owned device blocks of ``h2d_bytes`` / ``d2h_bytes`` bytes laid out like the
+        set's own (``offsets(i)``): many resident batches can be solved back to back."""
+        _native.raise_for(self._lib.lompc_set_solve_dev_at(self._h, in_block, out_block, stream))
+
+    def offsets(self, i: int):
+        """Byte offsets of segment ``i``: (lmbd, lmbd_r, gamma) in the input block, (w, cost) in the output block."""
+        o = (C.c_int64 * 5)()
+        _native.raise_for(self._lib.lompc_set_offsets(self._h, i, o))
+        return tuple(int(x) for x in o)
+
     def device_pointers(self, i: int):
         """(lmbd, lmbd_r, gamma, w, cost) device addresses of segment ``i``."""
         return self._dev_ptrs[i]

@@ -102,13 +102,15 @@ namespace {
 // Enqueues the kernels of one call on `s`: device blocks -> device blocks, or (host_blocks) the pinned host blocks
 // themselves - they are mapped into the device's address space, so the kernel's loads ARE the host->device transfer
 // and its stores the transfer back (per-QP status into the pinned info block, reduced by the host).
-int set_launch(lompc_set* S, int want_info, cudaStream_t s, bool host_blocks = false) {
+int set_launch(lompc_set* S, int want_info, cudaStream_t s, bool host_blocks = false, char* in_at = nullptr,
+               char* out_at = nullptr) {
   const int N = S->N;
-  char* const in = host_blocks ? S->h_in : S->d_in;
-  char* const outb = host_blocks ? S->h_out : S->d_out;
+  // in_at / out_at: caller-owned device blocks with the set's layout (lompc_set_solve_dev_at)
+  char* const in = in_at ? in_at : (host_blocks ? S->h_in : S->d_in);
+  char* const outb = out_at ? out_at : (host_blocks ? S->h_out : S->d_out);
   char* const info_b = host_blocks ? S->h_info : S->d_info;
-  const unsigned long long* epoch_src = reinterpret_cast<const unsigned long long*>(S->d_in);
-  unsigned long long* summary = host_blocks ? nullptr : reinterpret_cast<unsigned long long*>(S->d_out);
+  const unsigned long long* epoch_src = reinterpret_cast<const unsigned long long*>(in_at ? in_at : S->d_in);
+  unsigned long long* summary = host_blocks ? nullptr : reinterpret_cast<unsigned long long*>(outb);
   auto fill = [&](int i, lompc::SolveArgs& a, bool info) {
     const lompc_detail::HandleView v = lompc_detail::handle_view(S->hs[i]);
     memset(&a, 0, sizeof(a));
@@ -390,6 +392,24 @@ int lompc_set_solve_dev(lompc_set_t* S, int want_info, void* stream) {
   if (S->total == 0) return LOMPC_OK;
   CK(cudaSetDevice(S->device));
   return set_launch(S, want_info ? 1 : 0, static_cast<cudaStream_t>(stream));
+}
+
+int lompc_set_solve_dev_at(lompc_set_t* S, void* in_block, void* out_block, void* stream) {
+  if (!S || !in_block || !out_block) return LOMPC_ERR_ARG;
+  if (S->total == 0) return LOMPC_OK;
+  CK(cudaSetDevice(S->device));
+  return set_launch(S, 0, static_cast<cudaStream_t>(stream), false, static_cast<char*>(in_block),
+                    static_cast<char*>(out_block));
+}
+
+int lompc_set_offsets(const lompc_set_t* S, int i, int64_t* offsets) {
+  if (!S || i < 0 || i >= S->n || !offsets) return LOMPC_ERR_ARG;
+  offsets[0] = (int64_t)S->o_lm[i];
+  offsets[1] = (int64_t)S->o_lr[i];
+  offsets[2] = (int64_t)S->o_ga[i];
+  offsets[3] = (int64_t)S->o_w[i];
+  offsets[4] = (int64_t)S->o_c[i];
+  return LOMPC_OK;
 }
 
 int lompc_set_copy(lompc_set_t* S, int which, void* stream) {

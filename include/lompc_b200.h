@@ -148,6 +148,12 @@ int lompc_set_solve_host(lompc_set_t* s, int want_info);
 /* Launch only: inputs / outputs are the set's DEVICE blocks, asynchronous on `stream`.  summary_out (DEVICE
  * u64, may be NULL) receives epoch*4 + worst status; the epoch is read from the device in block.     */
 int lompc_set_solve_dev(lompc_set_t* s, int want_info, void* stream);
+/* The same launch on CALLER-OWNED device blocks that follow the set's layout (lompc_set_bytes gives their sizes,
+ * lompc_set_offsets the byte offsets of segment i: lmbd, lmbd_r, gamma inside the in block, w, cost inside the out
+ * block): lets a caller keep many batches resident and solve them back to back.  The first 8 bytes of out_block
+ * receive epoch*4 + worst status, the epoch being read from the first 8 bytes of in_block.                     */
+int lompc_set_solve_dev_at(lompc_set_t* s, void* in_block, void* out_block, void* stream);
+int lompc_set_offsets(const lompc_set_t* s, int i, int64_t* offsets /*[5]*/);
 /* Copies between the host and device blocks (which: 0 = in block host->device, 1 = out block device->host),
  * asynchronous on `stream`: for callers that mix the host views with lompc_set_solve_dev.            */
 int lompc_set_copy(lompc_set_t* s, int which, void* stream);
