@@ -1,5 +1,6 @@
 // C ABI of the B200-native LoMPC hot path (see include/lompc_b200.h).
 #include <atomic>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -894,11 +895,16 @@ int price_shard_poll(lompc_t* h, int it, int wait, int32_t* n_active) {
   if (h->ses.G == 0) return 1;
   if (!h->ring) return 0;
   volatile int32_t* slot = h->ring + 2 * (it % kRingSlots);
+  const auto t0 = std::chrono::steady_clock::now();
   for (unsigned spins = 1; slot[0] != it + 1; ++spins) {
     if (!wait) return 0;
-    if ((spins & 0xfffffu) == 0) {  // now and then: do not spin for ever on a dead context
+    if ((spins & 0xfffffu) == 0) {  // now and then: do not spin for ever on a dead context or a stuck peer
       const cudaError_t e = cudaPeekAtLastError();
       if (e != cudaSuccess) return cuda_fail(e, "price_shard_poll");
+      if (std::chrono::steady_clock::now() - t0 > std::chrono::seconds(30)) {
+        snprintf(g_cuda_err, sizeof(g_cuda_err), "price_shard_poll: iteration %d was not published within 30 s", it);
+        return LOMPC_ERR_CUDA;
+      }
     }
   }
   *n_active = slot[1];

@@ -92,6 +92,7 @@ struct lompc_set {
   bool mapped = true;  // the kernel reads / writes the pinned host blocks directly (no copy engine); LOMPC_SET_MAPPED=0: staged
   unsigned long long epoch = 0;
   bool pending = false;
+  bool pending_mapped = false;  // the call in flight wrote its per-QP status straight into the pinned info block
   // solver options / kernel choice of the handles when graph[] was captured (they are kernel arguments)
   double sig_tol[2][lompc::kMaxWarpSegs] = {};
   int sig_iter[2][lompc::kMaxWarpSegs] = {}, sig_var[2][lompc::kMaxWarpSegs] = {};
@@ -349,6 +350,7 @@ int lompc_set_solve_host_async(lompc_set_t* S, int want_info) {
     CK(cudaGraphLaunch(S->graph[want_info], S->stream));
   }
   S->pending = true;
+  S->pending_mapped = set_uses_host_blocks(S);
   return LOMPC_OK;
 }
 
@@ -358,7 +360,7 @@ int lompc_set_wait(lompc_set_t* S) {
   S->pending = false;
   CK(cudaSetDevice(S->device));
   CK(cudaStreamSynchronize(S->stream));
-  if (set_uses_host_blocks(S)) {  // the kernel wrote the per-QP status straight into the pinned info block
+  if (S->pending_mapped) {  // the kernel wrote the per-QP status straight into the pinned info block
     int worst = 0;
     for (int i = 0; i < S->n; ++i) {
       const int32_t* st = reinterpret_cast<const int32_t*>(S->h_info + S->o_st[i]);
