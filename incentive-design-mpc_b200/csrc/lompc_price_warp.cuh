@@ -28,6 +28,9 @@
 
 namespace lompc {
 
+#ifndef LOMPC_CHAIN_MINB
+#define LOMPC_CHAIN_MINB 1
+#endif
 constexpr int kMaxPivots = 32;  // solved EVs kept at a time (3 permanent: lowest gamma, virtual, highest gamma)
 constexpr int kQueueCap = 64;   // intervals between neighbouring pivots waiting for their verdict
 
@@ -366,7 +369,7 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
 
 // Grid = the groups: one warp (= one CTA) per group.
 template <int N>
-__global__ void __launch_bounds__(32, 1) price_group_warp_kernel(const __grid_constant__ Consts cs,
+__global__ void __launch_bounds__(32, LOMPC_CHAIN_MINB) price_group_warp_kernel(const __grid_constant__ Consts cs,
                                                                  const __grid_constant__ FusedArgs a) {
   extern __shared__ double smem[];
   const int g = blockIdx.x;
@@ -380,7 +383,7 @@ __global__ void __launch_bounds__(32, 1) price_group_warp_kernel(const __grid_co
 // Grid = the stations: one warp per station walks its P partitions in the reference's warm-start order
 // (see price_station_chain_kernel in lompc_price_fused.cuh).
 template <int N>
-__global__ void __launch_bounds__(32, 1) price_station_chain_warp_kernel(const __grid_constant__ Consts cs,
+__global__ void __launch_bounds__(32, LOMPC_CHAIN_MINB) price_station_chain_warp_kernel(const __grid_constant__ Consts cs,
                                                                          const __grid_constant__ FusedArgs a) {
   extern __shared__ double smem[];
   const int S = a.chain_S, s = a.chain_order ? a.chain_order[blockIdx.x] : (int)blockIdx.x;
