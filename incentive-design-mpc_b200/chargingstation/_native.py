@@ -71,6 +71,8 @@ SIGNATURES = {
     "price_set_loop_mode": (C.c_int, [C.c_void_p, C.c_int]),
     "price_last_qp_solves": (C.c_int64, [C.c_void_p]),
     "price_last_cycles": (C.c_int64, [C.c_void_p, C.c_int]),
+    "price_debug_force_nnqp_fallback": (C.c_int, [C.c_int]),
+    "price_debug_pivot_pool": (C.c_int, [C.c_int]),
     "price_shard_begin": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p,
                                     C.c_int, C.c_int, C.c_int, C.c_double, C.c_double] + [C.c_void_p] * 10 +
                           [C.c_int, C.c_void_p]),

@@ -145,6 +145,10 @@ class BiMPC:
                                                   params.gamma_lm[None], np.array([float(params.x0)]),
                                                   params.demand[None])
         self.last_info = {k: v[0] for k, v in info.items()}
+        if self.last_info["status"] != 0:
+            # the reference hands back the .value of unsolved cvxpy variables, i.e. None (bimpc.py:288-291), and its
+            # caller fails on the first slice; the last iterate stays available through solve_bimpc_batch
+            return None, None, None
         return ws[0], wl[0], ug[0]
 
     def solve_bimpc_batch(self, Mp_s, Mp_l, beta_s, beta_l, gamma_sm, gamma_lm, x0, demand):
@@ -174,6 +178,10 @@ class BiMPC:
                                               p(ug), p(st), p(it), p(obj))
         if rc != _native.ERR_NOT_CONVERGED:
             _native.raise_for(rc)
-        # solver failure is silent in the reference (.value is None, bimpc.py:288-291); here the
-        # status is reported and the last iterate returned
+        # a failed solve yields None in the reference (.value of an unsolved variable, bimpc.py:288-291); the batch
+        # call reports it per station in info["status"], warns, and returns the last iterate of those stations
+        if rc == _native.ERR_NOT_CONVERGED or np.any(st != 0):
+            import warnings
+            warnings.warn(f"BiMPC: {int(np.count_nonzero(st))} of {S} station(s) not solved to tolerance "
+                          "(infeasible or iteration cap) - see info['status']", RuntimeWarning, stacklevel=2)
         return ws, wl, ug, {"status": st, "iters": it, "objective": obj}

@@ -108,6 +108,7 @@ class ChargingStationFleet:
         self.lmbd_r0 = z(G)
         # ---- logs (reference schema, one leading station axis; filled step by step on the device)
         Tf = self.Tf
+        self.inexact_steps = 0  # steps that raised the warning below
         self.log = {"u_g": z(Tf, S), "x": z(Tf, S), "bimpc_iters": z(Tf, S, dtype=i32), "bimpc_status": z(Tf, S, dtype=i32)}
         for k in ("s", "l"):
             for name in ("w", "w_hat", "beta", "gamma_m", "avg_price", "price_red"):
@@ -241,6 +242,15 @@ class ChargingStationFleet:
             main.wait_event(done)
         self.price_loop_iters.append(loop_iters)
         mark("price_loops")
+        # the price loops above already synchronised with the host, so these reads cost one small copy each
+        n_bad = int(torch.count_nonzero(bi["status"]))
+        n_cap = sum(int(lib.price_last_cycles(self.solver[k]._h, w)) for k in ("s", "l") for w in (6, 7))
+        if n_bad or n_cap:
+            import warnings
+            warnings.warn(f"fleet step {t}: {n_bad} station(s) with an unsolved BiMPC (status in logs()['bimpc_status']), "
+                          f"{n_cap} price step(s) / LoMPC solve(s) stopped at their iteration cap", RuntimeWarning,
+                          stacklevel=2)
+        self.inexact_steps += bool(n_bad or n_cap)
         # ---- EV responses at the final prices
         for k in ("s", "l"):
             w, h = self.w[k], self.solver[k]._h

@@ -105,7 +105,7 @@ class LoMPC:
         assert lmbd.shape == (3 * self.N,)
         # lompc.py:87 asserts first; then cvxpy validates the nonneg Parameters (lompc.py:78-82).
         assert gamma <= self.y_max
-        if np.any(lmbd < 0) or lmbd_r < 0 or gamma < 0:
+        if not (np.all(lmbd >= 0) and lmbd_r >= 0 and gamma >= 0):  # NaN is rejected too, as cvxpy does
             raise ValueError("Parameter value must be nonnegative.")
         w, cost = self.solve_lompc_batch(lmbd[None, :], np.array([lmbd_r], dtype=np.float64),
                                          np.array([gamma], dtype=np.float64))

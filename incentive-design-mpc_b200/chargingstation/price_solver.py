@@ -143,7 +143,25 @@ class PriceSolver:
         _native.raise_for(self._lib.price_set_loop_mode(self._h, int(mode)))
 
     def last_pivot_overflows(self) -> int:
+        """Groups of the last parametric loop whose pivot pool ran out (their stuck intervals were solved EV by EV:
+        exact, informational)."""
         return int(self._lib.price_last_cycles(self._h, 5))
+
+    def last_nnqp_cap_hits(self) -> int:
+        """Groups of the last device-resident loop whose price step hit the cap of its active-set iteration."""
+        return int(self._lib.price_last_cycles(self._h, 6))
+
+    def last_nnqp_fallbacks(self) -> int:
+        """Groups of the last device-resident loop whose price step took the Lawson-Hanson fallback (informational)."""
+        return int(self._lib.price_last_cycles(self._h, 8))
+
+    def _warn_inexact(self) -> None:
+        n = self.last_nnqp_cap_hits()
+        q = int(self._lib.price_last_cycles(self._h, 7))
+        if n or q:
+            import warnings
+            warnings.warn(f"price loop: {n} group(s) with a price step stopped at its iteration cap, "
+                          f"{q} LoMPC solve(s) without status OK - prices may be inexact", RuntimeWarning, stacklevel=3)
 
     def get_gamma_sc(self) -> float:
         return self.gamma_sc
@@ -267,6 +285,7 @@ class PriceSolver:
             hist_ac.data_ptr() if history else None, hist_pred.data_ptr() if history else None, cap,
             C.byref(total), self._stream())
         _native.raise_for(rc)
+        self._warn_inexact()
         stats = {"iter": iters.cpu().numpy(), "price_before_reg": pre.cpu().numpy(),
                  "price_after_reg": post.cpu().numpy(), "w_k": w_k.cpu().numpy(), "total_iters": total.value}
         if history:

@@ -76,6 +76,9 @@ struct lompc_handle {
   // grow-only device workspace of the price loop + pinned poll word
   int variant;  // 0 auto, 1 = any-N shared-memory kernel, 2.. = register-kernel variants
   int loop_mode;  // price loop: 0 auto (fused one-CTA-per-group kernel when compiled for N), 1 = phase-split host loop
+  int last_qp_failures;               // LoMPC solves of that loop that ended without status OK (never observed)
+  int last_nnqp_fallbacks;            // groups of that loop that took the Lawson-Hanson fallback of the price step
+  int last_nnqp_cap_hits;             // groups of the last device-resident loop whose price step hit its active-set cap
   int last_pivot_overflows;           // groups of the last parametric loop whose pivot pool overflowed (expected 0)
   unsigned long long last_qp_solves;  // LoMPC QPs solved by the last fused price loop
   unsigned long long last_cycles[5];  // its SM cycles in the LoMPC passes / the price steps (summed over groups),
@@ -317,6 +320,9 @@ int lompc_create(int N, double delta, double theta, double y_max, double w_max, 
   h->loop_mode = 0;
   h->last_qp_solves = 0;
   h->last_pivot_overflows = 0;
+  h->last_nnqp_cap_hits = 0;
+  h->last_qp_failures = 0;
+  h->last_nnqp_fallbacks = 0;
   for (auto& c : h->last_cycles) c = 0;
   h->pws = nullptr;
   h->pws_bytes = 0;
@@ -371,8 +377,22 @@ int price_set_loop_mode(lompc_t* h, int mode) {
 
 int64_t price_last_qp_solves(const lompc_t* h) { return h ? (int64_t)h->last_qp_solves : 0; }
 
+int price_debug_force_nnqp_fallback(int on) {
+  CK(cudaMemcpyToSymbol(lompc::g_nnqp_force_fallback, &on, sizeof(int)));
+  return LOMPC_OK;
+}
+
+int price_debug_pivot_pool(int slots) {
+  if (slots < 4 || slots > 32) return LOMPC_ERR_ARG;
+  CK(cudaMemcpyToSymbol(lompc::g_pivot_pool, &slots, sizeof(int)));
+  return LOMPC_OK;
+}
+
 int64_t price_last_cycles(const lompc_t* h, int which) {
   if (h && which == 5) return h->last_pivot_overflows;
+  if (h && which == 6) return h->last_nnqp_cap_hits;
+  if (h && which == 7) return h->last_qp_failures;
+  if (h && which == 8) return h->last_nnqp_fallbacks;
   return (h && which >= 0 && which < 5) ? (int64_t)h->last_cycles[which] : 0;
 }
 
@@ -1089,6 +1109,9 @@ int price_solve_fused_entry(lompc_handle* h, int32_t G, int64_t B, const int32_t
     CK(cudaMemcpyAsync(h->poll, flags, 128, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     h->last_pivot_overflows = h->poll[16];
+    h->last_nnqp_cap_hits = h->poll[0];
+    h->last_qp_failures = h->poll[3];
+    h->last_nnqp_fallbacks = h->poll[17];
     if (total_iters) *total_iters = h->poll[2];
     h->last_qp_solves = *reinterpret_cast<unsigned long long*>(h->poll + 4);
     h->last_cycles[0] = *reinterpret_cast<unsigned long long*>(h->poll + 6);

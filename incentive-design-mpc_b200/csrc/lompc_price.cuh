@@ -41,7 +41,7 @@ struct PriceArgs {
   double* dec_pred;          // [G]
   int32_t* skip;             // [G] 1 = converged / empty
   int32_t* iters;            // [G]
-  int32_t* nnqp_status;      // [G] 0 ok, 1 = active-set iteration cap hit
+  int32_t* nnqp_status;      // [G] 0 ok, bit 0 = the price step's NNQP stopped at its iteration cap, bit 1 = it took the fallback
   int32_t* n_active;         // [1]
   double* hist_ac;           // [G,hist_cap] or NULL
   double* hist_pred;         // [G,hist_cap] or NULL
@@ -333,6 +333,131 @@ __device__ __forceinline__ void abar_solve(int Nrt, const double* fac, const dou
 // Scratch of one price step: (3r + 9N) doubles (the last 3N: the cached gains of A_bar).
 __host__ __device__ inline int price_step_scratch_doubles(int N, int r) { return 3 * r + 9 * N; }
 
+// Test hook: non-zero makes every price step take the fallback below (price_debug_force_nnqp_fallback()).
+__device__ int g_nnqp_force_fallback = 0;
+
+// Fallback of the price step's NNQP: Lawson-Hanson's primal active-set iteration (one index enters per outer
+// iteration - the most negative half gradient -, a ratio test along the way to the free-set solution drops the
+// blocking ones), started from l = 0.  It cannot cycle the way the primal-dual iteration of price_step_warp
+// does on a few degenerate groups (about 1 price step in 10^6 at fleet scale), at the price of one Riccati
+// solve per index instead of a handful per step; the oracle's NNLS (oracle/price_oracle.py::nnqp_exact) is the
+// same algorithm on the dense factor.  Same conventions as price_step_warp (every lane calls; LAM, TERM and
+// FREE are left as its converged branch leaves them).  Returns 0, or 1 when its own cap of 3r outer iterations
+// (Lawson-Hanson's customary bound) is hit.
+__device__ __noinline__ int nnqp_lawson_hanson(int N, int nb, double th, double m, double eps, double kappa, double gs,
+                                               const double* C3, const double* RHO, const double* FAC, double* LAM,
+                                               double* TERM, double* U, double* V, double* TD, double* KS,
+                                               double* KAPS, unsigned char* FREE, int lane) {
+  const unsigned full = 0xffffffffu;
+  const int r = nb * N;
+  const double inv2m = 1.0 / (2.0 * m), inv_eps = 1.0 / eps;
+  for (int i = lane; i < r; i += 32) {
+    LAM[i] = 0.0;
+    FREE[i] = 0;
+  }
+  __syncwarp();
+  int st = 1;
+  for (int oit = 0; oit <= 3 * r; ++oit) {
+    // half gradient P l - rho at the current (feasible) l, through v = A_bar^{-1} B'l
+    for (int k = lane; k < N; k += 32) {
+      const double coef[3] = {th, -th, C3[k]};
+      double u = 0.0;
+      for (int j = 0; j < nb; ++j) u += coef[j] * LAM[j * N + k];
+      U[k] = u;
+    }
+    __syncwarp();
+    abar_solve<0>(N, FAC, U, V, KAPS, lane);
+    __syncwarp();
+    double best = -1e-12 * gs;
+    int bi = 0x7fffffff;
+    for (int k = lane; k < N; k += 32) {
+      const double coef[3] = {th, -th, C3[k]};
+      const double v = V[k] * inv2m;
+      for (int j = 0; j < nb; ++j) {
+        const int i = j * N + k;
+        const double l = LAM[i];
+        const double Pl = eps * l + coef[j] * v;
+        TERM[i] = l * (Pl - 2.0 * RHO[i]);
+        const double hg = Pl - RHO[i];
+        if (FREE[i] == 0 && hg < best) {  // (FREE = 2: an index that entered and left again without a step)
+          best = hg;
+          bi = i;
+        }
+      }
+    }
+    for (int o = 16; o > 0; o >>= 1) {  // most negative half gradient, lowest index on ties
+      const double ob = __shfl_xor_sync(full, best, o);
+      const int oi = __shfl_xor_sync(full, bi, o);
+      if (ob < best || (ob == best && oi < bi)) {
+        best = ob;
+        bi = oi;
+      }
+    }
+    if (bi == 0x7fffffff) {
+      st = 0;
+      break;
+    }
+    if (oit == 3 * r) break;
+    if (lane == 0) FREE[bi] = 1;
+    __syncwarp();
+    for (int iit = 0; iit <= 3 * r; ++iit) {
+      // s = the minimiser over the free set (Woodbury, as in price_step_warp); kept in TERM
+      for (int k = lane; k < N; k += 32) {
+        const double coef[3] = {th, -th, C3[k]};
+        double t = 0.0, rhs = 0.0;
+        for (int j = 0; j < nb; ++j)
+          if (FREE[j * N + k] == 1) {
+            t += coef[j] * coef[j];
+            rhs += coef[j] * RHO[j * N + k];
+          }
+        TD[k] = t;
+        U[k] = rhs;
+      }
+      __syncwarp();
+      ric_solve<0>(N, TD, 2.0 * m * eps * kappa, 2.0 * m * eps, U, V, KS, KAPS, lane);
+      __syncwarp();
+      double alpha = 2.0;
+      for (int k = lane; k < N; k += 32) {
+        const double coef[3] = {th, -th, C3[k]};
+        for (int j = 0; j < nb; ++j) {
+          const int i = j * N + k;
+          if (FREE[i] != 1) continue;
+          const double sv = (RHO[i] - coef[j] * V[k]) * inv_eps;
+          TERM[i] = sv;
+          if (sv <= 0.0) alpha = fmin(alpha, LAM[i] / (LAM[i] - sv));  // l_i >= 0 >= s_i, not both 0 unless i just entered
+        }
+      }
+      for (int o = 16; o > 0; o >>= 1) alpha = fmin(alpha, __shfl_xor_sync(full, alpha, o));
+      if (!(alpha >= 0.0)) alpha = 0.0;  // 0/0 of an index that entered with a non-positive target
+      __syncwarp();
+      for (int k = lane; k < N; k += 32)
+        for (int j = 0; j < nb; ++j) {
+          const int i = j * N + k;
+          if (FREE[i] != 1) continue;
+          const double sv = TERM[i], l = LAM[i];
+          if (alpha > 1.0) {
+            LAM[i] = sv;
+          } else if (sv <= 0.0 && !(l / (l - sv) > alpha)) {  // the blocking indices leave at exactly 0
+            LAM[i] = 0.0;
+            FREE[i] = (i == bi && iit == 0) ? 2 : 0;
+          } else {
+            LAM[i] = fmax(l + alpha * (sv - l), 0.0);
+          }
+        }
+      __syncwarp();
+      if (alpha > 1.0) break;
+    }
+    if (FREE[bi] != 2)  // a step was taken: indices set aside (round-off made them enter with a non-positive target)
+      for (int i = lane; i < r; i += 32)  // may be tried again
+        if (FREE[i] == 2) FREE[i] = 0;
+    __syncwarp();
+  }
+  __syncwarp();
+  for (int i = lane; i < r; i += 32) FREE[i] = (FREE[i] == 1);
+  __syncwarp();
+  return st;
+}
+
 // The exact solution of the non-negative QP of the price step
 //     min_{l >= 0} l'P l + q'l,  P = Dphi A_bar^{-1} Dphi'/(2m) + eps I,  q = -2 P l_k - (phi(w_k) - phi(w_ref))
 // (price_solver.py:216-246) by a primal-dual active-set iteration, for ONE group by ONE WARP
@@ -476,7 +601,10 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
       st = 0;
       break;
     }
+    if (pit == 0 && g_nnqp_force_fallback) break;
   }
+  if (st != 0)  // (rare: see nnqp_lawson_hanson; bit 1 of the status reports its use)
+    st = 2 | nnqp_lawson_hanson(N, nb, th, m, eps, kappa, gs, C3, RHO, FAC, LAM, TERM, U, V, TD, KS, KAPS, FREE, lane);
   const double F1 = need_dec ? ordered_sum() : 0.0;
   __syncwarp();
   // ---- write back (price_solver.py:129,135-140)

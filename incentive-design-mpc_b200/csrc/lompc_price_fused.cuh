@@ -272,7 +272,8 @@ __device__ __forceinline__ bool group_loop_body(const Consts& cs, const FusedArg
     regularize_core(cs, a.r, WK, LM, pre, post);
     a.price_pre[g] = pre;
     a.price_post[g] = post;
-    if (nnqp_bad) atomicAdd(a.flags, 1);
+    if (nnqp_bad & 1) atomicAdd(a.flags, 1);
+    if (nnqp_bad & 2) atomicAdd(a.flags + 17, 1);  // groups that took the NNQP fallback (informational)
     atomicMax(a.flags + 2, it);
     if (a.qp_count) {
       atomicAdd(a.qp_count, solves);

@@ -31,6 +31,9 @@ namespace lompc {
 #ifndef LOMPC_CHAIN_MINB
 #define LOMPC_CHAIN_MINB 1
 #endif
+// Test hook: pivot slots the parametric loop may use (price_debug_pivot_pool(); 32 = all).  A small pool makes the
+// direct jobs of group_loop_warp, which a full pool needs about once in 10^4 groups, the common case.
+__device__ int g_pivot_pool = 32;
 constexpr int kMaxPivots = 32;  // solved EVs kept at a time (3 permanent: lowest gamma, virtual, highest gamma)
 constexpr int kQueueCap = 64;   // intervals between neighbouring pivots waiting for their verdict
 
@@ -152,6 +155,8 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
   for (int k = lane; k < 3 * N; k += 32) PW[k] = 0.0;
   __syncwarp();
 
+  const int pool_n = g_pivot_pool;
+  const unsigned pool = pool_n >= 32 ? 0xffffffffu : ((1u << (pool_n < nperm + 1 ? nperm + 1 : pool_n)) - 1u);
   double dual_cost = 0.0, lamdiff = 0.0, dec_pred = 0.0;  // lane 0
   int it = 0, nnqp_bad = 0, flag = 0;
   unsigned long long solves = 0, rounds = 0, k1_iters = 0;
@@ -170,18 +175,36 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
       QR[2] = 1; QR[3] = 2;
     }
     double wsum = 0.0;  // lane k < N: sum over the group's EVs of w_i[k]
-    bool force = false;
+    // direct job: EVs [dj_first, dj_first + dj_cnt) of an interval (dj_sa, dj_sb) that found no free pivot slots are
+    // solved one by one into the (idle) price-step scratch - exact, just without the saving
+    int dj_first = 0, dj_cnt = 0, dj_sa = 0, dj_sb = 0;
+    auto release = [&](int sx) {  // an interval lets go of an endpoint; slots nobody holds return to the pool
+      if (sx >= nperm) {
+        const unsigned long long rc = (refs >> (2 * sx)) & 3ull;
+        refs -= 1ull << (2 * sx);
+        if (rc == 1ull) {
+          used &= ~(1u << sx);
+          solved &= ~(1u << sx);
+        }
+      }
+    };
     __syncwarp();
     for (;;) {
-      // ---- solve phase: up to QPW unsolved pivots per round, one per lane group
+      // ---- solve phase: up to QPW unsolved pivots (or EVs of the direct job) per round, one per lane group
       unsigned pending = used & ~solved;
-      if (pending) {
+      const bool direct = !pending && dj_cnt > 0;
+      if (pending || direct) {
         int my_slot = -1, q = 0;
         unsigned batch = 0u;
-        for (unsigned m = pending; m && q < QPW; m &= m - 1, ++q) {
-          const int s = __ffs(m) - 1;
-          if (lane / LPQ == q) my_slot = s;
-          batch |= 1u << s;
+        if (direct) {
+          q = dj_cnt < QPW ? dj_cnt : QPW;
+          if (lane / LPQ < q) my_slot = lane / LPQ;  // (a row of the scratch, not a pivot slot)
+        } else {
+          for (unsigned m = pending; m && q < QPW; m &= m - 1, ++q) {
+            const int s = __ffs(m) - 1;
+            if (lane / LPQ == q) my_slot = s;
+            batch |= 1u << s;
+          }
         }
         solves += (unsigned long long)q;
         ++rounds;
@@ -189,14 +212,15 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
         const int s = my_slot < 0 ? 0 : my_slot;
         P.lm = LM;
         P.lr = lr;
-        P.gam = PG[s];
-        P.w_init = (it > 0 || s >= nperm) ? PW + s * N : nullptr;  // (a new pivot holds a copy of a neighbour's solution)
-        P.w_out = PW + s * N;
-        P.cost_out = (s == 1) ? SC + 0 : nullptr;
+        P.gam = direct ? GS[dj_first + s] : PG[s];
+        // (a new pivot holds a copy of a neighbour's solution; a direct solve starts from the interval's left end)
+        P.w_init = direct ? PW + dj_sa * N : ((it > 0 || s >= nperm) ? PW + s * N : nullptr);
+        P.w_out = direct ? WS + s * N : PW + s * N;
+        P.cost_out = (!direct && s == 1) ? SC + 0 : nullptr;
         P.status = nullptr;
-        P.iters = a.qp_count ? PIT + s : nullptr;
+        P.iters = (a.qp_count && !direct) ? PIT + s : nullptr;
         P.kkt_res = nullptr;
-        P.codes_out = PC + s * N;
+        P.codes_out = direct ? nullptr : PC + s * N;
         P.tol = a.qp_tol;
         P.max_iter = a.qp_max_iter;
         int st;
@@ -207,6 +231,18 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
           if (lane == 0) atomicAdd(a.flags + 3, 1);
         }
         __syncwarp();
+        if (direct) {
+          for (int t = 0; t < q; ++t)
+            if (lane < N) wsum += WS[t * N + lane];
+          dj_first += q;
+          dj_cnt -= q;
+          if (dj_cnt == 0) {
+            release(dj_sa);
+            release(dj_sb);
+          }
+          __syncwarp();
+          continue;
+        }
         // the real EVs just solved count once themselves
         for (unsigned m = batch & ~2u; m; m &= m - 1) {
           const int sv = __ffs(m) - 1;
@@ -226,7 +262,7 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
         const int fa = PFA[sa], lb = PLB[sb];
         const int cnt = lb - fa + 1;
         bool same = true;
-        if (cnt > 0 && !force) {
+        if (cnt > 0) {
           bool diff = false;
           if (lane < N) diff = PC[sa * N + lane] != PC[sb * N + lane];
           same = !__any_sync(full, diff);
@@ -239,24 +275,13 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
             const double wa = PW[sa * N + lane], wb = PW[sb * N + lane];
             wsum += cnt * wa + coef * (wb - wa);
           }
-          // release the interval's hold on its endpoints
-#pragma unroll
-          for (int t = 0; t < 2; ++t) {
-            const int sx = t ? sb : sa;
-            if (sx >= nperm) {
-              const unsigned long long rc = (refs >> (2 * sx)) & 3ull;
-              refs -= 1ull << (2 * sx);
-              if (rc == 1ull) {
-                used &= ~(1u << sx);
-                solved &= ~(1u << sx);
-              }
-            }
-          }
+          release(sa);
+          release(sb);
           progressed = true;
           continue;
         }
         const int k = cnt < QPW ? cnt : QPW;  // new pivots inside the interval
-        const unsigned freem = ~used;          // kMaxPivots == 32: every clear bit is a free slot
+        const unsigned freem = ~used & pool;   // kMaxPivots == 32: every clear bit is a free slot
         if (__popc(freem) >= k && wn + (k + 1) + (qn - e - 1) <= kQueueCap) {
           int prev = sa;
           unsigned fm = freem;
@@ -298,9 +323,16 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
         QW = t;
       }
       __syncwarp();
-      if (qn == 0) break;
-      if (!progressed && !(used & ~solved)) {
-        force = true;  // pool exhausted (never observed): interpolate across the remaining intervals, and say so
+      if (qn == 0 && dj_cnt == 0) break;
+      if (!progressed && !(used & ~solved) && dj_cnt == 0) {
+        // pool exhausted (about one group in 10^4 on the first step of a fleet): every slot is an endpoint of a
+        // waiting interval.  The last interval of the queue becomes the direct job; finishing it and, if need be, its
+        // neighbours (consecutive in the queue) returns their shared endpoints to the pool.
+        --qn;
+        dj_sa = QR[2 * qn];
+        dj_sb = QR[2 * qn + 1];
+        dj_first = PFA[dj_sa];
+        dj_cnt = PLB[dj_sb] - dj_first + 1;
         overflowed = 1;
       }
     }
@@ -344,8 +376,9 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
     regularize_core(cs, a.r, WK, LM, pre, post);
     a.price_pre[g] = pre;
     a.price_post[g] = post;
-    if (nnqp_bad) atomicAdd(a.flags, 1);
-    if (overflowed) atomicAdd(a.flags + 16, 1);  // (flags[4..15] hold the 64-bit counters)
+    if (nnqp_bad & 1) atomicAdd(a.flags, 1);
+    if (nnqp_bad & 2) atomicAdd(a.flags + 17, 1);  // groups that took the NNQP fallback (informational)
+    if (overflowed) atomicAdd(a.flags + 16, 1);  // informational (flags[4..15] hold the 64-bit counters)
     atomicMax(a.flags + 2, it);
     if (a.qp_count) {
       atomicAdd(a.qp_count, solves);

@@ -77,11 +77,11 @@ __global__ void __launch_bounds__(128) lompc_solve_kernel(const Consts cs, const
   const double lr = a.lmbd_r[row * a.lmbd_r_stride];
   const double gam = a.gamma[b];
   int st = LOMPC_ST_OK;
-  if (gam < 0.0 || lr < 0.0) st = LOMPC_ST_NEGATIVE;  // nonneg parameters, lompc.py:78-82
+  if (!(gam >= 0.0) || !(lr >= 0.0)) st = LOMPC_ST_NEGATIVE;  // nonneg parameters, lompc.py:78-82 (NaN is not nonneg)
   double l2sum = 0.0, gmax = 0.0;
   for (int k = 0; k < N; ++k) {
     const double l1 = lm[k], l2 = lm[N + k], l3 = lm[2 * N + k];
-    if (l1 < 0.0 || l2 < 0.0 || l3 < 0.0) st = LOMPC_ST_NEGATIVE;
+    if (!(l1 >= 0.0) || !(l2 >= 0.0) || !(l3 >= 0.0)) st = LOMPC_ST_NEGATIVE;
     const double g = cs.theta * (l1 - l2);
     const double d = 2.0 * (lr * cs.theta2 + cs.q_scale * l3) + cs.d_base;
     D[k * T] = d;

@@ -72,12 +72,12 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
   double* INV = GS + (GREG ? 0 : N * T);      // only when NSEG > 1
 #define LOMPC_G(k) (GREG ? GR[GREG ? (k) : 0] : GS[(k) * T])
   int st = LOMPC_ST_OK;
-  if (gam < 0.0 || lr < 0.0) st = LOMPC_ST_NEGATIVE;
+  if (!(gam >= 0.0) || !(lr >= 0.0)) st = LOMPC_ST_NEGATIVE;  // (NaN is not nonneg either)
   double l2sum = 0.0, gmax = 0.0;
   int dmin_hi = 0x7ff00000;  // high word of min_k d_k (d_k >= 0)
 #define LOMPC_STAGE_DATA(k, l1, l2, l3)                                      \
   {                                                                         \
-    if ((l1) < 0.0 || (l2) < 0.0 || (l3) < 0.0) st = LOMPC_ST_NEGATIVE;     \
+    if (!((l1) >= 0.0) || !((l2) >= 0.0) || !((l3) >= 0.0)) st = LOMPC_ST_NEGATIVE; \
     const double g_ = cs.theta * ((l1) - (l2));                             \
     if (GREG) GR[GREG ? (k) : 0] = g_; else GS[(k) * T] = g_;               \
     D[k] = 2.0 * (lr * cs.theta2 + cs.q_scale * (l3)) + cs.d_base;          \

@@ -183,7 +183,7 @@ __device__ __forceinline__ void solve_warp_core(const Consts& cs, const WarpProb
   const bool warm = P.w_init != nullptr;
   double W[SPL], D[SPL], G[SPL], WN[SPL];
   int CD[SPL], CDO[SPL];  // piece codes of W / of the parked iterate (see lompc_solve_reg.cuh: piece_table)
-  bool neg = (gam < 0.0) || (lr < 0.0);
+  bool neg = !(gam >= 0.0) || !(lr >= 0.0);  // nonneg parameters, lompc.py:78-82 (NaN is not nonneg)
   double l2loc = 0.0, gmaxloc = 0.0;
   int dmin_hi = 0x7ff00000;
 #pragma unroll
@@ -194,7 +194,7 @@ __device__ __forceinline__ void solve_warp_core(const Consts& cs, const WarpProb
       l2 = lm[N + k0 + j];
       l3 = lm[2 * N + k0 + j];
     }
-    neg |= (l1 < 0.0) || (l2 < 0.0) || (l3 < 0.0);
+    neg |= !(l1 >= 0.0) || !(l2 >= 0.0) || !(l3 >= 0.0);
     G[j] = cs.theta * (l1 - l2);
     D[j] = 2.0 * (lr * cs.theta2 + cs.q_scale * l3) + cs.d_base;
     dmin_hi = min(dmin_hi, __double2hiint(D[j]));

@@ -243,11 +243,22 @@ int price_solve_chain_dev(lompc_t* h, int32_t S, int32_t P, int64_t B, const int
  * EVs that bracket a change of active set are solved and the rest is interpolated ("avg"
  * tolerance type, price_solver.py:196-214); 3 = the thread-per-EV loop, one CTA per group.  All give the same
  * iteration counts and prices up to rounding.  price_last_qp_solves = LoMPC QPs solved by the last fused call;
- * price_last_cycles(h, 5) = groups of the last parametric call whose pivot pool overflowed (0 in every run so far). */
+ * price_last_cycles(h, 5) = groups of the last parametric call whose pool of 32 pivot slots ran out (about one group in
+ * 10^4 on a fleet's first step; the EVs of the stuck intervals are then solved one by one: exact, informational),
+ * price_last_cycles(h, 6) = groups of the last device-resident call whose price step (price_solver.py:216-246) ended
+ * inexact (its primal-dual active-set iteration cycles on about one degenerate step in 10^6; it then falls back to
+ * Lawson-Hanson's iteration, and only a cap hit THERE counts), price_last_cycles(h, 7) = LoMPC solves of that call
+ * that ended without status OK (both 0 in every run so far; the Python mirror warns on either),
+ * price_last_cycles(h, 8) = groups that took the fallback (informational).
+ * price_debug_force_nnqp_fallback: test hook - non-zero sends EVERY price step of the current device through the
+ * fallback (the parity tests of the price loop are run both ways); price_debug_pivot_pool: test hook - the pivot
+ * slots the parametric loop may use (4..32, default 32), so that a test can make slot shortage the common case. */
 int price_set_loop_mode(lompc_t* h, int mode);
 int64_t price_last_qp_solves(const lompc_t* h);
 /* SM cycles of the last fused call summed over groups: which = 0 LoMPC passes, 1 price steps. */
 int64_t price_last_cycles(const lompc_t* h, int which);
+int price_debug_force_nnqp_fallback(int on);
+int price_debug_pivot_pool(int slots);
 
 /* The same loop cut into the phases between which a multi-GPU caller
  * all-reduces, for EVs sharded over ranks (each rank passes its LOCAL EVs and

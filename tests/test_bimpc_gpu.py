@@ -85,8 +85,16 @@ def test_infeasible_station_reports_status():
     c = bo.example_consts(16, 12)
     par = list(draw_station(np.random.default_rng(5), c))
     par[7] = par[7] * 10.0  # demand far above u_g_max + battery: no feasible point
-    ws, wl, ug, info = _mirror(c).solve_bimpc_batch(*stack([par]))
+    from chargingstation.bimpc import BiMPCParameters
+    b = _mirror(c)
+    with pytest.warns(RuntimeWarning, match="not solved"):
+        ws, wl, ug, info = b.solve_bimpc_batch(*stack([par]))
     assert info["status"][0] != 0
+    # the scalar call hands back what the reference does for an unsolved problem: the .value of unsolved cvxpy
+    # variables, None (bimpc.py:288-291)
+    with pytest.warns(RuntimeWarning):
+        out = b.solve_bimpc(BiMPCParameters(*par))
+    assert out == (None, None, None) and b.last_info["status"] != 0
 
 
 @pytest.mark.parametrize("random_Mp", [False, True])

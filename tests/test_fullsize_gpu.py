@@ -31,10 +31,23 @@ def _lompc_consts(ev):
     return o, LoMPCConstants(o.delta, o.theta, o.y_max, o.w_max, o.ev_type)
 
 
+@pytest.fixture
+def nnqp_solver(request):
+    """The price step's NNQP (price_solver.py:216-246) through its usual primal-dual active-set iteration, or with
+    every step forced through the Lawson-Hanson fallback that otherwise runs about once in 10^6 steps."""
+    from chargingstation import _native
+    lib = _native.load()
+    forced = request.param == "lawson-hanson"
+    assert lib.price_debug_force_nnqp_fallback(int(forced)) == 0
+    yield forced
+    assert lib.price_debug_force_nnqp_fallback(0) == 0
+
+
+@pytest.mark.parametrize("nnqp_solver", ["primal-dual", "lawson-hanson"], indirect=True)
 @pytest.mark.parametrize("loop_mode", [3, 2], ids=["thread-per-EV", "parametric"])
 @pytest.mark.parametrize("ev", ["small", "large"])
 @pytest.mark.parametrize("price_type,lmbd_r", [("linear-convex", 0), ("linear", 0), ("linear-convex", 24)])
-def test_price_loop_n24_against_golden(ev, price_type, lmbd_r, loop_mode):
+def test_price_loop_n24_against_golden(ev, price_type, lmbd_r, loop_mode, nnqp_solver):
     """compute_optimal_prices (price_solver.py:79-174) at N = 24, three groups of 70 EVs chained through
     one PriceSolver (prev_prices warm start, :103-104,166): iteration counts equal to the oracle's, prices to 1e-7."""
     from chargingstation import settings
@@ -57,10 +70,47 @@ def test_price_loop_n24_against_golden(ev, price_type, lmbd_r, loop_mode):
         n = st["iter"]
         assert np.allclose(st["dual_cost_decrease_actual"], z[key + "_dec_actual"][g][:n], rtol=1e-5, atol=1e-7)
         assert np.allclose(st["dual_cost_decrease_predicted"], z[key + "_dec_predicted"][g][:n], rtol=1e-5, atol=1e-7)
-        assert ps.last_pivot_overflows() == 0
+        assert ps.last_pivot_overflows() == 0 and ps.last_nnqp_cap_hits() == 0
+        assert ps.last_nnqp_fallbacks() == (1 if nnqp_solver and st["iter"] > 0 else 0)
         w0, p0 = ps.get_w0_price0(lam[: ps.r], float(lmbd_r))
         assert np.max(np.abs(w0 - z[key + "_w0"][g])) <= 1e-8 * o.w_max
         assert abs(p0 - z[key + "_price0"][g]) <= 1e-7 * max(1.0, abs(z[key + "_price0"][g]))
+
+
+@pytest.mark.parametrize("pool", [4, 5, 8])
+def test_parametric_loop_with_a_short_pivot_pool(pool):
+    """The parametric loop keeps at most 32 solved EVs ("pivots") of a group; when every slot is an endpoint of an
+    interval that still has to be split (about one group in 10^4 on a fleet's first step) the EVs of the stuck
+    intervals are solved one by one instead.  With the pool cut to `pool` slots that path is the common case: the
+    result must not change - iteration counts equal to the golden ones, prices within the usual 1e-7 - at N = 24
+    (golden loops, 4 QPs per warp pass) and at N = 12 (8 per pass; the recorded steps of configs[0])."""
+    from chargingstation import _native, settings
+    from chargingstation.price_solver import PriceSolver
+    settings.PRINT_LEVEL = 0
+    lib = _native.load()
+    z = np.load(os.path.join(GOLD, "price_loop_n24_golden.npz"))
+    assert lib.price_debug_pivot_pool(3) != 0 and lib.price_debug_pivot_pool(33) != 0  # range check of the hook
+    assert lib.price_debug_pivot_pool(pool) == 0
+    try:
+        hit = 0
+        for key, ev, price_type, lmbd_r in (("small_linear-convex_lr0", "small", "linear-convex", 0.0),
+                                            ("large_linear_lr0", "large", "linear", 0.0),
+                                            ("large_linear-convex_lr24", "large", "linear-convex", 24.0)):
+            o, c = _lompc_consts(ev)
+            ps = PriceSolver(24, c, price_type)
+            ps.set_loop_mode(2)
+            for g in range(3):
+                ps.set_charge_levels(z[key + "_y0"][g])
+                lam, st = ps.compute_optimal_prices(z[key + "_w_ref"][g], lmbd_r)
+                gold = z[key + "_prices"][g]
+                assert st["iter"] == z[key + "_iters"][g], (key, g, st["iter"], z[key + "_iters"][g])
+                assert np.max(np.abs(lam - gold)) <= 1e-7 * max(1.0, np.max(np.abs(gold)))
+                hit += ps.last_pivot_overflows()
+        # N = 12: the recorded steps of the reference's example through the chain kernel
+        hit12 = _run_chain_teacher_forced("cfg0_unw", 2)
+        assert hit > 0 and hit12 > 0  # the path under test did run
+    finally:
+        assert lib.price_debug_pivot_pool(32) == 0
 
 
 def _chain_inputs(z, name, k):
@@ -97,6 +147,11 @@ def test_chain_kernel_fullsize_teacher_forced(name, loop_mode):
     """price_solve_chain_dev (the fleet's price loop; charging_station.py:265-305 for every station) on the
     oracle's recorded steps: per (step, EV type, partition) the iteration count equals the oracle's -
     including the group that runs into the cap of 1000 iterations (cfg0_exp, step 18) - and the prices agree."""
+    _run_chain_teacher_forced(name, loop_mode)
+
+
+def _run_chain_teacher_forced(name, loop_mode):
+    """Returns the number of groups whose pivot pool ran out (parametric loop; informational)."""
     import ctypes as C
     import torch
     from chargingstation import _native
@@ -104,6 +159,7 @@ def test_chain_kernel_fullsize_teacher_forced(name, loop_mode):
     lib = _native.load()
     z = np.load(os.path.join(GOLD, "fullsize_station_golden.npz"))
     dev = torch.device("cuda:0")
+    overflows = 0
     for k in ("s", "l"):
         steps, S, P, N, off, y0, w_ref, prev = _chain_inputs(z, name, k)
         o, c = _lompc_consts(k)
@@ -122,7 +178,8 @@ def test_chain_kernel_fullsize_teacher_forced(name, loop_mode):
                                        d_prices.data_ptr(), d_iters.data_ptr(), d_pre.data_ptr(), d_post.data_ptr(), None,
                                        C.byref(mx), torch.cuda.current_stream().cuda_stream)
         _native.raise_for(rc)
-        assert ps.last_pivot_overflows() == 0
+        assert ps.last_nnqp_cap_hits() == 0
+        overflows += ps.last_pivot_overflows()
         iters = d_iters.cpu().numpy().reshape(P, S)
         prices = d_prices.cpu().numpy().reshape(P, S, 3 * N)
         capped = 0
@@ -146,6 +203,7 @@ def test_chain_kernel_fullsize_teacher_forced(name, loop_mode):
                 capped += gold_it[p] == 999
         if name == "cfg0_exp" and k == "l":
             assert capped >= 1  # step 18, partition 6: oracle and kernel both hit the cap on the same group
+    return overflows
 
 
 @pytest.mark.parametrize("name", ["n24_unw", "cfg0_unw", "cfg0_exp"])
@@ -240,7 +298,8 @@ def test_config0_example_free_running(name, min_lock):
     assert int(st["ncharged_s"]) + int(st["ncharged_l"]) > 0
 
 
-def test_groups_that_hit_the_iteration_cap():
+@pytest.mark.parametrize("nnqp_solver", ["primal-dual", "lawson-hanson"], indirect=True)
+def test_groups_that_hit_the_iteration_cap(nnqp_solver):
     """Group instances on which the ORACLE loop stops at MAX_PRICE_SOLVER_ITERATIONS (settings.py:14): the device
     loop stops there too (iter == 999, price_solver.py:111,169) - the cap is a property of these inputs, not of
     the kernel."""
@@ -258,5 +317,6 @@ def test_groups_that_hit_the_iteration_cap():
         ps.prev_prices = z[f"capped_{i}_prev"].copy()
         lam, st = ps.compute_optimal_prices(z[f"capped_{i}_w_ref"], 0.0)
         assert st["iter"] == 999, (i, st["iter"])
+        assert ps.last_nnqp_cap_hits() == 0 and ps.last_nnqp_fallbacks() == int(nnqp_solver)
         gold = z[f"capped_{i}_prices"]
         assert np.max(np.abs(lam - gold)) <= 1e-4 * max(1.0, np.max(np.abs(gold)))

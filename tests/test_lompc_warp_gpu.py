@@ -126,6 +126,15 @@ def test_warp_kernel_edge_cases_and_status():
         lm2[3, 7] = -1.0
         with pytest.raises(ValueError):
             solver.solve_lompc_batch(lm2, 0.0, np.full(5, 0.2))
+        for variant in (0, 1, 4, 8):          # NaN parameters are invalid in every kernel (auto, registers, thread, warp)
+            lm2[3, 7] = np.nan
+            solver.set_kernel_variant(variant)
+            with pytest.raises(ValueError):
+                solver.solve_lompc_batch(lm2, 0.0, np.full(5, 0.2))
+            lm2[3, 7] = 0.1
+            with pytest.raises((ValueError, AssertionError)):
+                solver.solve_lompc_batch(lm2, 0.0, np.array([0.2, 0.2, np.nan, 0.2, 0.2]))
+        solver.set_kernel_variant(0)
         solver.set_solver_options(max_iter=1)
         with pytest.raises(RuntimeError):
             solver.solve_lompc_batch(lm, 0.0, np.full(5, 0.5))
@@ -191,7 +200,14 @@ def test_solve_set_error_conventions_and_async(mapped, monkeypatch):
     sset.lmbd[0][9, 3] = -0.5                # nonneg cv.Parameter, lompc.py:78-82
     with pytest.raises(ValueError):
         sset.solve()
+    sset.lmbd[0][9, 3] = np.nan              # NaN is not a nonneg value either (cvxpy rejects it the same way)
+    with pytest.raises(ValueError):
+        sset.solve()
     sset.lmbd[0][9, 3] = 0.5
+    sset.lmbd_r[1][2] = np.nan
+    with pytest.raises(ValueError):
+        sset.solve()
+    sset.lmbd_r[1][2] = 0.0
     sset.solve()                             # the failure of an earlier call does not stick
     assert sset.w[1].shape == good.shape
     small.set_solver_options(max_iter=1)
