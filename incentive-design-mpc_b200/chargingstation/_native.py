@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(os.path.dirname(_HERE), "csrc", "liblompc_b200.so")
+# LOMPC_B200_LIB: another build of the same library (tuning sweeps build variants next to the default one)
+LIB_PATH = os.environ.get("LOMPC_B200_LIB") or os.path.join(os.path.dirname(_HERE), "csrc", "liblompc_b200.so")
 
 OK = 0
 ERR_CONSTS, ERR_ARG, ERR_CUDA, ERR_GAMMA, ERR_NEGATIVE, ERR_NOT_CONVERGED, ERR_NO_DEVICE = (

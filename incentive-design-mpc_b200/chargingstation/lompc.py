@@ -88,7 +88,7 @@ class LoMPC:
 
     def set_kernel_variant(self, variant: int = 0) -> None:
         """0 = automatic; 1 = any-N shared-memory kernel; 2..7 = register-kernel shapes (tuning);
-        8 = the warp-cooperative latency kernel (include/lompc_b200.h)."""
+        8 = the warp-cooperative latency kernel; 9 = the register kernel with bulk-copied rows (include/lompc_b200.h)."""
         _native.raise_for(self._lib.lompc_set_kernel_variant(self._h, int(variant)))
 
     def solve_lompc(self, lmbd: np.ndarray, lmbd_r: float, gamma: float) -> tuple[np.ndarray, float]:

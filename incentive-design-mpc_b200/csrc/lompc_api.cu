@@ -138,8 +138,38 @@ int launch_solve_reg(const lompc_handle* h, const lompc::SolveArgs& a, cudaStrea
   return LOMPC_OK;
 }
 
+// The register kernel with the rows moved by the bulk-copy engine (lompc_solve_reg_tma_kernel): plain batches only.
+inline bool tma_rows_ok(const lompc::SolveArgs& a, int N) {
+  return !a.group_of && !a.skip && !a.w_init && !a.err_out && !a.w0_out && !a.price0_out && a.w_out &&
+         a.lmbd_stride == 3 * N && a.lmbd_r_stride == 1 && reinterpret_cast<uintptr_t>(a.lmbd) % 16 == 0 &&
+         reinterpret_cast<uintptr_t>(a.w_out) % 16 == 0;
+}
+
+template <int N, int NSEG, int T, int MINB, bool OUT_ALIAS>
+int launch_solve_reg_tma(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t stream) {
+  constexpr size_t smem = lompc::RegTmaSmem<N, NSEG, T, OUT_ALIAS>::bytes;
+  static_assert(smem <= 227 * 1024, "shared memory of one CTA");
+  static std::atomic<uint64_t> configured{0};
+  if (!device_flag_test(configured, h->device)) {
+    CK(cudaFuncSetAttribute(lompc::lompc_solve_reg_tma_kernel<N, NSEG, T, MINB, OUT_ALIAS>,
+                            cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    device_flag_set(configured, h->device);
+  }
+  const int64_t blocks = (a.B + T - 1) / T;
+  lompc::lompc_solve_reg_tma_kernel<N, NSEG, T, MINB, OUT_ALIAS><<<(unsigned)blocks, T, smem, stream>>>(h->cs, a);
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  CK(cudaGetLastError());
+  return LOMPC_OK;
+}
+
 template <int N, int NSEG>
 int launch_solve_reg_variant(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t stream) {
+  if (h->variant == 9 && tma_rows_ok(a, N)) {  // bulk-copy rows (batches that are not plain rows: the default below)
+    if constexpr (NSEG > 1)
+      return launch_solve_reg_tma<N, NSEG, 256, 1, true>(h, a, stream);
+    else
+      return launch_solve_reg_tma<N, NSEG, 64, 4, false>(h, a, stream);
+  }
   switch (h->variant) {
     // (the other shapes of round 1's sweep - 64x4 with g in shared memory, 128x3, 64x5, 128x2 - lost everywhere and
     // are no longer compiled; their numbers are kept)
@@ -153,6 +183,19 @@ int launch_solve_reg_variant(const lompc_handle* h, const lompc::SolveArgs& a, c
       // body is 50 KB and the kernel is instruction-fetch bound (ncu: no_instruction = 36 % of the stall samples,
       // spread evenly over the body) unless the warps of an SM run in step and share the fetched lines: ONE CTA of
       // 256 threads per SM (+17..21 % over 4 x 64) once the grid fills the GPU; latency-bound grids keep 64.
+      // Grids that fill the GPU at N = 24: rows by the bulk-copy engine (lompc_solve_reg_tma_kernel).  Measured
+      // (tools/time_k1.py, us per launch, per-thread loads / bulk copies): 65,536 QPs 41.0 / 38.9 small, 65.5 / 59.4
+      // large; 262,144: 116.7 / 104.4, 202.8 / 182.3; 524,288: 215.0 / 188.4 (2.44 -> 2.78 G QP/s), 389.1 / 344.1
+      // (1.35 -> 1.52 G).  Below that (16,384: 18.4 / 18.4, 30.7 / 32.8) and at N = 12, where a row is 288 B and the
+      // two CTA barriers cost more than the copies save (524,288 QPs: 94.4 / 110.6 us), the loads stay per-thread.
+      if constexpr (N == 24) {
+        if (a.B >= 65536 && tma_rows_ok(a, N)) {
+          if constexpr (NSEG > 1)
+            return launch_solve_reg_tma<N, NSEG, 256, 1, true>(h, a, stream);
+          else
+            return launch_solve_reg_tma<N, NSEG, 64, 4, false>(h, a, stream);
+        }
+      }
       if (NSEG > 1 && a.B >= 65536) return launch_solve_reg<N, NSEG, 256, 1, true>(h, a, stream);
       return launch_solve_reg<N, NSEG, 64, 4, true>(h, a, stream);
   }
@@ -364,7 +407,7 @@ int lompc_set_options(lompc_t* h, int max_iter, double tol) {
 }
 
 int lompc_set_kernel_variant(lompc_t* h, int variant) {
-  if (!h || variant < 0 || variant > 8 || variant == 2 || variant == 3 || variant == 5 || variant == 6) return LOMPC_ERR_ARG;
+  if (!h || variant < 0 || variant > 9 || variant == 2 || variant == 3 || variant == 5 || variant == 6) return LOMPC_ERR_ARG;
   h->variant = variant;
   return LOMPC_OK;
 }

@@ -59,7 +59,9 @@ __device__ __forceinline__ void piece_table(const Consts& cs, double* tab, int t
 // registers.  `smem_t` = this thread's column of the CTA's shared-memory arrays (base + t).
 // `lm` may point to global or shared memory (the fused price loop keeps the group's price
 // row in shared memory).  `warm`: W holds a feasible starting point on entry (else W = 0).
-template <int N, int NSEG, int T, bool GREG, bool OPT = true>
+// SYNC_SETUP: `lm` points into a staging area that ALIASES the shared-memory arrays (the bulk-copy kernel
+// below): the whole CTA passes a barrier between the last read of the price rows and the first write of the gains.
+template <int N, int NSEG, int T, bool GREG, bool OPT = true, bool SYNC_SETUP = false>
 __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, const double lr, const double gam,
                                           const double tol, const int max_iter, const bool warm, const bool vec,
                                           double* smem_t, const double* tab, double (&W)[N],
@@ -106,6 +108,7 @@ __device__ __forceinline__ void solve_reg(const Consts& cs, const double* lm, co
     }
   }
 #undef LOMPC_STAGE_DATA
+  if (SYNC_SETUP) __syncthreads();
   if (gam > cs.y_max) st = LOMPC_ST_BAD_GAMMA;
   const double c = cs.c, wmax = cs.w_max;
   const double gscale = fmax(1.0, gmax + c * N * cs.y_max);
@@ -497,6 +500,126 @@ __global__ void __launch_bounds__(T, MINB) lompc_solve_reg_kernel(const Consts c
   if (a.iters) a.iters[b] = it;
   if (a.kkt_res) a.kkt_res[b] = viol / gscale;
 #undef LOMPC_G
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// The same kernel with the rows moved by the bulk-copy engine (cp.async.bulk, SASS UBLKCP) instead of per-thread
+// loads and stores.  A thread's price row is 3N contiguous doubles, the rows of a warp are 576 B apart: every
+// LDG.128 of the kernel above touches 32 lines (32 passes through the L1 tag stage for 512 useful bytes; ncu: 10 M
+// of the kernel's 21 M L1 wavefronts are these loads, 3.3 M the result stores, and the L1 data pipe - which the
+// shared-memory traffic of the sweeps needs too - is the kernel's second-busiest unit).  Here every thread issues
+// ONE bulk copy of its row into shared memory (no L1 pass, no registers, no LSU work for the global side) and
+// reads it back with conflict-free LDS.128 (row stride 37 x 16 B: odd); the result row leaves through a
+// private 13 x 16 B slot and one bulk store.  The staging area of the price rows ALIASES the Riccati gain arrays:
+// a row is dead once d and g are in registers, the gains are first written after that (one CTA barrier in
+// between, solve_reg<SYNC_SETUP>), so the shared-memory footprint grows only by the result slots (T x 208 B).
+// Plain batches only: one row per QP (no group_of / skip / warm start / fused error outputs), 16-byte aligned.
+// OUT_ALIAS: the result slots alias the gain arrays too (one more CTA barrier, after the solve) - for the shape that
+// fills the SM's shared memory with ONE CTA, where the threads that finish early have nothing else to do anyway.
+template <int N, int NSEG, int T, bool OUT_ALIAS>
+struct RegTmaSmem {
+  static constexpr int kRowIn = 3 * N * 8 + 16;    // bytes between staged price rows (odd multiple of 16)
+  static constexpr int kRowOut = N * 8 + 16;       // bytes between result slots (odd multiple of 16)
+  static_assert((kRowIn / 16) % 2 == 1 && (kRowOut / 16) % 2 == 1, "conflict-free 16-byte accesses need odd strides");
+  static constexpr size_t kArrayBytes = RegSmem<N, NSEG, T, true>::kArrays * (size_t)N * T * 8;
+  static constexpr size_t kStageBytes = (size_t)T * kRowIn;
+  static constexpr size_t kRegion = ((kArrayBytes > kStageBytes ? kArrayBytes : kStageBytes) + 15) / 16 * 16;
+  static constexpr size_t oTab = kRegion;                                    // piece table
+  static constexpr size_t oTabEnd = oTab + RegSmem<N, NSEG, T, true>::kTab * 8;
+  static constexpr size_t oOut = OUT_ALIAS ? 0 : oTabEnd;                     // result slots
+  static constexpr size_t oBar = OUT_ALIAS ? oTabEnd : oOut + (size_t)T * kRowOut;  // mbarrier
+  static_assert(!OUT_ALIAS || (size_t)T * kRowOut <= kRegion, "result slots must fit the aliased region");
+  static constexpr size_t bytes = oBar + 16;
+};
+
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+
+template <int N, int NSEG, int T, int MINB, bool OUT_ALIAS>
+__global__ void __launch_bounds__(T, MINB) lompc_solve_reg_tma_kernel(const Consts cs, const SolveArgs a) {
+  using L = RegTmaSmem<N, NSEG, T, OUT_ALIAS>;
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  double* smem = reinterpret_cast<double*>(smem_raw);
+  double* tab = reinterpret_cast<double*>(smem_raw + L::oTab);
+  const int t = threadIdx.x;
+  const unsigned bar = smem_u32(smem_raw + L::oBar);
+  if (t == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(T));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  piece_table<NSEG>(cs, tab, t);
+  __syncthreads();
+  const int64_t b = (int64_t)blockIdx.x * T + t;
+  const bool active = b < a.B;
+  // ---- every thread: announce the bytes of its row, start the copy, arrive
+  if (active) {
+    const unsigned dst = smem_u32(smem_raw + (size_t)t * L::kRowIn);
+    const double* src = a.lmbd + b * (int64_t)(3 * N);
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(3 * N * 8) : "memory");
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(3 * N * 8), "r"(bar)
+                 : "memory");
+  } else {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  }
+  // (Tried: cp.async.bulk.prefetch.L2 of the row the NEXT CTA of this SM slot will load - 188 -> 198 us at 524,288
+  // small-EV QPs: the copies of the resident CTAs already keep the memory system busy, the extra requests only queue.)
+  // A thread past the end of the batch has to reach the barriers: it repeats a QP and writes nothing - the QP of its
+  // warp's first lane, so that the warp's votes (optimistic phase or not) are those of its real QPs.
+  const int64_t bw = (int64_t)blockIdx.x * T + (t & ~31);
+  const int tq_ = active ? t : (bw < a.B ? (t & ~31) : 0);
+  const int64_t bq = (int64_t)blockIdx.x * T + tq_;
+  const double lr = a.lmbd_r[bq];
+  const double gam = a.gamma[bq];
+  {
+    unsigned done = 0;
+    while (!done)
+      asm volatile(
+          "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n selp.u32 %0, 1, 0, p;\n}"
+          : "=r"(done)
+          : "r"(bar)
+          : "memory");
+  }
+  const double* lm = reinterpret_cast<const double*>(smem_raw + (size_t)tq_ * L::kRowIn);
+  double W[N], D[N], GR[N];
+  double l2sum, gscale, viol;
+  int st, it;
+  solve_reg<N, NSEG, T, true, true, true>(cs, lm, lr, gam, a.tol, a.max_iter, false, true, smem + t, tab, W, D, GR, l2sum,
+                                          gscale, viol, st, it);
+  if (OUT_ALIAS) __syncthreads();  // nobody reads or writes the gain arrays any more
+  if (!active) return;
+  const double c = cs.c, wmax = cs.w_max;
+  double slope[NSEG], brk[NSEG + 1];
+#pragma unroll
+  for (int i = 0; i <= NSEG; ++i) brk[i] = cs.brk[i];
+#pragma unroll
+  for (int j = 0; j < NSEG; ++j) slope[j] = cs.slope[j];
+  // ---- outputs: the result row through this thread's slot and one bulk store
+  double2* slot = reinterpret_cast<double2*>(smem_raw + L::oOut + (size_t)t * L::kRowOut);
+#pragma unroll
+  for (int k = 0; k < N; k += 2) slot[k / 2] = make_double2(W[k], W[k + 1]);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(a.w_out + b * (int64_t)N),
+               "r"(smem_u32(slot)), "r"(N * 8)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+  double cost = cs.theta * wmax * l2sum;
+  double s = 0.0;
+#pragma unroll
+  for (int k = 0; k < N; ++k) {
+    const double x = W[k];
+    s += x;
+    cost += x * fma(0.5 * D[k], x, GR[k]) + 0.5 * c * s * (s - 2.0 * gam);
+    if (NSEG > 1) {
+#pragma unroll
+      for (int j = 1; j < NSEG; ++j) cost += (slope[j] - slope[j - 1]) * dpos(x - brk[j]);
+    }
+    LOMPC_STAGE_FENCE();
+  }
+  if (a.cost_out) a.cost_out[b] = cost;
+  if (a.status) a.status[b] = st;
+  if (a.iters) a.iters[b] = it;
+  if (a.kkt_res) a.kkt_res[b] = viol / gscale;
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");  // the slot must outlive the store's read
 }
 
 }  // namespace lompc

@@ -65,11 +65,15 @@ double lompc_sc_modulus(const lompc_t* h);
 int lompc_set_options(lompc_t* h, int max_iter, double tol);
 
 /* Kernel choice: 0 = automatic (register-resident kernel for N = 12, 24 - 64 threads x 4 CTAs per SM; large EV
- * on grids that fill the GPU: one 256-thread CTA per SM - and the any-N shared-memory kernel otherwise),
+ * on grids that fill the GPU: one 256-thread CTA per SM; plain batches of >= 65,536 QPs at N = 24: the same
+ * kernel with bulk-copied rows, see 9 - and the any-N shared-memory kernel otherwise),
  * 1 = always the any-N kernel, 4 / 7 = one register-kernel shape regardless of the batch size (4 = 64 threads x
  * 4 CTAs per SM, 7 = 256 x 1; the other shapes of round 1's sweep are no longer compiled: LOMPC_ERR_ARG);
  * 8 = the warp-cooperative latency kernel (one QP per group of N/3 lanes, time-parallel sweeps; N = 12, 24,
- * 48, 96), which automatic mode picks for batches too small to fill the GPU with one QP per thread. */
+ * 48, 96), which automatic mode picks for batches too small to fill the GPU with one QP per thread;
+ * 9 = the register kernel with every row moved by the bulk-copy engine (cp.async.bulk into shared memory, one copy per
+ * row, result rows by bulk stores; N = 12, 24; batches that are not plain 16-byte aligned rows - broadcast prices, the
+ * group mode of the price loop, fused error outputs - run on the default shape). */
 int lompc_set_kernel_variant(lompc_t* h, int variant);
 
 /* Replaces LoMPC.solve_lompc (lompc.py:137-156), batched over B independent

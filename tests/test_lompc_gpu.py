@@ -268,3 +268,53 @@ def test_robustness_bound_of_the_reference_script(ev):
     bound = np.sqrt(N) * gamma_max_arr / 2
     assert np.all(w_err <= bound + 1e-12)
     assert np.all(w0_err <= bound * min(1.0, 1.0 / np.sqrt(kappa)) + 1e-12)
+
+
+@pytest.mark.parametrize("N", [12, 24])
+@pytest.mark.parametrize("ev", ["small", "large"])
+def test_bulk_copy_rows_kernel_is_bit_identical(ev, N):
+    """Kernel variant 9 moves every price row and every result row with the bulk-copy engine (cp.async.bulk through
+    shared memory) instead of per-thread loads and stores; the arithmetic is the register kernel's, so the results
+    must be the SAME BITS (w, iteration counts, statuses, residuals; the cost to rounding) - on dense and sparse prices (optimistic and safeguarded phases), on the hard cases, on a
+    batch that ends in the middle of a CTA, with statuses of invalid rows - and the golden vectors must hold."""
+    from chargingstation.lompc import LoMPC
+    o, c = _consts(ev)
+    rng = np.random.default_rng(900 + N)
+    thread = LoMPC(N, c)
+    thread.set_kernel_variant(4)
+    bulk = LoMPC(N, c)
+    bulk.set_kernel_variant(9)
+    for B, sparse in ((1, False), (63, False), (64, True), (1000, False), (4099, True), (70001, False)):
+        lm = o.theta * rng.random((B, 3 * N))
+        if sparse:
+            lm *= rng.random((B, 3 * N)) < 0.5
+        lr = 3 * N * o.delta * rng.random(B) * (rng.random(B) < 0.7)
+        gam = o.y_max * rng.random(B)
+        w_t, c_t, i_t = thread.solve_lompc_batch(lm, lr, gam, return_info=True)
+        w_b, c_b, i_b = bulk.solve_lompc_batch(lm, lr, gam, return_info=True)
+        assert np.array_equal(w_b, w_t), (B, sparse, np.abs(w_b - w_t).max(), np.flatnonzero(np.any(w_b != w_t, axis=1))[:8])
+        # (the cost is re-summed in each kernel's epilogue: same formula, the compiler's choice of fused operations)
+        assert np.max(np.abs(c_b - c_t) / np.maximum(1.0, np.abs(c_t))) <= 1e-12, (B, sparse)
+        assert np.array_equal(i_b["iters"], i_t["iters"]) and np.array_equal(i_b["status"], i_t["status"])
+        assert np.array_equal(i_b["kkt_res"], i_t["kkt_res"])
+        for b in range(0, B, max(1, B // 6)):
+            wo, co, _ = orc.solve_active_set(N, o, lm[b], lr[b], gam[b])
+            assert np.max(np.abs(w_b[b] - wo)) <= W_RTOL * o.w_max and abs(c_b[b] - co) <= C_RTOL * max(1, abs(co))
+    # invalid rows: same per-QP status, same exception (lompc.py:78-90)
+    lm = o.theta * rng.random((130, 3 * N))
+    lm[77, 5] = -1.0
+    with pytest.raises(ValueError):
+        bulk.solve_lompc_batch(lm, 0.0, np.full(130, 0.2))
+    with pytest.raises(AssertionError):
+        bulk.solve_lompc_batch(np.abs(lm), 0.0, np.where(np.arange(130) == 129, o.y_max + 0.01, 0.2))
+    # broadcast prices are not rows of the batch: served by the per-thread loads of the default shape
+    w_b, c_b = bulk.solve_lompc_batch(np.abs(lm[0]), 0.0, np.linspace(0.0, o.y_max, 130))
+    w_t, c_t = thread.solve_lompc_batch(np.abs(lm[0]), 0.0, np.linspace(0.0, o.y_max, 130))
+    assert np.array_equal(w_b, w_t) and np.array_equal(c_b, c_t)
+    z = np.load(os.path.join(os.path.dirname(__file__), "golden", "lompc_hard_cases.npz"))
+    for key in sorted(set("_".join(k.split("_")[:3]) for k in z.files)):
+        if key.split("_")[0] != ev or int(key.split("_")[1][1:]) != N:
+            continue
+        w, cost, info = bulk.solve_lompc_batch(z[key + "_lmbd"], z[key + "_lmbd_r"], z[key + "_gamma"], return_info=True)
+        assert np.all(info["status"] == 0), key
+        assert np.max(np.abs(w - z[key + "_w"])) <= W_RTOL * o.w_max, key

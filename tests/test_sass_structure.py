@@ -42,3 +42,26 @@ def test_sweeps_are_branch_free_and_spill_free(name, tmp_path):
     m = re.search(re.escape(KERNELS[name]) + r":\s*\n\s*REG:(\d+) STACK:(\d+)", res)
     assert m, "resource usage not found"
     assert int(m.group(1)) <= 255 and int(m.group(2)) <= 64, m.groups()
+
+
+TMA_KERNELS = {  # automatic mode at N = 24 from 65,536 QPs (lompc_api.cu: launch_solve_reg_variant)
+    "small": "_ZN5lompc26lompc_solve_reg_tma_kernelILi24ELi1ELi64ELi4ELb0EEEvNS_6ConstsENS_9SolveArgsE",
+    "large": "_ZN5lompc26lompc_solve_reg_tma_kernelILi24ELi4ELi256ELi1ELb1EEEvNS_6ConstsENS_9SolveArgsE",
+}
+
+
+@pytest.mark.parametrize("name", sorted(TMA_KERNELS))
+def test_bulk_copy_kernel_moves_rows_with_the_copy_engine(name):
+    """The saturating K1 kernel loads every price row with ONE bulk copy into shared memory (UBLKCP.S.G, completion
+    through an mbarrier: SYNCS...TRANS64), reads it with 36 LDS.128, and stores the result row with one bulk store
+    (UBLKCP.G.S): no wide per-thread global loads or stores are left (those touched 32 lines per instruction)."""
+    out = subprocess.run(["cuobjdump", "-sass", "-fun", TMA_KERNELS[name], LIB], capture_output=True, text=True).stdout
+    ops = [m.group(1) for m in re.finditer(r"/\*[0-9a-f]{4,}\*/\s+(?:@!?U?P\d+\s+)?([A-Z][A-Z0-9_.]*)", out)]
+    assert len(ops) > 2000, "kernel not found in the library"
+    assert sum(o.startswith("UBLKCP.S.G") for o in ops) == 1 and sum(o.startswith("UBLKCP.G.S") for o in ops) == 1
+    assert any(o.startswith("SYNCS.ARRIVE.TRANS64") for o in ops) and any("TRYWAIT" in o for o in ops)
+    assert sum(o.startswith("LDS.128") for o in ops) >= 36
+    assert not any(o.startswith("LDG.E.128") or o.startswith("STG.E.128") for o in ops)
+    res = subprocess.run(["cuobjdump", "-res-usage", LIB], capture_output=True, text=True).stdout
+    m = re.search(re.escape(TMA_KERNELS[name]) + r":\s*\n\s*REG:(\d+) STACK:(\d+)", res)
+    assert m and int(m.group(1)) <= 255 and int(m.group(2)) <= 64, m and m.groups()
