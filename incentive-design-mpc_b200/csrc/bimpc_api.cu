@@ -85,10 +85,7 @@ int bimpc_create(int N, int P, double delta, double c_g, double u_g_max, double 
   int occ = 1;
   CKH(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, bimpc::bimpc_solve_kernel, h->threads, h->smem));
   h->ctas_per_sm = occ < 1 ? 1 : occ;
-  {
-    const size_t nb = 2 * (size_t)P + 1, np = nb * (nb + 1) / 2;
-    CKH(cudaMalloc(&h->li, (size_t)h->sms * h->ctas_per_sm * N * np * sizeof(double)));
-  }
+  CKH(cudaMalloc(&h->li, (size_t)h->sms * h->ctas_per_sm * bimpc::global_scratch_doubles(N, P) * sizeof(double)));
   // stage weights of the charging cost: exp_rate^(k-N+1) (bimpc.py:255-257), ones otherwise
   std::vector<double> om(N, 1.0);
   if (cost_type == BIMPC_COST_EXP_UNWEIGHTED)

@@ -74,7 +74,21 @@ __device__ __forceinline__ double fast_rcp_dev(double x) {
 }
 #endif
 
-constexpr int kThreads = 128;
+#ifndef BIMPC_THREADS
+#define BIMPC_THREADS 128
+#endif
+#ifndef BIMPC_MINB
+#define BIMPC_MINB 3
+#endif
+#ifndef BIMPC_GVEC
+#define BIMPC_GVEC 0
+#endif
+constexpr int kThreads = BIMPC_THREADS;  // threads per station
+constexpr int kMinBlocks = BIMPC_MINB;   // stations per SM the register allocation is asked to allow
+// Of the nine [2P, N] vectors of a station's state (iterate, slacks, multipliers, residual, directions, barrier
+// diagonal) the last kGlobalVecs live in the CTA's global scratch (L2-resident, touched by thread-strided loops only)
+// instead of shared memory, so that more stations share an SM.
+constexpr int kGlobalVecs = BIMPC_GVEC;
 constexpr int kMaxN = 48;  // horizon cap (scratch of one station must fit 227 KB of shared memory)
 
 struct BiConsts {
@@ -104,14 +118,22 @@ struct BiArgs {
   double tol;
   int max_iter;
   long long* prof;        // BIMPC_PROFILE builds only: cycle counters
-  double* li_scratch;     // [CTAs, N, nb(nb+1)/2] packed inverse factors of the diagonal blocks (global memory,
-                          // L2-resident: keeping them out of shared memory lets 3 stations share an SM)
+  double* li_scratch;     // [CTAs, global_scratch_doubles()] packed inverse factors of the diagonal blocks [+ state
+                          // vectors] (global memory, L2-resident: keeping them out of shared memory lets several
+                          // stations share an SM)
 };
+
+// Doubles of per-CTA global scratch: the packed inverse factors of the N diagonal blocks + the state vectors that are
+// kept out of shared memory.
+BI_HD size_t global_scratch_doubles(int N, int P) {
+  const size_t nb = 2 * (size_t)P + 1;
+  return (size_t)N * (nb * (nb + 1) / 2) + (size_t)kGlobalVecs * 2 * P * N;
+}
 
 // Number of doubles of scratch one station needs (shared memory on the device).
 BI_HD size_t scratch_doubles(int N, int P, int T) {
   const int Q2 = 2 * P, QN = Q2 * N, nb = Q2 + 1;
-  return (size_t)9 * QN + (size_t)(QN + N) + 2 * (size_t)(nb * (nb + 1) / 2) + 2 * (size_t)nb * nb +
+  return (size_t)(9 - kGlobalVecs) * QN + (size_t)(QN + N) + 2 * (size_t)(nb * (nb + 1) / 2) + 2 * (size_t)nb * nb +
          (size_t)40 * N + 8 * (size_t)nb + 3 * (size_t)T + 5 * Q2 + 16;
 }
 
@@ -180,16 +202,22 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
   // dense block operations: thread (tx, ty) = (column, row group)
   const int nx = T < 32 ? T : 32, tx = tid % nx, ty = tid / nx, ny = T / nx;
   // ---- carve
-  double* W = sm;             // [Q2,N] iterate
-  double* S1 = W + QNmax;        // slack / multiplier of w >= 0
-  double* Z1 = S1 + QNmax;
-  double* S2 = Z1 + QNmax;       // slack / multiplier of w <= wmax
-  double* Z2 = S2 + QNmax;
-  double* RDW = Z2 + QNmax;      // dual residual, w block
-  double* DXA = RDW + QNmax;     // affine direction, w block
-  double* DX = DXA + QNmax;      // Newton right-hand side, then the current direction, w block
-  double* EW = DX + QNmax;       // barrier diagonal z1/s1 + z2/s2
-  double* XI = EW + QNmax;       // [N,nb] block-tridiagonal solve vector (cumulative coordinates)
+  // the nine [Q2,N] state vectors: slot v < 9 - kGlobalVecs in shared memory, the others in the CTA's global scratch
+  // (behind the inverse factors); ordered so that the ones the factorisation and the solves read stay on chip
+  double* gvec = LI + (size_t)N * npmax;
+  auto vec_at = [&](int v) {
+    return v < 9 - kGlobalVecs ? sm + (size_t)v * QNmax : gvec + (size_t)(v - (9 - kGlobalVecs)) * QNmax;
+  };
+  double* EW = vec_at(0);        // barrier diagonal z1/s1 + z2/s2
+  double* DX = vec_at(1);        // Newton right-hand side, then the current direction, w block
+  double* W = vec_at(2);         // [Q2,N] iterate
+  double* S1 = vec_at(3);        // slack / multiplier of w >= 0
+  double* Z1 = vec_at(4);
+  double* S2 = vec_at(5);        // slack / multiplier of w <= wmax
+  double* Z2 = vec_at(6);
+  double* DXA = vec_at(7);       // affine direction, w block
+  double* RDW = vec_at(8);       // dual residual, w block
+  double* XI = sm + (size_t)(9 - kGlobalVecs) * QNmax;  // [N,nb] block-tridiagonal solve vector (cumulative coordinates)
   double* LPS = XI + QNmax + N;  // [2,np] shared-memory copy of the inverse factor of the last two stages
   double* SW = LPS + 2 * (size_t)npmax;  // [nb,nb] Schur complement of the current stage
   double* XW = SW + nbmax * nbmax;  // [nb,nb] the identity the elimination turns into the inverse factor
@@ -779,11 +807,11 @@ BI_FN void solve_station(const BiConsts& c, const BiArgs& a, int st_idx, double*
 }
 
 #ifndef BIMPC_HOSTSIM
-__global__ void __launch_bounds__(kThreads, 3) bimpc_solve_kernel(const BiConsts c, const BiArgs a) {
+__global__ void __launch_bounds__(kThreads, kMinBlocks) bimpc_solve_kernel(const BiConsts c, const BiArgs a) {
   extern __shared__ double bimpc_smem[];
   for (int s = blockIdx.x; s < a.S; s += gridDim.x) {
-    solve_station(c, a, s, bimpc_smem, a.li_scratch + (size_t)blockIdx.x * c.N * ((2 * c.P + 1) * (2 * c.P + 2) / 2),
-                  threadIdx.x, blockDim.x);
+    solve_station(c, a, s, bimpc_smem, a.li_scratch + (size_t)blockIdx.x * global_scratch_doubles(c.N, c.P), threadIdx.x,
+                  blockDim.x);
     __syncthreads();
   }
 }

@@ -20,8 +20,7 @@ extern "C" int bimpc_hostsim_solve(int N, int P, double delta, double c_g, doubl
                   w_hat_s, w_hat_l, u_g, status, iters, objective, tol, max_iter, nullptr, nullptr};
   const size_t n = bimpc::scratch_doubles(N, P, 1);
   double* sm = (double*)malloc(n * sizeof(double));
-  const size_t nb = 2 * (size_t)P + 1;
-  double* li = (double*)malloc((size_t)N * (nb * (nb + 1) / 2) * sizeof(double));
+  double* li = (double*)malloc(bimpc::global_scratch_doubles(N, P) * sizeof(double));
   if (!sm || !li) return -1;
   for (int s = 0; s < S; ++s) bimpc::solve_station(c, a, s, sm, li, 0, 1);
   free(sm);

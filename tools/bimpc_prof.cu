@@ -18,7 +18,7 @@ int main() {
   double *ws, *wl, *ug, *obj; int32_t *st, *it; long long* prof;
   cudaMalloc(&ws, P * N * 8); cudaMalloc(&wl, P * N * 8); cudaMalloc(&ug, N * 8); cudaMalloc(&obj, 8);
   cudaMalloc(&st, 4); cudaMalloc(&it, 4); cudaMalloc(&prof, 64); cudaMemset(prof, 0, 64);
-  double* li; cudaMalloc(&li, (size_t)N * 25 * 26 / 2 * 8);
+  double* li; cudaMalloc(&li, bimpc::global_scratch_doubles(N, P) * 8);
   bimpc::BiArgs a{S, d_om, d_mp, d_mp, d_b, d_b, d_g, d_g, d_x0, d_dem, ws, wl, ug, st, it, obj, 1e-9, 100, prof, li};
   const size_t smem = bimpc::scratch_doubles(N, P, bimpc::kThreads) * 8;
   cudaFuncSetAttribute(bimpc::bimpc_solve_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
