@@ -77,11 +77,17 @@ __device__ __forceinline__ double fast_rcp_dev(double x) {
 #ifndef BIMPC_THREADS
 #define BIMPC_THREADS 128
 #endif
+// Stations per SM: the kernel hides the latency of its dependent, barrier-separated steps only by the number of
+// resident WARPS.  Measured on the BiMPC phase of a 4,096-station closed-loop step (round 2): 3 stations x 128 threads
+// (166 registers, all state in shared memory) 47.3 ms; 4 x 128 (register cap 128: no spills; 5 of the 9 state
+// vectors in global scratch so that 4 x 52 KB fit) 38.6 ms; 5 x 128 (96 registers, 16 B of spills, 7 vectors) 38.5 ms;
+// 6 x 128 (80 registers, 48 B of spills, all 9) 48.4 ms.  Fewer threads per station at the same number of warps per
+// SM (4 x 96, 5 x 64, 6 x 64) changes nothing (48.3 / 48.7 / 48.9 ms).
 #ifndef BIMPC_MINB
-#define BIMPC_MINB 3
+#define BIMPC_MINB 4
 #endif
 #ifndef BIMPC_GVEC
-#define BIMPC_GVEC 0
+#define BIMPC_GVEC 5
 #endif
 constexpr int kThreads = BIMPC_THREADS;  // threads per station
 constexpr int kMinBlocks = BIMPC_MINB;   // stations per SM the register allocation is asked to allow
@@ -143,12 +149,33 @@ BI_FN void block_reduce(double* RED, int tid, int T, double& sum, double& mx, do
   RED[T + tid] = mx;
   RED[2 * T + tid] = mn;
   BI_SYNC();
+#ifndef BIMPC_HOSTSIM
+  // Every thread needs the three results; computing them once per thread cost 8 % of the kernel's instructions at fleet
+  // scale (ncu, round 2).  Per WARP instead: lane 0 runs the ordered sum (same additions in the same order - the
+  // result does not change) and broadcasts it; maximum and minimum do not depend on the order and are folded by shuffles.
+  const unsigned full = 0xffffffffu;
+  const int lane = tid & 31;
+  double s = 0.0;
+  if (lane == 0)
+    for (int i = 0; i < T; ++i) s += RED[i];
+  s = __shfl_sync(full, s, 0);
+  double a = RED[T + lane], b = RED[2 * T + lane];
+  for (int i = lane + 32; i < T; i += 32) {
+    a = fmax(a, RED[T + i]);
+    b = fmin(b, RED[2 * T + i]);
+  }
+  for (int o = 16; o > 0; o >>= 1) {
+    a = fmax(a, __shfl_xor_sync(full, a, o));
+    b = fmin(b, __shfl_xor_sync(full, b, o));
+  }
+#else
   double s = 0.0, a = RED[T], b = RED[2 * T];
   for (int i = 0; i < T; ++i) {
     s += RED[i];
     a = fmax(a, RED[T + i]);
     b = fmin(b, RED[2 * T + i]);
   }
+#endif
   BI_SYNC();
   sum = s;
   mx = a;
@@ -180,6 +207,24 @@ BI_FN double col_part(const double* L, int i, int nb, const double* x, int part,
   return a0 + a1;
 }
 BI_FN double vec_dot(const double* a, const double* b, int n) {
+#ifndef BIMPC_HOSTSIM
+  // The same four accumulator chains and the same final additions as the loop below (same bits), formed once per
+  // WARP - lanes 0-3 run one chain each - instead of once per thread: every thread of the CTA needs the value, and
+  // 128 copies of a 25-term dot product were 16 % of the kernel's instructions at fleet scale (ncu, round 2).
+  // Every lane of the warp must call.
+  const unsigned full = 0xffffffffu;
+  const int lane = threadIdx.x & 31;
+  double acc = 0.0;
+  if (lane < 4) {
+    const int n4 = n & ~3;
+    for (int j = lane; j < n4; j += 4) acc = fma(a[j], b[j], acc);
+    if (lane == 0)
+      for (int j = n4; j < n; ++j) acc = fma(a[j], b[j], acc);
+  }
+  const double pr = acc + __shfl_down_sync(full, acc, 1);  // lane 0: a0 + a1, lane 2: a2 + a3
+  const double r = pr + __shfl_down_sync(full, pr, 2);     // lane 0: (a0 + a1) + (a2 + a3)
+  return __shfl_sync(full, r, 0);
+#else
   double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
   int j = 0;
   for (; j + 3 < n; j += 4) {
@@ -190,6 +235,7 @@ BI_FN double vec_dot(const double* a, const double* b, int n) {
   }
   for (; j < n; ++j) a0 += a[j] * b[j];
   return (a0 + a1) + (a2 + a3);
+#endif
 }
 
 // One station.  `sm` = scratch_doubles(N, P, T) doubles private to this CTA.
