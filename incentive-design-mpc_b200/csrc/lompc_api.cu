@@ -1096,6 +1096,15 @@ int launch_fused_warp(lompc_handle* h, const lompc::FusedArgs& a, cudaStream_t s
   return LOMPC_OK;
 }
 
+// Is there a device-resident loop for this handle?  N = 12, 24: the parametric and the thread-per-EV kernels; N = 48,
+// 96: the parametric kernel only ("avg" tolerance type, loop mode 0 or 2).  Otherwise: the phase-split loop.
+inline bool has_fused_loop(const lompc_handle* h, int tol_type_max) {
+  if (h->variant == 1 || h->loop_mode == 1) return false;
+  const int N = h->cs.N;
+  if (N == 12 || N == 24) return true;
+  return (N == 48 || N == 96) && !tol_type_max && (h->loop_mode == 2 || (h->loop_mode == 0 && kParametricLoopByDefault));
+}
+
 // compute_optimal_prices for whole groups resident on this GPU: one CTA per group, no host loop.
 int price_solve_fused(lompc_handle* h, const lompc::FusedArgs& a, cudaStream_t s) {
   const int N = h->cs.N;
@@ -1105,6 +1114,8 @@ int price_solve_fused(lompc_handle* h, const lompc::FusedArgs& a, cudaStream_t s
   if (parametric) {
     if (N == 24) return launch_fused_warp<24>(h, a, s);
     if (N == 12) return launch_fused_warp<12>(h, a, s);
+    if (N == 48) return launch_fused_warp<48>(h, a, s);
+    if (N == 96) return launch_fused_warp<96>(h, a, s);
   }
   if (h->cs.large) {
     if (N == 24) return launch_fused<24, 4, 64, 4, true>(h, a, s);
@@ -1182,7 +1193,7 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
   if (total_iters) *total_iters = 0;
   if (G == 0) return LOMPC_OK;
   CK(cudaSetDevice(h->device));
-  if ((h->cs.N == 24 || h->cs.N == 12) && h->variant != 1 && h->loop_mode != 1)
+  if (has_fused_loop(h, tol_type_max))
     return price_solve_fused_entry(h, G, B, group_off, y0, w_ref, lmbd_r, r, max_iter, tol_type_max, eps_reg, eps_tol,
                                    prices, iters, price_pre, price_post, w_k_out, hist_ac, hist_pred, hist_cap,
                                    total_iters, 0, 0, nullptr, nullptr, stream);
@@ -1228,7 +1239,7 @@ int price_solve_chain_dev(lompc_t* h, int32_t S, int32_t P, int64_t B, const int
     return LOMPC_ERR_ARG;
   if (max_group_iters) *max_group_iters = 0;
   CK(cudaSetDevice(h->device));
-  if (!((h->cs.N == 24 || h->cs.N == 12) && h->variant != 1 && h->loop_mode != 1)) {
+  if (!has_fused_loop(h, tol_type_max)) {
     // no fused kernel for this horizon: the same chain as P phase-split loops, one per partition slice
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     const int N = h->cs.N;

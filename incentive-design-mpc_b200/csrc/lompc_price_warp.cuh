@@ -53,14 +53,16 @@ struct WarpLoopSmem {
       (size_t)kDoubles * 8 + 3 * kMaxPivots * 4 + kMaxPivots * N + 4 * kQueueCap + 3 * N + 32;
 };
 
-// The loop of ONE group by one warp.  Same contract as group_loop_body (lompc_price_fused.cuh).
+// The loop of ONE group by one warp.  Same contract as group_loop_body (lompc_price_fused.cuh).  N = 12, 24 (the closed
+// loop's horizons) and 48, 96 (configs[4]'s: 16 / 32 lanes per QP, 2 / 1 QPs per warp pass).
 // Scratch in global memory (a.w_scratch rows b0 .., N doubles per EV): the sorted gammas and their
 // prefix sums (2n + 1 doubles; the launcher sizes the rows so that this fits for every n >= 1).
 template <int N, int NSEG>
 __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArgs& a, const int g, double* smem,
                                                 const double* p_in, double* p_out, double* p_out2) {
   constexpr int SPL = 3, LPQ = N / SPL, QPW = 32 / LPQ;
-  static_assert(N <= 32 && N % SPL == 0, "one lane per stage in the sums; N = 12 or 24");
+  static_assert(N % SPL == 0 && (32 % LPQ == 0) && N <= 96, "N = 12, 24, 48, 96");
+  constexpr int NW = (N + 31) / 32;  // stages per lane in the sums over the group (lane l: stages l, l + 32, ...)
   const int lane = threadIdx.x;
   const int b0 = a.group_off[g], b1 = a.group_off[g + 1];
   const int n = b1 - b0;
@@ -130,7 +132,7 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
   const double lr = a.lmbd_r[g];
   const double kappa = lr / cs.delta;
   const double tolg = sqrt((double)N) * y0_rng + a.eps_tol;  // price_solver.py:184
-  abar_factor<N>(N, kappa, WS + 3 * a.r + 6 * N, lane);
+  abar_factor<(N <= 24 ? N : 0)>(N, kappa, WS + 3 * a.r + 6 * N, lane);
   __syncwarp();
   // position of the virtual EV in the sorted list: EVs [0, vpos) have gamma <= gamma_sc
   int vpos;
@@ -174,7 +176,9 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
       QR[0] = 0; QR[1] = 1;
       QR[2] = 1; QR[3] = 2;
     }
-    double wsum = 0.0;  // lane k < N: sum over the group's EVs of w_i[k]
+    double wsum[NW];  // lane l, slot u: sum over the group's EVs of w_i[l + 32 u]
+#pragma unroll
+    for (int u = 0; u < NW; ++u) wsum[u] = 0.0;
     // direct job: EVs [dj_first, dj_first + dj_cnt) of an interval (dj_sa, dj_sb) that found no free pivot slots are
     // solved one by one into the (idle) price-step scratch - exact, just without the saving
     int dj_first = 0, dj_cnt = 0, dj_sa = 0, dj_sb = 0;
@@ -233,7 +237,9 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
         __syncwarp();
         if (direct) {
           for (int t = 0; t < q; ++t)
-            if (lane < N) wsum += WS[t * N + lane];
+#pragma unroll
+            for (int u = 0; u < NW; ++u)
+              if (lane + 32 * u < N) wsum[u] += WS[t * N + lane + 32 * u];
           dj_first += q;
           dj_cnt -= q;
           if (dj_cnt == 0) {
@@ -246,7 +252,9 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
         // the real EVs just solved count once themselves
         for (unsigned m = batch & ~2u; m; m &= m - 1) {
           const int sv = __ffs(m) - 1;
-          if (lane < N) wsum += PW[sv * N + lane];
+#pragma unroll
+          for (int u = 0; u < NW; ++u)
+            if (lane + 32 * u < N) wsum[u] += PW[sv * N + lane + 32 * u];
         }
         if (a.qp_count)
           for (unsigned m = batch; m; m &= m - 1) k1_iters += (unsigned long long)PIT[__ffs(m) - 1];
@@ -264,16 +272,22 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
         bool same = true;
         if (cnt > 0) {
           bool diff = false;
-          if (lane < N) diff = PC[sa * N + lane] != PC[sb * N + lane];
+#pragma unroll
+          for (int u = 0; u < NW; ++u)
+            if (lane + 32 * u < N) diff |= PC[sa * N + lane + 32 * u] != PC[sb * N + lane + 32 * u];
           same = !__any_sync(full, diff);
         }
         if (cnt <= 0 || same) {
-          if (cnt > 0 && lane < N) {
+          if (cnt > 0) {
             const double ga = PG[sa], gb = PG[sb];
             const double sg = GPS[lb + 1] - GPS[fa];
             const double coef = gb > ga ? (sg - cnt * ga) / (gb - ga) : 0.0;
-            const double wa = PW[sa * N + lane], wb = PW[sb * N + lane];
-            wsum += cnt * wa + coef * (wb - wa);
+#pragma unroll
+            for (int u = 0; u < NW; ++u)
+              if (lane + 32 * u < N) {
+                const double wa = PW[sa * N + lane + 32 * u], wb = PW[sb * N + lane + 32 * u];
+                wsum[u] += cnt * wa + coef * (wb - wa);
+              }
           }
           release(sa);
           release(sb);
@@ -298,7 +312,9 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
               QW[2 * wn] = (unsigned char)prev;
               QW[2 * wn + 1] = (unsigned char)sn;
             }
-            if (lane < N) PW[sn * N + lane] = PW[sa * N + lane];  // warm start: the left end's solution
+#pragma unroll
+            for (int u = 0; u < NW; ++u)  // warm start: the left end's solution
+              if (lane + 32 * u < N) PW[sn * N + lane + 32 * u] = PW[sa * N + lane + 32 * u];
             ++wn;
             prev = sn;
           }
@@ -336,7 +352,9 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
         overflowed = 1;
       }
     }
-    if (lane < N) WSUM[lane] = wsum;
+#pragma unroll
+    for (int u = 0; u < NW; ++u)
+      if (lane + 32 * u < N) WSUM[lane + 32 * u] = wsum[u];
     __syncwarp();
     // ================= lane 0: bookkeeping of the previous step, convergence test; all lanes: price step =================
     flag = 0;
@@ -362,8 +380,9 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
     if (flag != 0) break;
     {
       int st;
-      price_step_warp<N>(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, lane, it == 0, it > 0, a.hist_ac != nullptr,
-                         true, lamdiff, dec_pred, st);
+      // (unrolled recursions for the horizons of the closed loop, rolled ones for the long horizons of the sweep)
+      price_step_warp<(N <= 24 ? N : 0)>(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, lane, it == 0, it > 0,
+                                         a.hist_ac != nullptr, true, lamdiff, dec_pred, st);
       nnqp_bad |= st;
     }
     __syncwarp();

@@ -240,8 +240,8 @@ int price_solve_chain_dev(lompc_t* h, int32_t S, int32_t P, int64_t B, const int
                           double* price_pre, double* price_post, const int32_t* station_order,
                           int32_t* max_group_iters, void* stream);
 
-/* price_solve_dev / price_solve_chain_dev run, for the compiled horizons (N = 12, 24), ONE kernel that iterates
- * every group to convergence on the device.  Loop modes: 0 = automatic; 1 = the phase-split loop below (any N; the
+/* price_solve_dev / price_solve_chain_dev run, for the compiled horizons (N = 12, 24; N = 48, 96 with the parametric
+ * loop and the "avg" tolerance type), ONE kernel that iterates every group to convergence on the device.  Loop modes: 0 = automatic; 1 = the phase-split loop below (any N; the
  * path a multi-GPU caller drives); 2 = the PARAMETRIC loop, one warp per group: the EVs of a group differ only in
  * gamma and the QP's solution is piecewise affine in it, so only the extreme EVs, the virtual EV (gamma_sc) and the
  * EVs that bracket a change of active set are solved and the rest is interpolated ("avg"

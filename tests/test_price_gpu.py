@@ -305,3 +305,45 @@ def test_parametric_loop_degenerate_groups(ev):
         assert out[2][1] == out[3][1] == st_o["iter"], (name, out[2][1], out[3][1], st_o["iter"])
         small = np.abs(lam_o) <= 1e3
         assert np.max(np.abs(out[2][0] - lam_o)[small]) <= 1e-6 * max(1.0, np.max(np.abs(lam_o[small]))), name
+
+
+@pytest.mark.parametrize("N", [48, 96])
+@pytest.mark.parametrize("ev", ["small", "large"])
+def test_parametric_loop_long_horizons(ev, N):
+    """compute_optimal_prices (price_solver.py:79-174) at the long horizons of BASELINE configs[4]: the device-resident
+    parametric loop (16 / 32 lanes per QP) against the CPU oracle loop - iteration counts equal, prices within 1e-6 -
+    and against the phase-split loop (mode 1, the only path these horizons had before)."""
+    from chargingstation import settings
+    from chargingstation.lompc import LoMPCConstants
+    from chargingstation.price_solver import PriceSolver
+    settings.PRINT_LEVEL = 0
+    o = orc.small_ev_consts() if ev == "small" else orc.large_ev_consts()
+    c = LoMPCConstants(o.delta, o.theta, o.y_max, o.w_max, o.ev_type)
+    rng = np.random.default_rng(N + (ev == "large"))
+    G = 6
+    counts = np.array([1, 2, 9, 33, 47, 70])
+    off = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    spans = [0.0, 0.02, 0.05, 0.3, 0.04, 0.45]
+    y0 = np.concatenate([0.3 + sp * rng.random(n) for n, sp in zip(counts, spans)])
+    w_ref = o.w_max * rng.random((G, N)) * 0.6
+    out = {}
+    for mode in (2, 1):
+        ps = PriceSolver(N, c, "linear-convex")
+        ps.set_loop_mode(mode)
+        prices, st = ps.compute_optimal_prices_batch(off, y0, w_ref, np.zeros(G), np.zeros((G, 3 * N)), max_iter=60)
+        out[mode] = (prices, st["iter"].copy(), st["price_before_reg"].copy(), st["price_after_reg"].copy())
+        if mode == 2:
+            assert ps.last_nnqp_cap_hits() == 0
+            assert int(ps._lib.price_last_qp_solves(ps._h)) < int(np.sum((counts + 1) * (st["iter"] + 1)))  # it did interpolate
+    assert np.array_equal(out[2][1], out[1][1]), (out[2][1], out[1][1])
+    for g in range(G):
+        ora = po.PriceOracle(N, o, "linear-convex", fast=True)
+        ora.set_charge_levels(y0[off[g]: off[g + 1]])
+        lam_o, st_o = ora.compute_optimal_prices(w_ref[g], 0.0, max_iter=60)
+        assert out[2][1][g] == st_o["iter"], (g, out[2][1][g], st_o["iter"])
+        small = np.abs(lam_o) <= 1e3
+        for mode in (2, 1):
+            err = np.abs(out[mode][0][g] - lam_o)
+            assert np.max(err[small]) <= 1e-6 * max(1.0, np.max(np.abs(lam_o[small]))), (mode, g)
+            assert np.all(err[~small] <= 1e-3 * np.abs(lam_o[~small])), (mode, g)
+        assert abs(out[2][3][g] - st_o["price_after_reg"]) <= 1e-6 * max(1.0, abs(st_o["price_after_reg"]))
