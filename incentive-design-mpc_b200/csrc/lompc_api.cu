@@ -849,6 +849,9 @@ int price_shard_start(lompc_t* h, void* stream) {
   // the one synchronising check of a solve: y0 outside [0, y_max] anywhere in the (all-reduced) statistics
   CK(cudaMemcpyAsync(h->poll, S.nact, 8, cudaMemcpyDeviceToHost, s));
   CK(cudaStreamSynchronize(s));
+  // The stream is idle: every count the previous loop published has landed.  Clear the ring, so that price_shard_poll
+  // cannot take the tag a previous loop left in a slot for this loop's iteration of the same number.
+  if (h->ring) memset(h->ring, 0, kRingSlots * 2 * sizeof(int32_t));
   if (h->poll[1]) {
     S.active = false;
     return LOMPC_ERR_CONSTS;  // price_solver.py:71, raised by every rank
@@ -1216,16 +1219,32 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
   if (rc) return rc;
   rc = price_shard_start(h, stream);
   if (rc) return rc;
-  int it = 0;
-  for (; it < max_iter; ++it) {
+  // The host never synchronises inside the loop: iteration `it` is enqueued while the device may still be kDepth
+  // iterations behind; the active-group count of every iteration comes back through the pinned ring, and the loop
+  // ends at the first iteration that published 0 (converged groups are skipped on the device, so the iterations
+  // enqueued beyond that point are no-ops).  Same counts as the synchronous loop (price_shard_group_phase).
+  constexpr int kDepth = 4;
+  static_assert(kDepth < kRingSlots, "the ring must hold the iterations in flight");
+  int done_at = -1, it = 0;
+  for (; it < max_iter && done_at < 0; ++it) {
     rc = price_shard_ev_phase(h, stream);
     if (rc) return rc;
-    int32_t nact = 0;
-    rc = price_shard_group_phase(h, it, &nact, stream);
+    rc = price_shard_group_phase_async(h, it, stream);
     if (rc) return rc;
-    if (nact == 0) break;
+    if (it >= kDepth) {
+      int32_t nact = 0;
+      rc = price_shard_poll(h, it - kDepth, 1, &nact);
+      if (rc < 0) return rc;
+      if (nact == 0) done_at = it - kDepth;
+    }
   }
-  if (total_iters) *total_iters = it;
+  for (int j = (it > kDepth ? it - kDepth : 0); j < it && done_at < 0; ++j) {  // drain what is still in flight
+    int32_t nact = 0;
+    rc = price_shard_poll(h, j, 1, &nact);
+    if (rc < 0) return rc;
+    if (nact == 0) done_at = j;
+  }
+  if (total_iters) *total_iters = done_at >= 0 ? done_at : max_iter;
   return price_shard_finish(h, price_pre, price_post, w_k_out, stream);
 }
 
