@@ -18,6 +18,17 @@
 
 namespace lompc {
 
+// Unroll factor of the price step's recursions at a compile-time horizon NT: UF stages per loop trip (kFullUnroll: all
+// of them).  Fully unrolled code is fastest for a group on its own; at fleet scale (8 warps per SM at unrelated points
+// of a 290 KB kernel, instruction fetch the top stall) 4 stages per trip are: price loops of a 4,096-station step
+// 46.8 ms fully unrolled, 41.1 ms by 8, 40.0 ms by 4 (round 2) - the arithmetic is the same in every variant.
+constexpr int kFullUnroll = 1024;
+template <int NT, int UF>
+struct K3Unroll {
+  static constexpr int value = NT ? (UF < NT ? UF : NT) : 1;
+};
+
+
 struct PriceArgs {
   int G;
   int r;               // 2N ("linear") or 3N ("linear-convex"), price_solver.py:44-47
@@ -243,13 +254,13 @@ __device__ __forceinline__ void colsum_body(int N, int G, const int32_t* __restr
 // then formed by all lanes at once (off the chain), and lane 0 runs the forward substitution.
 // NT = compile-time horizon (fully unrolled: the loads of a stage are issued ahead of the chain) or
 // 0 for a run-time N (rolled, compact code: the fused price loop is instruction-fetch bound at fleet scale).
-template <int NT>
+template <int NT, int UF = kFullUnroll>
 __device__ __forceinline__ void ric_solve(int Nrt, const double* dvec, double dadd, double c, const double* bvec,
                                           double* x, double* K, double* KAP, int lane) {
   const int N = NT ? NT : Nrt;
   if (lane == 0) {
     double pa = 0.0, pb = 1.0, pr = 0.0;
-#pragma unroll(NT ? NT : 1)
+#pragma unroll(K3Unroll<NT, UF>::value)
     for (int k = N - 1; k >= 0; --k) {
       const double d = (dvec ? dvec[k] : 0.0) + dadd;
       const double gk = -bvec[k];
@@ -277,7 +288,7 @@ __device__ __forceinline__ void ric_solve(int Nrt, const double* dvec, double da
   __syncwarp();
   if (lane == 0) {
     double s = 0.0;
-#pragma unroll(NT ? NT : 1)
+#pragma unroll(K3Unroll<NT, UF>::value)
     for (int k = 0; k < N; ++k) {  // s_{k+1} = s_k + x_k = (1 - K_k) s_k - kappa_k: ONE dependent FMA per stage
       const double kk = K[k], kap = KAP[k];
       x[k] = -fma(kk, s, kap);
@@ -308,20 +319,20 @@ __device__ __forceinline__ void abar_factor(int Nrt, double kappa, double* fac, 
 }
 
 // x = A_bar^{-1} b with the cached gains (every lane must call; lane 0 runs the two chains, KAP is scratch).
-template <int NT>
+template <int NT, int UF = kFullUnroll>
 __device__ __forceinline__ void abar_solve(int Nrt, const double* fac, const double* bvec, double* x, double* KAP,
                                            int lane) {
   const int N = NT ? NT : Nrt;
   if (lane == 0) {
     double r = 0.0;
-#pragma unroll(NT ? NT : 1)
+#pragma unroll(K3Unroll<NT, UF>::value)
     for (int k = N - 1; k >= 0; --k) {  // kappa_k = (r_{k+1} - b_k)/(kappa + Q_k);  r_k = (1 - K_k) r_{k+1} + K_k b_k
       const double bk = bvec[k];
       KAP[k] = (r - bk) * fac[2 * N + k];
       r = fma(fac[N + k], r, fac[k] * bk);
     }
     double s = 0.0;
-#pragma unroll(NT ? NT : 1)
+#pragma unroll(K3Unroll<NT, UF>::value)
     for (int k = 0; k < N; ++k) {
       const double kap = KAP[k];
       x[k] = -fma(fac[k], s, kap);
@@ -472,7 +483,7 @@ __device__ __noinline__ int nnqp_lawson_hanson(int N, int nb, double th, double 
 // rarely changes between iterations, so a warm start costs one verification pass.  Sums that
 // feed statistics are taken by lane 0 in (k, j) order, so the result does not depend on the
 // number of lanes.
-template <int NT>
+template <int NT, int UF = kFullUnroll>
 __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double kappa, double eps, double* lk,
                                                 const double* wk, const double* wr, double* ws,
                                                 unsigned char* FREE, int lane, bool first, bool warm,
@@ -509,7 +520,7 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
   }
   if (!have_fac) abar_factor<NT>(N, kappa, FAC, lane);
   __syncwarp();
-  abar_solve<NT>(N, FAC, U, V, KAPS, lane);
+  abar_solve<NT, UF>(N, FAC, U, V, KAPS, lane);
   __syncwarp();
   double gs = 1.0;
   for (int k = lane; k < N; k += 32) {
@@ -558,7 +569,7 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
       U[k] = rhs;
     }
     __syncwarp();
-    ric_solve<NT>(N, TD, 2.0 * m * eps * kappa, 2.0 * m * eps, U, V, KS, KAPS, lane);  // z
+    ric_solve<NT, UF>(N, TD, 2.0 * m * eps * kappa, 2.0 * m * eps, U, V, KS, KAPS, lane);  // z
     __syncwarp();
     for (int k = lane; k < N; k += 32) {
       const double coef[3] = {th, -th, C3[k]};
@@ -575,7 +586,7 @@ __device__ __forceinline__ void price_step_warp(const Consts& cs, int r, double 
       U[k] = u;
     }
     __syncwarp();
-    abar_solve<NT>(N, FAC, U, V, KAPS, lane);  // v = A_bar^{-1} B' l
+    abar_solve<NT, UF>(N, FAC, U, V, KAPS, lane);  // v = A_bar^{-1} B' l
     __syncwarp();
     bool same = true;
     for (int k = lane; k < N; k += 32) {

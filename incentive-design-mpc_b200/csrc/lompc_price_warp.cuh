@@ -28,6 +28,9 @@
 
 namespace lompc {
 
+#ifndef LOMPC_K3_FLEET_UNROLL
+#define LOMPC_K3_FLEET_UNROLL 4
+#endif
 #ifndef LOMPC_CHAIN_MINB
 #define LOMPC_CHAIN_MINB 1
 #endif
@@ -380,9 +383,15 @@ __device__ __forceinline__ bool group_loop_warp(const Consts& cs, const FusedArg
     if (flag != 0) break;
     {
       int st;
-      // (unrolled recursions for the horizons of the closed loop, rolled ones for the long horizons of the sweep)
-      price_step_warp<(N <= 24 ? N : 0)>(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, lane, it == 0, it > 0,
-                                         a.hist_ac != nullptr, true, lamdiff, dec_pred, st);
+      // (unrolled recursions for the horizons of the closed loop - 4 stages per trip in launches of several waves,
+      // where the code size counts (K3Unroll), all of them otherwise -, rolled ones for the long horizons of the sweep)
+      if (N <= 24 && a.compact_step)
+        price_step_warp<(N <= 24 ? N : 0), LOMPC_K3_FLEET_UNROLL>(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, lane,
+                                                                  it == 0, it > 0, a.hist_ac != nullptr, true, lamdiff,
+                                                                  dec_pred, st);
+      else
+        price_step_warp<(N <= 24 ? N : 0)>(cs, a.r, kappa, a.eps_reg, LM, WK, WREF, WS, WSB, lane, it == 0, it > 0,
+                                           a.hist_ac != nullptr, true, lamdiff, dec_pred, st);
       nnqp_bad |= st;
     }
     __syncwarp();
