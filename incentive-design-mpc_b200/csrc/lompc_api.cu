@@ -16,6 +16,7 @@
 namespace {
 
 constexpr bool kParametricLoopByDefault = true;  // parity: tests/test_fullsize_gpu.py, tools/compare_loop_modes.py; timing: DESIGN.md 4
+std::atomic<bool> g_force_compact_step{false};  // test hook: price_debug_force_compact_step()
 constexpr int kRingSlots = 64;  // iterations the pinned n_active ring of the sharded price loop can hold
 
 thread_local char g_cuda_err[256] = "";
@@ -422,6 +423,11 @@ int64_t price_last_qp_solves(const lompc_t* h) { return h ? (int64_t)h->last_qp_
 
 int price_debug_force_nnqp_fallback(int on) {
   CK(cudaMemcpyToSymbol(lompc::g_nnqp_force_fallback, &on, sizeof(int)));
+  return LOMPC_OK;
+}
+
+int price_debug_force_compact_step(int on) {
+  g_force_compact_step.store(on != 0, std::memory_order_relaxed);
   return LOMPC_OK;
 }
 
@@ -1160,7 +1166,8 @@ int price_solve_fused_entry(lompc_handle* h, int32_t G, int64_t B, const int32_t
     a.w_scratch = reinterpret_cast<double*>(static_cast<char*>(h->pws) + 256);
     a.B = B;
     a.chain_S = chain_S; a.chain_P = chain_P; a.chain_prev = chain_prev; a.chain_order = chain_order;
-    a.compact_step = (chain_P > 0 ? chain_S : G) >= 2 * 148 * 4;  // CTAs of the launch vs. 2 resident waves
+    a.compact_step = g_force_compact_step.load(std::memory_order_relaxed) ||
+                     (chain_P > 0 ? chain_S : G) >= 2 * 148 * 4;  // CTAs of the launch vs. 2 resident waves
     rc = price_solve_fused(h, a, s);
     if (rc) return rc;
     CK(cudaMemcpyAsync(h->poll, flags, 128, cudaMemcpyDeviceToHost, s));

@@ -263,6 +263,9 @@ int64_t price_last_qp_solves(const lompc_t* h);
 int64_t price_last_cycles(const lompc_t* h, int which);
 int price_debug_force_nnqp_fallback(int on);
 int price_debug_pivot_pool(int slots);
+/* Test hook: non-zero makes every device-resident loop take the code path of fleet-scale launches (the compact price
+ * step: recursions unrolled 4 stages per trip; automatic from 1,184 groups / stations per launch). */
+int price_debug_force_compact_step(int on);
 
 /* The same loop cut into the phases between which a multi-GPU caller
  * all-reduces, for EVs sharded over ranks (each rank passes its LOCAL EVs and

@@ -150,6 +150,21 @@ def test_chain_kernel_fullsize_teacher_forced(name, loop_mode):
     _run_chain_teacher_forced(name, loop_mode)
 
 
+@pytest.mark.parametrize("loop_mode", [3, 2], ids=["thread-per-EV", "parametric"])
+@pytest.mark.parametrize("name", ["n24_unw", "cfg0_unw"])
+def test_chain_kernel_with_the_fleet_scale_price_step(name, loop_mode):
+    """Launches of several waves (from 1,184 stations) run a compact price step - the recursions unrolled 4 stages per
+    trip in the parametric loop, rolled in the thread-per-EV loop - that no small test would reach: the hook forces it
+    onto the recorded steps, which must still match the oracle's iteration counts and prices."""
+    from chargingstation import _native
+    lib = _native.load()
+    assert lib.price_debug_force_compact_step(1) == 0
+    try:
+        _run_chain_teacher_forced(name, loop_mode)
+    finally:
+        assert lib.price_debug_force_compact_step(0) == 0
+
+
 def _run_chain_teacher_forced(name, loop_mode):
     """Returns the number of groups whose pivot pool ran out (parametric loop; informational)."""
     import ctypes as C
