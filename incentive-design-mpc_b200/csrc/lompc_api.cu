@@ -167,7 +167,7 @@ template <int N, int NSEG>
 int launch_solve_reg_variant(const lompc_handle* h, const lompc::SolveArgs& a, cudaStream_t stream) {
   if (h->variant == 9 && tma_rows_ok(a, N)) {  // bulk-copy rows (batches that are not plain rows: the default below)
     if constexpr (NSEG > 1)
-      return launch_solve_reg_tma<N, NSEG, 256, 1, true>(h, a, stream);
+      return launch_solve_reg_tma<N, NSEG, 128, 2, true>(h, a, stream);
     else
       return launch_solve_reg_tma<N, NSEG, 64, 4, false>(h, a, stream);
   }
@@ -189,10 +189,13 @@ int launch_solve_reg_variant(const lompc_handle* h, const lompc::SolveArgs& a, c
       // large; 262,144: 116.7 / 104.4, 202.8 / 182.3; 524,288: 215.0 / 188.4 (2.44 -> 2.78 G QP/s), 389.1 / 344.1
       // (1.35 -> 1.52 G).  Below that (16,384: 18.4 / 18.4, 30.7 / 32.8) and at N = 12, where a row is 288 B and the
       // two CTA barriers cost more than the copies save (524,288 QPs: 94.4 / 110.6 us), the loads stay per-thread.
+      // CTA shape with bulk-copied rows (524,288 QPs): small EV 64 x 4: 188.4 us, 128 x 2: 194.6, 256 x 1: 229.3; large
+      // EV 128 x 2: 325.6 us (1.61 G QP/s), 64 x 4: 327.7, 256 x 1: 340.0 - two CTAs per SM cover each other's load
+      // and store phases, which the one-CTA shape the per-thread-load kernel prefers cannot.
       if constexpr (N == 24) {
         if (a.B >= 65536 && tma_rows_ok(a, N)) {
           if constexpr (NSEG > 1)
-            return launch_solve_reg_tma<N, NSEG, 256, 1, true>(h, a, stream);
+            return launch_solve_reg_tma<N, NSEG, 128, 2, true>(h, a, stream);
           else
             return launch_solve_reg_tma<N, NSEG, 64, 4, false>(h, a, stream);
         }

@@ -46,7 +46,7 @@ def test_sweeps_are_branch_free_and_spill_free(name, tmp_path):
 
 TMA_KERNELS = {  # automatic mode at N = 24 from 65,536 QPs (lompc_api.cu: launch_solve_reg_variant)
     "small": "_ZN5lompc26lompc_solve_reg_tma_kernelILi24ELi1ELi64ELi4ELb0EEEvNS_6ConstsENS_9SolveArgsE",
-    "large": "_ZN5lompc26lompc_solve_reg_tma_kernelILi24ELi4ELi256ELi1ELb1EEEvNS_6ConstsENS_9SolveArgsE",
+    "large": "_ZN5lompc26lompc_solve_reg_tma_kernelILi24ELi4ELi128ELi2ELb1EEEvNS_6ConstsENS_9SolveArgsE",
 }
 
 
