@@ -635,10 +635,17 @@ inline unsigned nblk(int64_t n, int t) { return (unsigned)((n + t - 1) / t); }
 int launch_group_step(const lompc_handle* h, const lompc::PriceArgs& p, int it, cudaStream_t s) {
   const int N = h->cs.N, wpc = 2;
   const size_t smem = (size_t)wpc * (lompc::price_step_scratch_doubles(N, p.r) + (p.r + 7) / 8) * sizeof(double);
-  if (smem > 48 * 1024) {
-    CK(cudaFuncSetAttribute(lompc::group_step_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  // (the horizons of the closed loop and of BASELINE configs[2] get the unrolled recursions of the price step)
+  if (N == 24) {
+    lompc::group_step_kernel<24><<<nblk(p.G, wpc), 32 * wpc, smem, s>>>(h->cs, p, it);
+  } else if (N == 12) {
+    lompc::group_step_kernel<12><<<nblk(p.G, wpc), 32 * wpc, smem, s>>>(h->cs, p, it);
+  } else {
+    if (smem > 48 * 1024) {
+      CK(cudaFuncSetAttribute(lompc::group_step_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    }
+    lompc::group_step_kernel<0><<<nblk(p.G, wpc), 32 * wpc, smem, s>>>(h->cs, p, it);
   }
-  lompc::group_step_kernel<<<nblk(p.G, wpc), 32 * wpc, smem, s>>>(h->cs, p, it);
   g_launches.fetch_add(1, std::memory_order_relaxed);
   CK(cudaGetLastError());
   return LOMPC_OK;

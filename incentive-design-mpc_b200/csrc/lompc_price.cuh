@@ -653,6 +653,7 @@ __device__ __forceinline__ void price_errors(int N, double kappa, const double* 
 // One WARP per group: errors, the convergence test (price_solver.py:121-127) and -- for
 // groups that go on -- the price step.  Dynamic shared memory: per warp
 // price_step_scratch_doubles() doubles + r bytes (rounded up to 8).
+template <int NT>  // compile-time horizon of the price step's recursions (unrolled), or 0 for any N
 __global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
   extern __shared__ double gs_smem[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
@@ -718,9 +719,9 @@ __global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
   __syncwarp();
   double lamdiff, dec;
   int st;
-  price_step_warp<0>(cs, r, kappa, p.eps_reg, p.lmbd + (size_t)g * 3 * N, p.w_k + (size_t)g * N,
-                  p.w_ref + (size_t)g * N, ws, FREE, lane, it == 0, warm, p.hist_ac != nullptr || p.want_dec, false,
-                  lamdiff, dec, st);
+  price_step_warp<NT>(cs, r, kappa, p.eps_reg, p.lmbd + (size_t)g * 3 * N, p.w_k + (size_t)g * N,
+                      p.w_ref + (size_t)g * N, ws, FREE, lane, it == 0, warm, p.hist_ac != nullptr || p.want_dec, false,
+                      lamdiff, dec, st);
   for (int i = lane; i < r; i += 32) gfree[i] = FREE[i];
   if (lane == 0) {
     p.nnqp_status[g] = st;
