@@ -237,8 +237,19 @@ __device__ __forceinline__ void colsum_body(int N, int G, const int32_t* __restr
     return;
   }
   const int b0 = off[g], b1 = off[g + 1];
+  // The additions stay in EV order (the reference's own, price_solver.py:205); the LOADS do not depend on each other:
+  // eight are issued before the first addition, so a group of 32 EVs costs 4 trips to L2 instead of 32.
   double sum = 0.0;
-  for (int b = b0; b < b1; ++b) sum += w_ev[(int64_t)b * N + k];
+  const double* col = w_ev + k;
+  int b = b0;
+  for (; b + 8 <= b1; b += 8) {
+    double v[8];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) v[u] = col[(int64_t)(b + u) * N];
+#pragma unroll
+    for (int u = 0; u < 8; ++u) sum += v[u];
+  }
+  for (; b < b1; ++b) sum += col[(int64_t)b * N];
   w_avg[idx] = sum_only ? sum : sum / (b1 - b0);  // sum_only: the caller all-reduces, then divides by the global count
   if (k == 0 && err_ev) {
     double m = 0.0;
