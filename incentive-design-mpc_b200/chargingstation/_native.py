@@ -89,6 +89,7 @@ SIGNATURES = {
     "lompc_ipc_free": (C.c_int, [C.c_int, C.c_void_p]),
     "price_shard_attach_peers": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.POINTER(C.c_void_p), C.c_size_t]),
     "price_shard_uses_peers": (C.c_int, [C.c_void_p]),
+    "price_shard_local_sums": (C.c_int, [C.c_void_p, C.c_int]),
     "price_shard_finish": (C.c_int, [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]),
     "price_w0_price0_dev": (C.c_int, [C.c_void_p, C.c_int32, C.c_int64] + [C.c_void_p] * 7),
     "lompc_measure_fp64_peak": (C.c_int, [C.c_int, C.c_int, _dp, _dp]),

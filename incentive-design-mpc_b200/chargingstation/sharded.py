@@ -151,6 +151,11 @@ class CudaShardBackend:
         _native.raise_for(rc)
         return self.stat_min, self.stat_max, self.stat_sum, self.stat_cnt
 
+    def local_sums(self) -> None:
+        """This rank holds every EV (one process): the group phase forms the column sums itself, ``ev_phase``
+        launches no column-sum kernel and leaves ``w_sum`` / ``err_max`` untouched.  Call after ``begin``."""
+        _native.raise_for(self.lib.price_shard_local_sums(self.ps._h, 1))
+
     def start(self):
         _native.raise_for(self.lib.price_shard_start(self.ps._h, self._stream()))
 
@@ -202,6 +207,8 @@ def compute_optimal_prices_sharded(price_solver, group_off_local, y0_local, w_re
     distributed = process_group is not None or (dist.is_available() and dist.is_initialized()
                                                 and dist.get_world_size() > 1)
     smin, smax, ssum, scnt = be.begin(group_off_local, y0_local, w_ref, lmbd_r, prev_prices, max_iter, history)
+    if not distributed and hasattr(be, "local_sums"):
+        be.local_sums()  # nothing to reduce: one launch less per iteration
     if distributed:  # set_charge_levels across ranks (price_solver.py:66-77)
         dist.all_reduce(smin, op=dist.ReduceOp.MIN, group=process_group)
         dist.all_reduce(smax, op=dist.ReduceOp.MAX, group=process_group)

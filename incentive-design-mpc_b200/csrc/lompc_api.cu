@@ -57,6 +57,7 @@ struct PriceSession {  // state of one (possibly sharded) compute_optimal_prices
   double *stat_min = nullptr, *stat_max = nullptr, *stat_sum = nullptr, *stat_cnt = nullptr;
   lompc::PriceArgs p;
   bool peer = false;            // the aggregate is exchanged through peer memory (price_shard_attach_peers)
+  bool local_sums = false;      // this rank holds every EV: column sums inside the group step (price_shard_local_sums)
   unsigned long long tag0 = 0;  // flag value of iteration 0 of this session, minus one
 };
 
@@ -869,6 +870,18 @@ int price_shard_begin(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off
   return LOMPC_OK;
 }
 
+// Group-step arguments of the session: with every EV on this rank the step forms the column sums itself.
+static lompc::PriceArgs shard_fused_sums(const lompc_t* h) {
+  const PriceSession& S = h->ses;
+  lompc::PriceArgs pa = S.p;
+  if (S.local_sums && !S.peer) {
+    pa.cs_w_ev = S.w_ev;
+    pa.cs_err_ev = S.p.tol_type_max ? S.err_ev : nullptr;
+    pa.cs_off = S.group_off;
+  }
+  return pa;
+}
+
 // The caller's stream waits for whatever the pipelined group phase left running on the side stream.
 static int shard_join_side(lompc_t* h, cudaStream_t s) {
   if (!h->side_pending) return LOMPC_OK;
@@ -919,6 +932,7 @@ int price_shard_ev_phase(lompc_t* h, void* stream) {
   const int it = S.ev_passes++;
   // the per-group column sums: into the caller's w_sum buffer (which it all-reduces), or - peer exchange - into
   // buffer it & 1 of this rank's peer region, followed by the flag on every rank
+  if (S.local_sums && !S.peer) return LOMPC_OK;  // the group step forms the sums itself (shard_fused_sums)
   if (S.peer) {
     double* sums = reinterpret_cast<double*>(h->peers.region[h->peers.rank] + lompc::kPeerFlagBytes) +
                    (size_t)(it & 1) * S.G * N;
@@ -947,7 +961,7 @@ int price_shard_group_phase(lompc_t* h, int it, int32_t* n_active, void* stream)
   }
   CK(cudaMemsetAsync(S.nact, 0, 4, s));
   {
-    int rc0 = launch_group_step(h, S.p, it, s);
+    int rc0 = launch_group_step(h, shard_fused_sums(h), it, s);
     if (rc0) return rc0;
   }
   CK(cudaMemcpyAsync(h->poll, S.nact, 8, cudaMemcpyDeviceToHost, s));
@@ -981,7 +995,7 @@ int price_shard_group_phase_async(lompc_t* h, int it, void* stream) {
   }
   // three launches per group phase: the step (which, with peers attached, first gathers the ranks' partial sums),
   // the gamma_sc solve, and the bookkeeping (which publishes the active count to the host ring and resets it)
-  lompc::PriceArgs pa = S.p;
+  lompc::PriceArgs pa = shard_fused_sums(h);
   pa.publish_ring = h->ring;
   pa.publish_slots = kRingSlots;
   // The gamma_sc solve and the bookkeeping of this iteration are needed by the NEXT group step only (w_k, the reset
@@ -1115,6 +1129,12 @@ int lompc_ipc_free(int device, void* dev_ptr) {
 }
 
 int price_shard_uses_peers(const lompc_t* h) { return (h && h->ses.peer) ? 1 : 0; }
+
+int price_shard_local_sums(lompc_t* h, int on) {
+  if (!h || !h->ses.active) return LOMPC_ERR_ARG;
+  h->ses.local_sums = on != 0;
+  return LOMPC_OK;
+}
 
 int price_shard_attach_peers(lompc_t* h, int rank, int world, void* const* regions, size_t region_bytes) {
   if (!h || world < 0 || world > lompc::kMaxPeers || (world > 0 && (!regions || rank < 0 || rank >= world)))
@@ -1291,6 +1311,7 @@ int price_solve_dev(lompc_t* h, int32_t G, int64_t B, const int32_t* group_off, 
   int rc = price_shard_begin(h, G, B, group_off, y0, w_ref, lmbd_r, r, max_iter, tol_type_max, eps_reg, eps_tol,
                              prices, iters, smin, smax, ssum, scnt, wsum, emax, hist_ac, hist_pred, hist_cap, stream);
   if (rc) return rc;
+  h->ses.local_sums = true;  // one process, every EV here
   rc = price_shard_start(h, stream);
   if (rc) return rc;
   // The host never synchronises inside the loop: iteration `it` is enqueued while the device may still be kDepth

@@ -69,6 +69,11 @@ struct PriceArgs {
   unsigned long long peer_tag0;  // flag value of iteration 0, minus one
   int32_t* peer_timeout;     // set to 1 when a rank did not deliver in time
   unsigned int* blocks_done; // colsum_kernel's "last block signals" counter
+  // ---- column sums formed inside group_step_kernel (one rank holds every EV: nothing to reduce between the EV
+  // phase and the group phase, price_shard_local_sums); NULL: w_avg / w_err_max were filled by colsum_kernel
+  const double* cs_w_ev;     // [B,N] the EVs' solutions
+  const double* cs_err_ev;   // [B] their error norms (tol type "max") or NULL
+  const int32_t* cs_off;     // [G+1]
 };
 
 constexpr size_t kPeerFlagBytes = 1024;  // head of a peer region: one 64-bit flag per rank
@@ -702,6 +707,33 @@ __global__ void group_step_kernel(const Consts cs, const PriceArgs p, int it) {
           sum += ld_relaxed_sys_f64(part + k);
         }
       p.w_avg[(size_t)g * N + k] = sum;
+    }
+    __syncwarp();
+  }
+  if (p.cs_w_ev) {
+    // colsum_kernel's work for this group, by its own warp (one launch less per iteration): lane k adds column k in
+    // EV order (price_solver.py:205) with eight independent loads in flight - the same additions, the same bits
+    const int b0 = p.cs_off[g], b1 = p.cs_off[g + 1];
+    for (int k = lane; k < N; k += 32) {
+      double sum = 0.0;
+      const double* col = p.cs_w_ev + k;
+      int b = b0;
+      for (; b + 8 <= b1; b += 8) {
+        double v[8];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) v[u] = col[(int64_t)(b + u) * N];
+#pragma unroll
+        for (int u = 0; u < 8; ++u) sum += v[u];
+      }
+      for (; b < b1; ++b) sum += col[(int64_t)b * N];
+      p.w_avg[(size_t)g * N + k] = sum;  // the SUM: price_errors divides by cnt
+    }
+    if (p.cs_err_ev) {
+      double m = 0.0;
+      for (int b = b0 + lane; b < b1; b += 32) m = fmax(m, p.cs_err_ev[b]);
+#pragma unroll
+      for (int d = 16; d >= 1; d >>= 1) m = fmax(m, __shfl_xor_sync(0xffffffffu, m, d));
+      if (lane == 0) p.w_err_max[g] = m;
     }
     __syncwarp();
   }

@@ -316,6 +316,11 @@ int lompc_ipc_free(int device, void* dev_ptr);
 int price_shard_attach_peers(lompc_t* h, int rank, int world, void* const* regions, size_t region_bytes);
 /* 1 if the current / last session exchanges through peer memory (the caller then skips its all-reduce). */
 int price_shard_uses_peers(const lompc_t* h);
+/* Call after price_shard_begin when THIS rank holds every EV of every group (world size 1, the reduction of
+ * price_solver.py:199-210 has nothing to add): the group phase then forms the per-group column sums itself (same
+ * additions in EV order) and price_shard_ev_phase neither launches the column-sum kernel nor fills w_sum / err_max.
+ * Ignored while peers are attached.  Session-scoped: price_shard_begin resets it. */
+int price_shard_local_sums(lompc_t* h, int on);
 
 /* PriceSolver.get_w0_price0 (price_solver.py:272-285) for every group:
  * w0[B] = first-step charge of each EV, price0[G] = mean first-step price.    */
