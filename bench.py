@@ -647,10 +647,29 @@ def sharded_leg(args, rank, world, dev):
                            if getattr(ps, "_peer_state", None) is not None and world > 1 else
                            ("dist.all_reduce (NCCL)" if world > 1 else "none (one rank)"))
         out["per_type"][ev] = {"ms": ms, "wall_ms": wall_ms, "iterations": loops, "us_per_iteration": ms * 1e3 / loops,
+                               # (a stand-alone dist.all_reduce of the same [G, N] buffer, for comparison: with the
+                               # peer exchange the loop itself makes no NCCL call)
                                "allreduce_us": ar_ms * 1e3, "allreduce_share": ar_ms * loops / ms if ms > 0 else 0.0,
                                "converged_groups": int(np.sum(it < MAX_IT - 1)), "iters_mean": float(it.mean()),
                                "qp_solves": qps, "price_checksum": float(np.sum(prices)),
                                "local_evs": int(hi - lo)}
+        if world == 1:
+            # the same 1,024 groups through the device-resident loop a one-GPU caller gets from
+            # PriceSolver.compute_optimal_prices_batch (one launch: a warp per group, parametric in gamma);
+            # reported beside the phase-split loop above, which is the code every N runs and the leg's `ms`
+            y0_all, zG = y0, np.zeros(G)
+            ps.compute_optimal_prices_batch(off, y0_all, w_ref, zG, np.zeros((G, 3 * N)), max_iter=3)
+            torch.cuda.synchronize()
+            r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            r0.record()
+            prices_r, stats_r = ps.compute_optimal_prices_batch(off, y0_all, w_ref, zG, np.zeros((G, 3 * N)),
+                                                                max_iter=MAX_IT)
+            r1.record()
+            torch.cuda.synchronize()
+            out["per_type"][ev]["resident_loop"] = {
+                "ms": r0.elapsed_time(r1), "iters_equal": bool(np.array_equal(np.asarray(stats_r["iter"]), it)),
+                "max_price_diff": float(np.max(np.abs(prices_r - prices))),
+                "note": "price_solve_dev through the class API with host arrays (its small copies are inside)"}
         tot_ms += ms
         tot_qp += qps
         tot_ar_ms += ar_ms * loops
