@@ -1022,11 +1022,44 @@ int price_shard_group_phase_async(lompc_t* h, int it, void* stream) {
     CK(cudaEventRecord(h->ev_fork, s));
     CK(cudaStreamWaitEvent(t, h->ev_fork, 0));
   }
-  int rc = launch_group_solve(h, S.G, S.p.lmbd, S.p.lmbd_r, S.gamma_sc, nullptr, S.skip, nullptr, S.w_k,
-                              S.cost_new, nullptr, nullptr, nullptr, t, S.w_k);
-  if (rc) return rc;
-  lompc::bookkeep_kernel<<<nblk(S.G, 128), 128, 0, t>>>(pa, it);
-  COUNT_LAUNCH();
+  // gamma_sc solve + bookkeeping: one launch where the warp-cooperative K1 would take the solve anyway
+  // (LOMPC_SHARD_FUSED_BK=0: always the two launches)
+  static const bool fuse_bk = [] { const char* e = getenv("LOMPC_SHARD_FUSED_BK"); return !(e && e[0] == '0'); }();
+  const int N = h->cs.N;
+  const bool sc_on_warps = lompc_detail::warp_kernel_supports(N, 3) &&
+                           (h->variant == 8 || (h->variant == 0 && S.G <= warp_kernel_max_batch(N)));
+  if (fuse_bk && sc_on_warps) {
+    lompc::SolveArgs a;
+    memset(&a, 0, sizeof(a));
+    a.B = S.G;
+    a.lmbd = S.p.lmbd;
+    a.lmbd_stride = 3 * (int64_t)N;
+    a.lmbd_r = S.p.lmbd_r;
+    a.lmbd_r_stride = 1;
+    a.gamma = S.gamma_sc;
+    a.w_out = S.w_k;
+    a.cost_out = S.cost_new;
+    a.max_iter = h->max_iter;
+    a.tol = h->tol;
+    a.skip = S.skip;
+    a.w_init = S.w_k;
+    const int qpw = 32 / (N / 3);
+    const unsigned warps = (unsigned)((S.G + qpw - 1) / qpw);
+    switch (N) {
+      case 12: lompc::sc_solve_bookkeep_kernel<12><<<warps, 32, 0, t>>>(h->cs, a, pa, it); break;
+      case 24: lompc::sc_solve_bookkeep_kernel<24><<<warps, 32, 0, t>>>(h->cs, a, pa, it); break;
+      case 48: lompc::sc_solve_bookkeep_kernel<48><<<warps, 32, 0, t>>>(h->cs, a, pa, it); break;
+      case 96: lompc::sc_solve_bookkeep_kernel<96><<<warps, 32, 0, t>>>(h->cs, a, pa, it); break;
+      default: return LOMPC_ERR_ARG;
+    }
+    COUNT_LAUNCH();
+  } else {
+    int rc = launch_group_solve(h, S.G, S.p.lmbd, S.p.lmbd_r, S.gamma_sc, nullptr, S.skip, nullptr, S.w_k,
+                                S.cost_new, nullptr, nullptr, nullptr, t, S.w_k);
+    if (rc) return rc;
+    lompc::bookkeep_kernel<<<nblk(S.G, 128), 128, 0, t>>>(pa, it);
+    COUNT_LAUNCH();
+  }
   CK(cudaGetLastError());
   if (overlap) {
     CK(cudaEventRecord(h->ev_join, t));

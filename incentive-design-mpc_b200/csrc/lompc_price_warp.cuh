@@ -460,4 +460,42 @@ __global__ void __launch_bounds__(32, LOMPC_CHAIN_MINB) price_station_chain_warp
   }
 }
 
+// Phase-split loop, second half of a group phase in ONE launch: the gamma_sc solves of iteration `it`
+// (price_solver.py:132, the warp-cooperative K1 in group mode: row = group, warm start from w_k) followed, per group,
+// by bookkeep_kernel's work (price_solver.py:135-137: the actual decrease from the cost this lane group has just
+// written, the new dual cost, the histories).  Warp 0 also publishes the active-group count of the iteration to the
+// host's ring and resets the counter: the launch is stream-ordered after group_step_kernel(it), and nothing else touches
+// the counter before group_step_kernel(it + 1), which is ordered after this launch.  Same arithmetic as the two
+// launches it replaces; a launch (and its place on the side stream's critical path) less per iteration.
+template <int N>
+__global__ void __launch_bounds__(32, 1) sc_solve_bookkeep_kernel(const __grid_constant__ Consts cs,
+                                                                  const __grid_constant__ SolveArgs a,
+                                                                  const __grid_constant__ PriceArgs p, const int it) {
+  constexpr int SPL = 3, LPQ = N / SPL, QPW = 32 / LPQ;
+  const int lane = threadIdx.x;
+  const int64_t b = (int64_t)blockIdx.x * QPW + lane / LPQ;
+  const bool live = b < a.B;
+  if (blockIdx.x == 0 && lane == 0 && p.publish_ring) {
+    volatile int32_t* slot = p.publish_ring + 2 * (it % p.publish_slots);
+    slot[1] = *p.n_active;
+    __threadfence_system();
+    slot[0] = it + 1;
+    *p.n_active = 0;
+  }
+  int st;
+  if (cs.large)
+    solve_warp<N, 4, SPL>(cs, a, b, live, lane, st);
+  else
+    solve_warp<N, 1, SPL>(cs, a, b, live, lane, st);
+  if (live && (lane & (LPQ - 1)) == 0 && !p.skip[b]) {  // the lane that stored cost_out[b] (group b)
+    const double cn = a.cost_out[b];
+    const double ac = cn - p.dual_cost[b] + p.lamdiff_phi[b];
+    p.dual_cost[b] = cn;
+    if (p.hist_ac && it < p.hist_cap) {
+      p.hist_ac[(size_t)b * p.hist_cap + it] = ac;
+      p.hist_pred[(size_t)b * p.hist_cap + it] = p.dec_pred[b];
+    }
+  }
+}
+
 }  // namespace lompc
