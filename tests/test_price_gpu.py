@@ -238,6 +238,47 @@ def test_sharded_phases_two_emulated_ranks(ev):
     assert np.max(np.abs(outs[0][0] - prices_ref)) <= 1e-8 * max(1.0, np.max(np.abs(prices_ref)))
 
 
+@pytest.mark.parametrize("ev", ["small", "large"])
+def test_phase_split_loop_variants_agree_bitwise(ev):
+    """The phase-split loop has a plain form (price_shard_ev_phase with its column-sum kernel, the synchronous
+    price_shard_group_phase with separate gamma_sc-solve and bookkeeping launches, everything on one stream) and the
+    pipelined one-process form (column sums inside the group step - price_shard_local_sums -, gamma_sc solve and
+    bookkeeping in one launch on a side stream beside the next EV phase).  Same kernels' arithmetic in the same order:
+    prices, iteration counts and the decrease histories (price_solver.py:135-137) must agree to the last bit."""
+    from chargingstation.price_solver import PriceSolver
+    from chargingstation.sharded import CudaShardBackend, compute_optimal_prices_sharded
+    o, c = _consts(ev)
+    N = 24
+    rng = np.random.default_rng(91)
+    sizes = [32, 7, 0, 41, 1, 32, 19]
+    off = np.concatenate([[0], np.cumsum(sizes)]).astype(np.int32)
+    G = len(sizes)
+    y0 = np.concatenate([np.sort(0.3 + 0.03 * g + 0.04 * rng.random(n)) for g, n in enumerate(sizes)])
+    w_ref = o.w_max * rng.random((G, N)) * 0.7
+    prev, zG, max_iter = np.zeros((G, 3 * N)), np.zeros(G), 80
+    # plain form, driven phase by phase
+    be = CudaShardBackend(PriceSolver(N, c, "linear-convex"))
+    be.begin(off, y0, w_ref, zG, prev, max_iter, True)
+    be.start()
+    for it in range(max_iter):
+        be.ev_phase()
+        if be.group_phase(it) == 0:
+            break
+    prices_a, st_a = be.finish(True)
+    # pipelined one-process form through the public function, and through price_solve_dev (loop mode 1)
+    prices_b, st_b = compute_optimal_prices_sharded(PriceSolver(N, c, "linear-convex"), off, y0, w_ref, zG, prev,
+                                                    history=True, max_iter=max_iter)
+    ps = PriceSolver(N, c, "linear-convex")
+    ps.set_loop_mode(1)
+    prices_c, st_c = ps.compute_optimal_prices_batch(off, y0, w_ref, zG, prev, history=True, max_iter=max_iter)
+    assert st_a["iter"].max() > 3  # the loop did iterate
+    for prices_x, st_x in ((prices_b, st_b), (prices_c, st_c)):
+        assert np.array_equal(st_x["iter"], st_a["iter"])
+        assert np.array_equal(prices_x, prices_a)
+        assert np.array_equal(st_x["w_k"], st_a["w_k"])
+        assert np.array_equal(st_x["hist_ac"], st_a["hist_ac"]) and np.array_equal(st_x["hist_pred"], st_a["hist_pred"])
+
+
 _REF_SCENARIOS = (  # the four families of test/test_price_solver.py:38-108: (name, nEVs, N, price_type, lmbd_r, max_charge)
     [("single", 1, 12, pt, 0.0, 1 / 3.0) for pt in ("linear", "linear-convex")] +
     [("multiple", 100, 12, "linear-convex", 0.0, 1 / 36.0)] +
