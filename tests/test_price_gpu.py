@@ -275,7 +275,8 @@ def test_phase_split_loop_variants_agree_bitwise(ev):
     for prices_x, st_x in ((prices_b, st_b), (prices_c, st_c)):
         assert np.array_equal(st_x["iter"], st_a["iter"])
         assert np.array_equal(prices_x, prices_a)
-        assert np.array_equal(st_x["w_k"], st_a["w_k"])
+        nonempty = np.asarray(sizes) > 0  # (an empty group is never solved: its w_k row is not defined)
+        assert np.array_equal(st_x["w_k"][nonempty], st_a["w_k"][nonempty])
         assert np.array_equal(st_x["hist_ac"], st_a["hist_ac"]) and np.array_equal(st_x["hist_pred"], st_a["hist_pred"])
 
 
