@@ -83,6 +83,9 @@ class OracleShardBackend:
                                                          self.gamma_sc[g])
         return active
 
+    def local_sums(self):  # (CudaShardBackend: price_shard_local_sums; here the sums are always formed in ev_phase)
+        self.local_sums_calls = getattr(self, "local_sums_calls", 0) + 1
+
     # the pipelined interface of CudaShardBackend: "enqueue" = run now, the count is published per iteration
     def group_phase_async(self, it):
         if not hasattr(self, "_published"):

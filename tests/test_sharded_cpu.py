@@ -85,6 +85,7 @@ def _worker(rank, world, port, out, pipelined=True, bad_y0=False):
         if rank == 0:
             out["prices"], out["iter"], out["total"] = prices, np.asarray(stats["iter"]), stats["total_iters"]
             out["async_calls"] = getattr(be, "async_calls", 0)
+            out["local_sums_calls"] = getattr(be, "local_sums_calls", 0)
     except AssertionError:
         out[f"assert_{rank}"] = True
     dist.destroy_process_group()
@@ -103,6 +104,7 @@ def test_two_rank_gloo_price_loop_matches_single_process(pipelined):
         mp.spawn(_worker, args=(world, port, out, pipelined), nprocs=world, join=True)
         prices, iters = np.array(out["prices"]), np.array(out["iter"])
         assert (out["async_calls"] > 0) == pipelined
+        assert out["local_sums_calls"] == 0  # ranks that must reduce never ask for the column sums to stay local
         assert out["total"] == max(iters[[0, 2, 3]])  # the loop ends when the last NON-EMPTY group has converged
     # reference: every group on its own, single process, the oracle's own loop
     o, N, off, y0, w_ref = _problem()
@@ -127,3 +129,39 @@ def test_bad_charge_level_on_one_rank_raises_on_every_rank():
         out = m.dict()
         mp.spawn(_worker, args=(world, port, out, True, True), nprocs=world, join=True)
         assert out.get("assert_0") and out.get("assert_1")
+
+
+def test_single_process_asks_for_local_sums():
+    """One process, no process group: compute_optimal_prices_sharded tells the backend that nothing has to be reduced
+    (price_shard_local_sums on the CUDA backend: the group phase forms the column sums itself) - once, after begin and
+    before start - and the result is the oracle's own loop."""
+    from fake_shard_backend import OracleShardBackend
+    o, N, off, y0, w_ref = _problem()
+    G = len(off) - 1
+
+    class Recording(OracleShardBackend):
+        calls = []
+
+        def begin(self, *a, **k):
+            self.calls.append("begin")
+            return super().begin(*a, **k)
+
+        def local_sums(self):
+            self.calls.append("local_sums")
+
+        def start(self):
+            self.calls.append("start")
+            return super().start()
+
+    be = Recording(N, o, "linear-convex")
+    prices, stats = compute_optimal_prices_sharded(None, off, y0, w_ref, np.zeros(G), np.zeros((G, 3 * N)),
+                                                   backend=be, max_iter=60)
+    assert be.calls[:3] == ["begin", "local_sums", "start"] and be.calls.count("local_sums") == 1
+    for g in range(G):
+        if off[g + 1] == off[g]:
+            continue
+        ora = po.PriceOracle(N, o, "linear-convex")
+        ora.set_charge_levels(y0[off[g]:off[g + 1]])
+        lam, st = ora.compute_optimal_prices(w_ref[g], 0.0, max_iter=60)
+        assert st["iter"] == np.asarray(stats["iter"])[g]
+        assert np.max(np.abs(lam - prices[g])) <= 1e-9 * max(1.0, np.max(np.abs(lam)))
