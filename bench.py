@@ -673,6 +673,10 @@ def sharded_leg(args, rank, world, dev):
         tot_ms += ms
         tot_qp += qps
         tot_ar_ms += ar_ms * loops
+    if world > 1:
+        out["allreduce_note"] = ("allreduce_us / allreduce_share: a stand-alone dist.all_reduce of the same [G, N] buffer "
+                                 "timed after the loop, for comparison - with the peer-memory exchange the loop itself "
+                                 "makes no NCCL call")
     out["ms"] = tot_ms
     out["qp_solves"] = tot_qp
     out["qp_per_s"] = tot_qp / (tot_ms * 1e-3)
